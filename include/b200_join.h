@@ -1,0 +1,205 @@
+/*
+ * b200_join.h — C-ABI of the B200 join library (libb200join.so).
+ *
+ * Part 1 re-declares, with the reference's exact signatures, the 16 operator
+ * symbols that query.c:ExecuteQuery imports (`nm -u query.o`).
+ * A build that replaces the reference's rhjoin.o preprocess.o results.o
+ * filter.o inter_res.o by this library and relinks the untouched handler.o
+ * query.o best_tree.o stats.o scheduler.o relation_map.o relation_list.o is a
+ * link-time drop-in (oracle/Makefile target `_ref/radixhash_b200_dropin`).
+ *
+ * Part 2 is what the shim adds: device lifecycle, relation registration
+ * (the hook after relation_map.c:InitRelationMap, handler.c:52), result
+ * read-back for tests, and the kernel-level entry points the parity tests and
+ * bench.py call.  Plain pointers and sizes only; no torch types.
+ *
+ * Error convention.  Part-1 operators follow the reference: a NULL `result*`
+ * means "empty => the whole query prints NULL" (query.c:360, 439); internal
+ * inconsistencies and CUDA failures print to stderr and exit(2) like
+ * rhjoin.c:285, filter.c:185, query.c:424 — there is no CPU fallback.
+ * Part-2 functions return 0 on success, non-zero on failure with the message
+ * available from b200_last_error().
+ */
+#ifndef B200_JOIN_H
+#define B200_JOIN_H
+
+#include "b200_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------
+ * Part 1 — the reference operator API (same names, arguments, meaning)
+ * ---------------------------------------------------------------------- */
+
+/* inter_res.h:11 / inter_res.c:26 — fresh, empty intermediate with one slot
+ * per query binding. */
+int InitInterResults(inter_res **head, int num_of_relations);
+
+/* inter_res.h:17 / inter_res.c:175 */
+void FreeInterResults(inter_res *var);
+
+/* filter.h:9 / filter.c:92-190 — scan `binding.column ⋄ (uint64)(int)value`
+ * over the base column (emits base row ids) or through the intermediate's
+ * row-id list (emits positions).  NULL when nothing qualifies. */
+result *Filter(inter_res *head, filter_pred *filter_p, relation_map *map,
+               int *query_relations);
+
+/* filter.h:15 / filter.c:11-89 — install a row-id list for a fresh binding,
+ * or compact every active column of the node that holds the binding. */
+int InsertSingleRowIdsToInterResult(inter_res **head, int relation_num,
+                                    result *res);
+
+/* inter_res.h:33 / inter_res.c:208-231 (+ScanInterResults 182-206) — the key
+ * vector a join consumes: col[i] for base rows, or col[T[b][p]] for every
+ * position p of the intermediate.  Returned lazily (no AoS materialisation). */
+relation *GetRelation(int given_rel, int column, inter_res *inter,
+                      relation_map *map, int *query_relations);
+
+/* rhjoin.h:9 / rhjoin.c:13-111 — all pairs (x,y) with keyR[x]==keyS[y].
+ * NULL only when an input is empty (rhjoin.c:15-16); an empty join returns a
+ * non-NULL result with current_load 0 (rhjoin.c:356-359). */
+result *RadixHashJoin(relation *relR, relation *relS, scheduler *sched);
+
+/* inter_res.h:26 / inter_res.c:34-152 */
+int InsertJoinToInterResults(inter_res *head, int rel1, int rel2, result *res);
+
+/* inter_res.h:61 / inter_res.c:352-361 */
+int AreActiveInInter(inter_res *inter, int rel1, int rel2);
+
+/* inter_res.h:64 / inter_res.c:363-389 — second predicate between two
+ * bindings of the same node: filter on the intermediate. */
+int JoinInterNode(inter_res **inter, relation_map *rel_map, int relation1,
+                  int column1, int relation2, int column2, int *relations);
+
+/* inter_res.h:48 / inter_res.c:265-318 */
+void MergeInterNodes(inter_res **inter);
+
+/* inter_res.h:68 / inter_res.c:391-428 */
+void CartesianInterResults(inter_res **inter);
+
+/* inter_res.h:55 / inter_res.c:320-339 — prints one line of SUM checksums. */
+void CalculateQueryResults(inter_res *inter, relation_map *map,
+                           batch_listnode *query);
+
+/* inter_res.h:58 / inter_res.c:341-350 */
+void PrintNullResults(batch_listnode *query);
+
+/* inter_res.h:44 / inter_res.c:234-263 — same-binding column equality
+ * (`0.1=0.2`).  The reference version is buggy; this one
+ * implements the contract: row ids / positions with col1 == col2. */
+result *SelfJoin(int given_rel, int column1, int column2, inter_res **inter,
+                 relation_map *map, int *query_relations);
+
+/* results.h:19 / results.c:144-153 */
+void FreeResult(result *head);
+
+/* preprocess.h:18 / preprocess.c:213-218 */
+void FreeRelation(relation *rel);
+
+/* ------------------------------------------------------------------------
+ * Part 2 — what the shim adds
+ * ---------------------------------------------------------------------- */
+
+/* Select the CUDA device, create the memory pool.  Idempotent.  Called
+ * implicitly (device 0, or $B200_DEVICE) by the first operator if omitted, so
+ * the reference's unmodified handler.o still works. */
+int  b200_init(int device);
+void b200_shutdown(void);
+const char *b200_last_error(void);
+/* 1 when the library was built from the CUDA sources (always, for this
+ * library; the CPU oracle exports the same symbol returning 0). */
+int  b200_is_cuda(void);
+
+/* Upload every column of `count` relations once (the contest's untimed
+ * preparation phase).  Device copies are keyed by the host column pointer.
+ * Columns that were never registered are uploaded on first use. */
+int  b200_register_relations(const relation_map *map, int count);
+/* Make an already device-resident column known under a host-side key pointer
+ * (bench.py: data generated in HBM).  `max_value` may be UINT64_MAX when
+ * unknown; it only selects the 32-bit-key kernels when < 2^32. */
+int  b200_register_device_column(const uint64_t *host_key,
+                                 const uint64_t *device_ptr, uint64_t n,
+                                 uint64_t max_value);
+/* (Re-)upload one column from a host buffer, synchronously on the calling
+ * thread's stream; used by the end-to-end bench arm. */
+int  b200_upload_column(const uint64_t *host_col, uint64_t n);
+void b200_unregister_all(void);
+
+/* The calling thread's CUDA stream (cudaStream_t as void*), so a caller can
+ * record events on it; b200_set_stream adopts a caller-owned stream. */
+void *b200_get_stream(void);
+int   b200_set_stream(void *cuda_stream);
+int   b200_synchronize(void);
+
+/* CalculateQueryResults without the printf: sums[i] for projection i and the
+ * number of rows of the final intermediate. */
+int  b200_calculate_sums(inter_res *inter, relation_map *map,
+                         batch_listnode *query, uint64_t *sums,
+                         uint64_t *num_rows);
+
+/* Read-back for tests: copy a result (row ids, or pairs as r[],s[]) and one
+ * intermediate column to host as uint64. */
+int  b200_result_kind(const result *res);               /* 1 row ids, 2 pairs */
+int  b200_result_rowids_to_host(const result *res, uint64_t *out);
+int  b200_result_pairs_to_host(const result *res, uint64_t *out_r,
+                               uint64_t *out_s);
+int  b200_inter_column_to_host(const inter_res *node, int binding,
+                               uint64_t *out);
+
+/* Kernel-level entry points, host buffers in and out (parity tests).
+ * K1 scan_filter (filter.c:115-170): ids==NULL scans col[0..n) and emits row
+ * ids; otherwise scans col[ids[p]] for p in [0,n_ids) and emits positions. */
+int  b200_scan_filter(const uint64_t *col, uint64_t n, const uint64_t *ids,
+                      uint64_t n_ids, char cmp, int value, uint64_t *out,
+                      uint64_t *out_n);
+/* K3-K5 radix partition (preprocess.c:13-178) on `radix_bits` low bits:
+ * out_hist[b], out_psum[b] (-1 for empty buckets, preprocess.c:91-96) and the
+ * partition-contiguous copy (keys and original positions). */
+int  b200_radix_partition(const uint64_t *keys, uint64_t n, int radix_bits,
+                          uint64_t *out_keys, uint64_t *out_row_ids,
+                          uint64_t *out_hist, int64_t *out_psum);
+/* K6-K7 partitioned hash join on two key vectors; writes up to `cap` pairs,
+ * always returns the true pair count in *out_m. */
+int  b200_hash_join_pairs(const uint64_t *keys_r, uint64_t n_r,
+                          const uint64_t *keys_s, uint64_t n_s,
+                          uint64_t *out_r, uint64_t *out_s, uint64_t cap,
+                          uint64_t *out_m);
+/* K9 checksum (inter_res.c:332-333): sum of col[ids[j]] mod 2^64. */
+int  b200_gather_sum(const uint64_t *col, uint64_t n, const uint64_t *ids,
+                     uint64_t m, uint64_t *out_sum);
+
+/* Tuning knobs for tests/bench (0 = library default): radix bits of the
+ * partition pass and forcing the 64-bit-key kernels. */
+int  b200_set_tuning(int radix_bits, int force_key64);
+
+/* The fused bench/serving entry: `0 1|0.c=1.c|…` style two-relation equi-join
+ * straight into SUM checksums — join(keys_r, keys_s) then, per projection i,
+ * sum over all matching pairs of proj[i][row id of side proj_side[i]]
+ * (0 = R, 1 = S).  No pair materialisation (the final join of a query is
+ * folded into inter_res.c:320-339's SUM).
+ *   location 0: every pointer is a HOST buffer; the call uploads them on its
+ *               stream, runs the join and copies sums back (end-to-end arm).
+ *   location 1: every pointer is a DEVICE buffer already resident in HBM.
+ * `max_key` (or UINT64_MAX) bounds both key vectors. */
+int  b200_join_sum(const uint64_t *keys_r, uint64_t n_r,
+                   const uint64_t *keys_s, uint64_t n_s, uint64_t max_key,
+                   int n_proj, const uint64_t *const *proj,
+                   const int *proj_side, int location, uint64_t *out_sums,
+                   uint64_t *out_matches);
+
+/* Per-kernel device times of the calling thread's last RadixHashJoin /
+ * b200_join_sum, measured with CUDA events on its stream when profiling is
+ * enabled with b200_set_profiling(1).  Names: "hist", "scan", "scatter_r",
+ * "scatter_s", "join".  Returns milliseconds, or a negative value if the
+ * kernel did not run. */
+int    b200_set_profiling(int on);
+double b200_last_kernel_ms(const char *name);
+/* Number of kernels this library launched since the counter was reset. */
+uint64_t b200_kernel_launches(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_JOIN_H */

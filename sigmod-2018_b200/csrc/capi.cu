@@ -1,0 +1,251 @@
+// capi.cu — Part 2 of include/b200_join.h: lifecycle, relation registration,
+// and the kernel-level / fused entry points the parity tests and bench.py call
+// through ctypes.  Plain pointers and sizes only.
+#include "../../include/b200_join.h"
+#include "engine.cuh"
+
+#include <cstring>
+#include <vector>
+
+using namespace b200;
+
+namespace {
+
+// temporary device copy of a host uint64 array
+DevBufPtr upload_u64(const uint64_t *host, uint64_t n) {
+    Context  &c = ctx();
+    DevBufPtr d = dev_alloc(n * sizeof(uint64_t));
+    if (n) B200_CUDA(cudaMemcpyAsync(d->ptr, host, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
+    return d;
+}
+
+// host uint64 ids -> device uint32 ids
+DevBufPtr upload_ids(const uint64_t *host, uint64_t n) {
+    DevBufPtr wide = upload_u64(host, n);
+    DevBufPtr ids  = dev_alloc(n * sizeof(uint32_t));
+    narrow_ids(wide->as<uint64_t>(), n, ids->as<uint32_t>());
+    return ids;
+}
+
+void download_ids(const uint32_t *d, uint64_t n, uint64_t *out) {
+    if (n == 0) return;
+    Context  &c   = ctx();
+    DevBufPtr tmp = dev_alloc(n * sizeof(uint64_t));
+    widen_ids(d, n, tmp->as<uint64_t>());
+    B200_CUDA(cudaMemcpyAsync(out, tmp->ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
+    B200_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+uint64_t host_max(const uint64_t *v, uint64_t n) {
+    uint64_t m = 0;
+    for (uint64_t i = 0; i < n; ++i) m = v[i] > m ? v[i] : m;
+    return m;
+}
+
+int fail(const char *msg) {
+    set_last_error(msg);
+    return 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_init(int device) {
+    request_device(device);
+    ensure_init();
+    (void)ctx();
+    return 0;
+}
+
+void b200_shutdown(void) {
+    cudaDeviceSynchronize();
+    unregister_all_columns();
+}
+
+const char *b200_last_error(void) { return last_error_string().c_str(); }
+
+int b200_is_cuda(void) { return 1; }
+
+int b200_register_relations(const relation_map *map, int count) {
+    for (int r = 0; r < count; ++r)
+        for (uint64_t j = 0; j < map[r].num_columns; ++j)
+            register_host_column(map[r].columns[j], map[r].num_tuples, false);
+    return 0;
+}
+
+int b200_register_device_column(const uint64_t *host_key, const uint64_t *device_ptr, uint64_t n,
+                                uint64_t max_value) {
+    register_device_column(host_key, device_ptr, n, max_value);
+    return 0;
+}
+
+int b200_upload_column(const uint64_t *host_col, uint64_t n) {
+    register_host_column(host_col, n, true);
+    return 0;
+}
+
+void b200_unregister_all(void) { unregister_all_columns(); }
+
+void *b200_get_stream(void) { return ctx().stream; }
+
+int b200_set_stream(void *cuda_stream) {
+    Context &c = ctx();
+    if (c.owns_stream && c.stream) {
+        cudaStreamSynchronize(c.stream);
+        cudaStreamDestroy(c.stream);
+    }
+    c.stream      = static_cast<cudaStream_t>(cuda_stream);
+    c.owns_stream = false;
+    return 0;
+}
+
+int b200_synchronize(void) {
+    B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    return 0;
+}
+
+int b200_set_tuning(int radix_bits, int force_key64) {
+    ensure_init();
+    tuning().radix_bits  = radix_bits;
+    tuning().force_key64 = force_key64;
+    return 0;
+}
+
+int b200_set_profiling(int on) {
+    set_profiling(on != 0);
+    return 0;
+}
+
+double b200_last_kernel_ms(const char *name) {
+    Context &c  = ctx();
+    auto     it = c.timers.find(name);
+    if (it == c.timers.end() || !it->second.used) return -1.0;
+    float ms = 0.f;
+    if (cudaEventSynchronize(it->second.stop) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, it->second.start, it->second.stop) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+uint64_t b200_kernel_launches(int reset) {
+    uint64_t v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return v;
+}
+
+// K1 (filter.c:115-170)
+int b200_scan_filter(const uint64_t *col, uint64_t n, const uint64_t *ids, uint64_t n_ids, char cmp, int value,
+                     uint64_t *out, uint64_t *out_n) {
+    if (n > kMaxRows || n_ids > kMaxRows) return fail("more than 2^32-1 rows");
+    if (cmp != '<' && cmp != '>' && cmp != '=') return fail("comparator must be <, > or =");
+    DevBufPtr d_col = upload_u64(col, n);
+    DevBufPtr d_ids = ids ? upload_ids(ids, n_ids) : nullptr;
+    KeySrc    src{d_col->as<uint64_t>(), d_ids ? d_ids->as<uint32_t>() : nullptr,
+               (uint32_t)(ids ? n_ids : n)};
+    IdList l = run_filter(src, cmp, value);
+    download_ids(l.ids->as<uint32_t>(), l.n, out);
+    *out_n = l.n;
+    return 0;
+}
+
+// K3-K5 (preprocess.c:13-178)
+int b200_radix_partition(const uint64_t *keys, uint64_t n, int radix_bits, uint64_t *out_keys,
+                         uint64_t *out_row_ids, uint64_t *out_hist, int64_t *out_psum) {
+    if (n > kMaxRows) return fail("more than 2^32-1 rows");
+    if (radix_bits < 0 || radix_bits > tuning().max_bits) return fail("radix_bits out of range");
+    Context  &c = ctx();
+    DevBufPtr d = upload_u64(keys, n);
+    KeyVec    kv;
+    kv.src     = KeySrc{d->as<uint64_t>(), nullptr, (uint32_t)n};
+    kv.max_val = host_max(keys, n);
+    PartitionOut   p      = run_partition(kv, radix_bits);
+    const uint32_t nparts = 1u << radix_bits;
+    std::vector<uint32_t> hist(nparts);
+    B200_CUDA(cudaMemcpyAsync(hist.data(), p.hist->ptr, nparts * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                              c.stream));
+    if (n) {
+        DevBufPtr k64 = dev_alloc(n * sizeof(uint64_t)), r64 = dev_alloc(n * sizeof(uint64_t));
+        unpack_partition(p, n, k64->as<uint64_t>(), r64->as<uint64_t>());
+        B200_CUDA(cudaMemcpyAsync(out_keys, k64->ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
+        B200_CUDA(cudaMemcpyAsync(out_row_ids, r64->ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                  c.stream));
+    }
+    B200_CUDA(cudaStreamSynchronize(c.stream));
+    // preprocess.c:83-102: psum is the running start, -1 for an empty bucket
+    int64_t run = 0;
+    for (uint32_t b = 0; b < nparts; ++b) {
+        out_hist[b] = hist[b];
+        out_psum[b] = hist[b] ? run : -1;
+        run += hist[b];
+    }
+    return 0;
+}
+
+// K6-K7 (rhjoin.c:13-111)
+int b200_hash_join_pairs(const uint64_t *keys_r, uint64_t n_r, const uint64_t *keys_s, uint64_t n_s,
+                         uint64_t *out_r, uint64_t *out_s, uint64_t cap, uint64_t *out_m) {
+    if (n_r > kMaxRows || n_s > kMaxRows) return fail("more than 2^32-1 rows");
+    *out_m = 0;
+    if (n_r == 0 || n_s == 0) return 0;   // rhjoin.c:15-16
+    DevBufPtr dr = upload_u64(keys_r, n_r), ds = upload_u64(keys_s, n_s);
+    KeyVec    R, S;
+    R.src     = KeySrc{dr->as<uint64_t>(), nullptr, (uint32_t)n_r};
+    S.src     = KeySrc{ds->as<uint64_t>(), nullptr, (uint32_t)n_s};
+    R.max_val = host_max(keys_r, n_r);
+    S.max_val = host_max(keys_s, n_s);
+    JoinResult j = run_join(R, S, JoinOut::Pairs, 0, nullptr);
+    *out_m       = j.m;
+    const uint64_t take = j.m < cap ? j.m : cap;
+    download_ids(j.r_ids->as<uint32_t>(), take, out_r);
+    download_ids(j.s_ids->as<uint32_t>(), take, out_s);
+    return 0;
+}
+
+// K9 (inter_res.c:332-333)
+int b200_gather_sum(const uint64_t *col, uint64_t n, const uint64_t *ids, uint64_t m, uint64_t *out_sum) {
+    if (n > kMaxRows || m > kMaxRows) return fail("more than 2^32-1 rows");
+    DevBufPtr       d_col = upload_u64(col, n);
+    DevBufPtr       d_ids = upload_ids(ids, m);
+    const uint64_t *cols[1] = {d_col->as<uint64_t>()};
+    const uint32_t *idp[1]  = {d_ids->as<uint32_t>()};
+    run_checksum(m, 1, cols, idp, out_sum);
+    return 0;
+}
+
+// fused join -> SUM (rhjoin.c:13-111 folded into inter_res.c:320-339)
+int b200_join_sum(const uint64_t *keys_r, uint64_t n_r, const uint64_t *keys_s, uint64_t n_s, uint64_t max_key,
+                  int n_proj, const uint64_t *const *proj, const int *proj_side, int location,
+                  uint64_t *out_sums, uint64_t *out_matches) {
+    if (n_r > kMaxRows || n_s > kMaxRows) return fail("more than 2^32-1 rows");
+    if (n_proj < 0 || n_proj > kMaxProj) return fail("at most 8 fused projections");
+    for (int k = 0; k < n_proj; ++k) out_sums[k] = 0;
+    *out_matches = 0;
+    if (n_r == 0 || n_s == 0) return 0;
+    std::vector<DevBufPtr> keep;
+    KeyVec                 R, S;
+    ProjDesc               pd[kMaxProj];
+    if (location == 0) {
+        // end-to-end arm: every input crosses PCIe inside the call
+        DevBufPtr dr = upload_u64(keys_r, n_r), ds = upload_u64(keys_s, n_s);
+        keep.push_back(dr);
+        keep.push_back(ds);
+        R.src = KeySrc{dr->as<uint64_t>(), nullptr, (uint32_t)n_r};
+        S.src = KeySrc{ds->as<uint64_t>(), nullptr, (uint32_t)n_s};
+        for (int k = 0; k < n_proj; ++k) {
+            DevBufPtr dp = upload_u64(proj[k], proj_side[k] == 0 ? n_r : n_s);
+            keep.push_back(dp);
+            pd[k] = ProjDesc{dp->as<uint64_t>(), nullptr, proj_side[k]};
+        }
+    } else {
+        R.src = KeySrc{keys_r, nullptr, (uint32_t)n_r};
+        S.src = KeySrc{keys_s, nullptr, (uint32_t)n_s};
+        for (int k = 0; k < n_proj; ++k) pd[k] = ProjDesc{proj[k], nullptr, proj_side[k]};
+    }
+    R.max_val = S.max_val = max_key;
+    JoinResult j = run_join(R, S, JoinOut::Sum, n_proj, pd);
+    for (int k = 0; k < n_proj; ++k) out_sums[k] = j.sums[k];
+    *out_matches = j.m;
+    return 0;
+}
+
+}  // extern "C"

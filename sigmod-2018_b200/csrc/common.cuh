@@ -1,0 +1,97 @@
+// common.cuh — runtime plumbing shared by every translation unit of
+// libb200join.so: error handling, the per-thread stream context, stream-ordered
+// device buffers, the launch counter and optional CUDA-event kernel timing.
+//
+// Error behaviour mirrors the reference's "print and exit(2)" convention
+// (rhjoin.c:285-286, filter.c:185-186, query.c:424-425): a CUDA failure inside
+// an operator is fatal.  There is no CPU fallback anywhere in this library.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <string>
+
+namespace b200 {
+
+[[noreturn]] void fatal(const char *file, int line, const char *what, const char *detail);
+void set_last_error(const std::string &msg);
+
+#define B200_CUDA(expr)                                                               \
+    do {                                                                              \
+        cudaError_t err__ = (expr);                                                   \
+        if (err__ != cudaSuccess)                                                     \
+            ::b200::fatal(__FILE__, __LINE__, #expr, cudaGetErrorString(err__));      \
+    } while (0)
+
+#define B200_REQUIRE(cond, msg)                                                       \
+    do {                                                                              \
+        if (!(cond)) ::b200::fatal(__FILE__, __LINE__, #cond, msg);                   \
+    } while (0)
+
+// Row ids and positions travel as 32-bit integers on the device; every length
+// that becomes a row id is checked against this bound at the API boundary.
+constexpr uint64_t kMaxRows = 0xFFFFFFFFull;
+
+struct KernelTimer {
+    cudaEvent_t start = nullptr, stop = nullptr;
+    bool        used  = false;
+};
+
+// One context per host thread: the reference fans a join out over pthreads
+// (scheduler.c); here every calling thread owns a CUDA stream and all of an
+// operator's kernels are enqueued on it in order.
+struct Context {
+    cudaStream_t stream       = nullptr;
+    bool         owns_stream  = false;
+    // pinned scratch for counters read back after a stream synchronise
+    unsigned long long *h_scratch = nullptr;   // 64 x u64, pinned
+    unsigned long long *d_scratch = nullptr;   // 64 x u64, device
+    std::map<std::string, KernelTimer> timers;
+    ~Context();
+};
+
+Context &ctx();                 // thread-local, created on first use
+void     ensure_init();         // device + pool, idempotent
+int      sm_count();
+bool     profiling_enabled();
+extern std::atomic<uint64_t> g_launches;
+
+// RAII timing scope: records events on the context stream when profiling is on.
+struct TimedScope {
+    KernelTimer *t = nullptr;
+    explicit TimedScope(const char *name);
+    ~TimedScope();
+};
+
+inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+#define B200_LAUNCH_CHECK()                                                           \
+    do {                                                                              \
+        ::b200::count_launch();                                                       \
+        B200_CUDA(cudaGetLastError());                                                \
+    } while (0)
+
+// Stream-ordered device buffer (cudaMallocAsync on the owning thread's stream).
+struct DevBuf {
+    void        *ptr   = nullptr;
+    size_t       bytes = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf(size_t nbytes, cudaStream_t s);
+    ~DevBuf();
+    DevBuf(const DevBuf &)            = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    template <typename T> T *as() const { return static_cast<T *>(ptr); }
+};
+using DevBufPtr = std::shared_ptr<DevBuf>;
+
+inline DevBufPtr dev_alloc(size_t nbytes) {
+    return std::make_shared<DevBuf>(nbytes, ctx().stream);
+}
+
+}  // namespace b200

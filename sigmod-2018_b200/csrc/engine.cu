@@ -1,0 +1,648 @@
+// engine.cu — runtime, column registry and kernel orchestration.
+// See engine.cuh for the interface and kernels.cuh for the reference loops
+// (file:line) each kernel replaces.
+#include "engine.cuh"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string t_last_error;
+
+void set_last_error(const std::string &msg) { t_last_error = msg; }
+const std::string &last_error_string() { return t_last_error; }
+
+[[noreturn]] void fatal(const char *file, int line, const char *what, const char *detail) {
+    // reference convention: diagnostics on stderr, exit(2) (rhjoin.c:285-286)
+    fprintf(stderr, "b200join fatal: %s:%d: %s: %s\n", file, line, what, detail ? detail : "");
+    fflush(stderr);
+    exit(2);
+}
+
+// ---------------------------------------------------------------------------
+// device + per-thread context
+// ---------------------------------------------------------------------------
+static std::once_flag g_init_once;
+static int            g_device   = -1;
+static int            g_sm_count = 0;
+static bool           g_profiling = false;
+std::atomic<uint64_t> g_launches{0};
+
+static void init_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        fatal(__FILE__, __LINE__, "cudaGetDeviceCount",
+              "no CUDA device: this library has no CPU fallback");
+    if (device < 0) {
+        const char *env = getenv("B200_DEVICE");
+        device          = env ? atoi(env) : 0;
+    }
+    B200_REQUIRE(device < count, "device index out of range");
+    B200_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    B200_CUDA(cudaGetDeviceProperties(&prop, device));
+    g_sm_count = prop.multiProcessorCount;
+    g_device   = device;
+    // keep freed blocks in the stream-ordered pool instead of returning them
+    cudaMemPool_t pool;
+    B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t threshold = UINT64_MAX;
+    B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    Tuning &t = tuning();
+    if (const char *v = getenv("B200_RADIX_BITS")) t.radix_bits = atoi(v);
+    if (const char *v = getenv("B200_FORCE_KEY64")) t.force_key64 = atoi(v);
+    if (const char *v = getenv("B200_CAP32")) t.cap32 = (uint32_t)atoi(v);
+    if (const char *v = getenv("B200_CAP64")) t.cap64 = (uint32_t)atoi(v);
+    if (const char *v = getenv("B200_SLICE")) t.slice = (uint32_t)atoi(v);
+    if (const char *v = getenv("B200_DEBUG")) t.debug = atoi(v);
+}
+
+static int g_requested_device = -1;
+void request_device(int device) { g_requested_device = device; }
+
+void ensure_init() {
+    std::call_once(g_init_once, [] { init_device(g_requested_device); });
+}
+int  device_index() { return g_device; }
+int  sm_count() { return g_sm_count; }
+bool profiling_enabled() { return g_profiling; }
+void set_profiling(bool on) { g_profiling = on; }
+
+Tuning &tuning() {
+    static Tuning t;
+    return t;
+}
+
+Context::~Context() {
+    // process teardown may already have destroyed the CUDA context: ignore errors
+    for (auto &kv : timers) {
+        if (kv.second.start) cudaEventDestroy(kv.second.start);
+        if (kv.second.stop) cudaEventDestroy(kv.second.stop);
+    }
+    if (h_scratch) cudaFreeHost(h_scratch);
+    if (d_scratch) cudaFree(d_scratch);
+    if (owns_stream && stream) cudaStreamDestroy(stream);
+}
+
+Context &ctx() {
+    static thread_local Context *c = nullptr;
+    if (!c) {
+        ensure_init();
+        B200_CUDA(cudaSetDevice(g_device));
+        // leaked on purpose at thread exit of the main thread: destroying CUDA
+        // objects from a thread_local destructor races with runtime teardown
+        c = new Context();
+        B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->owns_stream = true;
+        B200_CUDA(cudaMallocHost(&c->h_scratch, 64 * sizeof(unsigned long long)));
+        B200_CUDA(cudaMalloc(&c->d_scratch, 64 * sizeof(unsigned long long)));
+    }
+    return *c;
+}
+
+TimedScope::TimedScope(const char *name) {
+    if (!g_profiling) return;
+    Context &c = ctx();
+    t          = &c.timers[name];
+    if (!t->start) {
+        B200_CUDA(cudaEventCreate(&t->start));
+        B200_CUDA(cudaEventCreate(&t->stop));
+    }
+    t->used = true;
+    B200_CUDA(cudaEventRecord(t->start, c.stream));
+}
+TimedScope::~TimedScope() {
+    if (t) cudaEventRecord(t->stop, ctx().stream);
+}
+
+DevBuf::DevBuf(size_t nbytes, cudaStream_t s) : bytes(nbytes), stream(s) {
+    // never hand out NULL: a 0-row table must still read as "active"
+    B200_CUDA(cudaMallocAsync(&ptr, nbytes ? nbytes : 16, s));
+}
+DevBuf::~DevBuf() {
+    if (ptr) cudaFreeAsync(ptr, stream);
+}
+
+uint64_t read_counter(const unsigned long long *d_ptr) {
+    Context &c = ctx();
+    B200_CUDA(cudaMemcpyAsync(c.h_scratch, d_ptr, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                              c.stream));
+    B200_CUDA(cudaStreamSynchronize(c.stream));
+    return c.h_scratch[0];
+}
+
+int grid_for(uint64_t work_items, int per_block, int max_blocks_per_sm) {
+    uint64_t blocks = (work_items + per_block - 1) / per_block;
+    uint64_t cap    = (uint64_t)sm_count() * max_blocks_per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------
+// column registry (the hook after relation_map.c:InitRelationMap)
+// ---------------------------------------------------------------------------
+struct ColumnEntry {
+    uint64_t *owned   = nullptr;   // cudaMalloc'ed copy (nullptr for external)
+    DevColumn col;
+};
+static std::mutex                                       g_col_mu;
+static std::unordered_map<const uint64_t *, ColumnEntry> g_columns;
+
+static uint64_t device_column_max(const uint64_t *d, uint64_t n) {
+    Context &c = ctx();
+    B200_CUDA(cudaMemsetAsync(c.d_scratch + 8, 0, sizeof(unsigned long long), c.stream));
+    if (n) {
+        column_max_kernel<<<grid_for(n, 256 * 8, 8), 256, 0, c.stream>>>(d, n, c.d_scratch + 8);
+        B200_LAUNCH_CHECK();
+    }
+    return read_counter(c.d_scratch + 8);
+}
+
+static ColumnEntry upload_entry(const uint64_t *host_col, uint64_t n) {
+    B200_REQUIRE(n <= kMaxRows, "relation has more than 2^32-1 rows (32-bit device row ids)");
+    Context    &c = ctx();
+    ColumnEntry e;
+    B200_CUDA(cudaMalloc(&e.owned, n ? n * sizeof(uint64_t) : 16));
+    if (n)
+        B200_CUDA(cudaMemcpyAsync(e.owned, host_col, n * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                  c.stream));
+    e.col.d       = e.owned;
+    e.col.n       = n;
+    e.col.max_val = device_column_max(e.owned, n);   // also synchronises the copy
+    return e;
+}
+
+void register_host_column(const uint64_t *host_col, uint64_t n, bool replace) {
+    ensure_init();
+    {
+        std::lock_guard<std::mutex> lk(g_col_mu);
+        auto it = g_columns.find(host_col);
+        if (it != g_columns.end()) {
+            if (!replace) return;
+            if (it->second.owned && it->second.col.n == n) {
+                // refresh in place: the end-to-end bench arm re-uploads every step
+                Context &c = ctx();
+                if (n)
+                    B200_CUDA(cudaMemcpyAsync(it->second.owned, host_col, n * sizeof(uint64_t),
+                                              cudaMemcpyHostToDevice, c.stream));
+                return;
+            }
+            if (it->second.owned) cudaFree(it->second.owned);
+            g_columns.erase(it);
+        }
+    }
+    ColumnEntry e = upload_entry(host_col, n);
+    std::lock_guard<std::mutex> lk(g_col_mu);
+    g_columns[host_col] = e;
+}
+
+void register_device_column(const uint64_t *host_key, const uint64_t *dev, uint64_t n, uint64_t max_val) {
+    ensure_init();
+    B200_REQUIRE(n <= kMaxRows, "relation has more than 2^32-1 rows (32-bit device row ids)");
+    ColumnEntry e;
+    e.col.d       = dev;
+    e.col.n       = n;
+    e.col.max_val = max_val;
+    std::lock_guard<std::mutex> lk(g_col_mu);
+    auto it = g_columns.find(host_key);
+    if (it != g_columns.end() && it->second.owned) cudaFree(it->second.owned);
+    g_columns[host_key] = e;
+}
+
+DevColumn lookup_column(const uint64_t *host_col, uint64_t n) {
+    {
+        std::lock_guard<std::mutex> lk(g_col_mu);
+        auto it = g_columns.find(host_col);
+        if (it != g_columns.end()) return it->second.col;
+    }
+    // never registered (the reference's unmodified handler.o): upload on first use
+    register_host_column(host_col, n, false);
+    std::lock_guard<std::mutex> lk(g_col_mu);
+    return g_columns[host_col].col;
+}
+
+void unregister_all_columns() {
+    std::lock_guard<std::mutex> lk(g_col_mu);
+    for (auto &kv : g_columns)
+        if (kv.second.owned) cudaFree(kv.second.owned);
+    g_columns.clear();
+}
+
+// ---------------------------------------------------------------------------
+// kernel launch helpers
+// ---------------------------------------------------------------------------
+template <typename KernelT>
+static void allow_smem(KernelT kernel, size_t bytes) {
+    if (bytes > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+constexpr int kPartNT = 512;
+
+template <typename KeyT> struct PartCfg;
+template <> struct PartCfg<uint32_t> { static constexpr int U = 16; };   // 8192-tuple tiles, 64 KB stage
+template <> struct PartCfg<uint64_t> { static constexpr int U = 8; };    // 4096-tuple tiles, 64 KB stage
+
+template <typename KeyT>
+static void launch_hist(const KeySrc &src, int bits, uint32_t *ghist) {
+    constexpr int U    = PartCfg<KeyT>::U;
+    const size_t  smem = (size_t)(1u << bits) * sizeof(uint32_t);
+    auto          k    = radix_hist_kernel<kPartNT, U, KeyT>;
+    allow_smem(k, smem);
+    k<<<grid_for(src.n, kPartNT * U, 4), kPartNT, smem, ctx().stream>>>(src, (uint32_t)bits, ghist);
+    B200_LAUNCH_CHECK();
+}
+
+template <typename KeyT>
+static void launch_scatter(const KeySrc &src, int bits, uint32_t *cursor, void *out) {
+    using TupT         = typename TupOf<KeyT>::type;
+    constexpr int U    = PartCfg<KeyT>::U;
+    const size_t  smem = (size_t)kPartNT * U * sizeof(TupT) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
+    auto          k    = radix_scatter_kernel<kPartNT, U, KeyT>;
+    allow_smem(k, smem);
+    k<<<grid_for(src.n, kPartNT * U, 2), kPartNT, smem, ctx().stream>>>(src, (uint32_t)bits, cursor,
+                                                                        static_cast<TupT *>(out));
+    B200_LAUNCH_CHECK();
+}
+
+constexpr int kJoinNT = 512;
+constexpr int kJoinU  = 8;
+
+static size_t join_smem_bytes(bool key64, uint32_t cap, uint32_t slots_log2) {
+    return (size_t)cap * ((key64 ? 8 : 4) + 4 + 2) + ((size_t)2 << slots_log2);
+}
+
+template <typename KeyT, bool DIRECT, int MODE>
+static void launch_join_t(const JoinArgs &a, size_t smem) {
+    auto k = hash_join_kernel<kJoinNT, kJoinU, KeyT, DIRECT, MODE>;
+    allow_smem(k, smem);
+    int occ = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kJoinNT, smem));
+    B200_REQUIRE(occ >= 1, "hash_join_kernel does not fit on an SM");
+    int grid = sm_count() * occ;
+    if (DIRECT && (int)a.n_items_direct < grid) grid = (int)a.n_items_direct;
+    if (grid < 1) grid = 1;
+    k<<<grid, kJoinNT, smem, ctx().stream>>>(a);
+    B200_LAUNCH_CHECK();
+}
+
+template <typename KeyT, bool DIRECT>
+static void launch_join_m(const JoinArgs &a, int mode, size_t smem) {
+    if (mode == MODE_COUNT)
+        launch_join_t<KeyT, DIRECT, MODE_COUNT>(a, smem);
+    else if (mode == MODE_WRITE)
+        launch_join_t<KeyT, DIRECT, MODE_WRITE>(a, smem);
+    else
+        launch_join_t<KeyT, DIRECT, MODE_SUM>(a, smem);
+}
+
+static void launch_join(const JoinArgs &a, bool key64, bool direct, int mode) {
+    const size_t smem = join_smem_bytes(key64, a.cap, a.slots_log2);
+    if (key64) {
+        if (direct)
+            launch_join_m<uint64_t, true>(a, mode, smem);
+        else
+            launch_join_m<uint64_t, false>(a, mode, smem);
+    } else {
+        if (direct)
+            launch_join_m<uint32_t, true>(a, mode, smem);
+        else
+            launch_join_m<uint32_t, false>(a, mode, smem);
+    }
+}
+
+static uint32_t ceil_log2(uint64_t v) {
+    uint32_t l = 0;
+    while ((1ull << l) < v) ++l;
+    return l;
+}
+
+// ---------------------------------------------------------------------------
+// radix partition (K3-K5), standalone for the parity tests
+// ---------------------------------------------------------------------------
+PartitionOut run_partition(const KeyVec &kv, int bits) {
+    Context &c = ctx();
+    B200_REQUIRE(bits >= 0 && bits <= tuning().max_bits, "radix bits out of range");
+    PartitionOut  o;
+    o.key64               = tuning().force_key64 || kv.max_val > 0xFFFFFFFFull;
+    const uint32_t nparts = 1u << bits;
+    o.hist                = dev_alloc((size_t)nparts * sizeof(uint32_t));
+    DevBufPtr zeros       = dev_alloc((size_t)nparts * sizeof(uint32_t));
+    DevBufPtr plan        = dev_alloc((size_t)(5 * (nparts + 1)) * sizeof(uint32_t));
+    uint32_t *off_b = plan->as<uint32_t>(), *off_p = off_b + nparts + 1, *cur_b = off_p + nparts + 1,
+             *cur_p = cur_b + nparts + 1, *items = cur_p + nparts + 1;
+    B200_CUDA(cudaMemsetAsync(o.hist->ptr, 0, (size_t)nparts * sizeof(uint32_t), c.stream));
+    B200_CUDA(cudaMemsetAsync(zeros->ptr, 0, (size_t)nparts * sizeof(uint32_t), c.stream));
+    o.tuples = dev_alloc((size_t)kv.src.n * (o.key64 ? sizeof(Tup64) : sizeof(Tup32)));
+    if (kv.src.n == 0) return o;
+    if (o.key64)
+        launch_hist<uint64_t>(kv.src, bits, o.hist->as<uint32_t>());
+    else
+        launch_hist<uint32_t>(kv.src, bits, o.hist->as<uint32_t>());
+    partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(o.hist->as<uint32_t>(), zeros->as<uint32_t>(),
+                                                          nparts, 1u, 1u, off_b, off_p, cur_b, cur_p, items);
+    B200_LAUNCH_CHECK();
+    if (o.key64)
+        launch_scatter<uint64_t>(kv.src, bits, cur_b, o.tuples->ptr);
+    else
+        launch_scatter<uint32_t>(kv.src, bits, cur_b, o.tuples->ptr);
+    return o;
+}
+
+// ---------------------------------------------------------------------------
+// the join: RadixHashJoin (rhjoin.c:13-111) + optional fused SUM
+// ---------------------------------------------------------------------------
+JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, const ProjDesc *proj) {
+    Context    &c = ctx();
+    Tuning     &t = tuning();
+    JoinResult  res;
+    B200_REQUIRE(R.src.n > 0 && S.src.n > 0, "run_join called with an empty side");
+    B200_REQUIRE(nproj >= 0 && nproj <= kMaxProj, "too many fused projections");
+
+    // rhjoin.c:118-134 indexes the smaller bucket side; here the smaller
+    // relation is the build side for every partition.
+    const bool    swapped = S.src.n < R.src.n;
+    const KeyVec &B       = swapped ? S : R;
+    const KeyVec &P       = swapped ? R : S;
+    const bool    key64   = t.force_key64 || B.max_val > 0xFFFFFFFFull || P.max_val > 0xFFFFFFFFull;
+    const uint32_t cap    = key64 ? t.cap64 : t.cap32;
+    B200_REQUIRE(cap >= 32 && cap <= 65534, "table capacity must fit 16-bit chain links");
+    const uint32_t slots_log2 = ceil_log2(2ull * cap);
+
+    int bits = 0;
+    if (t.radix_bits > 0) {
+        bits = std::min(t.radix_bits, t.max_bits);
+    } else if (B.src.n > cap) {
+        // aim at ~70% of the table capacity per partition
+        bits = (int)ceil_log2((B.src.n * 10 + (uint64_t)cap * 7 - 1) / ((uint64_t)cap * 7));
+        bits = std::max(1, std::min(bits, t.max_bits));
+    }
+    const bool direct = bits == 0;
+
+    JoinArgs a;
+    memset(&a, 0, sizeof(a));
+    a.cap        = cap;
+    a.slots_log2 = slots_log2;
+    a.radix_bits = (uint32_t)bits;
+
+    // one allocation for the small control arrays
+    const uint32_t nparts = 1u << bits;
+    DevBufPtr ctrl = dev_alloc((64 + 7 * (size_t)(nparts + 1)) * sizeof(uint32_t) + 64 * sizeof(unsigned long long));
+    B200_CUDA(cudaMemsetAsync(ctrl->ptr, 0, ctrl->bytes, c.stream));
+    unsigned long long *d_u64   = ctrl->as<unsigned long long>();   // [0] total, [1] out_cursor, [8..16) sums
+    uint32_t           *d_u32   = reinterpret_cast<uint32_t *>(d_u64 + 64);
+    uint32_t           *d_work  = d_u32;   // work counter
+    uint32_t           *hist_b  = d_u32 + 64;
+    uint32_t           *hist_p  = hist_b + nparts + 1;
+    uint32_t           *off_b   = hist_p + nparts + 1;
+    uint32_t           *off_p   = off_b + nparts + 1;
+    uint32_t           *cur_b   = off_p + nparts + 1;
+    uint32_t           *cur_p   = cur_b + nparts + 1;
+    uint32_t           *items   = cur_p + nparts + 1;
+    a.work_counter = d_work;
+    a.total        = d_u64;
+    a.out_cursor   = d_u64 + 1;
+    a.sums         = d_u64 + 8;
+
+    DevBufPtr tup_b, tup_p;
+    uint64_t  n_items = 0;
+    if (direct) {
+        a.src_b = B.src;
+        a.src_p = P.src;
+        // slices big enough to amortise rebuilding the table, small enough to
+        // spread over the SMs
+        uint64_t slice = std::max<uint64_t>({4096, 4ull * std::min<uint64_t>(B.src.n, cap),
+                                             (P.src.n + 2ull * sm_count() - 1) / (2ull * sm_count())});
+        slice          = std::min<uint64_t>(slice, t.slice);
+        a.slice        = (uint32_t)slice;
+        const uint64_t rc = (B.src.n + cap - 1) / cap;
+        const uint64_t sc = (P.src.n + slice - 1) / slice;
+        B200_REQUIRE(rc * sc < (1ull << 31), "too many join work items");
+        a.sc_direct      = (uint32_t)sc;
+        a.n_items_direct = (uint32_t)(rc * sc);
+        n_items          = rc * sc;
+    } else {
+        a.slice = t.slice;
+        {
+            TimedScope ts("hist");
+            if (key64) {
+                launch_hist<uint64_t>(B.src, bits, hist_b);
+                launch_hist<uint64_t>(P.src, bits, hist_p);
+            } else {
+                launch_hist<uint32_t>(B.src, bits, hist_b);
+                launch_hist<uint32_t>(P.src, bits, hist_p);
+            }
+        }
+        {
+            TimedScope ts("scan");
+            partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, hist_p, nparts, cap, a.slice, off_b,
+                                                                  off_p, cur_b, cur_p, items);
+            B200_LAUNCH_CHECK();
+        }
+        const size_t tsz = key64 ? sizeof(Tup64) : sizeof(Tup32);
+        tup_b            = dev_alloc((size_t)B.src.n * tsz);
+        tup_p            = dev_alloc((size_t)P.src.n * tsz);
+        {
+            TimedScope ts("scatter_b");
+            if (key64)
+                launch_scatter<uint64_t>(B.src, bits, cur_b, tup_b->ptr);
+            else
+                launch_scatter<uint32_t>(B.src, bits, cur_b, tup_b->ptr);
+        }
+        {
+            TimedScope ts("scatter_p");
+            if (key64)
+                launch_scatter<uint64_t>(P.src, bits, cur_p, tup_p->ptr);
+            else
+                launch_scatter<uint32_t>(P.src, bits, cur_p, tup_p->ptr);
+        }
+        a.tup_b      = tup_b->ptr;
+        a.tup_p      = tup_p->ptr;
+        a.off_b      = off_b;
+        a.off_p      = off_p;
+        a.item_start = items;
+        a.nparts     = nparts;
+    }
+
+    if (mode == JoinOut::Sum) {
+        a.nproj = nproj;
+        for (int k = 0; k < nproj; ++k) {
+            a.proj[k] = proj[k];
+            // sides are given relative to (R, S); the kernel wants (build, probe)
+            a.proj[k].side = swapped ? 1 - proj[k].side : proj[k].side;
+        }
+        {
+            TimedScope ts("join");
+            launch_join(a, key64, direct, MODE_SUM);
+        }
+        B200_CUDA(cudaMemcpyAsync(c.h_scratch, d_u64, 16 * sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToHost, c.stream));
+        B200_CUDA(cudaStreamSynchronize(c.stream));
+        res.m = c.h_scratch[0];
+        for (int k = 0; k < nproj; ++k) res.sums[k] = c.h_scratch[8 + k];
+        return res;
+    }
+
+    // Pairs: count pass sizes the output exactly, write pass fills it.
+    if (!direct) {
+        B200_CUDA(cudaMemcpyAsync(c.h_scratch, items + nparts, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                  c.stream));
+        B200_CUDA(cudaStreamSynchronize(c.stream));
+        n_items = *reinterpret_cast<uint32_t *>(c.h_scratch);
+    }
+    DevBufPtr item_count = dev_alloc((n_items + 1) * sizeof(unsigned long long));
+    a.item_count         = item_count->as<unsigned long long>();
+    {
+        TimedScope ts("join");
+        launch_join(a, key64, direct, MODE_COUNT);
+    }
+    res.m = read_counter(a.total);
+    B200_REQUIRE(res.m <= kMaxRows, "join output exceeds 2^32-1 pairs (32-bit device positions)");
+    DevBufPtr out_b = dev_alloc(res.m * sizeof(uint32_t));
+    DevBufPtr out_p = dev_alloc(res.m * sizeof(uint32_t));
+    if (res.m) {
+        a.out_b = out_b->as<uint32_t>();
+        a.out_p = out_p->as<uint32_t>();
+        B200_CUDA(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), c.stream));
+        TimedScope ts("join_write");
+        launch_join(a, key64, direct, MODE_WRITE);
+    }
+    res.r_ids = swapped ? out_p : out_b;
+    res.s_ids = swapped ? out_b : out_p;
+    return res;
+}
+
+// ---------------------------------------------------------------------------
+// compaction scans, gathers, checksums
+// ---------------------------------------------------------------------------
+constexpr int kScanNT = 256;
+constexpr int kScanU  = 8;
+
+IdList run_filter(const KeySrc &src, char cmp, int value) {
+    Context &c = ctx();
+    IdList   out;
+    int      code;
+    switch (cmp) {
+        case '<': code = 0; break;
+        case '>': code = 1; break;
+        case '=': code = 2; break;
+        default:
+            // filter.c:184-186
+            fprintf(stderr, "Wrong comperator in filter function\n");
+            exit(2);
+    }
+    out.ids = dev_alloc((size_t)src.n * sizeof(uint32_t));
+    if (src.n == 0) return out;
+    B200_CUDA(cudaMemsetAsync(c.d_scratch, 0, sizeof(unsigned long long), c.stream));
+    // `uint64_t ⋄ int`: the int is converted to uint64_t (sign-extended)
+    const uint64_t constant = (uint64_t)(int64_t)value;
+    scan_filter_kernel<kScanNT, kScanU>
+        <<<grid_for(src.n, kScanNT * kScanU, 8), kScanNT, 0, c.stream>>>(src, code, constant,
+                                                                         out.ids->as<uint32_t>(), c.d_scratch);
+    B200_LAUNCH_CHECK();
+    out.n = read_counter(c.d_scratch);
+    return out;
+}
+
+IdList run_inter_equal(const uint64_t *col_a, const uint32_t *ta, const uint64_t *col_b, const uint32_t *tb,
+                       uint64_t n) {
+    Context &c = ctx();
+    IdList   out;
+    out.ids = dev_alloc((size_t)n * sizeof(uint32_t));
+    if (n == 0) return out;
+    B200_CUDA(cudaMemsetAsync(c.d_scratch, 0, sizeof(unsigned long long), c.stream));
+    inter_equal_kernel<kScanNT, kScanU><<<grid_for(n, kScanNT * kScanU, 8), kScanNT, 0, c.stream>>>(
+        col_a, ta, col_b, tb, (uint32_t)n, out.ids->as<uint32_t>(), c.d_scratch);
+    B200_LAUNCH_CHECK();
+    out.n = read_counter(c.d_scratch);
+    return out;
+}
+
+std::vector<DevBufPtr> run_gather(const uint32_t *pos, uint64_t m, const std::vector<const uint32_t *> &in) {
+    Context               &c = ctx();
+    std::vector<DevBufPtr> out;
+    for (size_t i = 0; i < in.size(); ++i) out.push_back(dev_alloc(m * sizeof(uint32_t)));
+    if (m == 0) return out;
+    for (size_t first = 0; first < in.size(); first += kMaxGather) {
+        GatherArgs g;
+        g.pos   = pos;
+        g.m     = (uint32_t)m;
+        g.ncols = (int)std::min<size_t>(kMaxGather, in.size() - first);
+        for (int k = 0; k < g.ncols; ++k) {
+            g.in[k]  = in[first + k];
+            g.out[k] = out[first + k]->as<uint32_t>();
+        }
+        gather_columns_kernel<<<grid_for(m, 256 * 4, 8), 256, 0, c.stream>>>(g);
+        B200_LAUNCH_CHECK();
+    }
+    return out;
+}
+
+void run_checksum(uint64_t m, int nproj, const uint64_t *const *cols, const uint32_t *const *ids,
+                  uint64_t *out_sums) {
+    Context &c = ctx();
+    for (int first = 0; first < nproj; first += kMaxProj) {
+        const int k = std::min(kMaxProj, nproj - first);
+        if (m == 0) {
+            for (int i = 0; i < k; ++i) out_sums[first + i] = 0;
+            continue;
+        }
+        ChecksumArgs a;
+        a.m     = (uint32_t)m;
+        a.nproj = k;
+        for (int i = 0; i < k; ++i) {
+            a.col[i] = cols[first + i];
+            a.ids[i] = ids[first + i];
+        }
+        a.sums = c.d_scratch + 16;
+        B200_CUDA(cudaMemsetAsync(a.sums, 0, kMaxProj * sizeof(unsigned long long), c.stream));
+        checksum_kernel<<<grid_for(m, 256 * 4, 8), 256, 0, c.stream>>>(a);
+        B200_LAUNCH_CHECK();
+        B200_CUDA(cudaMemcpyAsync(c.h_scratch + 16, a.sums, kMaxProj * sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToHost, c.stream));
+        B200_CUDA(cudaStreamSynchronize(c.stream));
+        for (int i = 0; i < k; ++i) out_sums[first + i] = c.h_scratch[16 + i];
+    }
+}
+
+void run_cartesian(const uint32_t *in, uint64_t n1, uint64_t n2, bool from_first, uint32_t *out) {
+    const uint64_t total = n1 * n2;
+    if (total == 0) return;
+    cartesian_kernel<<<grid_for(total, 256 * 4, 8), 256, 0, ctx().stream>>>(in, (uint32_t)n1, (uint32_t)n2,
+                                                                            from_first ? 1 : 0, out);
+    B200_LAUNCH_CHECK();
+}
+
+void widen_ids(const uint32_t *d_in, uint64_t n, uint64_t *d_out) {
+    if (n == 0) return;
+    widen_u32_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, ctx().stream>>>(d_in, n, d_out);
+    B200_LAUNCH_CHECK();
+}
+
+void narrow_ids(const uint64_t *d_in, uint64_t n, uint32_t *d_out) {
+    if (n == 0) return;
+    narrow_u64_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, ctx().stream>>>(d_in, n, d_out);
+    B200_LAUNCH_CHECK();
+}
+
+void unpack_partition(const PartitionOut &p, uint64_t n, uint64_t *d_keys, uint64_t *d_rids) {
+    if (n == 0) return;
+    if (p.key64)
+        unpack_tuples_kernel<Tup64><<<grid_for(n, 256 * 4, 8), 256, 0, ctx().stream>>>(p.tuples->as<Tup64>(), n,
+                                                                                       d_keys, d_rids);
+    else
+        unpack_tuples_kernel<Tup32><<<grid_for(n, 256 * 4, 8), 256, 0, ctx().stream>>>(p.tuples->as<Tup32>(), n,
+                                                                                       d_keys, d_rids);
+    B200_LAUNCH_CHECK();
+}
+
+}  // namespace b200

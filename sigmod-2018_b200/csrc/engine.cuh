@@ -1,0 +1,97 @@
+// engine.cuh — host-side orchestration of the join pipeline on one GPU:
+// column registry (device copies keyed by the host column pointer), lazy key
+// vectors, radix partition + shared-memory hash join in its three output
+// modes, compaction scans, gathers and checksums.  Everything runs on the
+// calling thread's stream (common.cuh).
+#pragma once
+
+#include "common.cuh"
+#include "types.cuh"
+
+#include <vector>
+
+namespace b200 {
+
+struct DevColumn {
+    const uint64_t *d       = nullptr;
+    uint64_t        n       = 0;
+    uint64_t        max_val = UINT64_MAX;
+};
+
+// Device copy of a host column (relation_map.columns[j]); uploads on a miss.
+DevColumn lookup_column(const uint64_t *host_col, uint64_t n);
+void      register_host_column(const uint64_t *host_col, uint64_t n, bool replace);
+void      register_device_column(const uint64_t *host_key, const uint64_t *dev, uint64_t n,
+                                 uint64_t max_val);
+void      unregister_all_columns();
+
+// Lazy key vector with ownership of the row-id list it reads through.
+struct KeyVec {
+    KeySrc    src{nullptr, nullptr, 0};
+    DevBufPtr ids_owner;
+    uint64_t  max_val = UINT64_MAX;
+};
+
+struct Tuning {
+    int      radix_bits  = 0;   // 0 = automatic
+    int      force_key64 = 0;
+    uint32_t cap32       = 8192;     // build tuples per shared-memory table, 32-bit keys
+    uint32_t cap64       = 4096;     // ... 64-bit keys
+    uint32_t slice       = 1u << 18; // probe tuples per work item
+    int      max_bits    = 12;
+    int      debug       = 0;
+};
+Tuning &tuning();
+
+enum class JoinOut { Pairs, Sum };
+
+struct JoinResult {
+    uint64_t  m = 0;              // number of matching pairs
+    DevBufPtr r_ids, s_ids;       // Pairs: 32-bit row ids, m each
+    uint64_t  sums[kMaxProj] = {0};
+};
+
+// proj[k].side is relative to the call: 0 = R side, 1 = S side.
+JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, const ProjDesc *proj);
+
+// Radix partition only (tests): tuples in partition order, hist and offsets.
+struct PartitionOut {
+    DevBufPtr tuples;    // Tup32 or Tup64
+    DevBufPtr hist;      // u32[nparts]
+    bool      key64 = false;
+};
+PartitionOut run_partition(const KeyVec &src, int radix_bits);
+
+// K1 / K11 compaction scans: returns a u32 list and its length.
+struct IdList {
+    DevBufPtr ids;
+    uint64_t  n = 0;
+};
+IdList run_filter(const KeySrc &src, char cmp, int value);
+IdList run_inter_equal(const uint64_t *col_a, const uint32_t *ta, const uint64_t *col_b,
+                       const uint32_t *tb, uint64_t n);
+
+// K8: out[c] = in[c][pos[i]] for every listed column.
+std::vector<DevBufPtr> run_gather(const uint32_t *pos, uint64_t m, const std::vector<const uint32_t *> &in);
+// K9
+void run_checksum(uint64_t m, int nproj, const uint64_t *const *cols, const uint32_t *const *ids,
+                  uint64_t *out_sums);
+
+// CartesianInterResults (inter_res.c:405-418): out[i*n2+j] = in[i] or in[j].
+void run_cartesian(const uint32_t *in, uint64_t n1, uint64_t n2, bool from_first, uint32_t *out);
+// width conversions between host-facing uint64 ids and device uint32 ids
+void widen_ids(const uint32_t *d_in, uint64_t n, uint64_t *d_out);
+void narrow_ids(const uint64_t *d_in, uint64_t n, uint32_t *d_out);
+void unpack_partition(const PartitionOut &p, uint64_t n, uint64_t *d_keys, uint64_t *d_rids);
+
+// runtime control (engine.cu)
+void               request_device(int device);   // before the first use
+int                device_index();
+void               set_profiling(bool on);
+const std::string &last_error_string();
+
+// small helpers
+uint64_t read_counter(const unsigned long long *d_ptr);   // D2H + sync on ctx stream
+int      grid_for(uint64_t work_items, int per_block, int max_blocks_per_sm);
+
+}  // namespace b200

@@ -1,0 +1,417 @@
+// operators.cu — Part 1 of include/b200_join.h: the reference's operator API
+// (the 16 symbols query.c:ExecuteQuery imports) implemented on device-resident
+// data.  Each function states the reference lines whose contract it keeps
+// (SURVEY Appendix B restates those contracts without the reference's linked
+// lists).  `relation`, `result` and `inter_data` are opaque to the caller, so
+// they carry device buffers behind the reference's public prefix.
+#include "../../include/b200_join.h"
+#include "engine.cuh"
+
+#include <cstring>
+#include <vector>
+
+using namespace b200;
+
+namespace {
+
+struct B200Relation : relation {
+    KeyVec kv;
+};
+
+enum ResultKind { kRowIds = 1, kPairs = 2 };
+struct B200Result : result {
+    int       kind = 0;
+    DevBufPtr a, b;   // row ids / (R ids, S ids)
+    uint64_t  n = 0;
+};
+
+struct B200InterData : inter_data {
+    std::vector<DevBufPtr> bufs;
+};
+
+B200InterData *idata(const inter_res *node) { return static_cast<B200InterData *>(node->data); }
+
+B200InterData *new_inter_data(int num_rel, uint64_t num_tuples) {
+    auto *d       = new B200InterData();
+    d->num_tuples = num_tuples;
+    d->table      = static_cast<uint64_t **>(calloc((size_t)num_rel, sizeof(uint64_t *)));
+    d->bufs.resize((size_t)num_rel);
+    return d;
+}
+void free_inter_data(B200InterData *d) {
+    free(d->table);
+    delete d;
+}
+void set_column(B200InterData *d, int b, DevBufPtr buf) {
+    d->table[b] = buf ? reinterpret_cast<uint64_t *>(buf->ptr) : nullptr;
+    d->bufs[(size_t)b] = std::move(buf);
+}
+const uint32_t *column_ids(const B200InterData *d, int b) {
+    return reinterpret_cast<const uint32_t *>(d->table[b]);
+}
+
+inter_res *new_node(int num_rel) {
+    auto *n             = static_cast<inter_res *>(malloc(sizeof(inter_res)));
+    n->next             = nullptr;
+    n->num_of_relations = num_rel;
+    n->data             = new_inter_data(num_rel, 0);
+    return n;
+}
+
+B200Result *new_result(int kind, uint64_t n, DevBufPtr a, DevBufPtr b) {
+    auto *r         = new B200Result();
+    r->buff         = nullptr;
+    r->next         = nullptr;
+    r->current_load = n;
+    r->kind         = kind;
+    r->n            = n;
+    r->a            = std::move(a);
+    r->b            = std::move(b);
+    return r;
+}
+
+// node that holds binding b, or NULL (filter.c:98-104, inter_res.c:184-189)
+inter_res *find_node(inter_res *head, int b) {
+    for (; head; head = head->next)
+        if (head->data->table[b] != nullptr) return head;
+    return nullptr;
+}
+
+// compact every active column of `node` through a list of positions
+// (filter.c:42-81)
+void compact_node(inter_res *node, const uint32_t *pos, uint64_t m) {
+    B200InterData                 *old = idata(node);
+    std::vector<const uint32_t *>  in;
+    std::vector<int>               which;
+    for (int j = 0; j < node->num_of_relations; ++j)
+        if (old->table[j]) {
+            in.push_back(column_ids(old, j));
+            which.push_back(j);
+        }
+    std::vector<DevBufPtr> out = run_gather(pos, m, in);
+    B200InterData         *nd  = new_inter_data(node->num_of_relations, m);
+    for (size_t k = 0; k < which.size(); ++k) set_column(nd, which[k], out[k]);
+    free_inter_data(old);
+    node->data = nd;
+}
+
+DevColumn binding_column(relation_map *map, int *query_relations, int binding, int column) {
+    relation_map &rm = map[query_relations[binding]];
+    return lookup_column(rm.columns[column], rm.num_tuples);
+}
+
+}  // namespace
+
+extern "C" {
+
+// inter_res.c:26-32
+int InitInterResults(inter_res **head, int num_of_rel) {
+    ensure_init();
+    *head = new_node(num_of_rel);
+    return 0;
+}
+
+// inter_res.c:175-180
+void FreeInterResults(inter_res *var) {
+    while (var) {
+        inter_res *next = var->next;
+        free_inter_data(idata(var));
+        free(var);
+        var = next;
+    }
+}
+
+// filter.c:92-190
+result *Filter(inter_res *head, filter_pred *filter_p, relation_map *map, int *query_relations) {
+    const int  rel  = filter_p->relation;
+    DevColumn  col  = binding_column(map, query_relations, rel, filter_p->column);
+    inter_res *node = find_node(head, rel);
+    KeySrc     src;
+    src.col = col.d;
+    if (node) {   // filter.c:124-133: scan through the row ids, emit positions
+        src.ids = column_ids(idata(node), rel);
+        src.n   = (uint32_t)node->data->num_tuples;
+    } else {      // filter.c:113-122: scan the base column, emit row ids
+        src.ids = nullptr;
+        src.n   = (uint32_t)col.n;
+    }
+    IdList l = run_filter(src, filter_p->comperator, filter_p->value);
+    if (l.n == 0) return nullptr;   // caller prints NULLs (query.c:360-369)
+    return new_result(kRowIds, l.n, l.ids, nullptr);
+}
+
+// filter.c:11-89.  Deviation (documented in DESIGN.md): the reference advances
+// the caller's head pointer while searching (filter.c:82) and dereferences
+// NULL when the binding is in no node and the first node is occupied
+// (SURVEY §8 quirk 2); here the list head is left alone and a new node is
+// appended in that case.
+int InsertSingleRowIdsToInterResult(inter_res **head, int relation_num, result *res) {
+    B200Result *r = static_cast<B200Result *>(res);
+    B200_REQUIRE(r && r->kind == kRowIds, "InsertSingleRowIdsToInterResult needs a row-id result");
+    inter_res *node = *head, *last = nullptr;
+    for (; node; last = node, node = node->next) {
+        if (node->data->num_tuples == 0) {   // filter.c:19-40: first instance of the node
+            B200InterData *d = idata(node);
+            d->num_tuples    = r->n;
+            set_column(d, relation_num, r->a);
+            return 1;
+        }
+        if (node->data->table[relation_num] != nullptr) {   // filter.c:42-81
+            compact_node(node, r->a->as<uint32_t>(), r->n);
+            return 1;
+        }
+    }
+    last->next = new_node(last->num_of_relations);
+    return InsertSingleRowIdsToInterResult(&last->next, relation_num, res);
+}
+
+// inter_res.c:208-231 (+182-206).  K2 is fused away: the key vector stays a
+// (column, row-id list) view and is read by the partition / join kernels.
+relation *GetRelation(int given_rel, int column, inter_res *inter, relation_map *map, int *query_relations) {
+    DevColumn  col  = binding_column(map, query_relations, given_rel, column);
+    inter_res *node = inter ? find_node(inter, given_rel) : nullptr;
+    auto      *rel  = new B200Relation();
+    rel->tuples     = nullptr;
+    rel->kv.src.col = col.d;
+    rel->kv.max_val = col.max_val;
+    if (node) {
+        B200InterData *d   = idata(node);
+        rel->kv.src.ids    = column_ids(d, given_rel);
+        rel->kv.ids_owner  = d->bufs[(size_t)given_rel];
+        rel->kv.src.n      = (uint32_t)d->num_tuples;
+        rel->num_tuples    = d->num_tuples;
+    } else {
+        rel->kv.src.ids = nullptr;
+        rel->kv.src.n   = (uint32_t)col.n;
+        rel->num_tuples = col.n;
+    }
+    return rel;
+}
+
+// rhjoin.c:13-111
+result *RadixHashJoin(relation *relR, relation *relS, scheduler *sched) {
+    (void)sched;   // kernels run on the calling thread's stream
+    if (relR->num_tuples == 0 || relS->num_tuples == 0) return nullptr;   // rhjoin.c:15-16
+    B200Relation *r = static_cast<B200Relation *>(relR);
+    B200Relation *s = static_cast<B200Relation *>(relS);
+    JoinResult    j = run_join(r->kv, s->kv, JoinOut::Pairs, 0, nullptr);
+    // an empty join is a non-NULL result with zero pairs (rhjoin.c:356-359)
+    return new_result(kPairs, j.m, j.r_ids, j.s_ids);
+}
+
+// inter_res.c:34-152
+int InsertJoinToInterResults(inter_res *head, int rel1, int rel2, result *res) {
+    B200Result *r = static_cast<B200Result *>(res);
+    B200_REQUIRE(r && r->kind == kPairs, "InsertJoinToInterResults needs a pair result");
+    inter_res *node = head, *last = nullptr;
+    for (; node; last = node, node = node->next) {
+        B200InterData *d = idata(node);
+        if (d->num_tuples == 0) {   // inter_res.c:39-62
+            d->num_tuples = r->n;
+            set_column(d, rel1, r->a);
+            set_column(d, rel2, r->b);
+            return 1;
+        }
+        const bool has1 = d->table[rel1] != nullptr, has2 = d->table[rel2] != nullptr;
+        if (has1 != has2) {   // inter_res.c:64-102 (rel1 active) / 104-141 (rel2 active)
+            const uint32_t *pos     = has1 ? r->a->as<uint32_t>() : r->b->as<uint32_t>();
+            DevBufPtr       fresh   = has1 ? r->b : r->a;
+            const int       new_rel = has1 ? rel2 : rel1;
+            compact_node(node, pos, r->n);
+            set_column(idata(node), new_rel, fresh);
+            return 1;
+        }
+    }
+    // inter_res.c:147-151: neither side lives in a node yet
+    last->next = new_node(last->num_of_relations);
+    InsertJoinToInterResults(last->next, rel1, rel2, res);
+    return 0;
+}
+
+// inter_res.c:352-361
+int AreActiveInInter(inter_res *inter, int rel1, int rel2) {
+    for (; inter; inter = inter->next)
+        if (inter->data->table[rel1] != nullptr && inter->data->table[rel2] != nullptr) return 1;
+    return 0;
+}
+
+// inter_res.c:363-389
+int JoinInterNode(inter_res **inter, relation_map *rel_map, int rel1, int col1, int rel2, int col2,
+                  int *relations) {
+    inter_res *node = *inter;
+    for (; node; node = node->next)
+        if (node->data->table[rel1] != nullptr && node->data->table[rel2] != nullptr) break;
+    if (!node) return 0;
+    DevColumn      ca = binding_column(rel_map, relations, rel1, col1);
+    DevColumn      cb = binding_column(rel_map, relations, rel2, col2);
+    B200InterData *d  = idata(node);
+    IdList l = run_inter_equal(ca.d, column_ids(d, rel1), cb.d, column_ids(d, rel2), d->num_tuples);
+    // the reference hands an empty list to InsertSingleRowIds... which then
+    // sees num_results == 0; the node simply becomes empty
+    compact_node(node, l.ids->as<uint32_t>(), l.n);
+    return 1;
+}
+
+// inter_res.c:265-318: a later node that shares an active binding with an
+// earlier one is folded into it through that binding's positions.
+void MergeInterNodes(inter_res **inter) {
+    for (inter_res *head = *inter; head; head = head->next) {
+        bool merged = true;
+        while (merged) {
+            merged = false;
+            for (inter_res *prev = head; prev->next && !merged; prev = prev->next) {
+                inter_res *cand = prev->next;
+                for (int i = 0; i < head->num_of_relations && !merged; ++i) {
+                    if (head->data->table[i] == nullptr || cand->data->table[i] == nullptr) continue;
+                    // inter_res.c:287-318: head.table[j][k] = cand.table[j][head.table[i][k]]
+                    B200InterData                *hd = idata(head);
+                    B200InterData                *cd = idata(cand);
+                    std::vector<const uint32_t *> in;
+                    std::vector<int>              which;
+                    for (int j = 0; j < head->num_of_relations; ++j)
+                        if (cd->table[j]) {
+                            in.push_back(column_ids(cd, j));
+                            which.push_back(j);
+                        }
+                    DevBufPtr              pos_owner = hd->bufs[(size_t)i];
+                    std::vector<DevBufPtr> out = run_gather(pos_owner->as<uint32_t>(), hd->num_tuples, in);
+                    for (size_t k = 0; k < which.size(); ++k) set_column(hd, which[k], out[k]);
+                    prev->next = cand->next;
+                    free_inter_data(cd);
+                    free(cand);
+                    merged = true;
+                }
+            }
+        }
+    }
+}
+
+// inter_res.c:391-428: cross product of the remaining nodes (tail first).
+void CartesianInterResults(inter_res **inter) {
+    inter_res *cur = *inter;
+    if (cur->next == nullptr) return;
+    CartesianInterResults(&cur->next);
+    inter_res     *nxt = cur->next;
+    B200InterData *a = idata(cur), *b = idata(nxt);
+    if (a->num_tuples * b->num_tuples == 0) return;   // inter_res.c:398
+    const uint64_t total = a->num_tuples * b->num_tuples;
+    B200_REQUIRE(total <= kMaxRows, "cartesian product exceeds 2^32-1 rows");
+    B200InterData *nd = new_inter_data(cur->num_of_relations, total);
+    for (int z = 0; z < cur->num_of_relations; ++z) {
+        const bool in_a = a->table[z] != nullptr, in_b = b->table[z] != nullptr;
+        if (!in_a && !in_b) continue;
+        DevBufPtr out = dev_alloc(total * sizeof(uint32_t));
+        run_cartesian(in_a ? column_ids(a, z) : column_ids(b, z), a->num_tuples, b->num_tuples, in_a,
+                      out->as<uint32_t>());
+        set_column(nd, z, out);
+    }
+    free_inter_data(a);
+    cur->data = nd;
+    free_inter_data(b);
+    free(nxt);
+    cur->next = nullptr;
+}
+
+// inter_res.c:320-339 without the printf
+int b200_calculate_sums(inter_res *inter, relation_map *map, batch_listnode *query, uint64_t *sums,
+                        uint64_t *num_rows) {
+    const int                      nv = query->views->num_of_elements;
+    std::vector<const uint64_t *>  cols((size_t)nv);
+    std::vector<const uint32_t *>  ids((size_t)nv);
+    B200InterData                 *d = idata(inter);
+    for (int i = 0; i < nv; ++i) {
+        // single-digit binding and column, as in inter_res.c:325-327
+        const int index  = query->views->data[i][0] - '0';
+        const int column = query->views->data[i][2] - '0';
+        DevColumn col    = binding_column(map, query->relations, index, column);
+        cols[(size_t)i]  = col.d;
+        ids[(size_t)i]   = column_ids(d, index);
+        B200_REQUIRE(ids[(size_t)i] != nullptr || d->num_tuples == 0,
+                     "projection on a binding that is not in the intermediate result");
+    }
+    run_checksum(d->num_tuples, nv, cols.data(), ids.data(), sums);
+    if (num_rows) *num_rows = d->num_tuples;
+    return 0;
+}
+
+// inter_res.c:320-339
+void CalculateQueryResults(inter_res *inter, relation_map *map, batch_listnode *query) {
+    const int             nv = query->views->num_of_elements;
+    std::vector<uint64_t> sums((size_t)nv);
+    b200_calculate_sums(inter, map, query, sums.data(), nullptr);
+    for (int i = 0; i < nv; ++i) {
+        printf("%lu", (unsigned long)sums[(size_t)i]);
+        if (i != nv - 1) printf(" ");
+    }
+    printf("\n");
+}
+
+// inter_res.c:341-350
+void PrintNullResults(batch_listnode *query) {
+    for (int i = 0; i < query->views->num_of_elements; ++i) {
+        printf("NULL");
+        if (i != query->views->num_of_elements - 1) printf(" ");
+    }
+    printf("\n");
+}
+
+// inter_res.c:234-263 (contract, not the reference's buggy indexing)
+result *SelfJoin(int given_rel, int column1, int column2, inter_res **inter, relation_map *map,
+                 int *query_relations) {
+    DevColumn  c1   = binding_column(map, query_relations, given_rel, column1);
+    DevColumn  c2   = binding_column(map, query_relations, given_rel, column2);
+    inter_res *node = find_node(*inter, given_rel);
+    IdList     l;
+    if (node) {
+        const uint32_t *t = column_ids(idata(node), given_rel);
+        l                 = run_inter_equal(c1.d, t, c2.d, t, node->data->num_tuples);
+    } else {
+        l = run_inter_equal(c1.d, nullptr, c2.d, nullptr, c1.n);
+    }
+    if (l.n == 0) return nullptr;
+    return new_result(kRowIds, l.n, l.ids, nullptr);
+}
+
+// results.c:144-153
+void FreeResult(result *head) {
+    if (head) delete static_cast<B200Result *>(head);
+}
+
+// preprocess.c:213-218
+void FreeRelation(relation *rel) {
+    if (rel) delete static_cast<B200Relation *>(rel);
+}
+
+// ---- read-back helpers for tests (Part 2) ---------------------------------
+int b200_result_kind(const result *res) { return res ? static_cast<const B200Result *>(res)->kind : 0; }
+
+static int ids_to_host(const uint32_t *d, uint64_t n, uint64_t *out) {
+    if (n == 0) return 0;
+    Context  &c   = ctx();
+    DevBufPtr tmp = dev_alloc(n * sizeof(uint64_t));
+    widen_ids(d, n, tmp->as<uint64_t>());
+    B200_CUDA(cudaMemcpyAsync(out, tmp->ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
+    B200_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int b200_result_rowids_to_host(const result *res, uint64_t *out) {
+    const B200Result *r = static_cast<const B200Result *>(res);
+    if (!r || r->kind != kRowIds) return 1;
+    return ids_to_host(r->a->as<uint32_t>(), r->n, out);
+}
+
+int b200_result_pairs_to_host(const result *res, uint64_t *out_r, uint64_t *out_s) {
+    const B200Result *r = static_cast<const B200Result *>(res);
+    if (!r || r->kind != kPairs) return 1;
+    ids_to_host(r->a->as<uint32_t>(), r->n, out_r);
+    return ids_to_host(r->b->as<uint32_t>(), r->n, out_s);
+}
+
+int b200_inter_column_to_host(const inter_res *node, int binding, uint64_t *out) {
+    const B200InterData *d = idata(node);
+    if (!d->table[binding]) return 1;
+    return ids_to_host(column_ids(d, binding), d->num_tuples, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,42 @@
+// types.cuh — plain data types shared between the kernels (kernels.cuh, only
+// included by engine.cu) and the host-side operator code.
+#pragma once
+
+#include <cstdint>
+
+namespace b200 {
+
+constexpr int kMaxGather = 8;
+constexpr int      kMaxProj  = 8;
+
+// Lazy key vector = the GetRelation contract (inter_res.c:182-231):
+// key(i) = col[i] when ids == nullptr, else col[ids[i]]; the row id handed to
+// the join is i itself (base row, or position in the intermediate).
+struct KeySrc {
+    const uint64_t *col;
+    const uint32_t *ids;
+    uint32_t        n;
+};
+
+struct Tup32 {
+    uint32_t key;
+    uint32_t rid;
+};
+struct alignas(16) Tup64 {
+    uint64_t key;
+    uint32_t rid;
+    uint32_t pad;
+};
+template <typename KeyT> struct TupOf;
+template <> struct TupOf<uint32_t> { using type = Tup32; };
+template <> struct TupOf<uint64_t> { using type = Tup64; };
+
+// One SUM projection of the fused final join: value = col[ids ? ids[r] : r]
+// where r is the build-side (side 0) or probe-side (side 1) row id of a match.
+struct ProjDesc {
+    const uint64_t *col;
+    const uint32_t *ids;
+    int             side;
+};
+
+}  // namespace b200
