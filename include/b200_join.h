@@ -170,6 +170,11 @@ int  b200_hash_join_pairs(const uint64_t *keys_r, uint64_t n_r,
 int  b200_gather_sum(const uint64_t *col, uint64_t n, const uint64_t *ids,
                      uint64_t m, uint64_t *out_sum);
 
+/* Fill a DEVICE buffer with rows [first, first+n) of a synthetic column of
+ * BASELINE.json's configs (kinds and parameters: include/b200_synth.h). */
+int  b200_synth_column(uint64_t *device_out, uint64_t first, uint64_t n,
+                       int kind, uint64_t k, uint64_t seed);
+
 /* Tuning knobs for tests/bench (0 = library default): radix bits of the
  * partition pass and forcing the 64-bit-key kernels. */
 int  b200_set_tuning(int radix_bits, int force_key64);

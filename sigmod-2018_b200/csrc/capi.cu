@@ -133,6 +133,13 @@ uint64_t b200_kernel_launches(int reset) {
     return v;
 }
 
+// synthetic column straight into a DEVICE buffer (include/b200_synth.h)
+int b200_synth_column(uint64_t *device_out, uint64_t first, uint64_t n, int kind, uint64_t k, uint64_t seed) {
+    run_synth_column(device_out, first, n, kind, k, seed);
+    B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    return 0;
+}
+
 // K1 (filter.c:115-170)
 int b200_scan_filter(const uint64_t *col, uint64_t n, const uint64_t *ids, uint64_t n_ids, char cmp, int value,
                      uint64_t *out, uint64_t *out_n) {

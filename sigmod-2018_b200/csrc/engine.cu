@@ -622,6 +622,12 @@ void run_cartesian(const uint32_t *in, uint64_t n1, uint64_t n2, bool from_first
     B200_LAUNCH_CHECK();
 }
 
+void run_synth_column(uint64_t *d_out, uint64_t first, uint64_t n, int kind, uint64_t k, uint64_t seed) {
+    if (n == 0) return;
+    synth_column_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, ctx().stream>>>(d_out, first, n, kind, k, seed);
+    B200_LAUNCH_CHECK();
+}
+
 void widen_ids(const uint32_t *d_in, uint64_t n, uint64_t *d_out) {
     if (n == 0) return;
     widen_u32_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, ctx().stream>>>(d_in, n, d_out);

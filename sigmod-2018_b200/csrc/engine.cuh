@@ -79,6 +79,7 @@ void run_checksum(uint64_t m, int nproj, const uint64_t *const *cols, const uint
 
 // CartesianInterResults (inter_res.c:405-418): out[i*n2+j] = in[i] or in[j].
 void run_cartesian(const uint32_t *in, uint64_t n1, uint64_t n2, bool from_first, uint32_t *out);
+void run_synth_column(uint64_t *d_out, uint64_t first, uint64_t n, int kind, uint64_t k, uint64_t seed);
 // width conversions between host-facing uint64 ids and device uint32 ids
 void widen_ids(const uint32_t *d_in, uint64_t n, uint64_t *d_out);
 void narrow_ids(const uint64_t *d_in, uint64_t n, uint32_t *d_out);

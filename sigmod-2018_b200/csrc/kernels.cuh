@@ -20,6 +20,7 @@
 #pragma once
 
 #include "types.cuh"
+#include "../../include/b200_synth.h"
 
 #include <cuda_runtime.h>
 
@@ -793,6 +794,15 @@ column_max_kernel(const uint64_t *__restrict__ col, uint64_t n, unsigned long lo
         m                          = o > m ? o : m;
     }
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// Synthetic columns of BASELINE.json's configs, generated in HBM
+// (include/b200_synth.h is the single definition shared with the CPU side).
+__global__ void __launch_bounds__(256)
+synth_column_kernel(uint64_t *__restrict__ out, uint64_t first, uint64_t n, int kind, uint64_t k, uint64_t seed) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = b200_synth_value(kind, first + i, k, seed);
 }
 
 // Widening copies for the read-back entry points (tests only).

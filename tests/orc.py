@@ -1,0 +1,252 @@
+"""ctypes binding of oracle/liboracle.so (the CPU restatement, oracle_join.c)
+plus a query-level executor built from its primitives that follows the
+reference's ExecuteQuery (query.c:325-467) and the operator contracts of
+SURVEY Appendix B.  Test infrastructure only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_DIR = ROOT / "oracle"
+LIB = ORACLE_DIR / "liboracle.so"
+u64p = C.POINTER(C.c_uint64)
+i64p = C.POINTER(C.c_int64)
+NULL_RESULT = 0xFFFFFFFFFFFFFFFF
+_lib = None
+
+
+def build() -> None:
+    src = ORACLE_DIR / "oracle_join.c"
+    if not LIB.exists() or LIB.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(ORACLE_DIR), "oracle"], check=True, capture_output=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(LIB))
+        L.orc_hash1.restype = C.c_uint64
+        L.orc_hash1.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_next_prime.restype = C.c_uint64
+        L.orc_next_prime.argtypes = [C.c_uint64]
+        L.orc_hash2.restype = C.c_uint64
+        L.orc_hash2.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_reorder.restype = C.c_int
+        L.orc_reorder.argtypes = [u64p, u64p, C.c_uint64, C.c_int, u64p, u64p, u64p, i64p]
+        L.orc_create_index.restype = C.c_uint64
+        L.orc_create_index.argtypes = [u64p, C.c_uint64, i64p, i64p]
+        L.orc_radix_hash_join.restype = C.c_uint64
+        L.orc_radix_hash_join.argtypes = [u64p, u64p, C.c_uint64, u64p, u64p, C.c_uint64, C.c_int, u64p, u64p,
+                                          C.c_uint64]
+        L.orc_filter.restype = C.c_uint64
+        L.orc_filter.argtypes = [u64p, C.c_uint64, u64p, C.c_uint64, C.c_char, C.c_int, u64p]
+        L.orc_gather.restype = None
+        L.orc_gather.argtypes = [u64p, u64p, C.c_uint64, u64p]
+        L.orc_inter_equal.restype = C.c_uint64
+        L.orc_inter_equal.argtypes = [u64p, u64p, u64p, u64p, C.c_uint64, u64p]
+        L.orc_checksum.restype = C.c_uint64
+        L.orc_checksum.argtypes = [u64p, u64p, C.c_uint64]
+        L.orc_join_sum.restype = C.c_uint64
+        L.orc_join_sum.argtypes = [u64p, C.c_uint64, u64p, C.c_uint64, C.c_int, C.c_int, C.POINTER(u64p),
+                                   C.POINTER(C.c_int), u64p]
+        L.orc_synth_column.restype = None
+        L.orc_synth_column.argtypes = [u64p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64]
+        _lib = L
+    return _lib
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _p(a):
+    return a.ctypes.data_as(u64p) if a is not None else None
+
+
+def hash1(num, n):
+    return int(lib().orc_hash1(num, n))
+
+
+def next_prime(n):
+    return int(lib().orc_next_prime(n))
+
+
+def reorder(keys, n_lsb, rids=None):
+    keys = _u64(keys)
+    rids = _u64(rids) if rids is not None else None
+    n = len(keys)
+    ok, orid = np.empty(max(n, 1), np.uint64), np.empty(max(n, 1), np.uint64)
+    hist, psum = np.empty(1 << n_lsb, np.uint64), np.empty(1 << n_lsb, np.int64)
+    lib().orc_reorder(_p(keys), _p(rids), n, n_lsb, _p(ok), _p(orid), _p(hist), psum.ctypes.data_as(i64p))
+    return ok[:n], orid[:n], hist, psum
+
+
+def create_index(keys):
+    keys = _u64(keys)
+    prime = int(lib().orc_create_index(_p(keys), len(keys), None, None))
+    bucket, chain = np.empty(prime, np.int64), np.empty(max(len(keys), 1), np.int64)
+    lib().orc_create_index(_p(keys), len(keys), bucket.ctypes.data_as(i64p), chain.ctypes.data_as(i64p))
+    return prime, bucket, chain[: len(keys)]
+
+
+def radix_hash_join(keys_r, keys_s, n_lsb=4):
+    """Pairs in the reference's output order, or None for its NULL result."""
+    kr, ks = _u64(keys_r), _u64(keys_s)
+    m = int(lib().orc_radix_hash_join(_p(kr), None, len(kr), _p(ks), None, len(ks), n_lsb, None, None, 0))
+    if m == NULL_RESULT:
+        return None
+    out_r, out_s = np.empty(max(m, 1), np.uint64), np.empty(max(m, 1), np.uint64)
+    lib().orc_radix_hash_join(_p(kr), None, len(kr), _p(ks), None, len(ks), n_lsb, _p(out_r), _p(out_s), m)
+    return out_r[:m], out_s[:m]
+
+
+def filter_scan(col, cmp, value, ids=None):
+    col = _u64(col)
+    ids = _u64(ids) if ids is not None else None
+    out = np.empty(max(len(ids) if ids is not None else len(col), 1), np.uint64)
+    m = int(lib().orc_filter(_p(col), len(col), _p(ids), len(ids) if ids is not None else 0, cmp.encode(),
+                             int(value), _p(out)))
+    return out[:m].copy()
+
+
+def gather(col, pos):
+    col, pos = _u64(col), _u64(pos)
+    out = np.empty(max(len(pos), 1), np.uint64)
+    lib().orc_gather(_p(col), _p(pos), len(pos), _p(out))
+    return out[: len(pos)]
+
+
+def inter_equal(col_a, id_a, col_b, id_b, n):
+    out = np.empty(max(n, 1), np.uint64)
+    m = int(lib().orc_inter_equal(_p(_u64(col_a)), _p(_u64(id_a)) if id_a is not None else None, _p(_u64(col_b)),
+                                  _p(_u64(id_b)) if id_b is not None else None, n, _p(out)))
+    return out[:m].copy()
+
+
+def checksum(col, ids):
+    col, ids = _u64(col), _u64(ids)
+    return int(lib().orc_checksum(_p(col), _p(ids), len(ids)))
+
+
+def join_sum(keys_r, keys_s, proj, proj_side, n_lsb=4):
+    kr, ks = _u64(keys_r), _u64(keys_s)
+    pj = [_u64(p) for p in proj]
+    ptrs = (u64p * max(len(pj), 1))(*[_p(p) for p in pj])
+    sides = (C.c_int * max(len(pj), 1))(*proj_side)
+    sums = np.zeros(max(len(pj), 1), np.uint64)
+    m = int(lib().orc_join_sum(_p(kr), len(kr), _p(ks), len(ks), n_lsb, len(pj), ptrs, sides, _p(sums)))
+    return [int(s) for s in sums[: len(pj)]], m
+
+
+def synth_column(n, kind, k, seed, first=0):
+    out = np.empty(max(n, 1), np.uint64)
+    lib().orc_synth_column(_p(out), first, n, kind, k, seed & 0xFFFFFFFFFFFFFFFF)
+    return out[:n]
+
+
+# --------------------------------------------------------------------------
+# query-level oracle: ExecuteQuery (query.c:325-467) over the primitives
+# --------------------------------------------------------------------------
+def _parse(text):
+    rel_s, pred_s, view_s = text.strip().split("|")
+    relations = [int(t) for t in rel_s.split()]
+    filters, joins = [], []
+    for p in pred_s.split("&"):
+        m = re.fullmatch(r"(\d+)\.(\d+)([<>=])(\d+)(?:\.(\d+))?", p.strip())
+        b1, c1, op, rhs, c2 = m.groups()
+        if c2 is None:
+            filters.insert(0, (int(b1), int(c1), op, int(rhs)))   # query.c:150-157: list head
+        else:
+            joins.append((int(b1), int(c1), int(rhs), int(c2)))
+    views = [(int(v[0]), int(v[2])) for v in view_s.split()]
+    return relations, filters, joins, views
+
+
+def execute_query(text, relations, n_lsb=4):
+    """`relations[r]` is a list of uint64 columns.  Returns the output line the
+    reference prints.  The intermediate is a list of nodes, each a dict
+    binding -> row-id column (inter_res.h); joins run in textual order.
+
+    Spec-clean where the reference has defects the GPU library does not
+    reproduce (filters on several bindings and
+    same-binding self joins work here); quirk 1 (an empty last join prints
+    zeros, not NULL) IS reproduced because it is the reference's behaviour on
+    valid input."""
+    rels, filters, joins, views = _parse(text)
+    col = lambda b, c: relations[rels[b]][c]
+    nodes = []   # list of dict {binding: ids}, all columns of a node equally long
+    null_line = " ".join(["NULL"] * len(views))
+
+    def find(b):
+        for nd in nodes:
+            if b in nd:
+                return nd
+        return None
+
+    def compact(nd, pos):
+        for k in list(nd):
+            nd[k] = gather(nd[k], pos)
+
+    for b, c, op, k in filters:
+        nd = find(b)
+        hits = filter_scan(col(b, c), op, k, nd[b] if nd else None)
+        if len(hits) == 0:
+            return null_line
+        if nd:
+            compact(nd, hits)      # filter.c:42-81
+        else:
+            nodes.append({b: hits})   # filter.c:19-40
+    for b1, c1, b2, c2 in joins:
+        if b1 == b2:   # SelfJoin contract
+            nd = find(b1)
+            ids = nd[b1] if nd else None
+            n = len(ids) if nd else len(col(b1, c1))
+            hits = inter_equal(col(b1, c1), ids, col(b1, c2), ids, n)
+            if len(hits) == 0:
+                return null_line
+            if nd:
+                compact(nd, hits)
+            else:
+                nodes.append({b1: hits})
+            continue
+        n1, n2 = find(b1), find(b2)
+        if n1 is not None and n1 is n2:   # JoinInterNode, inter_res.c:363-389
+            hits = inter_equal(col(b1, c1), n1[b1], col(b2, c2), n1[b2], len(n1[b1]))
+            compact(n1, hits)
+            continue
+        k1 = gather(col(b1, c1), n1[b1]) if n1 else _u64(col(b1, c1))   # GetRelation
+        k2 = gather(col(b2, c2), n2[b2]) if n2 else _u64(col(b2, c2))
+        pairs = radix_hash_join(k1, k2, n_lsb)
+        if pairs is None:
+            return null_line       # rhjoin.c:15-16 -> query.c:439-449
+        p1, p2 = pairs
+        # InsertJoinToInterResults (+ MergeInterNodes when both sides lived in nodes)
+        new = {}
+        if n1:
+            for k in n1:
+                new[k] = gather(n1[k], p1)
+            nodes.remove(n1)
+        else:
+            new[b1] = p1.copy()
+        if n2:
+            for k in n2:
+                new[k] = gather(n2[k], p2)
+            nodes.remove(n2)
+        else:
+            new[b2] = p2.copy()
+        nodes.insert(0, new)
+    while len(nodes) > 1:          # CartesianInterResults, inter_res.c:391-428
+        a, b = nodes[0], nodes[1]
+        na, nb = len(next(iter(a.values()))), len(next(iter(b.values())))
+        new = {k: np.repeat(v, nb) for k, v in a.items()}
+        new.update({k: np.tile(v, na) for k, v in b.items()})
+        nodes[:2] = [new]
+    nd = nodes[0]
+    return " ".join(str(checksum(col(b, c), nd[b])) for b, c in views)

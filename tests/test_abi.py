@@ -1,0 +1,71 @@
+"""The C-ABI boundary without a GPU: headers are valid C, the library loads and
+exports every declared symbol, the struct layouts equal the reference's."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+REFERENCE_OPERATOR_SYMBOLS = [  # `nm -u query.o` of the reference, SURVEY §8b
+    "InitInterResults", "FreeInterResults", "Filter", "InsertSingleRowIdsToInterResult", "GetRelation",
+    "RadixHashJoin", "InsertJoinToInterResults", "AreActiveInInter", "JoinInterNode", "MergeInterNodes",
+    "CartesianInterResults", "CalculateQueryResults", "PrintNullResults", "SelfJoin", "FreeResult", "FreeRelation",
+]
+
+
+def test_headers_compile_as_c():
+    for h in ("b200_abi.h", "b200_join.h", "b200_synth.h"):
+        subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Werror", "-Wno-unused-function", "-fsyntax-only", "-x", "c",
+                        str(ROOT / "include" / h)], check=True)
+
+
+def test_library_exports_every_declared_symbol(b200):
+    L = b200.load_library()
+    declared = b200.declared_symbols()
+    assert set(REFERENCE_OPERATOR_SYMBOLS) <= set(declared)
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.b200_is_cuda() == 1
+
+
+def test_no_cpu_fallback_when_library_missing(b200, tmp_path):
+    with pytest.raises(ImportError):
+        b200.load_library(tmp_path / "libb200join.so")
+
+
+def test_struct_layouts_match_reference(b200):
+    """Sizes/offsets of the reference's structs.h on LP64 (checked against the
+    compiled reference by test_reference_struct_layout below when available)."""
+    h = b200.host
+    assert C.sizeof(h.CResult) == 24 and h.CResult.current_load.offset == 16
+    assert C.sizeof(h.CRelation) == 16
+    assert C.sizeof(h.CInterData) == 16 and h.CInterData.table.offset == 8
+    assert C.sizeof(h.CInterRes) == 24 and h.CInterRes.next.offset == 16
+    assert C.sizeof(h.CColumnStats) == 32
+    assert C.sizeof(h.CRelationMap) == 32 and h.CRelationMap.columns.offset == 16
+    assert C.sizeof(h.CFilterPred) == 16 and h.CFilterPred.comperator.offset == 12
+    assert C.sizeof(h.CBatchListnode) == 40 and h.CBatchListnode.views.offset == 24
+
+
+def test_reference_struct_layout(tmp_path):
+    """include/b200_abi.h against the reference's own structs.h, compiled side
+    by side (build container only: needs /root/reference)."""
+    ref = Path("/root/reference/structs.h")
+    if not ref.exists():
+        pytest.skip("/root/reference not present")
+    src = tmp_path / "layout.c"
+    fields = [("relation", "num_tuples"), ("result", "current_load"), ("inter_data", "table"),
+              ("inter_res", "next"), ("relation_map", "columns"), ("relation_map", "col_stats"),
+              ("filter_pred", "comperator"), ("batch_listnode", "views"), ("batch_listnode", "relations"),
+              ("column_stats", "d"), ("query_string_array", "num_of_elements")]
+    body = "".join(f'printf("{t}.{f} %zu %zu\\n", sizeof({t}), offsetof({t}, {f}));\n' for t, f in fields)
+    outs = []
+    for inc in ('"/root/reference/structs.h"', f'"{ROOT}/include/b200_abi.h"'):
+        src.write_text(f"#include <stdio.h>\n#include <stddef.h>\n#include {inc}\nint main(void){{{body}return 0;}}\n")
+        exe = tmp_path / "layout"
+        subprocess.run(["gcc", "-w", str(src), "-o", str(exe)], check=True)
+        outs.append(subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout)
+    assert outs[0] == outs[1]
