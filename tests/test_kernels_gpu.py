@@ -1,0 +1,153 @@
+"""Parity of the CUDA kernels (through the C-ABI) with the oracle restatement
+and the committed golden vectors of the reference.  Bit-exact: everything is
+u64 integer work.  Pair/partition ORDER is not compared (SURVEY §8 quirk 7:
+only multisets reach the checksums)."""
+import numpy as np
+import pytest
+
+from golden_cases import GOLDEN, col, join_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def sorted_pairs(r, s):
+    order = np.lexsort((s, r))
+    return np.stack([np.asarray(r)[order], np.asarray(s)[order]])
+
+
+# ---- K1 scan_filter (filter.c:92-190) --------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 2047, 2048, 2049, 100003, 1 << 20])
+@pytest.mark.parametrize("cmp", ["<", ">", "="])
+def test_scan_filter_base_column(gpu, orc, n, cmp):
+    c = col(n, 100, 1000 + n)
+    got = gpu.scan_filter(c, cmp, 37)
+    assert np.array_equal(np.sort(got), orc.filter_scan(c, cmp, 37))   # ascending row ids in the oracle
+
+
+@pytest.mark.parametrize("n_ids", [0, 1, 1000, 70001])
+def test_scan_filter_through_row_ids_emits_positions(gpu, orc, n_ids):
+    c = col(5000, 1000, 3)
+    ids = col(n_ids, 5000, 4)
+    for cmp in "<>=":
+        got = gpu.scan_filter(c, cmp, 500, ids)
+        assert np.array_equal(np.sort(got), orc.filter_scan(c, cmp, 500, ids))
+
+
+def test_scan_filter_constant_is_a_c_int(gpu, orc):
+    c = np.array([0, 5, 2**31 - 1, 2**31, 2**63, 2**64 - 1], np.uint64)
+    for cmp, k in [(">", 2**31 - 1), ("<", 1), ("=", 0), (">", 0)]:
+        assert np.array_equal(np.sort(gpu.scan_filter(c, cmp, k)), orc.filter_scan(c, cmp, k))
+
+
+# ---- K3-K5 radix partition (preprocess.c:13-178) ---------------------------
+@pytest.mark.parametrize("n,bits,domain", [(0, 4, 10), (1, 4, 10), (1000, 4, 1 << 20), (8192, 6, 1 << 30),
+                                           (8193, 4, 16), (300007, 10, 1 << 28), (300007, 12, 1 << 40),
+                                           (1 << 20, 11, 1 << 24), (50000, 1, 7)])
+def test_radix_partition_matches_oracle(gpu, orc, n, bits, domain):
+    keys = col(n, domain, 77 + n)
+    gk, gr, gh, gp = gpu.radix_partition(keys, bits)
+    ok, orid, oh, op = orc.reorder(keys, bits)
+    assert np.array_equal(gh, oh)          # histogram (HistJob + merge)
+    assert np.array_equal(gp, op)          # psum incl. -1 for empty buckets
+    assert np.array_equal(keys[gr.astype(np.int64)], gk)   # row ids travel with their keys
+    start = 0
+    for b in range(1 << bits):             # same multiset in every partition
+        h = int(oh[b])
+        if h:
+            assert np.array_equal(np.sort(gr[start:start + h]), np.sort(orid[start:start + h])), b
+        start += h
+
+
+def test_radix_partition_golden_histograms(gpu):
+    for case in GOLDEN["reorders"]:
+        kr = join_inputs({"nr": case["n"], "ns": 1, "domain": case["domain"], "seed": case["seed"]})[0]
+        _, _, gh, gp = gpu.radix_partition(kr, GOLDEN["n_lsb"])
+        assert [int(x) for x in gh] == case["hist"] and [int(x) for x in gp] == case["psum"]
+
+
+# ---- K6-K7 build + probe (rhjoin.c:13-111) ---------------------------------
+@pytest.mark.parametrize("i", range(len(GOLDEN["joins"])))
+def test_join_pairs_golden(gpu, orc, i):
+    case = GOLDEN["joins"][i]
+    kr, ks, pay_r, pay_s = join_inputs(case)
+    r, s, m = gpu.hash_join_pairs(kr, ks)
+    assert m == case["m"] == len(r)
+    assert orc.checksum(pay_r, r) == case["sum_r"] and orc.checksum(pay_s, s) == case["sum_s"]
+    o = orc.radix_hash_join(kr, ks, GOLDEN["n_lsb"])
+    assert np.array_equal(sorted_pairs(r, s), sorted_pairs(*o))
+
+
+@pytest.mark.parametrize("nr,ns,domain,bits", [
+    (100000, 300000, 1 << 16, 0),      # automatic
+    (100000, 300000, 1 << 16, 3),      # forced partition count, build chunks > table capacity
+    (20000, 20000, 3, 0),              # massive duplicates on both sides: 3 keys
+    (5000, 5000, 1, 0),                # one key: full cross product, 25M pairs
+    (70000, 10, 1 << 50, 0),           # 64-bit keys, probe side tiny (sides swap)
+    (1 << 18, 1 << 20, 1 << 18, 12),
+])
+def test_join_pairs_shapes(gpu, orc, nr, ns, domain, bits):
+    kr, ks = col(nr, domain, nr + 1), col(ns, domain, ns + 2)
+    gpu.lib().b200_set_tuning(bits, 0)
+    try:
+        r, s, m = gpu.hash_join_pairs(kr, ks)
+    finally:
+        gpu.lib().b200_set_tuning(0, 0)
+    o_r, o_s = orc.radix_hash_join(kr, ks, 4)
+    assert m == len(o_r)
+    assert np.array_equal(kr[r.astype(np.int64)], ks[s.astype(np.int64)])
+    if m <= 2_000_000:
+        assert np.array_equal(sorted_pairs(r, s), sorted_pairs(o_r, o_s))
+    else:   # order-free digest of the multiset
+        mix = lambda a, b: int(((a * np.uint64(0x9E3779B97F4A7C15)) ^ (b + np.uint64(0x1234567))).sum(dtype=np.uint64))
+        assert mix(r, s) == mix(o_r, o_s)
+
+
+def test_join_64bit_and_32bit_key_kernels_agree(gpu, orc):
+    kr, ks = col(50000, 1 << 20, 5), col(200000, 1 << 20, 6)
+    want = sorted_pairs(*orc.radix_hash_join(kr, ks, 4))
+    for force64 in (0, 1):
+        gpu.lib().b200_set_tuning(0, force64)
+        try:
+            r, s, _ = gpu.hash_join_pairs(kr, ks)
+        finally:
+            gpu.lib().b200_set_tuning(0, 0)
+        assert np.array_equal(sorted_pairs(r, s), want)
+
+
+def test_join_empty_inputs(gpu):
+    e, k = np.empty(0, np.uint64), np.arange(10, dtype=np.uint64)
+    assert gpu.hash_join_pairs(e, k)[2] == 0 and gpu.hash_join_pairs(k, e)[2] == 0
+    assert gpu.hash_join_pairs(k, k + np.uint64(100))[2] == 0
+
+
+# ---- K9 checksum (inter_res.c:320-339) -------------------------------------
+@pytest.mark.parametrize("m", [0, 1, 255, 256, 100001])
+def test_gather_sum(gpu, orc, m):
+    c = col(4096, 1 << 63, 9) * np.uint64(3)          # forces wrap-around mod 2^64
+    ids = col(m, 4096, 10)
+    assert gpu.gather_sum(c, ids) == orc.checksum(c, ids)
+
+
+# ---- fused join -> SUM (the bench path) -------------------------------------
+@pytest.mark.parametrize("i", range(len(GOLDEN["joins"])))
+def test_join_sum_golden(gpu, i):
+    case = GOLDEN["joins"][i]
+    kr, ks, pay_r, pay_s = join_inputs(case)
+    sums, m = gpu.join_sum(kr, ks, [pay_r, pay_s, pay_r], [0, 1, 0])
+    assert m == case["m"] and sums == [case["sum_r"], case["sum_s"], case["sum_r"]]
+    sums, m = gpu.join_sum(ks, kr, [pay_r, pay_s], [1, 0])      # sides swapped
+    assert m == case["m"] and sums == [case["sum_r"], case["sum_s"]]
+
+
+@pytest.mark.parametrize("kr_bits,ks_bits", [(12, 16), (16, 20), (20, 22)])
+def test_join_sum_config2_shape_scaled_down(gpu, orc, kr_bits, ks_bits):
+    """BASELINE config 2 at reduced size: unique permutation keys, probe
+    selectivity 2^(kr-ks), checked against the oracle's full pipeline."""
+    nr, ns = 1 << kr_bits, 1 << ks_bits
+    kr = orc.synth_column(nr, 0, kr_bits, gpu.SEED_R)
+    ks = orc.synth_column(ns, 0, ks_bits, gpu.SEED_S)
+    pr = orc.synth_column(nr, 1, 0, gpu.SEED_R + 1)
+    ps = orc.synth_column(ns, 1, 0, gpu.SEED_S + 1)
+    want, m = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
+    got, gm = gpu.join_sum(kr, ks, [pr, ps], [0, 1])
+    assert m == gm == nr and got == want

@@ -1,0 +1,120 @@
+"""The reference's operator API on the GPU library, driven the way the
+reference's only caller (query.c:ExecuteQuery) drives it, against the golden
+lines of the reference, the oracle executor and the shipped `small` workload."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from golden_cases import GOLDEN, col, load_small, query_relations, small_queries
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.mark.parametrize("i", range(len(GOLDEN["queries"])))
+def test_query_golden_lines(gpu, i):
+    case = GOLDEN["queries"][i]
+    rm = gpu.RelationMapArray(query_relations(case))
+    assert gpu.execute_query(case["query"], rm).line() == case["line"]
+
+
+EXTRA = [
+    "0 1 2|0.0=1.0&0.1=2.1&1.2=2.2|2.0 1.1",                 # triangle: JoinInterNode
+    "0 1 2|0.0=1.0&0.1<30&1.1>20&2.2=5&1.2=2.1|0.2 1.0 2.0",  # filters on three bindings
+    "0 1 2 0|0.0=1.0&1.1=2.1&2.2=3.2&3.0<20|3.1 0.1",
+    "0 1|0.1=0.2&0.0=1.0|1.1 0.0",                            # same-binding self join
+    "0 1 2|0.0=1.0&0.1=1.1&1.2=2.2&0.2=2.0|0.0 1.0 2.0",
+    "0 1|0.0=1.0|0.0 0.0 1.1 1.1",                            # duplicated projections
+]
+
+
+@pytest.mark.parametrize("q", EXTRA)
+def test_queries_against_oracle_executor(gpu, orc, q):
+    rels = [[col(n, 48, 4000 + 10 * r + c) for c in range(3)] for r, n in enumerate([700, 1100, 400])]
+    rm = gpu.RelationMapArray(rels)
+    assert gpu.execute_query(q, rm).line() == orc.execute_query(q, rels)
+
+
+def test_operator_level_walkthrough(gpu, orc):
+    """Filter -> InsertSingleRowIds -> GetRelation -> RadixHashJoin ->
+    InsertJoinToInterResults, reading every intermediate back (Appendix B)."""
+    import ctypes as C
+    h, L = gpu.host, gpu.lib()
+    rels = [[col(3000, 200, 50), col(3000, 50, 51)], [col(5000, 200, 52), col(5000, 1 << 20, 53)]]
+    rm = gpu.RelationMapArray(rels)
+    rm.register()
+    binds = (C.c_int * 2)(0, 1)
+    inter = C.POINTER(h.CInterRes)()
+    L.InitInterResults(C.byref(inter), 2)
+    fp = h.CFilterPred(0, 1, 25, b"<")
+    res = L.Filter(inter, C.byref(fp), rm.array, binds)
+    want_ids = orc.filter_scan(rels[0][1], "<", 25)
+    assert res and res.contents.current_load == len(want_ids) and L.b200_result_kind(res) == 1
+    got = np.empty(len(want_ids), np.uint64)
+    L.b200_result_rowids_to_host(res, got.ctypes.data_as(h.u64p))
+    assert np.array_equal(np.sort(got), want_ids)
+    L.InsertSingleRowIdsToInterResult(C.byref(inter), 0, res)
+    L.FreeResult(res)
+    assert inter.contents.data.contents.num_tuples == len(want_ids)
+    r0 = L.GetRelation(0, 0, inter, rm.array, binds)
+    r1 = L.GetRelation(1, 0, inter, rm.array, binds)
+    assert r0.contents.num_tuples == len(want_ids) and r1.contents.num_tuples == 5000
+    jr = L.RadixHashJoin(r0, r1, None)
+    L.FreeRelation(r0)
+    L.FreeRelation(r1)
+    t0 = np.empty(len(want_ids), np.uint64)
+    L.b200_inter_column_to_host(inter, 0, t0.ctypes.data_as(h.u64p))
+    o_r, o_s = orc.radix_hash_join(rels[0][0][t0.astype(np.int64)], rels[1][0], 4)
+    assert jr and jr.contents.current_load == len(o_r) and L.b200_result_kind(jr) == 2
+    L.InsertJoinToInterResults(inter, 0, 1, jr)
+    L.FreeResult(jr)
+    m = len(o_r)
+    c0, c1 = np.empty(m, np.uint64), np.empty(m, np.uint64)
+    L.b200_inter_column_to_host(inter, 0, c0.ctypes.data_as(h.u64p))
+    L.b200_inter_column_to_host(inter, 1, c1.ctypes.data_as(h.u64p))
+    assert np.array_equal(rels[0][0][c0.astype(np.int64)], rels[1][0][c1.astype(np.int64)])
+    want = np.stack([t0[o_r.astype(np.int64)], o_s])
+    assert np.array_equal(np.sort(c0 * np.uint64(1 << 20) + c1), np.sort(want[0] * np.uint64(1 << 20) + want[1]))
+    assert L.AreActiveInInter(inter, 0, 1) == 1
+    L.FreeInterResults(inter)
+
+
+def test_small_workload_execute_query(gpu):
+    """BASELINE config 1 at operator level: all 50 small.work queries equal the
+    reference's golden small.result."""
+    rels = load_small()
+    if rels is None:
+        pytest.skip("small workload data not present (oracle/_ref/small)")
+    rm = gpu.RelationMapArray(rels)
+    rm.register()
+    queries, golden = small_queries()
+    for q, want in zip(queries, golden):
+        assert gpu.execute_query(q, rm).line() == want, q
+
+
+def test_small_workload_dropin_binary():
+    """BASELINE config 1 through the link-time drop-in: the reference's own
+    handler.o/query.o/best_tree.o/stats.o/relation_map.o over libb200join.so,
+    fed the harness protocol on stdin; output must equal small.result."""
+    exe = ROOT / "oracle" / "_ref" / "radixhash_b200"
+    small = ROOT / "oracle" / "_ref" / "small"
+    if not exe.exists() or not (small / "r0").exists():
+        pytest.skip("drop-in binary / small workload not built (make -C oracle ref dropin)")
+    stdin = (small / "small.init").read_text() + "Done\n" + (small / "small.work").read_text()
+    out = subprocess.run([str(exe)], input=stdin, capture_output=True, text=True, cwd=small, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout == (small / "small.result").read_text()
+
+
+def test_small_workload_through_the_contest_harness():
+    exe = ROOT / "oracle" / "_ref" / "radixhash_b200"
+    harness = ROOT / "oracle" / "_ref" / "harness"
+    small = ROOT / "oracle" / "_ref" / "small"
+    if not exe.exists() or not harness.exists() or not (small / "r0").exists():
+        pytest.skip("harness / drop-in binary not built")
+    out = subprocess.run([str(harness), "small.init", "small.work", "small.result", str(exe)], capture_output=True,
+                         text=True, cwd=small, timeout=600)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-2000:]
+    assert int(out.stdout.strip().split()[-1]) >= 0     # elapsed ms
