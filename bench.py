@@ -289,7 +289,7 @@ def run_b200_arm(args):
     # ---- per-kernel device times (profiling events on, outside the timed region) ----
     L.b200_set_profiling(1)
     per_kernel = {}
-    for _ in range(3):
+    for _ in range(9):
         step()
         torch.cuda.synchronize()
         for name in ("hist", "scan", "scatter_b", "scatter_p", "join"):
@@ -297,6 +297,7 @@ def run_b200_arm(args):
             if v >= 0:
                 per_kernel.setdefault(name, []).append(v)
     L.b200_set_profiling(0)
+    per_kernel_range = {k: [min(v), max(v)] for k, v in per_kernel.items()}
     per_kernel = {k: statistics.median(v) for k, v in per_kernel.items()}
 
     # ---- end to end through the C-ABI with HOST buffers (N = 1 shard per rank) ----
@@ -373,7 +374,7 @@ def run_b200_arm(args):
                     "achieved_encoded": enc / dur / 1e9, "frac_encoded": enc / dur / 1e9 / peak,
                     "launch_ms": per_kernel[dom], "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)",
                     "bytes_per_launch_canonical": canon, "bytes_per_launch_encoded": enc,
-                    "per_kernel_ms": per_kernel}
+                    "per_kernel_ms": per_kernel, "per_kernel_ms_min_max": per_kernel_range}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

@@ -126,6 +126,18 @@ int  b200_register_device_column(const uint64_t *host_key,
  * thread's stream; used by the end-to-end bench arm. */
 int  b200_upload_column(const uint64_t *host_col, uint64_t n);
 void b200_unregister_all(void);
+/* Drop the device copies of these relations' columns.  Device copies are keyed
+ * by the HOST column pointer, so a caller that frees or rewrites a registered
+ * host column (the reference never does: its columns are a read-only mmap for
+ * the life of the process, relation_map.c:24-31) must call this first. */
+int  b200_unregister_relations(const relation_map *map, int count);
+
+/* Device memory for callers that keep columns resident in HBM and pass DEVICE
+ * pointers (location 1 of b200_join_sum, b200_register_device_column). */
+void *b200_device_malloc(uint64_t bytes);
+void  b200_device_free(void *device_ptr);
+int   b200_copy_to_device(void *device_dst, const void *host_src, uint64_t bytes);
+int   b200_copy_to_host(void *host_dst, const void *device_src, uint64_t bytes);
 
 /* The calling thread's CUDA stream (cudaStream_t as void*), so a caller can
  * record events on it; b200_set_stream adopts a caller-owned stream. */

@@ -87,6 +87,43 @@ int b200_upload_column(const uint64_t *host_col, uint64_t n) {
 
 void b200_unregister_all(void) { unregister_all_columns(); }
 
+int b200_unregister_relations(const relation_map *map, int count) {
+    for (int r = 0; r < count; ++r)
+        for (uint64_t j = 0; j < map[r].num_columns; ++j) unregister_column(map[r].columns[j]);
+    return 0;
+}
+
+// device memory for callers that keep relations resident in HBM (location = 1)
+void *b200_device_malloc(uint64_t bytes) {
+    ensure_init();
+    (void)ctx();
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+        cudaGetLastError();
+        set_last_error("cudaMalloc failed");
+        return nullptr;
+    }
+    return p;
+}
+
+void b200_device_free(void *device_ptr) {
+    if (device_ptr) cudaFree(device_ptr);
+}
+
+int b200_copy_to_device(void *device_dst, const void *host_src, uint64_t bytes) {
+    Context &c = ctx();
+    B200_CUDA(cudaMemcpyAsync(device_dst, host_src, bytes, cudaMemcpyHostToDevice, c.stream));
+    B200_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int b200_copy_to_host(void *host_dst, const void *device_src, uint64_t bytes) {
+    Context &c = ctx();
+    B200_CUDA(cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, c.stream));
+    B200_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
 void *b200_get_stream(void) { return ctx().stream; }
 
 int b200_set_stream(void *cuda_stream) {

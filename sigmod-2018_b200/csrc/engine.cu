@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -63,6 +64,11 @@ static void init_device(int device) {
     if (const char *v = getenv("B200_CAP64")) t.cap64 = (uint32_t)atoi(v);
     if (const char *v = getenv("B200_SLICE")) t.slice = (uint32_t)atoi(v);
     if (const char *v = getenv("B200_DEBUG")) t.debug = atoi(v);
+    if (const char *v = getenv("B200_SCATTER_CFG")) t.scatter_cfg = atoi(v);
+    if (const char *v = getenv("B200_L2_FETCH")) {
+        // granularity hint for L2 fills of the random payload gathers (32, 64 or 128)
+        B200_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v)));
+    }
 }
 
 static int g_requested_device = -1;
@@ -218,11 +224,25 @@ void register_device_column(const uint64_t *host_key, const uint64_t *dev, uint6
     g_columns[host_key] = e;
 }
 
+void unregister_column(const uint64_t *host_col) {
+    std::lock_guard<std::mutex> lk(g_col_mu);
+    auto it = g_columns.find(host_col);
+    if (it == g_columns.end()) return;
+    if (it->second.owned) cudaFree(it->second.owned);
+    g_columns.erase(it);
+}
+
 DevColumn lookup_column(const uint64_t *host_col, uint64_t n) {
     {
         std::lock_guard<std::mutex> lk(g_col_mu);
         auto it = g_columns.find(host_col);
-        if (it != g_columns.end()) return it->second.col;
+        if (it != g_columns.end()) {
+            // a different length under the same host pointer is a stale entry
+            // (the caller freed and re-used the memory): upload again
+            if (it->second.col.n == n) return it->second.col;
+            if (it->second.owned) cudaFree(it->second.owned);
+            g_columns.erase(it);
+        }
     }
     // never registered (the reference's unmodified handler.o): upload on first use
     register_host_column(host_col, n, false);
@@ -248,13 +268,21 @@ static void allow_smem(KernelT kernel, size_t bytes) {
 
 constexpr int kPartNT = 512;
 
-template <typename KeyT> struct PartCfg;
-template <> struct PartCfg<uint32_t> { static constexpr int U = 16; };   // 8192-tuple tiles, 64 KB stage
-template <> struct PartCfg<uint64_t> { static constexpr int U = 8; };    // 4096-tuple tiles, 64 KB stage
+// scatter configurations (Tuning::scatter_cfg): threads, keys per thread, CTAs per SM
+//   0: 512 x 16 (32-bit keys) / 512 x 8 (64-bit), 2 CTAs/SM  -> 64 KB stage each
+//   1: 512 x 32 / 512 x 16, 1 CTA/SM                          -> 128 KB stage
+//   2: 1024 x 16 / 1024 x 8, 1 CTA/SM                         -> 128 KB stage, 32 warps
+template <typename KeyT, int CFG> struct PartCfg;
+template <> struct PartCfg<uint32_t, 0> { static constexpr int NT = 512, U = 16, MINB = 2; };
+template <> struct PartCfg<uint64_t, 0> { static constexpr int NT = 512, U = 8, MINB = 2; };
+template <> struct PartCfg<uint32_t, 1> { static constexpr int NT = 512, U = 32, MINB = 1; };
+template <> struct PartCfg<uint64_t, 1> { static constexpr int NT = 512, U = 16, MINB = 1; };
+template <> struct PartCfg<uint32_t, 2> { static constexpr int NT = 1024, U = 16, MINB = 1; };
+template <> struct PartCfg<uint64_t, 2> { static constexpr int NT = 1024, U = 8, MINB = 1; };
 
 template <typename KeyT>
 static void launch_hist(const KeySrc &src, int bits, uint32_t *ghist) {
-    constexpr int U    = PartCfg<KeyT>::U;
+    constexpr int U    = PartCfg<KeyT, 0>::U;
     const size_t  smem = (size_t)(1u << bits) * sizeof(uint32_t);
     auto          k    = radix_hist_kernel<kPartNT, U, KeyT>;
     allow_smem(k, smem);
@@ -262,61 +290,90 @@ static void launch_hist(const KeySrc &src, int bits, uint32_t *ghist) {
     B200_LAUNCH_CHECK();
 }
 
+template <typename KeyT, int CFG>
+static void launch_scatter_c(const KeySrc &src, int bits, uint32_t *cursor, void *out) {
+    using TupT            = typename TupOf<KeyT>::type;
+    constexpr int NT      = PartCfg<KeyT, CFG>::NT;
+    constexpr int U       = PartCfg<KeyT, CFG>::U;
+    constexpr int MINB    = PartCfg<KeyT, CFG>::MINB;
+    const size_t  smem    = (size_t)NT * U * sizeof(TupT) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
+    auto          k       = radix_scatter_kernel<NT, U, MINB, KeyT>;
+    allow_smem(k, smem);
+    k<<<grid_for(src.n, NT * U, MINB), NT, smem, ctx().stream>>>(src, (uint32_t)bits, cursor,
+                                                                 static_cast<TupT *>(out));
+    B200_LAUNCH_CHECK();
+}
+
 template <typename KeyT>
 static void launch_scatter(const KeySrc &src, int bits, uint32_t *cursor, void *out) {
-    using TupT         = typename TupOf<KeyT>::type;
-    constexpr int U    = PartCfg<KeyT>::U;
-    const size_t  smem = (size_t)kPartNT * U * sizeof(TupT) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
-    auto          k    = radix_scatter_kernel<kPartNT, U, KeyT>;
-    allow_smem(k, smem);
-    k<<<grid_for(src.n, kPartNT * U, 2), kPartNT, smem, ctx().stream>>>(src, (uint32_t)bits, cursor,
-                                                                        static_cast<TupT *>(out));
-    B200_LAUNCH_CHECK();
+    switch (tuning().scatter_cfg) {
+        case 0: launch_scatter_c<KeyT, 0>(src, bits, cursor, out); break;
+        case 2: launch_scatter_c<KeyT, 2>(src, bits, cursor, out); break;
+        default: launch_scatter_c<KeyT, 1>(src, bits, cursor, out); break;
+    }
 }
 
 constexpr int kJoinNT = 512;
 constexpr int kJoinU  = 8;
 
-static size_t join_smem_bytes(bool key64, uint32_t cap, uint32_t slots_log2) {
-    return (size_t)cap * ((key64 ? 8 : 4) + 4 + 2) + ((size_t)2 << slots_log2);
-}
-
-template <typename KeyT, bool DIRECT, int MODE>
-static void launch_join_t(const JoinArgs &a, size_t smem) {
-    auto k = hash_join_kernel<kJoinNT, kJoinU, KeyT, DIRECT, MODE>;
+template <typename KernelT>
+static void launch_persistent_join(KernelT k, const JoinArgs &a, bool direct, size_t smem) {
     allow_smem(k, smem);
     int occ = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kJoinNT, smem));
-    B200_REQUIRE(occ >= 1, "hash_join_kernel does not fit on an SM");
+    B200_REQUIRE(occ >= 1, "join kernel does not fit on an SM");
     int grid = sm_count() * occ;
-    if (DIRECT && (int)a.n_items_direct < grid) grid = (int)a.n_items_direct;
+    if (direct && (int)a.n_items_direct < grid) grid = (int)a.n_items_direct;
     if (grid < 1) grid = 1;
     k<<<grid, kJoinNT, smem, ctx().stream>>>(a);
     B200_LAUNCH_CHECK();
 }
 
-template <typename KeyT, bool DIRECT>
-static void launch_join_m(const JoinArgs &a, int mode, size_t smem) {
+// 64-bit keys: chained table (hash_join_kernel)
+template <bool DIRECT>
+static void launch_join64(const JoinArgs &a, int mode, size_t smem) {
     if (mode == MODE_COUNT)
-        launch_join_t<KeyT, DIRECT, MODE_COUNT>(a, smem);
+        launch_persistent_join(hash_join_kernel<kJoinNT, kJoinU, uint64_t, DIRECT, MODE_COUNT, 0>, a, DIRECT, smem);
     else if (mode == MODE_WRITE)
-        launch_join_t<KeyT, DIRECT, MODE_WRITE>(a, smem);
+        launch_persistent_join(hash_join_kernel<kJoinNT, kJoinU, uint64_t, DIRECT, MODE_WRITE, 0>, a, DIRECT, smem);
+    else if (a.nproj <= 2)
+        launch_persistent_join(hash_join_kernel<kJoinNT, kJoinU, uint64_t, DIRECT, MODE_SUM, 2>, a, DIRECT, smem);
+    else if (a.nproj <= 4)
+        launch_persistent_join(hash_join_kernel<kJoinNT, kJoinU, uint64_t, DIRECT, MODE_SUM, 4>, a, DIRECT, smem);
     else
-        launch_join_t<KeyT, DIRECT, MODE_SUM>(a, smem);
+        launch_persistent_join(hash_join_kernel<kJoinNT, kJoinU, uint64_t, DIRECT, MODE_SUM, kMaxProj>, a, DIRECT, smem);
+}
+
+// 32-bit keys: two-choice bucketised table (bucket_join_kernel)
+constexpr int kJoinG = 4;
+template <bool DIRECT>
+static void launch_join32(const JoinArgs &a, int mode, size_t smem) {
+    if (mode == MODE_COUNT)
+        launch_persistent_join(bucket_join_kernel<kJoinNT, kJoinG, DIRECT, MODE_COUNT, 0>, a, DIRECT, smem);
+    else if (mode == MODE_WRITE)
+        launch_persistent_join(bucket_join_kernel<kJoinNT, kJoinG, DIRECT, MODE_WRITE, 0>, a, DIRECT, smem);
+    else if (a.nproj <= 2)
+        launch_persistent_join(bucket_join_kernel<kJoinNT, kJoinG, DIRECT, MODE_SUM, 2>, a, DIRECT, smem);
+    else if (a.nproj <= 4)
+        launch_persistent_join(bucket_join_kernel<kJoinNT, kJoinG, DIRECT, MODE_SUM, 4>, a, DIRECT, smem);
+    else
+        launch_persistent_join(bucket_join_kernel<kJoinNT, kJoinG, DIRECT, MODE_SUM, kMaxProj>, a, DIRECT, smem);
 }
 
 static void launch_join(const JoinArgs &a, bool key64, bool direct, int mode) {
-    const size_t smem = join_smem_bytes(key64, a.cap, a.slots_log2);
     if (key64) {
+        const size_t smem = TableView<uint64_t>::bytes(a.cap, a.slots_log2);
         if (direct)
-            launch_join_m<uint64_t, true>(a, mode, smem);
+            launch_join64<true>(a, mode, smem);
         else
-            launch_join_m<uint64_t, false>(a, mode, smem);
+            launch_join64<false>(a, mode, smem);
     } else {
+        const size_t smem = ((size_t)6 << a.slots_log2) +
+                            (mode == MODE_COUNT ? (size_t)8 * (kJoinNT / 32) : (size_t)8 * kWarpQueue * (kJoinNT / 32));
         if (direct)
-            launch_join_m<uint32_t, true>(a, mode, smem);
+            launch_join32<true>(a, mode, smem);
         else
-            launch_join_m<uint32_t, false>(a, mode, smem);
+            launch_join32<false>(a, mode, smem);
     }
 }
 
@@ -333,7 +390,7 @@ PartitionOut run_partition(const KeyVec &kv, int bits) {
     Context &c = ctx();
     B200_REQUIRE(bits >= 0 && bits <= tuning().max_bits, "radix bits out of range");
     PartitionOut  o;
-    o.key64               = tuning().force_key64 || kv.max_val > 0xFFFFFFFFull;
+    o.key64               = tuning().force_key64 || kv.max_val >= 0xFFFFFFFFull;
     const uint32_t nparts = 1u << bits;
     o.hist                = dev_alloc((size_t)nparts * sizeof(uint32_t));
     DevBufPtr zeros       = dev_alloc((size_t)nparts * sizeof(uint32_t));
@@ -373,18 +430,24 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     const bool    swapped = S.src.n < R.src.n;
     const KeyVec &B       = swapped ? S : R;
     const KeyVec &P       = swapped ? R : S;
-    const bool    key64   = t.force_key64 || B.max_val > 0xFFFFFFFFull || P.max_val > 0xFFFFFFFFull;
+    // 0xFFFFFFFF is the empty-slot marker of the 32-bit table
+    const bool    key64   = t.force_key64 || B.max_val >= 0xFFFFFFFFull || P.max_val >= 0xFFFFFFFFull;
     const uint32_t cap    = key64 ? t.cap64 : t.cap32;
     B200_REQUIRE(cap >= 32 && cap <= 65534, "table capacity must fit 16-bit chain links");
-    const uint32_t slots_log2 = ceil_log2(2ull * cap);
+    const uint32_t slots_log2 = key64 ? TableView<uint64_t>::slots_log2_for(cap) : TableView<uint32_t>::slots_log2_for(cap);
+    // expected largest partition under a uniform split: mean + 5 sigma (a larger one is split into build chunks)
+    auto fits = [&](int b) {
+        const double mean = (double)B.src.n / (double)(1ull << b);
+        return mean + 5.0 * sqrt(mean) <= (double)cap;
+    };
 
     int bits = 0;
     if (t.radix_bits > 0) {
         bits = std::min(t.radix_bits, t.max_bits);
     } else if (B.src.n > cap) {
-        // aim at ~70% of the table capacity per partition
-        bits = (int)ceil_log2((B.src.n * 10 + (uint64_t)cap * 7 - 1) / ((uint64_t)cap * 7));
-        bits = std::max(1, std::min(bits, t.max_bits));
+        // fewest partitions whose build side fits one table (longer runs per scatter tile)
+        bits = 1;
+        while (bits < t.max_bits && !fits(bits)) ++bits;
     }
     const bool direct = bits == 0;
 

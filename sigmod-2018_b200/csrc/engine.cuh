@@ -24,6 +24,7 @@ void      register_host_column(const uint64_t *host_col, uint64_t n, bool replac
 void      register_device_column(const uint64_t *host_key, const uint64_t *dev, uint64_t n,
                                  uint64_t max_val);
 void      unregister_all_columns();
+void      unregister_column(const uint64_t *host_col);
 
 // Lazy key vector with ownership of the row-id list it reads through.
 struct KeyVec {
@@ -35,9 +36,10 @@ struct KeyVec {
 struct Tuning {
     int      radix_bits  = 0;   // 0 = automatic
     int      force_key64 = 0;
-    uint32_t cap32       = 8192;     // build tuples per shared-memory table, 32-bit keys
-    uint32_t cap64       = 4096;     // ... 64-bit keys
-    uint32_t slice       = 1u << 18; // probe tuples per work item
+    uint32_t cap32       = 8704;     // build tuples per shared-memory table, 32-bit keys
+    uint32_t cap64       = 6144;     // ... 64-bit keys
+    uint32_t slice       = 1u << 16; // probe tuples per work item
+    int      scatter_cfg = 1;        // see engine.cu PartCfg
     int      max_bits    = 12;
     int      debug       = 0;
 };

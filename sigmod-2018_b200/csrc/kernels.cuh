@@ -227,19 +227,96 @@ partition_plan_kernel(const uint32_t *__restrict__ hist_b, const uint32_t *__res
 // preprocess.c:350-359; the reference's parallel variant re-scans the input
 // once per bucket, preprocess.c:262-296).
 //
-// Per tile of NT*U keys: (1) coalesced key loads, (2) shared-memory atomics
+// Per tile of NT*U keys: (1) the keys are already in registers (prefetched
+// while the previous tile was being copied out), (2) shared-memory atomics
 // give every tuple its rank inside its partition, (3) a block scan turns the
 // tile histogram into local offsets and reserves the tile's run in every
 // partition with ONE global atomicAdd per non-empty partition, (4) tuples are
 // written to shared memory in partition order, (5) copied out so that a warp
 // stores consecutive addresses inside each run.  All CTAs advance the same
 // 2^bits cursors, so the write frontier is a few hundred KB and partially
-// written sectors are completed in L2 before they reach HBM.
+// written sectors are completed in L2 before they reach HBM (ncu: DRAM write
+// bytes = 1.0 x the tuple bytes).
+// The kernel is bound by the SM's load/store pipe, not by HBM (ncu: l1tex is
+// the busiest unit), so full, aligned tiles run a predicate-free instance
+// (FULL) and ranks are packed two per register.
 // Order inside a partition is not the reference's (stable) order; only the
 // multiset matters downstream.
 // ---------------------------------------------------------------------------
-template <int NT, int U, typename KeyT>
-__global__ void __launch_bounds__(NT, 2)
+template <int NT, int U, typename KeyT, bool FULL>
+__device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U], uint64_t base, uint32_t count,
+                                             bool vec, uint64_t nbase, uint32_t ncount, bool nvec, bool has_next,
+                                             uint32_t nbins, uint32_t mask, uint32_t per,
+                                             typename TupOf<KeyT>::type *stage, uint32_t *cnt, uint32_t *loc,
+                                             uint32_t *gdelta, uint32_t *warp_sums, uint32_t *__restrict__ cursor,
+                                             typename TupOf<KeyT>::type *__restrict__ out) {
+    using TupT = typename TupOf<KeyT>::type;
+    const uint32_t tid = threadIdx.x;
+    uint32_t rank2[(U + 1) / 2];   // two 16-bit ranks per register
+#pragma unroll
+    for (int j = 0; j < (U + 1) / 2; ++j) rank2[j] = 0;
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const uint32_t li = FULL ? ((uint32_t)((j >> 1) * NT) + tid) * 2u + (uint32_t)(j & 1)
+                                 : tile_local_index<NT, U>(j, vec);
+        if (FULL || li < count) {
+            const uint32_t r = atomicAdd(&cnt[(uint32_t)keys[j] & mask], 1u);
+            rank2[j >> 1] |= r << (16 * (j & 1));
+        }
+    }
+    __syncthreads();
+    {
+        const uint32_t first = tid * per;
+        uint32_t       s     = 0;
+        for (uint32_t k = 0; k < per; ++k)
+            if (first + k < nbins) s += cnt[first + k];
+        uint32_t run = block_exclusive_scan<NT>(s, warp_sums);
+        for (uint32_t k = 0; k < per; ++k) {
+            const uint32_t b = first + k;
+            if (b < nbins) {
+                const uint32_t c = cnt[b];
+                loc[b]           = run;
+                if (c) gdelta[b] = atomicAdd(&cursor[b], c) - run;
+                run += c;
+                cnt[b] = 0;   // ready for the next tile
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const uint32_t li = FULL ? ((uint32_t)((j >> 1) * NT) + tid) * 2u + (uint32_t)(j & 1)
+                                 : tile_local_index<NT, U>(j, vec);
+        if (FULL || li < count) {
+            TupT t;
+            t.key = keys[j];
+            t.rid = (uint32_t)base + li;
+            if constexpr (sizeof(KeyT) == 8) t.pad = 0;
+            stage[loc[(uint32_t)keys[j] & mask] + ((rank2[j >> 1] >> (16 * (j & 1))) & 0xFFFFu)] = t;
+        }
+    }
+    __syncthreads();
+    // keys[] and the ranks are dead: put the next tile's loads in flight before
+    // the copy-out so their latency hides behind the stores
+    if (has_next) load_tile_keys<NT, U, KeyT>(src, nbase, ncount, nvec, keys);
+    if constexpr (FULL) {
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const uint32_t i = (uint32_t)(k * NT) + tid;
+            const TupT     t = stage[i];
+            out[gdelta[(uint32_t)t.key & mask] + i] = t;
+        }
+    } else {
+        for (uint32_t i = tid; i < count; i += NT) {
+            const TupT t = stage[i];
+            out[gdelta[(uint32_t)t.key & mask] + i] = t;
+        }
+    }
+    __syncthreads();
+}
+
+template <int NT, int U, int MINB, typename KeyT>
+__global__ void __launch_bounds__(NT, MINB)
 radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cursor,
                      typename TupOf<KeyT>::type *__restrict__ out) {
     using TupT = typename TupOf<KeyT>::type;
@@ -253,60 +330,37 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
     uint32_t *gdelta = loc + nbins;
     __shared__ uint32_t warp_sums[NT / 32 + 1];
 
+    // row ids are 32-bit: tile bases fit 32 bits as well
     const uint64_t n      = src.n;
     const uint64_t ntiles = (n + TILE - 1) / TILE;
     const bool     vec_ok = src.ids == nullptr && ((reinterpret_cast<uintptr_t>(src.col) & 15) == 0);
     const uint32_t per    = (nbins + NT - 1) / NT;
 
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (uint32_t b = threadIdx.x; b < nbins; b += NT) cnt[b] = 0;
+    KeyT     keys[U];
+    uint64_t tile = blockIdx.x;
+    if (tile < ntiles) {
         const uint64_t base  = tile * TILE;
         const uint32_t count = (uint32_t)min((uint64_t)TILE, n - base);
-        const bool     vec   = vec_ok && count == TILE;
-        for (uint32_t b = threadIdx.x; b < nbins; b += NT) cnt[b] = 0;
-        KeyT keys[U];
-        load_tile_keys<NT, U, KeyT>(src, base, count, vec, keys);
-        __syncthreads();
-        uint16_t rank[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            if (tile_local_index<NT, U>(j, vec) < count)
-                rank[j] = (uint16_t)atomicAdd(&cnt[(uint32_t)keys[j] & mask], 1u);
-        }
-        __syncthreads();
-        {
-            const uint32_t first = threadIdx.x * per;
-            uint32_t       s     = 0;
-            for (uint32_t k = 0; k < per; ++k)
-                if (first + k < nbins) s += cnt[first + k];
-            uint32_t run = block_exclusive_scan<NT>(s, warp_sums);
-            for (uint32_t k = 0; k < per; ++k) {
-                const uint32_t b = first + k;
-                if (b < nbins) {
-                    const uint32_t c = cnt[b];
-                    loc[b]           = run;
-                    if (c) gdelta[b] = atomicAdd(&cursor[b], c) - run;
-                    run += c;
-                }
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const uint32_t li = tile_local_index<NT, U>(j, vec);
-            if (li < count) {
-                TupT t;
-                t.key = keys[j];
-                t.rid = (uint32_t)(base + li);
-                if constexpr (sizeof(KeyT) == 8) t.pad = 0;
-                stage[loc[(uint32_t)keys[j] & mask] + rank[j]] = t;
-            }
-        }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < count; i += NT) {
-            const TupT t = stage[i];
-            out[gdelta[(uint32_t)t.key & mask] + i] = t;
-        }
-        __syncthreads();
+        load_tile_keys<NT, U, KeyT>(src, base, count, vec_ok && count == TILE, keys);
+    }
+    __syncthreads();
+
+    for (; tile < ntiles; tile += gridDim.x) {
+        const uint64_t base     = tile * TILE;
+        const uint32_t count    = (uint32_t)min((uint64_t)TILE, n - base);
+        const bool     vec      = vec_ok && count == TILE;
+        const uint64_t ntile    = tile + gridDim.x;
+        const bool     has_next = ntile < ntiles;
+        const uint64_t nbase    = ntile * TILE;
+        const uint32_t ncount   = has_next ? (uint32_t)min((uint64_t)TILE, n - nbase) : 0u;
+        const bool     nvec     = vec_ok && ncount == TILE;
+        if (vec)
+            scatter_tile<NT, U, KeyT, true>(src, keys, base, count, vec, nbase, ncount, nvec, has_next, nbins, mask,
+                                            per, stage, cnt, loc, gdelta, warp_sums, cursor, out);
+        else
+            scatter_tile<NT, U, KeyT, false>(src, keys, base, count, vec, nbase, ncount, nvec, has_next, nbins, mask,
+                                             per, stage, cnt, loc, gdelta, warp_sums, cursor, out);
     }
 }
 
@@ -319,7 +373,15 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
 // bucket[]/chain[] arrays in DRAM and hashes with `% prime`; here heads/next
 // are 16-bit, the hash is multiplicative on the key bits above the radix) and
 // streams the probe slice through it (rhjoin.c:141-217), comparing full keys,
-// so duplicates on both sides yield the cross product.
+// so duplicates on both sides yield the cross product.  Only keys and chain
+// links live in shared memory; the build row id of a match is re-read from the
+// partition buffer (still L2-resident).
+//
+// Matches are not handled inside the chain walk: the lane pushes
+// (table index, probe row id) into its warp's shared-memory queue, and the
+// warp drains the queue 32 entries at a time with every lane active, so the
+// gathers of a drain are all in flight together and the probe loop never
+// waits on them.
 //   MODE_COUNT: count matches per item (sizes the pair output exactly)
 //   MODE_WRITE: materialise (build row id, probe row id) pairs
 //   MODE_SUM  : fold the pairs straight into the SUM checksums
@@ -329,6 +391,7 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
 // used when the build side already fits a shared-memory table.
 // ---------------------------------------------------------------------------
 enum JoinMode { MODE_COUNT = 0, MODE_WRITE = 1, MODE_SUM = 2 };
+constexpr int kWarpQueue = 64;   // entries per warp; drained when >= 32
 
 struct JoinArgs {
     KeySrc          src_b, src_p;   // DIRECT
@@ -356,34 +419,233 @@ __device__ __forceinline__ uint32_t table_hash(KeyT key, uint32_t radix_bits, ui
     }
 }
 
-template <int NT, int U, typename KeyT, bool DIRECT, int MODE>
+template <typename KeyT> struct ProbeTup {
+    KeyT     key;
+    uint32_t rid;
+};
+
+// Shared-memory table entry access.  32-bit keys: one 8-byte word per build
+// tuple {key, next} so a chain step is a single LDS.64; 64-bit keys: a key
+// array and a 16-bit link array.
+template <typename KeyT> struct TableView;
+// 32-bit keys: bucketised open addressing.  A bucket is four key slots (one
+// LDS.128 per probe step, four compares), a parallel 16-bit array maps a slot
+// to the build tuple's position in its chunk.  Slots = 2^slots_log2 >= 1.75 x cap.
+// 0xFFFFFFFF marks an empty slot; the 32-bit-key kernels only run when the
+// column maxima are below it (engine.cu).  Duplicate build keys simply occupy
+// several slots; a probe walks on to the next bucket only while buckets are full.
+constexpr uint32_t kEmptyKey32 = 0xFFFFFFFFu;
+template <> struct TableView<uint32_t> {
+    uint4    *keys4;
+    uint16_t *idx;
+    uint32_t  bmask;   // number of buckets - 1
+    __device__ __forceinline__ TableView(unsigned char *smem, uint32_t cap, uint32_t slots_log2) {
+        keys4 = reinterpret_cast<uint4 *>(smem);
+        idx   = reinterpret_cast<uint16_t *>(smem + ((size_t)4 << slots_log2));
+        bmask = (1u << (slots_log2 - 2)) - 1u;
+    }
+    __device__ __forceinline__ void clear(uint32_t tid, uint32_t nt) {
+        for (uint32_t b = tid; b <= bmask; b += nt) keys4[b] = make_uint4(kEmptyKey32, kEmptyKey32, kEmptyKey32, kEmptyKey32);
+    }
+    __device__ __forceinline__ void insert(uint32_t i, uint32_t key, uint32_t hash_bucket) {
+        uint32_t *keys = reinterpret_cast<uint32_t *>(keys4);
+        uint32_t  b    = hash_bucket;
+        for (;;) {
+#pragma unroll
+            for (uint32_t s = 0; s < 4; ++s) {
+                const uint32_t slot = b * 4u + s;
+                if (keys[slot] == kEmptyKey32 && atomicCAS(&keys[slot], kEmptyKey32, key) == kEmptyKey32) {
+                    idx[slot] = (uint16_t)i;
+                    return;
+                }
+            }
+            b = (b + 1u) & bmask;
+        }
+    }
+    static __host__ __device__ uint32_t slots_log2_for(uint32_t cap) {
+        uint32_t l = 4;   // slots >= 1.75 x cap: load factor <= 0.57
+        while ((uint64_t)4 << l < (uint64_t)7 * cap) ++l;
+        return l;
+    }
+    static __host__ __device__ size_t bytes(uint32_t cap, uint32_t slots_log2) {
+        (void)cap;
+        return ((size_t)4 << slots_log2) + ((size_t)2 << slots_log2);
+    }
+};
+template <> struct TableView<uint64_t> {
+    uint64_t *keys;
+    uint16_t *next;
+    uint16_t *heads;
+    uint32_t  nslots;
+    __device__ __forceinline__ TableView(unsigned char *smem, uint32_t cap, uint32_t slots_log2) {
+        keys   = reinterpret_cast<uint64_t *>(smem);
+        next   = reinterpret_cast<uint16_t *>(keys + cap);
+        heads  = next + cap;
+        nslots = 1u << slots_log2;
+    }
+    __device__ __forceinline__ void clear(uint32_t tid, uint32_t nt) {
+        for (uint32_t s = tid; s < nslots; s += nt) heads[s] = (uint16_t)kEmpty16;
+    }
+    __device__ __forceinline__ void insert(uint32_t i, uint64_t key, uint32_t h) {
+        unsigned short *slot = reinterpret_cast<unsigned short *>(&heads[h]);
+        unsigned short  old  = *slot, assumed;
+        do {
+            assumed = old;
+            old     = atomicCAS(slot, assumed, (unsigned short)i);
+        } while (old != assumed);
+        put(i, key, old);
+    }
+    static __host__ __device__ uint32_t slots_log2_for(uint32_t cap) {
+        uint32_t l = 4;
+        while ((1u << l) < cap) ++l;
+        return l;
+    }
+    __device__ __forceinline__ void put(uint32_t i, uint64_t key, uint32_t nx) {
+        keys[i] = key;
+        next[i] = (uint16_t)nx;
+    }
+    __device__ __forceinline__ void get(uint32_t i, uint64_t &key, uint32_t &nx) const {
+        key = keys[i];
+        nx  = next[i];
+    }
+    static __host__ __device__ size_t bytes(uint32_t cap, uint32_t slots_log2) {
+        return (size_t)cap * 10 + ((size_t)2 << slots_log2);
+    }
+};
+
+// NP = number of fused SUM projections the kernel is compiled for (>= nproj)
+template <int NT, int U, typename KeyT, bool DIRECT, int MODE, int NP>
 __global__ void __launch_bounds__(NT)
 hash_join_kernel(const JoinArgs a) {
     using TupT = typename TupOf<KeyT>::type;
+    constexpr int NW = NT / 32;
+    constexpr int NPA = NP > 0 ? NP : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    KeyT     *t_keys  = reinterpret_cast<KeyT *>(smem_raw);
-    uint32_t *t_rids  = reinterpret_cast<uint32_t *>(t_keys + a.cap);
-    uint16_t *t_next  = reinterpret_cast<uint16_t *>(t_rids + a.cap);
-    uint16_t *t_heads = t_next + a.cap;
-    const uint32_t nslots = 1u << a.slots_log2;
+    TableView<KeyT> tab(smem_raw, a.cap, a.slots_log2);
+    // 32-bit keys hash to a bucket of four slots, 64-bit keys to a chain head
+    const uint32_t hash_log2 = sizeof(KeyT) == 4 ? a.slots_log2 - 2 : a.slots_log2;
 
-    __shared__ uint32_t           s_item[5];   // valid, b_start, b_count, p_start, p_count
+    __shared__ uint32_t           s_item[6];   // valid, b_start, b_count, p_start, p_count, w
     __shared__ uint32_t           s_cursor;
     __shared__ unsigned long long s_base;
     __shared__ unsigned long long s_cnt;
+    __shared__ uint32_t           wq_cnt[NW];
+    __shared__ uint2              wq[MODE == MODE_COUNT ? 1 : NW][MODE == MODE_COUNT ? 1 : kWarpQueue];
 
-    const int lane = threadIdx.x & 31;
+    const uint32_t tid  = threadIdx.x;
+    const int      lane = tid & 31;
+    const int      wid  = tid >> 5;
     const TupT *tup_b = static_cast<const TupT *>(a.tup_b);
     const TupT *tup_p = static_cast<const TupT *>(a.tup_p);
 
     unsigned long long my_matches = 0;
-    unsigned long long my_sum[kMaxProj];
+    unsigned long long my_sum[NPA];
+    unsigned long long pend[NPA];   // values loaded by the previous drain
 #pragma unroll
-    for (int k = 0; k < kMaxProj; ++k) my_sum[k] = 0;
+    for (int k = 0; k < NPA; ++k) my_sum[k] = pend[k] = 0;
+    if (lane == 0) wq_cnt[wid] = 0;
+
+    uint32_t b_start = 0;
+
+    // drain `take` (<= 32) queue entries [have - take, have) of this warp, one per lane
+    auto drain = [&](uint32_t have, uint32_t take) {
+        if constexpr (MODE != MODE_COUNT) {
+            const bool     mine = (uint32_t)lane < take;
+            const uint2    e    = wq[wid][mine ? have - take + lane : 0];
+            uint32_t       brid = 0;
+            if (mine) {
+                if constexpr (DIRECT) brid = b_start + e.x;
+                else brid = tup_b[b_start + e.x].rid;
+            }
+            if constexpr (MODE == MODE_SUM) {
+#pragma unroll
+                for (int k = 0; k < NPA; ++k) {
+                    my_sum[k] += pend[k];
+                    pend[k] = 0;
+                    if (k < a.nproj && mine) {
+                        const uint32_t r  = a.proj[k].side == 0 ? brid : e.y;
+                        const uint32_t rr = a.proj[k].ids ? __ldg(a.proj[k].ids + r) : r;
+                        pend[k]           = __ldg(a.proj[k].col + rr);
+                    }
+                }
+            } else {
+                uint32_t pos = 0;
+                if (lane == 0) pos = atomicAdd(&s_cursor, take);
+                pos = __shfl_sync(kFullMask, pos, 0);
+                if (mine) {
+                    a.out_b[s_base + pos + lane] = brid;
+                    a.out_p[s_base + pos + lane] = e.y;
+                }
+            }
+        }
+    };
+
+    // one match of table position `idx` with probe row `prid`
+    auto on_match = [&](uint32_t idx, uint32_t prid) {
+        if constexpr (MODE != MODE_COUNT) {
+            const uint32_t slot = atomicAdd(&wq_cnt[wid], 1u);
+            if (slot < (uint32_t)kWarpQueue) {
+                wq[wid][slot] = make_uint2(idx, prid);
+            } else {
+                // queue full (many matches per probe): handle the match in place
+                uint32_t brid;
+                if constexpr (DIRECT) brid = b_start + idx;
+                else brid = tup_b[b_start + idx].rid;
+                if constexpr (MODE == MODE_SUM) {
+#pragma unroll
+                    for (int kk = 0; kk < NPA; ++kk) {
+                        if (kk < a.nproj) {
+                            const uint32_t r  = a.proj[kk].side == 0 ? brid : prid;
+                            const uint32_t rr = a.proj[kk].ids ? __ldg(a.proj[kk].ids + r) : r;
+                            my_sum[kk] += __ldg(a.proj[kk].col + rr);
+                        }
+                    }
+                } else {
+                    const uint32_t pos = atomicAdd(&s_cursor, 1u);
+                    a.out_b[s_base + pos] = brid;
+                    a.out_p[s_base + pos] = prid;
+                }
+            }
+        }
+    };
+
+    // one probe tuple through the table; returns the number of matches pushed or counted
+    auto probe_one = [&](KeyT key, uint32_t prid) -> uint32_t {
+        uint32_t nh = 0;
+        if constexpr (sizeof(KeyT) == 4) {
+            uint32_t b = table_hash<KeyT>(key, a.radix_bits, hash_log2);
+            for (;;) {
+                const uint4 k = tab.keys4[b];
+                uint32_t    m = (k.x == key ? 1u : 0u) | (k.y == key ? 2u : 0u) | (k.z == key ? 4u : 0u) |
+                             (k.w == key ? 8u : 0u);
+                while (m) {
+                    const uint32_t s = __ffs(m) - 1;
+                    m &= m - 1u;
+                    ++nh;
+                    on_match(tab.idx[b * 4u + s], prid);
+                }
+                if (k.x == kEmptyKey32 || k.y == kEmptyKey32 || k.z == kEmptyKey32 || k.w == kEmptyKey32) break;
+                b = (b + 1u) & tab.bmask;
+            }
+        } else {
+            uint32_t idx = tab.heads[table_hash<KeyT>(key, a.radix_bits, hash_log2)];
+            while (idx != kEmpty16) {
+                KeyT     k;
+                uint32_t nx;
+                tab.get(idx, k, nx);
+                if (k == key) {
+                    ++nh;
+                    on_match(idx, prid);
+                }
+                idx = nx;
+            }
+        }
+        return nh;
+    };
 
     for (;;) {
         // ---- fetch one work item (warp 0) ---------------------------------
-        if (threadIdx.x < 32) {
+        if (tid < 32) {
             uint32_t w = 0;
             if (lane == 0) w = atomicAdd(a.work_counter, 1u);
             w = __shfl_sync(kFullMask, w, 0);
@@ -432,149 +694,107 @@ hash_join_kernel(const JoinArgs a) {
                 s_item[2] = bc;
                 s_item[3] = ps;
                 s_item[4] = pc;
+                s_item[5] = w;
                 s_cnt     = 0ull;
                 s_cursor  = 0u;
             }
             if constexpr (MODE == MODE_WRITE) {
                 if (lane == 0 && valid) s_base = atomicAdd(a.out_cursor, a.item_count[w]);
             }
-            if constexpr (MODE == MODE_COUNT) {
-                if (lane == 0) s_item[0] = valid | (w << 1);   // keep w for the per-item count
-            }
         }
         __syncthreads();
-        const uint32_t item_word = s_item[0];
-        if ((item_word & 1u) == 0u) break;
-        const uint32_t b_start = s_item[1], b_count = s_item[2];
+        if (s_item[0] == 0u) break;
+        b_start                = s_item[1];
+        const uint32_t b_count = s_item[2];
         const uint32_t p_start = s_item[3], p_count = s_item[4];
+        const uint32_t item_w  = s_item[5];
+
+        auto load_probe = [&](uint32_t li, ProbeTup<KeyT> &t) {
+            if (li < p_count) {
+                if constexpr (DIRECT) {
+                    t.rid = p_start + li;
+                    t.key = (KeyT)(a.src_p.ids ? __ldg(a.src_p.col + ld_stream_u32(a.src_p.ids + t.rid))
+                                               : ld_stream_u64(a.src_p.col + t.rid));
+                } else if constexpr (sizeof(KeyT) == 8) {
+                    const ulonglong2 v = ld_stream_u64x2(reinterpret_cast<const uint64_t *>(tup_p + p_start + li));
+                    t.key = v.x;
+                    t.rid = (uint32_t)v.y;
+                } else {
+                    const uint64_t v = ld_stream_u64(reinterpret_cast<const uint64_t *>(tup_p + p_start + li));
+                    t.key = (uint32_t)v;
+                    t.rid = (uint32_t)(v >> 32);
+                }
+            } else {
+                t.key = 0;
+                t.rid = 0;
+            }
+        };
+        // first probe batch in flight while the table is built
+        ProbeTup<KeyT> cur[U], nxt[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) load_probe((uint32_t)(j * NT) + tid, cur[j]);
 
         // ---- build (K6) ---------------------------------------------------
-        for (uint32_t s = threadIdx.x; s < nslots; s += NT) t_heads[s] = (uint16_t)kEmpty16;
+        tab.clear(tid, NT);
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < b_count; i += NT) {
-            KeyT     key;
-            uint32_t rid;
+        for (uint32_t i = tid; i < b_count; i += NT) {
+            KeyT key;
             if constexpr (DIRECT) {
-                rid = b_start + i;
+                const uint32_t rid = b_start + i;
                 key = (KeyT)(a.src_b.ids ? a.src_b.col[a.src_b.ids[rid]] : a.src_b.col[rid]);
             } else {
-                const TupT t = tup_b[b_start + i];
-                key          = t.key;
-                rid          = t.rid;
+                key = tup_b[b_start + i].key;
             }
-            t_keys[i] = key;
-            t_rids[i] = rid;
-            const uint32_t  h    = table_hash<KeyT>(key, a.radix_bits, a.slots_log2);
-            unsigned short *slot = reinterpret_cast<unsigned short *>(&t_heads[h]);
-            unsigned short  old  = *slot, assumed;
-            do {
-                assumed = old;
-                old     = atomicCAS(slot, assumed, (unsigned short)i);
-            } while (old != assumed);
-            t_next[i] = old;
+            tab.insert(i, key, table_hash<KeyT>(key, a.radix_bits, hash_log2));
         }
         __syncthreads();
 
         // ---- probe (K7) ---------------------------------------------------
         unsigned long long item_matches = 0;
+        uint32_t           queued       = 0;   // warp-uniform mirror of wq_cnt[wid]
         for (uint32_t off = 0; off < p_count; off += NT * U) {
-            KeyT     pkey[U];
-            uint32_t prid[U];
-            bool     pval[U];
-            if constexpr (DIRECT) {
-                if (a.src_p.ids) {
-                    uint32_t id[U];
 #pragma unroll
-                    for (int j = 0; j < U; ++j) {
-                        const uint32_t li = off + j * NT + threadIdx.x;
-                        pval[j]           = li < p_count;
-                        prid[j]           = p_start + li;
-                        id[j]             = pval[j] ? ld_stream_u32(a.src_p.ids + prid[j]) : 0u;
-                    }
-#pragma unroll
-                    for (int j = 0; j < U; ++j)
-                        pkey[j] = pval[j] ? (KeyT)__ldg(a.src_p.col + id[j]) : (KeyT)0;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < U; ++j) {
-                        const uint32_t li = off + j * NT + threadIdx.x;
-                        pval[j]           = li < p_count;
-                        prid[j]           = p_start + li;
-                        pkey[j] = pval[j] ? (KeyT)ld_stream_u64(a.src_p.col + prid[j]) : (KeyT)0;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < U; ++j) {
-                    const uint32_t li = off + j * NT + threadIdx.x;
-                    pval[j]           = li < p_count;
-                    if (pval[j]) {
-                        if constexpr (sizeof(KeyT) == 8) {
-                            const ulonglong2 v = ld_stream_u64x2(
-                                reinterpret_cast<const uint64_t *>(tup_p + p_start + li));
-                            pkey[j] = v.x;
-                            prid[j] = (uint32_t)v.y;
-                        } else {
-                            const uint64_t v =
-                                ld_stream_u64(reinterpret_cast<const uint64_t *>(tup_p + p_start + li));
-                            pkey[j] = (uint32_t)v;
-                            prid[j] = (uint32_t)(v >> 32);
-                        }
-                    } else {
-                        pkey[j] = 0;
-                        prid[j] = 0;
-                    }
-                }
-            }
+            for (int j = 0; j < U; ++j) load_probe(off + (uint32_t)(NT * U + j * NT) + tid, nxt[j]);
+            const bool full_round = off + NT * U <= p_count;
 #pragma unroll
             for (int j = 0; j < U; ++j) {
-                uint32_t idx = kEmpty16;
-                if (pval[j]) idx = t_heads[table_hash<KeyT>(pkey[j], a.radix_bits, a.slots_log2)];
-                // warp-synchronous chain walk: every lane stays in the loop
-                // until the longest chain of the warp is exhausted
-                while (__any_sync(kFullMask, idx != kEmpty16)) {
-                    const bool live = idx != kEmpty16;
-                    const bool hit  = live && t_keys[live ? idx : 0] == pkey[j];
-                    if constexpr (MODE == MODE_COUNT) {
-                        item_matches += hit ? 1ull : 0ull;
-                    } else if constexpr (MODE == MODE_SUM) {
-                        if (hit) {
-                            ++my_matches;
-                            const uint32_t brid = t_rids[idx];
-#pragma unroll
-                            for (int k = 0; k < kMaxProj; ++k) {
-                                if (k < a.nproj) {
-                                    const uint32_t r  = a.proj[k].side == 0 ? brid : prid[j];
-                                    const uint32_t rr = a.proj[k].ids ? __ldg(a.proj[k].ids + r) : r;
-                                    my_sum[k] += __ldg(a.proj[k].col + rr);
-                                }
-                            }
+                uint32_t nh = 0;
+                if (full_round || off + (uint32_t)(j * NT) + tid < p_count) nh = probe_one(cur[j].key, cur[j].rid);
+                if constexpr (MODE == MODE_COUNT) {
+                    item_matches += nh;
+                } else {
+                    my_matches += nh;
+                    queued += __reduce_add_sync(kFullMask, nh);
+                    if (queued >= 32u) {
+                        __syncwarp();
+                        uint32_t have = min(queued, (uint32_t)kWarpQueue);
+                        while (have >= 32u) {
+                            drain(have, 32u);
+                            have -= 32u;
                         }
-                    } else {
-                        const unsigned hits = __ballot_sync(kFullMask, hit);
-                        if (hits) {
-                            const int leader = __ffs(hits) - 1;
-                            uint32_t  basepos = 0;
-                            if (lane == leader) basepos = atomicAdd(&s_cursor, (uint32_t)__popc(hits));
-                            basepos = __shfl_sync(kFullMask, basepos, leader);
-                            if (hit) {
-                                const unsigned long long pos =
-                                    s_base + basepos + __popc(hits & ((1u << lane) - 1u));
-                                a.out_b[pos] = t_rids[idx];
-                                a.out_p[pos] = prid[j];
-                            }
-                        }
+                        __syncwarp();
+                        if (lane == 0) wq_cnt[wid] = have;
+                        __syncwarp();
+                        queued = have;
                     }
-                    if (live) idx = t_next[idx];
                 }
             }
+#pragma unroll
+            for (int j = 0; j < U; ++j) cur[j] = nxt[j];
+        }
+        if constexpr (MODE != MODE_COUNT) {
+            // leftovers of this item (queue entries are relative to this item's build chunk)
+            __syncwarp();
+            if (queued) drain(queued, queued);
+            __syncwarp();
+            if (lane == 0) wq_cnt[wid] = 0;
         }
         if constexpr (MODE == MODE_COUNT) {
             const unsigned long long ws = warp_sum_u64(item_matches);
             if (lane == 0 && ws) atomicAdd(&s_cnt, ws);
             __syncthreads();
-            if (threadIdx.x == 0) {
-                a.item_count[item_word >> 1] = s_cnt;
+            if (tid == 0) {
+                a.item_count[item_w] = s_cnt;
                 if (s_cnt) atomicAdd(a.total, s_cnt);
             }
         }
@@ -586,9 +806,404 @@ hash_join_kernel(const JoinArgs a) {
         const unsigned long long wm = warp_sum_u64(my_matches);
         if (lane == 0 && wm) atomicAdd(a.total, wm);
 #pragma unroll
-        for (int k = 0; k < kMaxProj; ++k) {
+        for (int k = 0; k < NPA; ++k) {
             if (k < a.nproj) {
-                const unsigned long long ws = warp_sum_u64(my_sum[k]);
+                const unsigned long long ws = warp_sum_u64(my_sum[k] + pend[k]);
+                if (lane == 0 && wm) atomicAdd(a.sums + k, ws);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K6 + K7 (+K9) for 32-bit keys: two-choice bucketised table.
+//
+// hash_join_kernel above walks data-dependent chains; ncu showed it bound by
+// instruction issue and shared-memory latency (about 100 warp instructions per
+// probe round, one dependent LDS after the other).  This kernel keeps the same
+// work-item scheme and match queue but makes the probe branch-free:
+//   * a bucket is four 32-bit key slots (one LDS.128); every key has two
+//     candidate buckets (two multiplicative hashes of the bits above the
+//     radix); the build puts it into the emptier one, so with <= 0.57 load a
+//     bucket practically never overflows and a probe is exactly two LDS.128 and
+//     eight compares, issued for a group of G probes back to back;
+//   * slot -> position of the build tuple in its chunk is a parallel 16-bit
+//     array, read only on a match;
+//   * a match is appended to the warp's queue at a slot computed from a
+//     ballot (no atomics); the queue is drained 32 entries at a time with all
+//     lanes active (build row id re-read from the partition buffer, payload
+//     gathers of a drain all in flight together, consumed at the next drain).
+// If a key finds both buckets full (heavy duplicates) it spills into the next
+// non-full bucket after its second one and the CTA flags the table; probes of
+// a flagged table also scan that run of full buckets.  0xFFFFFFFF marks an
+// empty slot: the 32-bit kernels run only when all keys are below it.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t saddr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t match4(const uint4 &k, uint32_t key) {
+    return (k.x == key ? 1u : 0u) | (k.y == key ? 2u : 0u) | (k.z == key ? 4u : 0u) | (k.w == key ? 8u : 0u);
+}
+__device__ __forceinline__ uint32_t used4(const uint4 &k) {
+    return (k.x != kEmptyKey32 ? 1u : 0u) | (k.y != kEmptyKey32 ? 2u : 0u) | (k.z != kEmptyKey32 ? 4u : 0u) |
+           (k.w != kEmptyKey32 ? 8u : 0u);
+}
+
+// work item of the join kernels: (build chunk, probe slice)
+struct JoinItem {
+    uint32_t valid, b_start, b_count, p_start, p_count, w;
+};
+
+template <bool DIRECT>
+__device__ __forceinline__ JoinItem fetch_join_item(const JoinArgs &a, int lane) {
+    JoinItem it{0, 0, 0, 0, 0, 0};
+    uint32_t w = 0;
+    if (lane == 0) w = atomicAdd(a.work_counter, 1u);
+    w    = __shfl_sync(kFullMask, w, 0);
+    it.w = w;
+    if constexpr (DIRECT) {
+        if (w < a.n_items_direct) {
+            it.valid           = 1;
+            const uint32_t rch = w / a.sc_direct;
+            const uint32_t ssl = w % a.sc_direct;
+            it.b_start         = rch * a.cap;
+            it.b_count         = min(a.cap, a.src_b.n - it.b_start);
+            it.p_start         = ssl * a.slice;
+            it.p_count         = min(a.slice, a.src_p.n - it.p_start);
+        }
+    } else {
+        const uint32_t n_items = a.item_start[a.nparts];
+        if (w < n_items) {
+            it.valid    = 1;
+            uint32_t lo = 0, hi = a.nparts;   // 32-ary search: item_start[p] <= w < item_start[p+1]
+            while (hi - lo > 1) {
+                const uint32_t step = (hi - lo + 31) / 32;
+                const uint32_t idx  = lo + (uint32_t)lane * step;
+                const bool     le   = idx < hi && a.item_start[idx] <= w;
+                const uint32_t c    = __popc(__ballot_sync(kFullMask, le));   // >= 1
+                const uint32_t nlo  = lo + (c - 1) * step;
+                hi                  = min(hi, nlo + step);
+                lo                  = nlo;
+            }
+            const uint32_t p   = lo;
+            const uint32_t k   = w - a.item_start[p];
+            const uint32_t b0  = a.off_b[p], b1 = a.off_b[p + 1];
+            const uint32_t p0  = a.off_p[p], p1 = a.off_p[p + 1];
+            const uint32_t sc  = (p1 - p0 + a.slice - 1) / a.slice;
+            const uint32_t rch = k / sc, ssl = k % sc;
+            it.b_start         = b0 + rch * a.cap;
+            it.b_count         = min(a.cap, b1 - it.b_start);
+            it.p_start         = p0 + ssl * a.slice;
+            it.p_count         = min(a.slice, p1 - it.p_start);
+        }
+    }
+    return it;
+}
+
+template <int NT, int G, bool DIRECT, int MODE, int NP>
+__global__ void __launch_bounds__(NT, 2)
+bucket_join_kernel(const JoinArgs a) {
+    constexpr int NW  = NT / 32;
+    constexpr int NPA = NP > 0 ? NP : 1;
+    constexpr int QN  = MODE == MODE_COUNT ? 1 : kWarpQueue;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: keys [4 << L bytes] | idx [2 << L bytes] | queues [NW * QN * 8 bytes]
+    const uint32_t L        = a.slots_log2;
+    const uint32_t blog     = L - 2;                 // log2(number of buckets)
+    const uint32_t bmask    = (1u << blog) - 1u;
+    const uint32_t s_keys   = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t s_idx    = s_keys + (4u << L);
+    const uint32_t s_queue  = s_idx + (2u << L);
+    uint32_t      *keys     = reinterpret_cast<uint32_t *>(smem_raw);
+    uint16_t      *idxs     = reinterpret_cast<uint16_t *>(smem_raw + ((size_t)4 << L));
+
+    __shared__ uint32_t           s_item[6];
+    __shared__ uint32_t           s_cursor;
+    __shared__ uint32_t           s_spill;
+    __shared__ unsigned long long s_base;
+    __shared__ unsigned long long s_cnt;
+
+    const uint32_t tid    = threadIdx.x;
+    const uint32_t lane   = tid & 31u;
+    const uint32_t wid    = tid >> 5;
+    const uint32_t lt     = (1u << lane) - 1u;
+    const uint32_t my_q   = s_queue + wid * (uint32_t)(QN * 8);
+    const Tup32 *tup_b = static_cast<const Tup32 *>(a.tup_b);
+    const Tup32 *tup_p = static_cast<const Tup32 *>(a.tup_p);
+    const uint32_t hshift = 32u - blog;
+
+    unsigned long long my_matches = 0;
+    unsigned long long my_sum[NPA], pend[NPA];
+#pragma unroll
+    for (int k = 0; k < NPA; ++k) my_sum[k] = pend[k] = 0;
+    uint32_t b_start = 0;
+    uint32_t queued  = 0;   // warp-uniform number of entries in this warp's queue
+
+    auto handle_inline = [&](uint32_t pos_in_chunk, uint32_t prid) {
+        uint32_t brid;
+        if constexpr (DIRECT) brid = b_start + pos_in_chunk;
+        else brid = tup_b[b_start + pos_in_chunk].rid;
+        if constexpr (MODE == MODE_SUM) {
+#pragma unroll
+            for (int k = 0; k < NPA; ++k) {
+                if (k < a.nproj) {
+                    const uint32_t r  = a.proj[k].side == 0 ? brid : prid;
+                    const uint32_t rr = a.proj[k].ids ? __ldg(a.proj[k].ids + r) : r;
+                    my_sum[k] += __ldg(a.proj[k].col + rr);
+                }
+            }
+        } else if constexpr (MODE == MODE_WRITE) {
+            const uint32_t pos    = atomicAdd(&s_cursor, 1u);
+            a.out_b[s_base + pos] = brid;
+            a.out_p[s_base + pos] = prid;
+        }
+    };
+
+    // drain `take` (<= 32) entries [have - take, have) of this warp's queue, one per lane
+    auto drain = [&](uint32_t have, uint32_t take) {
+        if constexpr (MODE != MODE_COUNT) {
+            const bool  mine = lane < take;
+            const uint2 e    = lds_v2(my_q + (mine ? have - take + lane : 0u) * 8u);
+            uint32_t    brid = 0;
+            if (mine) {
+                if constexpr (DIRECT) brid = b_start + e.x;
+                else brid = tup_b[b_start + e.x].rid;
+            }
+            if constexpr (MODE == MODE_SUM) {
+#pragma unroll
+                for (int k = 0; k < NPA; ++k) {
+                    my_sum[k] += pend[k];
+                    pend[k] = 0;
+                    if (k < a.nproj && mine) {
+                        const uint32_t r  = a.proj[k].side == 0 ? brid : e.y;
+                        const uint32_t rr = a.proj[k].ids ? __ldg(a.proj[k].ids + r) : r;
+                        pend[k]           = __ldg(a.proj[k].col + rr);
+                    }
+                }
+            } else {
+                uint32_t pos = 0;
+                if (lane == 0) pos = atomicAdd(&s_cursor, take);
+                pos = __shfl_sync(kFullMask, pos, 0);
+                if (mine) {
+                    a.out_b[s_base + pos + lane] = brid;
+                    a.out_p[s_base + pos + lane] = e.y;
+                }
+            }
+        }
+    };
+
+    // all matches of one probe in the 4-slot bucket `b` (match nibble m); converged call
+    auto emit = [&](uint32_t m, uint32_t b, uint32_t prid) {
+        const uint32_t act = __ballot_sync(kFullMask, m != 0u);
+        if (act == 0u) return;
+        if (m) {
+            const uint32_t s   = __ffs(m) - 1u;
+            const uint32_t pos = lds_u16(s_idx + (b * 4u + s) * 2u);
+            my_matches += __popc(m);
+            if constexpr (MODE != MODE_COUNT) {
+                const uint32_t slot = queued + __popc(act & lt);
+                if (slot < (uint32_t)QN) sts_v2(my_q + slot * 8u, pos, prid);
+                else handle_inline(pos, prid);
+                m &= m - 1u;
+                while (m) {   // further duplicates of the key in the same bucket
+                    const uint32_t s2 = __ffs(m) - 1u;
+                    m &= m - 1u;
+                    handle_inline(lds_u16(s_idx + (b * 4u + s2) * 2u), prid);
+                }
+            }
+        }
+        if constexpr (MODE != MODE_COUNT) {
+            queued = min(queued + (uint32_t)__popc(act), (uint32_t)QN);
+            __syncwarp();
+            while (queued >= 32u) {
+                drain(queued, 32u);
+                queued -= 32u;
+            }
+            __syncwarp();
+        }
+    };
+
+    for (;;) {
+        if (tid < 32) {
+            const JoinItem it = fetch_join_item<DIRECT>(a, (int)lane);
+            if (lane == 0) {
+                s_item[0] = it.valid;
+                s_item[1] = it.b_start;
+                s_item[2] = it.b_count;
+                s_item[3] = it.p_start;
+                s_item[4] = it.p_count;
+                s_item[5] = it.w;
+                s_cnt     = 0ull;
+                s_cursor  = 0u;
+                s_spill   = 0u;
+                if constexpr (MODE == MODE_WRITE) {
+                    if (it.valid) s_base = atomicAdd(a.out_cursor, a.item_count[it.w]);
+                }
+            }
+        }
+        __syncthreads();
+        if (s_item[0] == 0u) break;
+        b_start                = s_item[1];
+        const uint32_t b_count = s_item[2];
+        const uint32_t p_start = s_item[3], p_count = s_item[4];
+        const uint32_t item_w  = s_item[5];
+
+        auto load_probe = [&](uint32_t li, uint32_t &key, uint32_t &rid) {
+            key = kEmptyKey32;   // never matches
+            rid = 0;
+            if (li < p_count) {
+                if constexpr (DIRECT) {
+                    rid = p_start + li;
+                    key = (uint32_t)(a.src_p.ids ? __ldg(a.src_p.col + ld_stream_u32(a.src_p.ids + rid))
+                                                 : ld_stream_u64(a.src_p.col + rid));
+                } else {
+                    const uint64_t v = ld_stream_u64(reinterpret_cast<const uint64_t *>(tup_p + p_start + li));
+                    key              = (uint32_t)v;
+                    rid              = (uint32_t)(v >> 32);
+                }
+            }
+        };
+        // first group in flight while the table is built
+        uint32_t ckey[G], crid[G], nkey[G], nrid[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) load_probe((uint32_t)(j * NT) + tid, ckey[j], crid[j]);
+
+        // ---- build (K6) ---------------------------------------------------
+        for (uint32_t s = tid; s < (1u << L); s += NT) keys[s] = kEmptyKey32;
+        __syncthreads();
+        for (uint32_t i = tid; i < b_count; i += NT) {
+            uint32_t key;
+            if constexpr (DIRECT) {
+                const uint32_t rid = b_start + i;
+                key = (uint32_t)(a.src_b.ids ? a.src_b.col[a.src_b.ids[rid]] : a.src_b.col[rid]);
+            } else {
+                key = tup_b[b_start + i].key;
+            }
+            const uint32_t x  = key >> a.radix_bits;
+            const uint32_t h1 = (x * 0x9E3779B1u) >> hshift;
+            uint32_t       h2 = (x * 0x85EBCA77u) >> hshift;
+            if (h2 == h1) h2 = (h1 + 1u) & bmask;
+            bool     done    = false;
+            uint32_t spill_b = (h2 + 1u) & bmask;
+            while (!done) {
+                const uint32_t u1 = used4(lds_v4(s_keys + h1 * 16u));
+                const uint32_t u2 = used4(lds_v4(s_keys + h2 * 16u));
+                uint32_t       b, u;
+                if (u1 != 15u && __popc(u1) <= __popc(u2)) { b = h1; u = u1; }
+                else if (u2 != 15u) { b = h2; u = u2; }
+                else if (u1 != 15u) { b = h1; u = u1; }
+                else {
+                    // both candidate buckets full: next non-full bucket after h2
+                    s_spill = 1u;
+                    for (;;) {
+                        u = used4(lds_v4(s_keys + spill_b * 16u));
+                        if (u != 15u) break;
+                        spill_b = (spill_b + 1u) & bmask;
+                    }
+                    b = spill_b;
+                }
+                const uint32_t s    = __ffs(~u & 15u) - 1u;
+                const uint32_t slot = b * 4u + s;
+                if (atomicCAS(&keys[slot], kEmptyKey32, key) == kEmptyKey32) {
+                    idxs[slot] = (uint16_t)i;
+                    done       = true;
+                }
+            }
+        }
+        __syncthreads();
+        const bool spilled = s_spill != 0u;
+
+        // ---- probe (K7) ---------------------------------------------------
+        for (uint32_t off = 0; off < p_count; off += NT * G) {
+#pragma unroll
+            for (int j = 0; j < G; ++j) load_probe(off + (uint32_t)(NT * G + j * NT) + tid, nkey[j], nrid[j]);
+            uint32_t h1[G], h2[G], m1[G], m2[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const uint32_t x = ckey[j] >> a.radix_bits;
+                h1[j]            = (x * 0x9E3779B1u) >> hshift;
+                h2[j]            = (x * 0x85EBCA77u) >> hshift;
+                if (h2[j] == h1[j]) h2[j] = (h1[j] + 1u) & bmask;
+            }
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const uint4 k1 = lds_v4(s_keys + h1[j] * 16u);
+                const uint4 k2 = lds_v4(s_keys + h2[j] * 16u);
+                const bool  ok = ckey[j] != kEmptyKey32;   // padding lanes of the last round
+                m1[j]          = ok ? match4(k1, ckey[j]) : 0u;
+                m2[j]          = ok ? match4(k2, ckey[j]) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                emit(m1[j], h1[j], crid[j]);
+                emit(m2[j], h2[j], crid[j]);
+            }
+            if (spilled) {
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    // run of full buckets after h2 (where spilled keys live); h1 was already counted
+                    uint32_t b    = (h2[j] + 1u) & bmask;
+                    bool     more = ckey[j] != kEmptyKey32;
+                    while (__any_sync(kFullMask, more)) {
+                        uint32_t m = 0;
+                        if (more) {
+                            const uint4 k = lds_v4(s_keys + b * 16u);
+                            if (b != h1[j]) m = match4(k, ckey[j]);
+                            more = used4(k) == 15u && b != h2[j];
+                        }
+                        emit(m, b, crid[j]);
+                        b = (b + 1u) & bmask;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                ckey[j] = nkey[j];
+                crid[j] = nrid[j];
+            }
+        }
+        if constexpr (MODE != MODE_COUNT) {
+            // leftovers of this item (queue entries are relative to this item's build chunk)
+            __syncwarp();
+            if (queued) drain(queued, queued);
+            queued = 0;
+            __syncwarp();
+        }
+        if constexpr (MODE == MODE_COUNT) {
+            const unsigned long long ws = warp_sum_u64(my_matches);
+            my_matches                  = 0;
+            if (lane == 0 && ws) atomicAdd(&s_cnt, ws);
+            __syncthreads();
+            if (tid == 0) {
+                a.item_count[item_w] = s_cnt;
+                if (s_cnt) atomicAdd(a.total, s_cnt);
+            }
+        }
+        __syncthreads();   // table and s_item are reused by the next item
+    }
+
+    if constexpr (MODE == MODE_SUM) {
+        const unsigned long long wm = warp_sum_u64(my_matches);
+        if (lane == 0 && wm) atomicAdd(a.total, wm);
+#pragma unroll
+        for (int k = 0; k < NPA; ++k) {
+            if (k < a.nproj) {
+                const unsigned long long ws = warp_sum_u64(my_sum[k] + pend[k]);
                 if (lane == 0 && wm) atomicAdd(a.sums + k, ws);
             }
         }

@@ -22,7 +22,7 @@ __all__ = [
     "LIB_PATH", "load_library", "lib", "declared_symbols",
     "RelationMapArray", "parse_query", "execute_query", "QueryResult",
     "scan_filter", "radix_partition", "hash_join_pairs", "gather_sum", "join_sum",
-    "join_sum_device", "synth_column_device", "kernel_launches", "last_kernel_ms",
+    "join_sum_device", "synth_column_device", "DeviceColumn", "kernel_launches", "last_kernel_ms",
     "SYNTH_PERM", "SYNTH_PAYLOAD", "SYNTH_ZIPF", "SYNTH_UNIFORM", "SYNTH_IOTA",
     "SEED_R", "SEED_S",
 ]
@@ -155,6 +155,11 @@ def _declare(L: C.CDLL) -> None:
         "b200_register_device_column": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
         "b200_upload_column": (C.c_int, [C.c_void_p, C.c_uint64]),
         "b200_unregister_all": (None, []),
+        "b200_unregister_relations": (C.c_int, [P(CRelationMap), C.c_int]),
+        "b200_device_malloc": (C.c_void_p, [C.c_uint64]),
+        "b200_device_free": (None, [C.c_void_p]),
+        "b200_copy_to_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+        "b200_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
         "b200_get_stream": (C.c_void_p, []),
         "b200_set_stream": (C.c_int, [C.c_void_p]),
         "b200_synchronize": (C.c_int, []),
@@ -220,12 +225,25 @@ class RelationMapArray:
             self.array[r].num_columns = len(cols)
             self.array[r].columns = ptrs
             self.array[r].col_stats = stats
+        # device copies are keyed by host pointer: drop entries a previous, freed
+        # array may have left under the same addresses
+        self.unregister()
 
     def __len__(self):
         return len(self.columns)
 
     def register(self):
         _check(lib().b200_register_relations(self.array, len(self)))
+
+    def unregister(self):
+        if _lib is not None:
+            _lib.b200_unregister_relations(self.array, len(self))
+
+    def __del__(self):
+        try:
+            self.unregister()
+        except Exception:
+            pass
 
 
 # --------------------------------------------------------------------------
@@ -411,6 +429,33 @@ def join_sum_device(keys_r: int, n_r: int, keys_s: int, n_s: int, proj: list[int
     m = C.c_uint64(0)
     _check(lib().b200_join_sum(keys_r, n_r, keys_s, n_s, max_key, len(proj), ptrs, sides, 1, sums, C.byref(m)))
     return [int(s) for s in sums[: len(proj)]], int(m.value)
+
+
+class DeviceColumn:
+    """n uint64 values in HBM owned through the C-ABI (no torch)."""
+
+    def __init__(self, n: int):
+        self.n = n
+        self.ptr = lib().b200_device_malloc(8 * n)
+        if not self.ptr:
+            raise MemoryError("b200_device_malloc failed")
+
+    def to_host(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.n - first if count is None else count
+        out = np.empty(max(count, 1), np.uint64)
+        _check(lib().b200_copy_to_host(out.ctypes.data, self.ptr + 8 * first, 8 * count))
+        return out[:count]
+
+    def free(self):
+        if self.ptr:
+            lib().b200_device_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def synth_column_device(device_ptr: int, first: int, n: int, kind: int, k: int, seed: int) -> None:
