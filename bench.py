@@ -82,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -364,13 +364,18 @@ def run_b200_arm(args):
         "scatter_b": ((8 + 16) * n_b, (8 + 8) * n_b),
         "join": (16 * (n_p + n_b) + 16 * nr // world, 8 * (n_p + n_b) + 16 * nr // world),
     }
+    traffic = {}
+    tpath = ROOT / "profiles" / "r1_traffic.json"
+    if tpath.exists():
+        traffic = json.loads(tpath.read_text())
     roofline = None
     if per_kernel:
         dom = max((k for k in per_kernel if k in kernel_bytes), key=lambda k: per_kernel[k])
         canon, enc = kernel_bytes[dom]
         dur = per_kernel[dom] * 1e-3
         roofline = {"bound": "hbm", "kernel": dom, "achieved": canon / dur / 1e9, "peak": peak,
-                    "unit": "GB/s", "frac": canon / dur / 1e9 / peak, "traffic": None,
+                    "unit": "GB/s", "frac": canon / dur / 1e9 / peak,
+                    "traffic": traffic.get(dom) if world == 1 else None, "traffic_source": traffic.get("source"),
                     "achieved_encoded": enc / dur / 1e9, "frac_encoded": enc / dur / 1e9 / peak,
                     "launch_ms": per_kernel[dom], "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)",
                     "bytes_per_launch_canonical": canon, "bytes_per_launch_encoded": enc,
@@ -406,7 +411,7 @@ def run_b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")

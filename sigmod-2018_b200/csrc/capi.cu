@@ -278,12 +278,12 @@ int b200_join_sum(const uint64_t *keys_r, uint64_t n_r, const uint64_t *keys_s, 
         for (int k = 0; k < n_proj; ++k) {
             DevBufPtr dp = upload_u64(proj[k], proj_side[k] == 0 ? n_r : n_s);
             keep.push_back(dp);
-            pd[k] = ProjDesc{dp->as<uint64_t>(), nullptr, proj_side[k]};
+            pd[k] = ProjDesc{dp->as<uint64_t>(), nullptr, proj_side[k], nullptr};
         }
     } else {
         R.src = KeySrc{keys_r, nullptr, (uint32_t)n_r};
         S.src = KeySrc{keys_s, nullptr, (uint32_t)n_s};
-        for (int k = 0; k < n_proj; ++k) pd[k] = ProjDesc{proj[k], nullptr, proj_side[k]};
+        for (int k = 0; k < n_proj; ++k) pd[k] = ProjDesc{proj[k], nullptr, proj_side[k], nullptr};
     }
     R.max_val = S.max_val = max_key;
     JoinResult j = run_join(R, S, JoinOut::Sum, n_proj, pd);

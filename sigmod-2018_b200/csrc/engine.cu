@@ -65,6 +65,7 @@ static void init_device(int device) {
     if (const char *v = getenv("B200_SLICE")) t.slice = (uint32_t)atoi(v);
     if (const char *v = getenv("B200_DEBUG")) t.debug = atoi(v);
     if (const char *v = getenv("B200_SCATTER_CFG")) t.scatter_cfg = atoi(v);
+    if (const char *v = getenv("B200_EARLY_MAT")) t.early_mat = atoi(v);
     if (const char *v = getenv("B200_L2_FETCH")) {
         // granularity hint for L2 fills of the random payload gathers (32, 64 or 128)
         B200_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v)));
@@ -313,6 +314,27 @@ static void launch_scatter(const KeySrc &src, int bits, uint32_t *cursor, void *
     }
 }
 
+// build-side scatter with early-materialised projections (radix_scatter_pay_kernel)
+template <typename KeyT, int NPAY>
+static void launch_scatter_pay_n(const KeySrc &src, int bits, uint32_t *cursor, void *out, const PayArgs &pay) {
+    using TupT         = typename TupOf<KeyT>::type;
+    constexpr int NT   = 1024;   // 8192-tuple tiles, one CTA per SM
+    constexpr int U    = 8;
+    const size_t  smem = (size_t)NT * U * (sizeof(TupT) + 8 * NPAY) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
+    auto          k    = radix_scatter_pay_kernel<NT, U, KeyT, NPAY>;
+    allow_smem(k, smem);
+    k<<<grid_for(src.n, NT * U, 1), NT, smem, ctx().stream>>>(src, (uint32_t)bits, cursor, static_cast<TupT *>(out),
+                                                               pay);
+    B200_LAUNCH_CHECK();
+}
+template <typename KeyT>
+static void launch_scatter_pay(const KeySrc &src, int bits, uint32_t *cursor, void *out, const PayArgs &pay, int npay) {
+    if (npay == 1)
+        launch_scatter_pay_n<KeyT, 1>(src, bits, cursor, out, pay);
+    else
+        launch_scatter_pay_n<KeyT, 2>(src, bits, cursor, out, pay);
+}
+
 constexpr int kJoinNT = 512;
 constexpr int kJoinU  = 8;
 
@@ -344,20 +366,27 @@ static void launch_join64(const JoinArgs &a, int mode, size_t smem) {
         launch_persistent_join(hash_join_kernel<kJoinNT, kJoinU, uint64_t, DIRECT, MODE_SUM, kMaxProj>, a, DIRECT, smem);
 }
 
-// 32-bit keys: two-choice bucketised table (bucket_join_kernel)
+// 32-bit keys, partitioned: tag table (tag_join_kernel)
 constexpr int kJoinG = 4;
-template <bool DIRECT>
+static uint32_t tag_slots_log2_for(uint32_t cap) {
+    uint32_t l = 4;   // slots >= 1.75 x cap: load factor <= 0.57
+    while ((uint64_t)4 << l < (uint64_t)7 * cap) ++l;
+    return l;
+}
+static size_t tag_join_smem(uint32_t cap, uint32_t slots_log2) {
+    return ((size_t)4 << slots_log2) + (size_t)4 * cap + (size_t)8 * kTagQueue * (kJoinNT / 32);
+}
 static void launch_join32(const JoinArgs &a, int mode, size_t smem) {
     if (mode == MODE_COUNT)
-        launch_persistent_join(bucket_join_kernel<kJoinNT, kJoinG, DIRECT, MODE_COUNT, 0>, a, DIRECT, smem);
+        launch_persistent_join(tag_join_kernel<kJoinNT, kJoinG, MODE_COUNT, 0>, a, false, smem);
     else if (mode == MODE_WRITE)
-        launch_persistent_join(bucket_join_kernel<kJoinNT, kJoinG, DIRECT, MODE_WRITE, 0>, a, DIRECT, smem);
+        launch_persistent_join(tag_join_kernel<kJoinNT, kJoinG, MODE_WRITE, 0>, a, false, smem);
     else if (a.nproj <= 2)
-        launch_persistent_join(bucket_join_kernel<kJoinNT, kJoinG, DIRECT, MODE_SUM, 2>, a, DIRECT, smem);
+        launch_persistent_join(tag_join_kernel<kJoinNT, kJoinG, MODE_SUM, 2>, a, false, smem);
     else if (a.nproj <= 4)
-        launch_persistent_join(bucket_join_kernel<kJoinNT, kJoinG, DIRECT, MODE_SUM, 4>, a, DIRECT, smem);
+        launch_persistent_join(tag_join_kernel<kJoinNT, kJoinG, MODE_SUM, 4>, a, false, smem);
     else
-        launch_persistent_join(bucket_join_kernel<kJoinNT, kJoinG, DIRECT, MODE_SUM, kMaxProj>, a, DIRECT, smem);
+        launch_persistent_join(tag_join_kernel<kJoinNT, kJoinG, MODE_SUM, kMaxProj>, a, false, smem);
 }
 
 static void launch_join(const JoinArgs &a, bool key64, bool direct, int mode) {
@@ -368,12 +397,8 @@ static void launch_join(const JoinArgs &a, bool key64, bool direct, int mode) {
         else
             launch_join64<false>(a, mode, smem);
     } else {
-        const size_t smem = ((size_t)6 << a.slots_log2) +
-                            (mode == MODE_COUNT ? (size_t)8 * (kJoinNT / 32) : (size_t)8 * kWarpQueue * (kJoinNT / 32));
-        if (direct)
-            launch_join32<true>(a, mode, smem);
-        else
-            launch_join32<false>(a, mode, smem);
+        B200_REQUIRE(!direct, "32-bit keys are joined partitioned");
+        launch_join32(a, mode, tag_join_smem(a.cap, a.slots_log2));
     }
 }
 
@@ -390,7 +415,7 @@ PartitionOut run_partition(const KeyVec &kv, int bits) {
     Context &c = ctx();
     B200_REQUIRE(bits >= 0 && bits <= tuning().max_bits, "radix bits out of range");
     PartitionOut  o;
-    o.key64               = tuning().force_key64 || kv.max_val >= 0xFFFFFFFFull;
+    o.key64               = tuning().force_key64 || kv.max_val > 0xFFFFFFFFull;
     const uint32_t nparts = 1u << bits;
     o.hist                = dev_alloc((size_t)nparts * sizeof(uint32_t));
     DevBufPtr zeros       = dev_alloc((size_t)nparts * sizeof(uint32_t));
@@ -430,11 +455,14 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     const bool    swapped = S.src.n < R.src.n;
     const KeyVec &B       = swapped ? S : R;
     const KeyVec &P       = swapped ? R : S;
-    // 0xFFFFFFFF is the empty-slot marker of the 32-bit table
-    const bool    key64   = t.force_key64 || B.max_val >= 0xFFFFFFFFull || P.max_val >= 0xFFFFFFFFull;
-    const uint32_t cap    = key64 ? t.cap64 : t.cap32;
-    B200_REQUIRE(cap >= 32 && cap <= 65534, "table capacity must fit 16-bit chain links");
-    const uint32_t slots_log2 = key64 ? TableView<uint64_t>::slots_log2_for(cap) : TableView<uint32_t>::slots_log2_for(cap);
+    // A build side that fits one shared-memory table is joined without a
+    // partition pass (DIRECT), by the chained-table kernel on 64-bit keys.
+    const bool direct = t.radix_bits <= 0 && B.src.n <= t.cap64;
+    // 32-bit keys (8-byte partition tuples, tag-table kernel) when every key fits
+    const bool key64 = direct || t.force_key64 || B.max_val > 0xFFFFFFFFull || P.max_val > 0xFFFFFFFFull;
+    const uint32_t cap = key64 ? t.cap64 : t.cap32;
+    B200_REQUIRE(cap >= 32 && cap <= (key64 ? 65534u : 16382u), "table capacity out of range");
+    const uint32_t slots_log2 = key64 ? TableView<uint64_t>::slots_log2_for(cap) : tag_slots_log2_for(cap);
     // expected largest partition under a uniform split: mean + 5 sigma (a larger one is split into build chunks)
     auto fits = [&](int b) {
         const double mean = (double)B.src.n / (double)(1ull << b);
@@ -442,14 +470,17 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     };
 
     int bits = 0;
-    if (t.radix_bits > 0) {
-        bits = std::min(t.radix_bits, t.max_bits);
-    } else if (B.src.n > cap) {
-        // fewest partitions whose build side fits one table (longer runs per scatter tile)
-        bits = 1;
-        while (bits < t.max_bits && !fits(bits)) ++bits;
+    if (!direct) {
+        // the tag table needs radix_bits + slots_log2 >= 16 (tag <= 16 bits)
+        const int min_bits = key64 ? 1 : std::max(2, 16 - (int)slots_log2);
+        if (t.radix_bits > 0) {
+            bits = std::max(min_bits, std::min(t.radix_bits, t.max_bits));
+        } else {
+            // fewest partitions whose build side fits one table (longer runs per scatter tile)
+            bits = min_bits;
+            while (bits < t.max_bits && !fits(bits)) ++bits;
+        }
     }
-    const bool direct = bits == 0;
 
     JoinArgs a;
     memset(&a, 0, sizeof(a));
@@ -477,6 +508,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     a.sums         = d_u64 + 8;
 
     DevBufPtr tup_b, tup_p;
+    DevBufPtr part_vals[kMaxProj];
     uint64_t  n_items = 0;
     if (direct) {
         a.src_b = B.src;
@@ -514,9 +546,26 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         const size_t tsz = key64 ? sizeof(Tup64) : sizeof(Tup32);
         tup_b            = dev_alloc((size_t)B.src.n * tsz);
         tup_p            = dev_alloc((size_t)P.src.n * tsz);
+        // early materialisation: the first two build-side projections of a fused
+        // SUM travel with the build tuples into partition order (32-bit-key path)
+        PayArgs pay{};
+        int     npay = 0;
+        if (mode == JoinOut::Sum && !key64 && t.early_mat) {
+            for (int k = 0; k < nproj && npay < 2; ++k) {
+                const int side_b = swapped ? 1 : 0;   // proj[].side is relative to (R, S)
+                if (proj[k].side != side_b) continue;
+                part_vals[k]  = dev_alloc((size_t)B.src.n * sizeof(uint64_t));
+                pay.col[npay] = proj[k].col;
+                pay.ids[npay] = proj[k].ids;
+                pay.out[npay] = part_vals[k]->as<uint64_t>();
+                ++npay;
+            }
+        }
         {
             TimedScope ts("scatter_b");
-            if (key64)
+            if (npay > 0)
+                launch_scatter_pay<uint32_t>(B.src, bits, cur_b, tup_b->ptr, pay, npay);
+            else if (key64)
                 launch_scatter<uint64_t>(B.src, bits, cur_b, tup_b->ptr);
             else
                 launch_scatter<uint32_t>(B.src, bits, cur_b, tup_b->ptr);
@@ -538,10 +587,13 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
 
     if (mode == JoinOut::Sum) {
         a.nproj = nproj;
+        a.need_brid = 0;
         for (int k = 0; k < nproj; ++k) {
             a.proj[k] = proj[k];
             // sides are given relative to (R, S); the kernel wants (build, probe)
-            a.proj[k].side = swapped ? 1 - proj[k].side : proj[k].side;
+            a.proj[k].side      = swapped ? 1 - proj[k].side : proj[k].side;
+            a.proj[k].part_vals = part_vals[k] ? part_vals[k]->as<uint64_t>() : nullptr;
+            if (a.proj[k].side == 0 && !a.proj[k].part_vals) a.need_brid = 1;
         }
         {
             TimedScope ts("join");

@@ -364,6 +364,96 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
     }
 }
 
+// Build-side scatter that also carries up to NPAY projected columns into
+// partition order (early materialisation): the SUM of a build-side projection
+// then reads pay_out[k][position in the partition buffer] — a dense, L2-resident
+// window — instead of one random DRAM gather per match (measured on B200:
+// random 8-byte gathers run at ~40 G/s whatever their L2 fetch size).  The build
+// side is the small relation, so this kernel is the plain variant of
+// radix_scatter_kernel: no prefetch, no predicate-free instance.
+struct PayArgs {
+    const uint64_t *col[2];
+    const uint32_t *ids[2];
+    uint64_t       *out[2];
+};
+template <int NT, int U, typename KeyT, int NPAY>
+__global__ void __launch_bounds__(NT)
+radix_scatter_pay_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cursor,
+                         typename TupOf<KeyT>::type *__restrict__ out, PayArgs pay) {
+    using TupT = typename TupOf<KeyT>::type;
+    constexpr uint32_t TILE = NT * U;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TupT     *stage  = reinterpret_cast<TupT *>(smem_raw);
+    uint64_t *pstage = reinterpret_cast<uint64_t *>(stage + TILE);   // [NPAY][TILE]
+    uint32_t *cnt    = reinterpret_cast<uint32_t *>(pstage + (size_t)NPAY * TILE);
+    const uint32_t nbins = 1u << radix_bits;
+    const uint32_t mask  = nbins - 1u;
+    uint32_t *loc    = cnt + nbins;
+    uint32_t *gdelta = loc + nbins;
+    __shared__ uint32_t warp_sums[NT / 32 + 1];
+
+    const uint64_t n      = src.n;
+    const uint64_t ntiles = (n + TILE - 1) / TILE;
+    const uint32_t per    = (nbins + NT - 1) / NT;
+    for (uint32_t b = threadIdx.x; b < nbins; b += NT) cnt[b] = 0;
+    __syncthreads();
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t base  = tile * TILE;
+        const uint32_t count = (uint32_t)min((uint64_t)TILE, n - base);
+        KeyT     keys[U];
+        uint16_t rank[U];
+        load_tile_keys<NT, U, KeyT>(src, base, count, false, keys);
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+            if ((uint32_t)(j * NT) + threadIdx.x < count)
+                rank[j] = (uint16_t)atomicAdd(&cnt[(uint32_t)keys[j] & mask], 1u);
+        __syncthreads();
+        {
+            const uint32_t first = threadIdx.x * per;
+            uint32_t       s     = 0;
+            for (uint32_t k = 0; k < per; ++k)
+                if (first + k < nbins) s += cnt[first + k];
+            uint32_t run = block_exclusive_scan<NT>(s, warp_sums);
+            for (uint32_t k = 0; k < per; ++k) {
+                const uint32_t b = first + k;
+                if (b < nbins) {
+                    const uint32_t c = cnt[b];
+                    loc[b]           = run;
+                    if (c) gdelta[b] = atomicAdd(&cursor[b], c) - run;
+                    run += c;
+                    cnt[b] = 0;
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const uint32_t li = (uint32_t)(j * NT) + threadIdx.x;
+            if (li < count) {
+                const uint32_t rid = (uint32_t)base + li;
+                const uint32_t pos = loc[(uint32_t)keys[j] & mask] + rank[j];
+                TupT           t;
+                t.key = keys[j];
+                t.rid = rid;
+                if constexpr (sizeof(KeyT) == 8) t.pad = 0;
+                stage[pos] = t;
+#pragma unroll
+                for (int k = 0; k < NPAY; ++k)
+                    pstage[(size_t)k * TILE + pos] = pay.col[k][pay.ids[k] ? pay.ids[k][rid] : rid];
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < count; i += NT) {
+            const TupT     t = stage[i];
+            const uint32_t o = gdelta[(uint32_t)t.key & mask] + i;
+            out[o]           = t;
+#pragma unroll
+            for (int k = 0; k < NPAY; ++k) pay.out[k][o] = pstage[(size_t)k * TILE + i];
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K6 + K7 (+K9): per-partition build and probe in shared memory.
 //
@@ -405,6 +495,7 @@ struct JoinArgs {
     unsigned long long *out_cursor;   // WRITE
     uint32_t       *out_b, *out_p;    // WRITE
     int             nproj;            // SUM
+    int             need_brid;        // SUM: some build-side projection is gathered through the row id
     ProjDesc        proj[kMaxProj];
     unsigned long long *sums;
 };
@@ -816,27 +907,27 @@ hash_join_kernel(const JoinArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// K6 + K7 (+K9) for 32-bit keys: two-choice bucketised table.
+// K6 + K7 (+K9) for 32-bit keys: tag table, one shared-memory access per probe.
 //
-// hash_join_kernel above walks data-dependent chains; ncu showed it bound by
-// instruction issue and shared-memory latency (about 100 warp instructions per
-// probe round, one dependent LDS after the other).  This kernel keeps the same
-// work-item scheme and match queue but makes the probe branch-free:
-//   * a bucket is four 32-bit key slots (one LDS.128); every key has two
-//     candidate buckets (two multiplicative hashes of the bits above the
-//     radix); the build puts it into the emptier one, so with <= 0.57 load a
-//     bucket practically never overflows and a probe is exactly two LDS.128 and
-//     eight compares, issued for a group of G probes back to back;
-//   * slot -> position of the build tuple in its chunk is a parallel 16-bit
-//     array, read only on a match;
-//   * a match is appended to the warp's queue at a slot computed from a
-//     ballot (no atomics); the queue is drained 32 entries at a time with all
-//     lanes active (build row id re-read from the partition buffer, payload
-//     gathers of a drain all in flight together, consumed at the next drain).
-// If a key finds both buckets full (heavy duplicates) it spills into the next
-// non-full bucket after its second one and the CTA flags the table; probes of
-// a flagged table also scan that run of full buckets.  0xFFFFFFFF marks an
-// empty slot: the 32-bit kernels run only when all keys are below it.
+// hash_join_kernel above walks data-dependent chains with full keys in shared
+// memory; ncu showed the probe bound by the SM's L1/shared-memory pipe (random
+// LDS cost ~3.5 wavefronts per warp whatever their width, and every chain step
+// is another one) and by instruction issue (~100 warp instructions per probe).
+// This kernel makes a probe ONE 32-bit LDS:
+//   * y = mix(key >> radix_bits) is a bijection on the 32 - radix_bits bits
+//     that differ inside a partition; slot = low L bits of y, tag = the rest
+//     (<= 16 bits).  Slot and tag together identify the key exactly, so a tag
+//     match IS a key match: no key array in shared memory, no verification;
+//   * a slot word is [tag | has_next | position of the build tuple in its
+//     chunk]; build tuples that collide in a slot are chained through a second
+//     word array of the same format (tagnext[pos] = word of the next element);
+//   * the probe never branches per lane: lanes whose slot word has a matching
+//     tag, or a chain behind it, push an 8-byte entry into the warp's queue at
+//     a position computed from ballots; the queue is drained 32 entries at a
+//     time with every lane active (chain walks re-push the matches they find;
+//     payload gathers of a drain are all in flight together and are consumed
+//     by the next drain).
+// Used for partitioned joins with radix_bits >= 2 and keys below 2^32 - 1.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
     uint4 v;
@@ -915,37 +1006,61 @@ __device__ __forceinline__ JoinItem fetch_join_item(const JoinArgs &a, int lane)
     return it;
 }
 
-template <int NT, int G, bool DIRECT, int MODE, int NP>
+constexpr uint32_t kTagShift  = 15;
+constexpr uint32_t kNextBit   = 0x4000u;
+constexpr uint32_t kIdxMask   = 0x3FFFu;
+constexpr uint32_t kEmptyWord = 0xFFFFBFFFu;   // tag all ones (never a real tag), no chain
+constexpr int      kTagQueue  = 96;            // entries per warp (<= 31 left + 64 pushed per probe)
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+// invertible on the low nb bits: odd multiply, xor-shift by >= nb/2, odd multiply
+__device__ __forceinline__ uint32_t mix_bijective(uint32_t x, uint32_t nb_mask, uint32_t half) {
+    x = (x * 0x9E3779B1u) & nb_mask;
+    x ^= x >> half;
+    x = (x * 0x85EBCA6Bu) & nb_mask;
+    return x;
+}
+__device__ __forceinline__ uint64_t ld_gather_u64(const uint64_t *p) {
+    uint64_t v;   // random 8-byte gather: fetch 64 B from DRAM, not the default 128 B
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+template <int NT, int G, int MODE, int NP>
 __global__ void __launch_bounds__(NT, 2)
-bucket_join_kernel(const JoinArgs a) {
+tag_join_kernel(const JoinArgs a) {
     constexpr int NW  = NT / 32;
     constexpr int NPA = NP > 0 ? NP : 1;
-    constexpr int QN  = MODE == MODE_COUNT ? 1 : kWarpQueue;
+    constexpr int QN  = kTagQueue;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: keys [4 << L bytes] | idx [2 << L bytes] | queues [NW * QN * 8 bytes]
-    const uint32_t L        = a.slots_log2;
-    const uint32_t blog     = L - 2;                 // log2(number of buckets)
-    const uint32_t bmask    = (1u << blog) - 1u;
-    const uint32_t s_keys   = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const uint32_t s_idx    = s_keys + (4u << L);
-    const uint32_t s_queue  = s_idx + (2u << L);
-    uint32_t      *keys     = reinterpret_cast<uint32_t *>(smem_raw);
-    uint16_t      *idxs     = reinterpret_cast<uint16_t *>(smem_raw + ((size_t)4 << L));
+    // layout: slots [4 << L bytes] | tagnext [4 * cap bytes] | queues [NW * QN * 8 bytes]
+    const uint32_t L       = a.slots_log2;
+    const uint32_t smask   = (1u << L) - 1u;
+    const uint32_t nb      = 32u - a.radix_bits;
+    const uint32_t nb_mask = 0xFFFFFFFFu >> a.radix_bits;
+    const uint32_t half    = (nb + 1u) / 2u;
+    const uint32_t s_slots = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t s_next  = s_slots + (4u << L);
+    const uint32_t s_queue = s_next + 4u * a.cap;
+    uint32_t      *slots   = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t      *tagnext = slots + (1u << L);
 
     __shared__ uint32_t           s_item[6];
     __shared__ uint32_t           s_cursor;
-    __shared__ uint32_t           s_spill;
     __shared__ unsigned long long s_base;
     __shared__ unsigned long long s_cnt;
 
-    const uint32_t tid    = threadIdx.x;
-    const uint32_t lane   = tid & 31u;
-    const uint32_t wid    = tid >> 5;
-    const uint32_t lt     = (1u << lane) - 1u;
-    const uint32_t my_q   = s_queue + wid * (uint32_t)(QN * 8);
+    const uint32_t tid  = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const uint32_t wid  = tid >> 5;
+    const uint32_t lt   = (1u << lane) - 1u;
+    const uint32_t my_q = s_queue + wid * (uint32_t)(QN * 8);
     const Tup32 *tup_b = static_cast<const Tup32 *>(a.tup_b);
     const Tup32 *tup_p = static_cast<const Tup32 *>(a.tup_p);
-    const uint32_t hshift = 32u - blog;
 
     unsigned long long my_matches = 0;
     unsigned long long my_sum[NPA], pend[NPA];
@@ -954,93 +1069,96 @@ bucket_join_kernel(const JoinArgs a) {
     uint32_t b_start = 0;
     uint32_t queued  = 0;   // warp-uniform number of entries in this warp's queue
 
-    auto handle_inline = [&](uint32_t pos_in_chunk, uint32_t prid) {
-        uint32_t brid;
-        if constexpr (DIRECT) brid = b_start + pos_in_chunk;
-        else brid = tup_b[b_start + pos_in_chunk].rid;
-        if constexpr (MODE == MODE_SUM) {
-#pragma unroll
-            for (int k = 0; k < NPA; ++k) {
-                if (k < a.nproj) {
-                    const uint32_t r  = a.proj[k].side == 0 ? brid : prid;
-                    const uint32_t rr = a.proj[k].ids ? __ldg(a.proj[k].ids + r) : r;
-                    my_sum[k] += __ldg(a.proj[k].col + rr);
-                }
-            }
-        } else if constexpr (MODE == MODE_WRITE) {
-            const uint32_t pos    = atomicAdd(&s_cursor, 1u);
-            a.out_b[s_base + pos] = brid;
-            a.out_p[s_base + pos] = prid;
-        }
-    };
-
-    // drain `take` (<= 32) entries [have - take, have) of this warp's queue, one per lane
-    auto drain = [&](uint32_t have, uint32_t take) {
+    // one match (build tuple at position pos of the chunk, probe row prid), handled in place
+    auto handle_inline = [&](uint32_t pos, uint32_t prid) {
+        ++my_matches;
         if constexpr (MODE != MODE_COUNT) {
-            const bool  mine = lane < take;
-            const uint2 e    = lds_v2(my_q + (mine ? have - take + lane : 0u) * 8u);
-            uint32_t    brid = 0;
-            if (mine) {
-                if constexpr (DIRECT) brid = b_start + e.x;
-                else brid = tup_b[b_start + e.x].rid;
-            }
+            const uint32_t brid = tup_b[b_start + pos].rid;
             if constexpr (MODE == MODE_SUM) {
 #pragma unroll
                 for (int k = 0; k < NPA; ++k) {
-                    my_sum[k] += pend[k];
-                    pend[k] = 0;
-                    if (k < a.nproj && mine) {
-                        const uint32_t r  = a.proj[k].side == 0 ? brid : e.y;
-                        const uint32_t rr = a.proj[k].ids ? __ldg(a.proj[k].ids + r) : r;
-                        pend[k]           = __ldg(a.proj[k].col + rr);
+                    if (k < a.nproj) {
+                        if (a.proj[k].part_vals) {
+                            my_sum[k] += a.proj[k].part_vals[b_start + pos];
+                        } else {
+                            const uint32_t r  = a.proj[k].side == 0 ? brid : prid;
+                            const uint32_t rr = a.proj[k].ids ? __ldg(a.proj[k].ids + r) : r;
+                            my_sum[k] += ld_gather_u64(a.proj[k].col + rr);
+                        }
                     }
                 }
             } else {
-                uint32_t pos = 0;
-                if (lane == 0) pos = atomicAdd(&s_cursor, take);
-                pos = __shfl_sync(kFullMask, pos, 0);
-                if (mine) {
-                    a.out_b[s_base + pos + lane] = brid;
-                    a.out_p[s_base + pos + lane] = e.y;
-                }
+                const uint32_t pos_out    = atomicAdd(&s_cursor, 1u);
+                a.out_b[s_base + pos_out] = brid;
+                a.out_p[s_base + pos_out] = prid;
             }
         }
     };
 
-    // all matches of one probe in the 4-slot bucket `b` (match nibble m); converged call
-    auto emit = [&](uint32_t m, uint32_t b, uint32_t prid) {
-        const uint32_t act = __ballot_sync(kFullMask, m != 0u);
-        if (act == 0u) return;
-        if (m) {
-            const uint32_t s   = __ffs(m) - 1u;
-            const uint32_t pos = lds_u16(s_idx + (b * 4u + s) * 2u);
-            my_matches += __popc(m);
-            if constexpr (MODE != MODE_COUNT) {
-                const uint32_t slot = queued + __popc(act & lt);
-                if (slot < (uint32_t)QN) sts_v2(my_q + slot * 8u, pos, prid);
-                else handle_inline(pos, prid);
-                m &= m - 1u;
-                while (m) {   // further duplicates of the key in the same bucket
-                    const uint32_t s2 = __ffs(m) - 1u;
-                    m &= m - 1u;
-                    handle_inline(lds_u16(s_idx + (b * 4u + s2) * 2u), prid);
+    // pop `take` (<= 32) entries, one per lane: a match entry is completed, a chain entry is walked
+    // and the matches it finds are pushed back (or completed in place when the queue is full)
+    auto drain = [&](uint32_t take) {
+        queued -= take;
+        const bool  mine = lane < take;
+        const uint2 e    = lds_v2(my_q + (queued + (mine ? lane : 0u)) * 8u);
+        const uint32_t t = e.x >> kTagShift;
+        // ---- match entries ----
+        const bool is_match = mine && (e.x & kNextBit) == 0u;
+        if constexpr (MODE == MODE_SUM) {
+            const uint32_t bpos = b_start + (e.x & kIdxMask);
+            uint32_t       brid = 0;
+            if (is_match && a.need_brid) brid = tup_b[bpos].rid;
+#pragma unroll
+            for (int k = 0; k < NPA; ++k) {
+                my_sum[k] += pend[k];
+                pend[k] = 0;
+                if (k < a.nproj && is_match) {
+                    if (a.proj[k].part_vals) {
+                        pend[k] = a.proj[k].part_vals[bpos];   // dense window of this partition, L2-resident
+                    } else {
+                        const uint32_t r  = a.proj[k].side == 0 ? brid : e.y;
+                        const uint32_t rr = a.proj[k].ids ? __ldg(a.proj[k].ids + r) : r;
+                        pend[k]           = ld_gather_u64(a.proj[k].col + rr);
+                    }
                 }
             }
-        }
-        if constexpr (MODE != MODE_COUNT) {
-            queued = min(queued + (uint32_t)__popc(act), (uint32_t)QN);
-            __syncwarp();
-            while (queued >= 32u) {
-                drain(queued, 32u);
-                queued -= 32u;
+            my_matches += is_match ? 1u : 0u;
+        } else if constexpr (MODE == MODE_WRITE) {
+            const uint32_t bal = __ballot_sync(kFullMask, is_match);
+            uint32_t       pos = 0;
+            if (lane == 0 && bal) pos = atomicAdd(&s_cursor, (uint32_t)__popc(bal));
+            pos = __shfl_sync(kFullMask, pos, 0);
+            if (is_match) {
+                const uint32_t o  = pos + __popc(bal & lt);
+                a.out_b[s_base + o] = tup_b[b_start + (e.x & kIdxMask)].rid;
+                a.out_p[s_base + o] = e.y;
             }
-            __syncwarp();
+        } else {
+            my_matches += is_match ? 1u : 0u;
         }
+        // ---- chain entries ----
+        bool     walking = mine && (e.x & kNextBit) != 0u;
+        uint32_t pos     = e.x & kIdxMask;
+        while (__any_sync(kFullMask, walking)) {
+            uint32_t w = kEmptyWord;
+            if (walking) w = lds_u32(s_next + pos * 4u);
+            const bool     hit = walking && (w >> kTagShift) == t;
+            const uint32_t bal = __ballot_sync(kFullMask, hit);
+            if (hit) {
+                const uint32_t slot = queued + __popc(bal & lt);
+                if (slot < (uint32_t)QN) sts_v2(my_q + slot * 8u, (t << kTagShift) | (w & kIdxMask), e.y);
+                else handle_inline(w & kIdxMask, e.y);
+            }
+            queued  = min(queued + (uint32_t)__popc(bal), (uint32_t)QN);
+            walking = walking && (w & kNextBit) != 0u;
+            pos     = w & kIdxMask;
+        }
+        __syncwarp();
     };
 
     for (;;) {
         if (tid < 32) {
-            const JoinItem it = fetch_join_item<DIRECT>(a, (int)lane);
+            const JoinItem it = fetch_join_item<false>(a, (int)lane);
             if (lane == 0) {
                 s_item[0] = it.valid;
                 s_item[1] = it.b_start;
@@ -1050,7 +1168,6 @@ bucket_join_kernel(const JoinArgs a) {
                 s_item[5] = it.w;
                 s_cnt     = 0ull;
                 s_cursor  = 0u;
-                s_spill   = 0u;
                 if constexpr (MODE == MODE_WRITE) {
                     if (it.valid) s_base = atomicAdd(a.out_cursor, a.item_count[it.w]);
                 }
@@ -1064,18 +1181,12 @@ bucket_join_kernel(const JoinArgs a) {
         const uint32_t item_w  = s_item[5];
 
         auto load_probe = [&](uint32_t li, uint32_t &key, uint32_t &rid) {
-            key = kEmptyKey32;   // never matches
-            rid = 0;
+            key = 0;
+            rid = 0xFFFFFFFFu;   // padding lane of the last round
             if (li < p_count) {
-                if constexpr (DIRECT) {
-                    rid = p_start + li;
-                    key = (uint32_t)(a.src_p.ids ? __ldg(a.src_p.col + ld_stream_u32(a.src_p.ids + rid))
-                                                 : ld_stream_u64(a.src_p.col + rid));
-                } else {
-                    const uint64_t v = ld_stream_u64(reinterpret_cast<const uint64_t *>(tup_p + p_start + li));
-                    key              = (uint32_t)v;
-                    rid              = (uint32_t)(v >> 32);
-                }
+                const uint64_t v = ld_stream_u64(reinterpret_cast<const uint64_t *>(tup_p + p_start + li));
+                key              = (uint32_t)v;
+                rid              = (uint32_t)(v >> 32);
             }
         };
         // first group in flight while the table is built
@@ -1084,91 +1195,53 @@ bucket_join_kernel(const JoinArgs a) {
         for (int j = 0; j < G; ++j) load_probe((uint32_t)(j * NT) + tid, ckey[j], crid[j]);
 
         // ---- build (K6) ---------------------------------------------------
-        for (uint32_t s = tid; s < (1u << L); s += NT) keys[s] = kEmptyKey32;
+        for (uint32_t s = tid; s <= smask; s += NT) slots[s] = kEmptyWord;
         __syncthreads();
         for (uint32_t i = tid; i < b_count; i += NT) {
-            uint32_t key;
-            if constexpr (DIRECT) {
-                const uint32_t rid = b_start + i;
-                key = (uint32_t)(a.src_b.ids ? a.src_b.col[a.src_b.ids[rid]] : a.src_b.col[rid]);
-            } else {
-                key = tup_b[b_start + i].key;
-            }
-            const uint32_t x  = key >> a.radix_bits;
-            const uint32_t h1 = (x * 0x9E3779B1u) >> hshift;
-            uint32_t       h2 = (x * 0x85EBCA77u) >> hshift;
-            if (h2 == h1) h2 = (h1 + 1u) & bmask;
-            bool     done    = false;
-            uint32_t spill_b = (h2 + 1u) & bmask;
-            while (!done) {
-                const uint32_t u1 = used4(lds_v4(s_keys + h1 * 16u));
-                const uint32_t u2 = used4(lds_v4(s_keys + h2 * 16u));
-                uint32_t       b, u;
-                if (u1 != 15u && __popc(u1) <= __popc(u2)) { b = h1; u = u1; }
-                else if (u2 != 15u) { b = h2; u = u2; }
-                else if (u1 != 15u) { b = h1; u = u1; }
-                else {
-                    // both candidate buckets full: next non-full bucket after h2
-                    s_spill = 1u;
-                    for (;;) {
-                        u = used4(lds_v4(s_keys + spill_b * 16u));
-                        if (u != 15u) break;
-                        spill_b = (spill_b + 1u) & bmask;
-                    }
-                    b = spill_b;
-                }
-                const uint32_t s    = __ffs(~u & 15u) - 1u;
-                const uint32_t slot = b * 4u + s;
-                if (atomicCAS(&keys[slot], kEmptyKey32, key) == kEmptyKey32) {
-                    idxs[slot] = (uint16_t)i;
-                    done       = true;
-                }
-            }
+            const uint32_t key = tup_b[b_start + i].key;
+            const uint32_t y   = mix_bijective(key >> a.radix_bits, nb_mask, half);
+            const uint32_t h   = y & smask;
+            const uint32_t t   = y >> L;
+            uint32_t       old = slots[h], assumed;
+            do {
+                assumed            = old;
+                const uint32_t nw  = (t << kTagShift) | (assumed != kEmptyWord ? kNextBit : 0u) | i;
+                old                = atomicCAS(&slots[h], assumed, nw);
+            } while (old != assumed);
+            tagnext[i] = old;
         }
         __syncthreads();
-        const bool spilled = s_spill != 0u;
 
         // ---- probe (K7) ---------------------------------------------------
         for (uint32_t off = 0; off < p_count; off += NT * G) {
 #pragma unroll
             for (int j = 0; j < G; ++j) load_probe(off + (uint32_t)(NT * G + j * NT) + tid, nkey[j], nrid[j]);
-            uint32_t h1[G], h2[G], m1[G], m2[G];
+            uint32_t w[G], t[G];
 #pragma unroll
             for (int j = 0; j < G; ++j) {
-                const uint32_t x = ckey[j] >> a.radix_bits;
-                h1[j]            = (x * 0x9E3779B1u) >> hshift;
-                h2[j]            = (x * 0x85EBCA77u) >> hshift;
-                if (h2[j] == h1[j]) h2[j] = (h1[j] + 1u) & bmask;
+                const uint32_t y = mix_bijective(ckey[j] >> a.radix_bits, nb_mask, half);
+                t[j]             = y >> L;
+                w[j]             = lds_u32(s_slots + (y & smask) * 4u);
             }
 #pragma unroll
             for (int j = 0; j < G; ++j) {
-                const uint4 k1 = lds_v4(s_keys + h1[j] * 16u);
-                const uint4 k2 = lds_v4(s_keys + h2[j] * 16u);
-                const bool  ok = ckey[j] != kEmptyKey32;   // padding lanes of the last round
-                m1[j]          = ok ? match4(k1, ckey[j]) : 0u;
-                m2[j]          = ok ? match4(k2, ckey[j]) : 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < G; ++j) {
-                emit(m1[j], h1[j], crid[j]);
-                emit(m2[j], h2[j], crid[j]);
-            }
-            if (spilled) {
-#pragma unroll
-                for (int j = 0; j < G; ++j) {
-                    // run of full buckets after h2 (where spilled keys live); h1 was already counted
-                    uint32_t b    = (h2[j] + 1u) & bmask;
-                    bool     more = ckey[j] != kEmptyKey32;
-                    while (__any_sync(kFullMask, more)) {
-                        uint32_t m = 0;
-                        if (more) {
-                            const uint4 k = lds_v4(s_keys + b * 16u);
-                            if (b != h1[j]) m = match4(k, ckey[j]);
-                            more = used4(k) == 15u && b != h2[j];
-                        }
-                        emit(m, b, crid[j]);
-                        b = (b + 1u) & bmask;
-                    }
+                const bool     ok    = crid[j] != 0xFFFFFFFFu;
+                const bool     is_m  = ok && (w[j] >> kTagShift) == t[j];
+                const bool     has_n = ok && (w[j] & kNextBit) != 0u;
+                const uint32_t act_m = __ballot_sync(kFullMask, is_m);
+                const uint32_t act_c = __ballot_sync(kFullMask, has_n);
+                if (act_m | act_c) {
+                    // queued <= 31 here and a probe adds <= 64 entries: no overflow (QN = 96)
+                    if (is_m)
+                        sts_v2(my_q + (queued + __popc(act_m & lt)) * 8u, (t[j] << kTagShift) | (w[j] & kIdxMask),
+                               crid[j]);
+                    queued += __popc(act_m);
+                    if (has_n)
+                        sts_v2(my_q + (queued + __popc(act_c & lt)) * 8u,
+                               (t[j] << kTagShift) | kNextBit | (w[j] & kIdxMask), crid[j]);
+                    queued += __popc(act_c);
+                    __syncwarp();
+                    while (queued >= 32u) drain(32u);
                 }
             }
 #pragma unroll
@@ -1177,13 +1250,9 @@ bucket_join_kernel(const JoinArgs a) {
                 crid[j] = nrid[j];
             }
         }
-        if constexpr (MODE != MODE_COUNT) {
-            // leftovers of this item (queue entries are relative to this item's build chunk)
-            __syncwarp();
-            if (queued) drain(queued, queued);
-            queued = 0;
-            __syncwarp();
-        }
+        // leftovers of this item (queue entries are relative to this item's build chunk)
+        __syncwarp();
+        while (queued) drain(min(queued, 32u));
         if constexpr (MODE == MODE_COUNT) {
             const unsigned long long ws = warp_sum_u64(my_matches);
             my_matches                  = 0;

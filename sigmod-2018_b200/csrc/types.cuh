@@ -37,6 +37,10 @@ struct ProjDesc {
     const uint64_t *col;
     const uint32_t *ids;
     int             side;
+    // build-side projections only: the projected values already permuted into
+    // partition order by the scatter (value of build tuple i of the partition
+    // buffer), or nullptr when the value is gathered through the row id
+    const uint64_t *part_vals;
 };
 
 }  // namespace b200
