@@ -20,9 +20,11 @@ sides, per-partition shared-memory build + probe, SUM projection.
   cpu_baseline  the reference's own CPU join (oracle/_ref/ref_driver, built
           from the unmodified reference) on a bounded sample, host cores stated
 
-N > 1 (torchrun, one rank per GPU): R and S start position-sharded; the small
-build side is all-gathered over NCCL (broadcast plan), every rank
-joins its S shard locally, the checksums are all-reduced.  Strong scaling.
+N > 1 (torchrun, one rank per GPU): R and S start position-sharded; every rank
+scatters its build shard into ALL ranks' partition buffers with P2P stores over
+NVLink (the broadcast of the small side fused into the scatter kernel, SURVEY
+§8e), partitions its probe shard locally, joins, and the checksums are
+all-reduced (sharding.BroadcastScatterJoin).  Strong scaling.
 
 `--impl reference` times the reference's CPU implementation (rank 0 only).
 """
@@ -225,28 +227,25 @@ def run_b200_arm(args):
     r1 = synth(nr_loc, r_first, b200.SYNTH_PAYLOAD, 0, b200.SEED_R + 1)
     s0 = synth(ns_loc, s_first, b200.SYNTH_PERM, KS_BITS, b200.SEED_S)
     s1 = synth(ns_loc, s_first, b200.SYNTH_PAYLOAD, 0, b200.SEED_S + 1)
+    plan = None
     if world > 1:
-        r0_all = torch.empty(nr, dtype=torch.int64, device=dev)
-        r1_all = torch.empty(nr, dtype=torch.int64, device=dev)
+        plan = b200.sharding.BroadcastScatterJoin(b200, torch, dist, rank, world, nr, nr_loc, ns_loc, 1, dev)
     torch.cuda.synchronize()
 
-    def step():
-        """One pass of the hot path; returns ([sum R.c1, sum S.c1], matches) of this rank's shard."""
+    def step(kr=None, pr=None, ks=None, ps=None):
+        """One pass of the hot path; returns ([sum R.c1, sum S.c1], matches): this rank's at N = 1, the
+        all-reduced result at N > 1 (sharding.BroadcastScatterJoin)."""
+        kr, pr = (r0 if kr is None else kr), (r1 if pr is None else pr)
+        ks, ps = (s0 if ks is None else ks), (s1 if ps is None else ps)
         if world > 1:
-            dist.all_gather_into_tensor(r0_all, r0)     # broadcast plan: replicate the small build side
-            dist.all_gather_into_tensor(r1_all, r1)
-            kr, pr = r0_all, r1_all
-        else:
-            kr, pr = r0, r1
-        return b200.join_sum_device(kr.data_ptr(), nr, s0.data_ptr(), ns_loc, [pr.data_ptr(), s1.data_ptr()], [0, 1],
+            return plan.step(kr.data_ptr(), [pr.data_ptr()], ks.data_ptr(), [pr.data_ptr(), ps.data_ptr()], [0, 1])
+        return b200.join_sum_device(kr.data_ptr(), nr, ks.data_ptr(), ns_loc, [pr.data_ptr(), ps.data_ptr()], [0, 1],
                                     max_key)
 
     def reduce_sums(sums, m):
-        t = torch.tensor([np.uint64(x).astype(np.int64) for x in sums] + [m], dtype=torch.int64, device=dev)
         if world > 1:
-            dist.all_reduce(t)                           # u64 sums mod 2^64 == wrapping int64 sums
-        v = t.cpu().numpy().view(np.uint64)
-        return [int(x) for x in v[:-1]], int(v[-1])
+            return sums, m          # plan.step already all-reduced them
+        return [int(x) for x in sums], int(m)
 
     def barrier():
         if world > 1:
@@ -292,7 +291,7 @@ def run_b200_arm(args):
     for _ in range(9):
         step()
         torch.cuda.synchronize()
-        for name in ("hist", "scan", "scatter_b", "scatter_p", "join"):
+        for name in ("hist", "scan", "scatter_b", "broadcast", "scatter_p", "join"):
             v = b200.last_kernel_ms(name)
             if v >= 0:
                 per_kernel.setdefault(name, []).append(v)
@@ -313,13 +312,9 @@ def run_b200_arm(args):
 
         def e2e_step():
             if world > 1:
-                # every rank uploads its shard; R is exchanged on the device as in step()
-                d_r0, d_r1 = host["r0"].to(dev, non_blocking=True), host["r1"].to(dev, non_blocking=True)
-                dist.all_gather_into_tensor(r0_all, d_r0)
-                dist.all_gather_into_tensor(r1_all, d_r1)
-                d_s0, d_s1 = host["s0"].to(dev, non_blocking=True), host["s1"].to(dev, non_blocking=True)
-                return b200.join_sum_device(r0_all.data_ptr(), nr, d_s0.data_ptr(), ns_loc,
-                                            [r1_all.data_ptr(), d_s1.data_ptr()], [0, 1], max_key)
+                # every rank uploads its shards, then the same multi-GPU plan as step()
+                d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+                return step(d["r0"], d["r1"], d["s0"], d["s1"])
             ptrs = (C.c_void_p * 2)(host["r1"].data_ptr(), host["s1"].data_ptr())
             sides = (C.c_int * 2)(0, 1)
             out = (C.c_uint64 * 2)()
@@ -395,8 +390,9 @@ def run_b200_arm(args):
                                "SUM projection", "query": QUERY, "rows_build": nr, "rows_probe": ns,
                    "matches": nr, "seeds": [hex(b200.SEED_R), hex(b200.SEED_S)],
                    "l2": "inputs (4.6 GB) larger than L2; no flush",
-                   "parallelism": "single GPU" if world == 1 else f"S position-sharded x{world}, R all-gathered (NCCL), "
-                                                                  "u64 all-reduce of sums"},
+                   "parallelism": "single GPU" if world == 1 else
+                   f"R and S position-sharded x{world}; build shard scattered into every rank's partition buffers "
+                   "by P2P stores over NVLink (CUDA IPC), probe shard partitioned locally, u64 all-reduce of sums"},
         "hbm": {"canonical_bytes_per_step": canon_bytes, "achieved_gbs": canon_bytes / t_s / 1e9 / world,
                 "frac_of_peak": canon_bytes / t_s / 1e9 / world / peak, "peak_gbs": peak, "peak_source": peak_kind},
         "checksums": sums, "matches": m,
@@ -409,6 +405,10 @@ def run_b200_arm(args):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version there) get stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

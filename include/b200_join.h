@@ -206,6 +206,43 @@ int  b200_join_sum(const uint64_t *keys_r, uint64_t n_r,
                    const int *proj_side, int location, uint64_t *out_sums,
                    uint64_t *out_matches);
 
+/* ---- staged join on caller-owned DEVICE buffers (multi-GPU plans) ----------
+ * One process per GPU drives the phases of rhjoin.c:13-111 separately so that
+ * the exchange between GPUs can sit between them (sigmod-2018_b200/sharding.py):
+ *   hist      counts of key & (2^bits - 1)              (preprocess.c:181-195)
+ *   scatter   into partition order at caller-computed cursors; the build shard
+ *             is partitioned locally and each partition segment is then copied
+ *             to d_dst_start[p] inside up to 8 destination buffers — this
+ *             GPU's and its peers' IPC-mapped ones (broadcast over NVLink with
+ *             256-byte stores) — together with up to two payload columns
+ *   join_sum  per-partition build + probe + SUM on this GPU's buffers
+ * 32-bit keys only (all keys < 2^32); row ids are rid_base + position.
+ * b200_ipc_* wrap cudaIpcGetMemHandle / OpenMemHandle for buffers obtained from
+ * b200_device_malloc. */
+int   b200_ipc_export(const void *device_ptr, unsigned char *out_handle64);
+void *b200_ipc_import(const unsigned char *handle64);
+int   b200_ipc_close(void *imported_ptr);
+int   b200_radix_bits_for(uint64_t n_build);
+int   b200_stage_hist(const uint64_t *d_keys, uint64_t n, int radix_bits,
+                      uint32_t *d_hist);
+int   b200_stage_scatter_build(const uint64_t *d_keys, uint64_t n,
+                               uint32_t rid_base, int radix_bits,
+                               const uint32_t *d_hist_local,
+                               const uint32_t *d_dst_start, int ndst,
+                               void *const *tup_dst, int npay,
+                               const uint64_t *const *pay_cols,
+                               uint64_t *const *pay_dst);
+int   b200_stage_scatter_probe(const uint64_t *d_keys, uint64_t n,
+                               int radix_bits, uint32_t *d_cursor,
+                               void *d_tup_out);
+int   b200_stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b,
+                          const void *d_tup_p, const uint32_t *d_hist_p,
+                          int radix_bits, int n_proj,
+                          const uint64_t *const *proj_cols,
+                          const int *proj_side,
+                          const uint64_t *const *proj_part_vals,
+                          uint64_t *out_sums, uint64_t *out_matches);
+
 /* Per-kernel device times of the calling thread's last RadixHashJoin /
  * b200_join_sum, measured with CUDA events on its stream when profiling is
  * enabled with b200_set_profiling(1).  Names: "hist", "scan", "scatter_r",

@@ -9,5 +9,5 @@ There is no CPU fallback: importing `host` without the built library raises.
 The directory name contains a dash, so load it with
 `importlib` (see `tests/conftest.py`: it is registered as `sigmod2018_b200`).
 """
-from . import host  # noqa: F401
+from . import host, sharding  # noqa: F401
 from .host import *  # noqa: F401,F403

@@ -4,6 +4,7 @@
 #include "../../include/b200_join.h"
 #include "engine.cuh"
 
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -290,6 +291,86 @@ int b200_join_sum(const uint64_t *keys_r, uint64_t n_r, const uint64_t *keys_s, 
     for (int k = 0; k < n_proj; ++k) out_sums[k] = j.sums[k];
     *out_matches = j.m;
     return 0;
+}
+
+// ---- staged join + CUDA IPC (multi-GPU, one process per GPU) ---------------
+int b200_ipc_export(const void *device_ptr, unsigned char *out_handle64) {
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, const_cast<void *>(device_ptr)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail("cudaIpcGetMemHandle failed (the buffer must come from b200_device_malloc)");
+    }
+    static_assert(sizeof(h) == 64, "IPC handle size");
+    memcpy(out_handle64, &h, 64);
+    return 0;
+}
+
+void *b200_ipc_import(const unsigned char *handle64) {
+    ensure_init();
+    (void)ctx();
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        set_last_error("cudaIpcOpenMemHandle failed (no peer access between the two GPUs?)");
+        return nullptr;
+    }
+    return p;
+}
+
+int b200_ipc_close(void *imported_ptr) {
+    return cudaIpcCloseMemHandle(imported_ptr) == cudaSuccess ? 0 : fail("cudaIpcCloseMemHandle failed");
+}
+
+int b200_stage_hist(const uint64_t *d_keys, uint64_t n, int radix_bits, uint32_t *d_hist) {
+    if (n > kMaxRows) return fail("more than 2^32-1 rows");
+    stage_hist(d_keys, n, radix_bits, d_hist);
+    return 0;
+}
+
+int b200_stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int radix_bits,
+                             const uint32_t *d_hist_local, const uint32_t *d_dst_start, int ndst,
+                             void *const *tup_dst, int npay, const uint64_t *const *pay_cols,
+                             uint64_t *const *pay_dst) {
+    if (n > kMaxRows) return fail("more than 2^32-1 rows");
+    if (ndst < 1 || ndst > 8 || npay < 0 || npay > 2) return fail("ndst must be 1..8 and npay 0..2");
+    stage_scatter_build(d_keys, n, rid_base, radix_bits, d_hist_local, d_dst_start, ndst, tup_dst, npay, pay_cols,
+                        pay_dst);
+    return 0;
+}
+
+int b200_stage_scatter_probe(const uint64_t *d_keys, uint64_t n, int radix_bits, uint32_t *d_cursor, void *d_tup_out) {
+    if (n > kMaxRows) return fail("more than 2^32-1 rows");
+    stage_scatter_probe(d_keys, n, radix_bits, d_cursor, d_tup_out);
+    return 0;
+}
+
+int b200_stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p, const uint32_t *d_hist_p,
+                        int radix_bits, int n_proj, const uint64_t *const *proj_cols, const int *proj_side,
+                        const uint64_t *const *proj_part_vals, uint64_t *out_sums, uint64_t *out_matches) {
+    if (n_proj < 0 || n_proj > kMaxProj) return fail("at most 8 fused projections");
+    ProjDesc pd[kMaxProj];
+    for (int k = 0; k < n_proj; ++k)
+        pd[k] = ProjDesc{proj_cols[k], nullptr, proj_side[k], proj_part_vals ? proj_part_vals[k] : nullptr};
+    JoinResult j = stage_join_sum(d_tup_b, d_hist_b, d_tup_p, d_hist_p, radix_bits, n_proj, pd);
+    for (int k = 0; k < n_proj; ++k) out_sums[k] = j.sums[k];
+    *out_matches = j.m;
+    return 0;
+}
+
+int b200_radix_bits_for(uint64_t n_build) {
+    // the library's automatic choice for a 32-bit-key build side of n_build rows
+    const Tuning  &t    = tuning();
+    const uint32_t L    = 14;
+    int            bits = 2;
+    (void)L;
+    auto fits = [&](int b) {
+        const double mean = (double)n_build / (double)(1ull << b);
+        return mean + 5.0 * sqrt(mean) <= (double)t.cap32;
+    };
+    while (bits < t.max_bits && !fits(bits)) ++bits;
+    return bits;
 }
 
 }  // extern "C"

@@ -329,7 +329,9 @@ static void launch_scatter_pay_n(const KeySrc &src, int bits, uint32_t *cursor, 
 }
 template <typename KeyT>
 static void launch_scatter_pay(const KeySrc &src, int bits, uint32_t *cursor, void *out, const PayArgs &pay, int npay) {
-    if (npay == 1)
+    if (npay == 0)
+        launch_scatter_pay_n<KeyT, 0>(src, bits, cursor, out, pay);
+    else if (npay == 1)
         launch_scatter_pay_n<KeyT, 1>(src, bits, cursor, out, pay);
     else
         launch_scatter_pay_n<KeyT, 2>(src, bits, cursor, out, pay);
@@ -764,6 +766,131 @@ void unpack_partition(const PartitionOut &p, uint64_t n, uint64_t *d_keys, uint6
         unpack_tuples_kernel<Tup32><<<grid_for(n, 256 * 4, 8), 256, 0, ctx().stream>>>(p.tuples->as<Tup32>(), n,
                                                                                        d_keys, d_rids);
     B200_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------
+// staged join on caller-owned device buffers (32-bit keys): the multi-GPU plans
+// of sharding.py call the phases separately so that the exchange can sit
+// between them.  Every phase runs on the calling thread's stream.
+// ---------------------------------------------------------------------------
+void stage_hist(const uint64_t *d_keys, uint64_t n, int bits, uint32_t *d_hist) {
+    Context &c = ctx();
+    B200_REQUIRE(bits >= 2 && bits <= tuning().max_bits, "radix bits out of range");
+    B200_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) << bits, c.stream));
+    if (n == 0) return;
+    KeySrc src{d_keys, nullptr, (uint32_t)n};
+    TimedScope ts("hist");
+    launch_hist<uint32_t>(src, bits, d_hist);
+}
+
+void stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int bits, const uint32_t *d_hist_local,
+                         const uint32_t *d_dst_start, int ndst, void *const *tup_dst, int npay,
+                         const uint64_t *const *pay_cols, uint64_t *const *pay_dst) {
+    B200_REQUIRE(ndst >= 1 && ndst <= kMaxPeers && npay >= 0 && npay <= 2, "bad destination / payload count");
+    if (n == 0) return;
+    Context       &c      = ctx();
+    const uint32_t nparts = 1u << bits;
+    // 1. partition the local shard into a staging buffer (local offsets from the local histogram)
+    DevBufPtr ctrl = dev_alloc(5 * (size_t)(nparts + 1) * sizeof(uint32_t));
+    uint32_t *off_l = ctrl->as<uint32_t>(), *off_x = off_l + nparts + 1, *cur_l = off_x + nparts + 1,
+             *cur_x = cur_l + nparts + 1, *items = cur_x + nparts + 1;
+    partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_local, d_hist_local, nparts, 1u, 1u, off_l, off_x,
+                                                          cur_l, cur_x, items);
+    B200_LAUNCH_CHECK();
+    DevBufPtr stage_tup = dev_alloc(n * sizeof(Tup32));
+    DevBufPtr stage_pay[2];
+    PayArgs   pay{};
+    pay.ndst     = 0;
+    pay.rid_base = rid_base;
+    for (int k = 0; k < npay; ++k) {
+        stage_pay[k] = dev_alloc(n * sizeof(uint64_t));
+        pay.col[k]   = pay_cols[k];
+        pay.ids[k]   = nullptr;
+        pay.out[k]   = stage_pay[k]->as<uint64_t>();
+    }
+    KeySrc src{d_keys, nullptr, (uint32_t)n};
+    {
+        TimedScope ts("scatter_b");
+        launch_scatter_pay<uint32_t>(src, bits, cur_l, stage_tup->ptr, pay, npay);
+    }
+    // 2. copy every partition segment to its place in the global layout of all destinations
+    SegCopyArgs s{};
+    s.src_tup   = stage_tup->as<uint64_t>();
+    s.src_off   = off_l;
+    s.dst_start = d_dst_start;
+    s.ndst      = ndst;
+    s.npay      = npay;
+    for (int d = 0; d < ndst; ++d) s.dst_tup[d] = static_cast<uint64_t *>(tup_dst[d]);
+    for (int k = 0; k < npay; ++k) {
+        s.src_pay[k] = stage_pay[k]->as<uint64_t>();
+        for (int d = 0; d < ndst; ++d) s.dst_pay[k][d] = pay_dst[k * ndst + d];
+    }
+    {
+        TimedScope ts("broadcast");
+        segment_broadcast_kernel<<<nparts, 256, 0, c.stream>>>(s);
+        B200_LAUNCH_CHECK();
+    }
+}
+
+void stage_scatter_probe(const uint64_t *d_keys, uint64_t n, int bits, uint32_t *d_cursor, void *d_tup_out) {
+    if (n == 0) return;
+    KeySrc src{d_keys, nullptr, (uint32_t)n};
+    TimedScope ts("scatter_p");
+    launch_scatter<uint32_t>(src, bits, d_cursor, d_tup_out);
+}
+
+JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p, const uint32_t *d_hist_p,
+                          int bits, int nproj, const ProjDesc *proj) {
+    Context   &c = ctx();
+    Tuning    &t = tuning();
+    JoinResult res;
+    B200_REQUIRE(nproj >= 0 && nproj <= kMaxProj, "too many fused projections");
+    const uint32_t nparts = 1u << bits;
+    const uint32_t cap    = t.cap32;
+    JoinArgs a;
+    memset(&a, 0, sizeof(a));
+    a.cap        = cap;
+    a.slots_log2 = tag_slots_log2_for(cap);
+    a.radix_bits = (uint32_t)bits;
+    a.slice      = t.slice;
+    B200_REQUIRE(bits + (int)a.slots_log2 >= 16, "radix bits too small for the tag table");
+    DevBufPtr ctrl = dev_alloc((64 + 5 * (size_t)(nparts + 1)) * sizeof(uint32_t) + 64 * sizeof(unsigned long long));
+    B200_CUDA(cudaMemsetAsync(ctrl->ptr, 0, ctrl->bytes, c.stream));
+    unsigned long long *d_u64 = ctrl->as<unsigned long long>();
+    uint32_t           *d_u32 = reinterpret_cast<uint32_t *>(d_u64 + 64);
+    uint32_t *off_b = d_u32 + 64, *off_p = off_b + nparts + 1, *cur_b = off_p + nparts + 1,
+             *cur_p = cur_b + nparts + 1, *items = cur_p + nparts + 1;
+    a.work_counter = d_u32;
+    a.total        = d_u64;
+    a.out_cursor   = d_u64 + 1;
+    a.sums         = d_u64 + 8;
+    {
+        TimedScope ts("scan");
+        partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_b, d_hist_p, nparts, cap, a.slice, off_b, off_p,
+                                                              cur_b, cur_p, items);
+        B200_LAUNCH_CHECK();
+    }
+    a.tup_b      = d_tup_b;
+    a.tup_p      = d_tup_p;
+    a.off_b      = off_b;
+    a.off_p      = off_p;
+    a.item_start = items;
+    a.nparts     = nparts;
+    a.nproj      = nproj;
+    a.need_brid  = 0;
+    for (int k = 0; k < nproj; ++k) {
+        a.proj[k] = proj[k];
+        if (a.proj[k].side == 0 && !a.proj[k].part_vals) a.need_brid = 1;
+    }
+    {
+        TimedScope ts("join");
+        launch_join(a, false, false, MODE_SUM);
+    }
+    B200_CUDA(cudaMemcpyAsync(c.h_scratch, d_u64, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+    B200_CUDA(cudaStreamSynchronize(c.stream));
+    res.m = c.h_scratch[0];
+    for (int k = 0; k < nproj; ++k) res.sums[k] = c.h_scratch[8 + k];
+    return res;
 }
 
 }  // namespace b200

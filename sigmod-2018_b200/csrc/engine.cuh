@@ -88,6 +88,16 @@ void widen_ids(const uint32_t *d_in, uint64_t n, uint64_t *d_out);
 void narrow_ids(const uint64_t *d_in, uint64_t n, uint32_t *d_out);
 void unpack_partition(const PartitionOut &p, uint64_t n, uint64_t *d_keys, uint64_t *d_rids);
 
+// staged join on caller-owned device buffers (multi-GPU plans), 32-bit keys
+void       stage_hist(const uint64_t *d_keys, uint64_t n, int bits, uint32_t *d_hist);
+void       stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int bits,
+                               const uint32_t *d_hist_local, const uint32_t *d_dst_start, int ndst,
+                               void *const *tup_dst, int npay, const uint64_t *const *pay_cols,
+                               uint64_t *const *pay_dst);
+void       stage_scatter_probe(const uint64_t *d_keys, uint64_t n, int bits, uint32_t *d_cursor, void *d_tup_out);
+JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p,
+                          const uint32_t *d_hist_p, int bits, int nproj, const ProjDesc *proj);
+
 // runtime control (engine.cu)
 void               request_device(int device);   // before the first use
 int                device_index();

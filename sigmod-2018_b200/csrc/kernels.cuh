@@ -371,10 +371,19 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
 // random 8-byte gathers run at ~40 G/s whatever their L2 fetch size).  The build
 // side is the small relation, so this kernel is the plain variant of
 // radix_scatter_kernel: no prefetch, no predicate-free instance.
+constexpr int kMaxPeers = 8;
 struct PayArgs {
     const uint64_t *col[2];
     const uint32_t *ids[2];
     uint64_t       *out[2];
+    // multi-GPU broadcast-scatter: when ndst > 0 every tuple (and payload) is
+    // stored into ndst destination buffers with the same layout — this GPU's
+    // own and its peers' (CUDA IPC mappings, written over NVLink) — instead of
+    // `out`; row ids are rid_base + position so they stay global
+    int       ndst;
+    uint32_t  rid_base;
+    void     *tup_dst[kMaxPeers];
+    uint64_t *pay_dst[2][kMaxPeers];
 };
 template <int NT, int U, typename KeyT, int NPAY>
 __global__ void __launch_bounds__(NT)
@@ -434,7 +443,7 @@ radix_scatter_pay_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__
                 const uint32_t pos = loc[(uint32_t)keys[j] & mask] + rank[j];
                 TupT           t;
                 t.key = keys[j];
-                t.rid = rid;
+                t.rid = pay.rid_base + rid;
                 if constexpr (sizeof(KeyT) == 8) t.pad = 0;
                 stage[pos] = t;
 #pragma unroll
@@ -446,11 +455,47 @@ radix_scatter_pay_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__
         for (uint32_t i = threadIdx.x; i < count; i += NT) {
             const TupT     t = stage[i];
             const uint32_t o = gdelta[(uint32_t)t.key & mask] + i;
-            out[o]           = t;
+            if (pay.ndst == 0) {
+                out[o] = t;
 #pragma unroll
-            for (int k = 0; k < NPAY; ++k) pay.out[k][o] = pstage[(size_t)k * TILE + i];
+                for (int k = 0; k < NPAY; ++k) pay.out[k][o] = pstage[(size_t)k * TILE + i];
+            } else {
+                for (int d = 0; d < pay.ndst; ++d) {
+                    static_cast<TupT *>(pay.tup_dst[d])[o] = t;
+#pragma unroll
+                    for (int k = 0; k < NPAY; ++k) pay.pay_dst[k][d][o] = pstage[(size_t)k * TILE + i];
+                }
+            }
         }
         __syncthreads();
+    }
+}
+
+// Multi-GPU broadcast of a locally partitioned build shard: CTA p
+// copies this GPU's segment of partition p (tuples and up to two payload
+// columns) to its place inside the GLOBAL partition layout of every
+// destination buffer — this GPU's own and the peers' CUDA-IPC mappings.  The
+// stores of a warp are 256 contiguous bytes, so they travel over NVLink as
+// full packets (scattering 8-byte tuples straight into peer memory measured
+// 134 GB/s).
+struct SegCopyArgs {
+    const uint64_t *src_tup;       // 8-byte tuples {key32, rid32}
+    const uint64_t *src_pay[2];
+    const uint32_t *src_off;       // [nparts + 1] local partition offsets
+    const uint32_t *dst_start;     // [nparts] start of this GPU's segment in the global layout
+    int             ndst, npay;
+    uint64_t       *dst_tup[kMaxPeers];
+    uint64_t       *dst_pay[2][kMaxPeers];
+};
+__global__ void __launch_bounds__(256) segment_broadcast_kernel(const SegCopyArgs s) {
+    const uint32_t p     = blockIdx.x;
+    const uint32_t first = s.src_off[p];
+    const uint32_t count = s.src_off[p + 1] - first;
+    const uint32_t dst   = s.dst_start[p];
+    for (int d = 0; d < s.ndst; ++d) {
+        for (uint32_t i = threadIdx.x; i < count; i += 256) s.dst_tup[d][dst + i] = s.src_tup[first + i];
+        for (int k = 0; k < s.npay; ++k)
+            for (uint32_t i = threadIdx.x; i < count; i += 256) s.dst_pay[k][d][dst + i] = s.src_pay[k][first + i];
     }
 }
 

@@ -1,0 +1,185 @@
+"""Host-side multi-GPU plan of the join, one process per GPU.
+
+Broadcast plan (small build side): every relation starts position-sharded;
+the build side's columns are all-gathered, every rank joins the full build
+side with its probe shard, and the k u64 checksums plus the match count are
+all-reduced.  u64 sums mod 2^64 are reduced as wrapping int64 sums (NCCL and
+gloo have no uint64 SUM).  Works on any torch.distributed backend; the CPU
+tests run it under gloo with the oracle as the local join.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
+    """[first, first + count) of `n` rows for `rank`; the last rank takes the remainder."""
+    per = n // world
+    first = rank * per
+    count = per if rank < world - 1 else n - first
+    return first, count
+
+
+def u64_to_i64(values) -> list[int]:
+    return [int(np.uint64(v).astype(np.int64)) for v in values]
+
+
+def i64_to_u64(values) -> list[int]:
+    return [int(np.int64(v).astype(np.uint64)) for v in values]
+
+
+def allreduce_checksums(sums, matches, dist=None, device=None):
+    """Sum the per-rank checksums (mod 2^64) and match counts over all ranks."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return [int(s) % (1 << 64) for s in sums], int(matches)
+    import torch
+    t = torch.tensor(u64_to_i64(sums) + [int(matches)], dtype=torch.int64, device=device)
+    dist.all_reduce(t)
+    out = i64_to_u64(t.cpu().tolist())
+    return out[:-1], out[-1]
+
+
+def allgather_column(shard, total_rows: int, dist, out=None):
+    """All-gather a position-sharded int64 column (shard_bounds: the last rank may be longer)."""
+    import torch
+    world = dist.get_world_size()
+    per = total_rows // world
+    if per * world == total_rows:
+        if out is None:
+            out = torch.empty(total_rows, dtype=shard.dtype, device=shard.device)
+        dist.all_gather_into_tensor(out, shard)
+        return out
+    # ragged: pad every shard to the longest one, gather, trim
+    longest = total_rows - per * (world - 1)
+    padded = torch.zeros(longest, dtype=shard.dtype, device=shard.device)
+    padded[: shard.numel()] = shard
+    buf = torch.empty(world * longest, dtype=shard.dtype, device=shard.device)
+    dist.all_gather_into_tensor(buf, padded)
+    parts = [buf[r * longest: r * longest + (per if r < world - 1 else longest)] for r in range(world)]
+    return torch.cat(parts)
+
+
+class BroadcastScatterJoin:
+    """Config-2-shaped join over `world` GPUs, one process each (broadcast plan).
+
+    Relations start position-sharded.  Per step and rank:
+      1. histogram of the local build shard and of the local probe shard (radix_hist_kernel);
+      2. the build histograms are all-gathered (a few KB, NCCL) and turned into this rank's
+         scatter cursors inside the GLOBAL partition layout (tiny torch ops on the device);
+      3. the build shard is partitioned ONCE, locally, and every partition segment is copied to
+         its place in the global partition layout of every rank's build buffer — peer buffers are
+         CUDA-IPC mappings, the copy kernel's 256-byte stores travel over NVLink (no all-gather of
+         raw columns, no second partition pass on the receivers); up to two build-side SUM
+         columns travel with the tuples (early materialisation);
+      4. the probe shard is scattered locally; a stream-ordered all-reduce is the barrier that
+         tells every rank the peers' stores have landed;
+      5. per-partition build + probe + SUM on local buffers, then the k checksums and the match
+         count are all-reduced.
+    The probe side never moves.  `dist` may be None (world = 1: the same phases, no exchange),
+    which is how the single-GPU test drives the staged C-ABI.
+    """
+
+    def __init__(self, b200, torch, dist, rank, world, n_build_total, n_build_local, n_probe_local, n_pay, device):
+        import ctypes as C
+        self.b, self.torch, self.dist, self.rank, self.world = b200, torch, dist, rank, world
+        self.C = C
+        L = b200.lib()
+        self.L = L
+        self.n_build_total, self.n_build_local, self.n_probe_local = n_build_total, n_build_local, n_probe_local
+        self.n_pay = n_pay
+        self.bits = int(L.b200_radix_bits_for(n_build_total))
+        self.P = 1 << self.bits
+        self.device = device
+        # build-partition buffers live in cudaMalloc memory so they can be exported over CUDA IPC
+        self.tup_b = b200.DeviceColumn(max(n_build_total, 1))
+        self.pay_b = [b200.DeviceColumn(max(n_build_total, 1)) for _ in range(n_pay)]
+        self.tup_p = b200.DeviceColumn(max(n_probe_local, 1))
+        self.hist = torch.zeros((2, self.P), dtype=torch.int32, device=device)      # [build, probe] local
+        self.hist_all = torch.zeros((world, self.P), dtype=torch.int32, device=device)
+        self.token = torch.zeros(1, dtype=torch.int32, device=device)
+        self.peer_tup = [self.tup_b.ptr] * 1
+        self.peer_pay = [[p.ptr] for p in self.pay_b]
+        self._imported = []
+        if world > 1:
+            handles = [self._export(self.tup_b.ptr)] + [self._export(p.ptr) for p in self.pay_b]
+            gathered = [None] * world
+            dist.all_gather_object(gathered, handles)
+            self.peer_tup, self.peer_pay = [], [[] for _ in range(n_pay)]
+            for r in range(world):
+                if r == rank:
+                    self.peer_tup.append(self.tup_b.ptr)
+                    for k in range(n_pay):
+                        self.peer_pay[k].append(self.pay_b[k].ptr)
+                else:
+                    self.peer_tup.append(self._import(gathered[r][0]))
+                    for k in range(n_pay):
+                        self.peer_pay[k].append(self._import(gathered[r][1 + k]))
+
+    def _export(self, ptr):
+        buf = self.C.create_string_buffer(64)
+        if self.L.b200_ipc_export(ptr, buf) != 0:
+            raise RuntimeError("b200_ipc_export failed")
+        return bytes(buf.raw)
+
+    def _import(self, handle):
+        p = self.L.b200_ipc_import(handle)
+        if not p:
+            raise RuntimeError("b200_ipc_import failed: " + (self.L.b200_last_error() or b"").decode())
+        self._imported.append(p)
+        return p
+
+    def step(self, build_keys_ptr, build_pay_ptrs, probe_keys_ptr, proj_cols, proj_side):
+        """proj_cols[k]: device pointer of projection k — for a build-side projection (side 0) it must be
+        one of build_pay_ptrs (it is read through the early-materialised copy); a probe-side projection
+        (side 1) is this rank's local column, indexed by the local probe row id."""
+        C, L, torch = self.C, self.L, self.torch
+        P, bits, world, rank = self.P, self.bits, self.world, self.rank
+        h_b, h_p = self.hist[0], self.hist[1]
+        assert L.b200_stage_hist(build_keys_ptr, self.n_build_local, bits, h_b.data_ptr()) == 0
+        assert L.b200_stage_hist(probe_keys_ptr, self.n_probe_local, bits, h_p.data_ptr()) == 0
+        if world > 1:
+            self.dist.all_gather_into_tensor(self.hist_all.view(-1), h_b)
+            total_b = self.hist_all.sum(0, dtype=torch.int32)
+            before_me = self.hist_all[:rank].sum(0, dtype=torch.int32) if rank else torch.zeros_like(total_b)
+        else:
+            total_b, before_me = h_b.clone(), torch.zeros_like(h_b)
+        start_b = torch.cumsum(total_b, 0, dtype=torch.int32) - total_b          # partition starts, global layout
+        cur_b = (start_b + before_me).contiguous()
+        cur_p = (torch.cumsum(h_p, 0, dtype=torch.int32) - h_p).contiguous()
+        ndst = len(self.peer_tup)
+        tup_dst = (C.c_void_p * ndst)(*self.peer_tup)
+        npay = self.n_pay
+        pay_cols = (C.c_void_p * max(npay, 1))(*build_pay_ptrs[:npay])
+        flat = [self.peer_pay[k][d] for k in range(npay) for d in range(ndst)]
+        pay_dst = (C.c_void_p * max(len(flat), 1))(*flat)
+        assert L.b200_stage_scatter_build(build_keys_ptr, self.n_build_local, rank * self.n_build_local, bits,
+                                          h_b.data_ptr(), cur_b.data_ptr(), ndst, tup_dst, npay, pay_cols,
+                                          pay_dst) == 0
+        assert L.b200_stage_scatter_probe(probe_keys_ptr, self.n_probe_local, bits, cur_p.data_ptr(),
+                                          self.tup_p.ptr) == 0
+        if world > 1:
+            self.dist.all_reduce(self.token)      # stream-ordered barrier: every peer's scatter has completed
+        k = len(proj_cols)
+        cols = (C.c_void_p * max(k, 1))(*proj_cols)
+        sides = (C.c_int * max(k, 1))(*proj_side)
+        part = []
+        for col, side in zip(proj_cols, proj_side):
+            if side == 0:
+                part.append(self.pay_b[build_pay_ptrs.index(col)].ptr)
+            else:
+                part.append(None)
+        part_vals = (C.c_void_p * max(k, 1))(*part)
+        sums = (C.c_uint64 * max(k, 1))()
+        m = C.c_uint64(0)
+        total_b = total_b.contiguous()
+        assert L.b200_stage_join_sum(self.tup_b.ptr, total_b.data_ptr(), self.tup_p.ptr, h_p.data_ptr(), bits, k, cols,
+                                     sides, part_vals, sums, C.byref(m)) == 0
+        # the all-reduce of the checksums also ends the step on every rank: no peer can start
+        # overwriting this rank's build buffers before its join has finished
+        return allreduce_checksums([int(s) for s in sums[:k]], int(m.value), self.dist if world > 1 else None,
+                                   self.device)
+
+    def close(self):
+        for p in self._imported:
+            self.L.b200_ipc_close(p)
+        self._imported = []

@@ -151,3 +151,59 @@ def test_join_sum_config2_shape_scaled_down(gpu, orc, kr_bits, ks_bits):
     want, m = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
     got, gm = gpu.join_sum(kr, ks, [pr, ps], [0, 1])
     assert m == gm == nr and got == want
+
+
+# ---- staged join (the phases the multi-GPU plan drives), single GPU ----------
+@pytest.mark.parametrize("kr_bits,ks_bits", [(15, 18), (18, 21)])
+def test_staged_join_matches_fused_join(gpu, orc, kr_bits, ks_bits):
+    """sharding.BroadcastScatterJoin with world = 1: hist -> cursors -> scatter (build side with an
+    early-materialised payload, through the multi-destination path) -> join_sum, against the oracle."""
+    torch = pytest.importorskip("torch")
+    nr, ns = 1 << kr_bits, 1 << ks_bits
+    kr = orc.synth_column(nr, 0, kr_bits, gpu.SEED_R)
+    ks = orc.synth_column(ns, 0, ks_bits, gpu.SEED_S)
+    pr = orc.synth_column(nr, 1, 0, gpu.SEED_R + 1)
+    ps = orc.synth_column(ns, 1, 0, gpu.SEED_S + 1)
+    want, wm = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
+    dev = torch.device("cuda:0")
+    gpu.lib().b200_set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        t = {n: torch.from_numpy(a.view(np.int64).copy()).to(dev) for n, a in
+             [("kr", kr), ("ks", ks), ("pr", pr), ("ps", ps)]}
+        plan = gpu.sharding.BroadcastScatterJoin(gpu, torch, None, 0, 1, nr, nr, ns, 1, dev)
+        for _ in range(2):     # buffers are reused across steps
+            got, m = plan.step(t["kr"].data_ptr(), [t["pr"].data_ptr()], t["ks"].data_ptr(),
+                               [t["pr"].data_ptr(), t["ps"].data_ptr()], [0, 1])
+            assert m == wm and got == want
+        plan.close()
+    finally:
+        torch.cuda.synchronize()   # the library keeps using torch's (default) stream afterwards
+
+
+# ---- BASELINE config 4 shape (scaled down): Zipf(theta = 1) probe keys over a unique build side ----
+@pytest.mark.parametrize("kr_bits,ns", [(12, 200_000), (17, 3_000_000)])
+def test_join_sum_zipf_probe_side(gpu, orc, kr_bits, ns):
+    nr = 1 << kr_bits
+    kr = orc.synth_column(nr, 0, kr_bits, gpu.SEED_R)            # every key of [0, 2^k) once
+    ks = orc.synth_column(ns, 2, kr_bits, 99)                     # hottest key ~ 1/(k+1) of all probes
+    pr = orc.synth_column(nr, 1, 0, 5)
+    ps = orc.synth_column(ns, 1, 0, 6)
+    want, wm = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
+    assert wm == ns                                               # every probe matches exactly once
+    got, m = gpu.join_sum(kr, ks, [pr, ps], [0, 1])
+    assert m == wm and got == want
+    got, m = gpu.join_sum(ks, kr, [ps, pr], [0, 1])               # skewed side first: it becomes the probe side anyway
+    assert m == wm and got == [want[1], want[0]]
+
+
+def test_join_skewed_build_side_duplicates(gpu, orc):
+    """Zipf keys on BOTH sides: long duplicate chains in the tables and many matches per probe."""
+    kr = orc.synth_column(60_000, 2, 10, 1)
+    ks = orc.synth_column(80_000, 2, 10, 2)
+    pr, ps = orc.synth_column(60_000, 1, 0, 3), orc.synth_column(80_000, 1, 0, 4)
+    want, wm = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
+    got, m = gpu.join_sum(kr, ks, [pr, ps], [0, 1])
+    assert m == wm and got == want
+    r, s, mp = gpu.hash_join_pairs(kr[:20000], ks[:20000])
+    o_r, o_s = orc.radix_hash_join(kr[:20000], ks[:20000], 4)
+    assert mp == len(o_r) and orc.checksum(pr, r) == orc.checksum(pr, o_r) and orc.checksum(ps, s) == orc.checksum(ps, o_s)

@@ -118,3 +118,50 @@ def test_small_workload_through_the_contest_harness():
                          text=True, cwd=small, timeout=600)
     assert out.returncode == 0, (out.stdout + out.stderr)[-2000:]
     assert int(out.stdout.strip().split()[-1]) >= 0     # elapsed ms
+
+
+# ---- BASELINE config 3 (scaled down): 4-way chain join, range/equality filters on the fact
+# relation, 3-column SUM projection — the reference itself (oracle/_ref/ref_driver), the link-time
+# drop-in (the reference's query.o/best_tree.o over libb200join.so) and the operator API must print
+# the same line.  All filters sit on binding 0, constants < 2^31 (quirk 5).
+CONFIG3_QUERY = "0 1 2 3|0.1=1.0&1.1=2.0&2.1=3.0&0.3>2499&0.3<7500&0.4=1|0.2 1.2 3.1"
+CONFIG3_SPECS = [
+    "synth:{f}:iota,uni{d1}@11,pay@12,uni10000@13,uni4@14",       # F: pk, fk->D1, measure, filter cols
+    "synth:{d1}:iota,uni{d2}@21,pay@22",                           # D1: pk, fk->D2, payload
+    "synth:{d2}:iota,uni{d3}@31,pay@32",                           # D2
+    "synth:{d3}:iota,pay@41",                                      # D3
+]
+
+
+def _config3_relations(orc, f, d1, d2, d3):
+    iota = lambda n: np.arange(n, dtype=np.uint64)
+    uni = lambda n, mod, seed: orc.synth_column(n, 3, mod, seed)
+    pay = lambda n, seed: orc.synth_column(n, 1, 0, seed)
+    return [[iota(f), uni(f, d1, 11), pay(f, 12), uni(f, 10000, 13), uni(f, 4, 14)],
+            [iota(d1), uni(d1, d2, 21), pay(d1, 22)],
+            [iota(d2), uni(d2, d3, 31), pay(d2, 32)],
+            [iota(d3), pay(d3, 41)]]
+
+
+@pytest.mark.parametrize("f,d1,d2,d3", [(200_000, 1 << 14, 1 << 10, 1 << 6), (3_000_000, 1 << 18, 1 << 14, 1 << 10)])
+def test_config3_chain_join_matches_the_reference(gpu, orc, f, d1, d2, d3):
+    ref_driver = ROOT / "oracle" / "_ref" / "ref_driver"
+    if not ref_driver.exists():
+        pytest.skip("oracle/_ref/ref_driver not built")
+    specs = [s.format(f=f, d1=d1, d2=d2, d3=d3) for s in CONFIG3_SPECS]
+    want = subprocess.run([str(ref_driver), "-t", "8", *specs, "--", CONFIG3_QUERY], capture_output=True, text=True,
+                          timeout=600)
+    assert want.returncode == 0, want.stderr[-1000:]
+    want_line = want.stdout.splitlines()[0]
+    assert "NULL" not in want_line
+    # operator API (textual join order)
+    rels = _config3_relations(orc, f, d1, d2, d3)
+    rm = gpu.RelationMapArray(rels)
+    assert gpu.execute_query(CONFIG3_QUERY, rm).line() == want_line
+    # the reference's own ExecuteQuery + JoinEnum over the CUDA operators
+    drop = ROOT / "oracle" / "_ref" / "b200_driver"
+    if drop.exists():
+        got = subprocess.run([str(drop), "-t", "1", *specs, "--", CONFIG3_QUERY], capture_output=True, text=True,
+                             timeout=600)
+        assert got.returncode == 0, got.stderr[-1000:]
+        assert got.stdout.splitlines()[0] == want_line
