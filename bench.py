@@ -260,12 +260,12 @@ def run_b200_arm(args):
         dist.all_reduce(want)
     want = [int(x) for x in want.cpu().numpy().view(np.uint64)]
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # nvidia-smi needs a moment to start: it samples warm-up and timed steps
     for _ in range(args.warmup):
         sums, m = step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     b200.kernel_launches(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -291,7 +291,7 @@ def run_b200_arm(args):
     for _ in range(9):
         step()
         torch.cuda.synchronize()
-        for name in ("hist", "scan", "scatter_b", "broadcast", "scatter_p", "join"):
+        for name in ("hist", "hist_b", "hist_p", "scan", "scatter_b", "broadcast", "scatter_p", "join"):
             v = b200.last_kernel_ms(name)
             if v >= 0:
                 per_kernel.setdefault(name, []).append(v)
@@ -354,7 +354,8 @@ def run_b200_arm(args):
     # canonical widths: key 8 B, partition tuple 16 B; encoded: the 8-B packed tuple used for keys < 2^32
     n_p, n_b = ns_loc, nr
     kernel_bytes = {
-        "hist": (8 * (n_p + n_b), 8 * (n_p + n_b)),
+        "hist_p": (8 * n_p, 8 * n_p),
+        "hist_b": (8 * n_b, 8 * n_b),
         "scatter_p": ((8 + 16) * n_p, (8 + 8) * n_p),
         "scatter_b": ((8 + 16) * n_b, (8 + 8) * n_b),
         "join": (16 * (n_p + n_b) + 16 * nr // world, 8 * (n_p + n_b) + 16 * nr // world),

@@ -245,8 +245,8 @@ int   b200_stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b,
 
 /* Per-kernel device times of the calling thread's last RadixHashJoin /
  * b200_join_sum, measured with CUDA events on its stream when profiling is
- * enabled with b200_set_profiling(1).  Names: "hist", "scan", "scatter_r",
- * "scatter_s", "join".  Returns milliseconds, or a negative value if the
+ * enabled with b200_set_profiling(1).  Names: "hist_b", "hist_p", "scan",
+ * "scatter_b", "scatter_p", "join" (b = build side, p = probe side).  Returns milliseconds, or a negative value if the
  * kernel did not run. */
 int    b200_set_profiling(int on);
 double b200_last_kernel_ms(const char *name);

@@ -30,6 +30,6 @@ for name, (proj, sides) in variants.items():
     times = {}
     for _ in range(6):
         sums, m = b200.join_sum_device(r0.ptr, nr, s0.ptr, ns, proj, sides, ns - 1)
-        for k in ("hist", "scan", "scatter_b", "scatter_p", "join"):
+        for k in ("hist_b", "hist_p", "scan", "scatter_b", "scatter_p", "join"):
             times.setdefault(k, []).append(b200.last_kernel_ms(k))
     print(f"{name:16s} m={m} " + " ".join(f"{k}={statistics.median(v[1:]):.3f}" for k, v in times.items()))

@@ -66,6 +66,7 @@ static void init_device(int device) {
     if (const char *v = getenv("B200_DEBUG")) t.debug = atoi(v);
     if (const char *v = getenv("B200_SCATTER_CFG")) t.scatter_cfg = atoi(v);
     if (const char *v = getenv("B200_EARLY_MAT")) t.early_mat = atoi(v);
+    if (const char *v = getenv("B200_OVERLAP")) t.overlap = atoi(v);
     if (const char *v = getenv("B200_L2_FETCH")) {
         // granularity hint for L2 fills of the random payload gathers (32, 64 or 128)
         B200_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v)));
@@ -94,6 +95,9 @@ Context::~Context() {
         if (kv.second.start) cudaEventDestroy(kv.second.start);
         if (kv.second.stop) cudaEventDestroy(kv.second.stop);
     }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side_stream) cudaStreamDestroy(side_stream);
     if (h_scratch) cudaFreeHost(h_scratch);
     if (d_scratch) cudaFree(d_scratch);
     if (owns_stream && stream) cudaStreamDestroy(stream);
@@ -109,6 +113,9 @@ Context &ctx() {
         c = new Context();
         B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->owns_stream = true;
+        B200_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+        B200_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        B200_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         B200_CUDA(cudaMallocHost(&c->h_scratch, 64 * sizeof(unsigned long long)));
         B200_CUDA(cudaMalloc(&c->d_scratch, 64 * sizeof(unsigned long long)));
     }
@@ -261,6 +268,14 @@ void unregister_all_columns() {
 // ---------------------------------------------------------------------------
 // kernel launch helpers
 // ---------------------------------------------------------------------------
+// stream the launch_* helpers enqueue on: the context stream unless a scope
+// redirects them to the side stream
+static thread_local cudaStream_t t_launch_override = nullptr;
+static cudaStream_t launch_stream() { return t_launch_override ? t_launch_override : ctx().stream; }
+struct SideStreamScope {
+    explicit SideStreamScope(cudaStream_t s) { t_launch_override = s; }
+    ~SideStreamScope() { t_launch_override = nullptr; }
+};
 template <typename KernelT>
 static void allow_smem(KernelT kernel, size_t bytes) {
     if (bytes > 48 * 1024)
@@ -282,12 +297,12 @@ template <> struct PartCfg<uint32_t, 2> { static constexpr int NT = 1024, U = 16
 template <> struct PartCfg<uint64_t, 2> { static constexpr int NT = 1024, U = 8, MINB = 1; };
 
 template <typename KeyT>
-static void launch_hist(const KeySrc &src, int bits, uint32_t *ghist) {
+static void launch_hist(const KeySrc &src, int bits, uint32_t *ghist, int ctas_per_sm = 4) {
     constexpr int U    = PartCfg<KeyT, 0>::U;
     const size_t  smem = (size_t)(1u << bits) * sizeof(uint32_t);
     auto          k    = radix_hist_kernel<kPartNT, U, KeyT>;
     allow_smem(k, smem);
-    k<<<grid_for(src.n, kPartNT * U, 4), kPartNT, smem, ctx().stream>>>(src, (uint32_t)bits, ghist);
+    k<<<grid_for(src.n, kPartNT * U, ctas_per_sm), kPartNT, smem, launch_stream()>>>(src, (uint32_t)bits, ghist);
     B200_LAUNCH_CHECK();
 }
 
@@ -300,7 +315,7 @@ static void launch_scatter_c(const KeySrc &src, int bits, uint32_t *cursor, void
     const size_t  smem    = (size_t)NT * U * sizeof(TupT) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
     auto          k       = radix_scatter_kernel<NT, U, MINB, KeyT>;
     allow_smem(k, smem);
-    k<<<grid_for(src.n, NT * U, MINB), NT, smem, ctx().stream>>>(src, (uint32_t)bits, cursor,
+    k<<<grid_for(src.n, NT * U, MINB), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor,
                                                                  static_cast<TupT *>(out));
     B200_LAUNCH_CHECK();
 }
@@ -323,7 +338,7 @@ static void launch_scatter_pay_n(const KeySrc &src, int bits, uint32_t *cursor, 
     const size_t  smem = (size_t)NT * U * (sizeof(TupT) + 8 * NPAY) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
     auto          k    = radix_scatter_pay_kernel<NT, U, KeyT, NPAY>;
     allow_smem(k, smem);
-    k<<<grid_for(src.n, NT * U, 1), NT, smem, ctx().stream>>>(src, (uint32_t)bits, cursor, static_cast<TupT *>(out),
+    k<<<grid_for(src.n, NT * U, 1), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor, static_cast<TupT *>(out),
                                                                pay);
     B200_LAUNCH_CHECK();
 }
@@ -375,20 +390,41 @@ static uint32_t tag_slots_log2_for(uint32_t cap) {
     while ((uint64_t)4 << l < (uint64_t)7 * cap) ++l;
     return l;
 }
+template <typename KernelT>
+static void launch_persistent_join_nt(KernelT k, const JoinArgs &a, size_t smem, int nt) {
+    allow_smem(k, smem);
+    int occ = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, nt, smem));
+    B200_REQUIRE(occ >= 1, "join kernel does not fit on an SM");
+    k<<<sm_count() * occ, nt, smem, ctx().stream>>>(a);
+    B200_LAUNCH_CHECK();
+}
+template <int NT, int MINB>
+static void launch_join32_cfg(const JoinArgs &a, int mode, size_t smem) {
+    if (mode == MODE_COUNT)
+        launch_persistent_join_nt(tag_join_kernel<NT, MINB, kJoinG, MODE_COUNT, 0>, a, smem, NT);
+    else if (mode == MODE_WRITE)
+        launch_persistent_join_nt(tag_join_kernel<NT, MINB, kJoinG, MODE_WRITE, 0>, a, smem, NT);
+    else if (a.nproj <= 2)
+        launch_persistent_join_nt(tag_join_kernel<NT, MINB, kJoinG, MODE_SUM, 2>, a, smem, NT);
+    else if (a.nproj <= 4)
+        launch_persistent_join_nt(tag_join_kernel<NT, MINB, kJoinG, MODE_SUM, 4>, a, smem, NT);
+    else
+        launch_persistent_join_nt(tag_join_kernel<NT, MINB, kJoinG, MODE_SUM, kMaxProj>, a, smem, NT);
+}
+static bool tag_join_big(uint32_t cap, uint32_t slots_log2) {
+    // two 512-thread CTAs per SM while the table allows it, else one 1024-thread CTA
+    return ((size_t)4 << slots_log2) + (size_t)4 * cap + (size_t)8 * kTagQueue * 16 > 113 * 1024;
+}
 static size_t tag_join_smem(uint32_t cap, uint32_t slots_log2) {
-    return ((size_t)4 << slots_log2) + (size_t)4 * cap + (size_t)8 * kTagQueue * (kJoinNT / 32);
+    const int nw = tag_join_big(cap, slots_log2) ? 32 : 16;
+    return ((size_t)4 << slots_log2) + (size_t)4 * cap + (size_t)8 * kTagQueue * nw;
 }
 static void launch_join32(const JoinArgs &a, int mode, size_t smem) {
-    if (mode == MODE_COUNT)
-        launch_persistent_join(tag_join_kernel<kJoinNT, kJoinG, MODE_COUNT, 0>, a, false, smem);
-    else if (mode == MODE_WRITE)
-        launch_persistent_join(tag_join_kernel<kJoinNT, kJoinG, MODE_WRITE, 0>, a, false, smem);
-    else if (a.nproj <= 2)
-        launch_persistent_join(tag_join_kernel<kJoinNT, kJoinG, MODE_SUM, 2>, a, false, smem);
-    else if (a.nproj <= 4)
-        launch_persistent_join(tag_join_kernel<kJoinNT, kJoinG, MODE_SUM, 4>, a, false, smem);
+    if (tag_join_big(a.cap, a.slots_log2))
+        launch_join32_cfg<1024, 1>(a, mode, smem);
     else
-        launch_persistent_join(tag_join_kernel<kJoinNT, kJoinG, MODE_SUM, kMaxProj>, a, false, smem);
+        launch_join32_cfg<512, 2>(a, mode, smem);
 }
 
 static void launch_join(const JoinArgs &a, bool key64, bool direct, int mode) {
@@ -463,7 +499,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     // 32-bit keys (8-byte partition tuples, tag-table kernel) when every key fits
     const bool key64 = direct || t.force_key64 || B.max_val > 0xFFFFFFFFull || P.max_val > 0xFFFFFFFFull;
     const uint32_t cap = key64 ? t.cap64 : t.cap32;
-    B200_REQUIRE(cap >= 32 && cap <= (key64 ? 65534u : 16382u), "table capacity out of range");
+    B200_REQUIRE(cap >= 32 && cap <= (key64 ? 65534u : 32766u), "table capacity out of range");
     const uint32_t slots_log2 = key64 ? TableView<uint64_t>::slots_log2_for(cap) : tag_slots_log2_for(cap);
     // expected largest partition under a uniform split: mean + 5 sigma (a larger one is split into build chunks)
     auto fits = [&](int b) {
@@ -473,8 +509,8 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
 
     int bits = 0;
     if (!direct) {
-        // the tag table needs radix_bits + slots_log2 >= 16 (tag <= 16 bits)
-        const int min_bits = key64 ? 1 : std::max(2, 16 - (int)slots_log2);
+        // the tag table needs radix_bits + slots_log2 >= 17 (tag <= 15 bits)
+        const int min_bits = key64 ? 1 : std::max(2, 17 - (int)slots_log2);
         if (t.radix_bits > 0) {
             bits = std::max(min_bits, std::min(t.radix_bits, t.max_bits));
         } else {
@@ -509,7 +545,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     a.out_cursor   = d_u64 + 1;
     a.sums         = d_u64 + 8;
 
-    DevBufPtr tup_b, tup_p;
+    DevBufPtr tup_b, tup_p, keep_alive;
     DevBufPtr part_vals[kMaxProj];
     uint64_t  n_items = 0;
     if (direct) {
@@ -529,22 +565,6 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         n_items          = rc * sc;
     } else {
         a.slice = t.slice;
-        {
-            TimedScope ts("hist");
-            if (key64) {
-                launch_hist<uint64_t>(B.src, bits, hist_b);
-                launch_hist<uint64_t>(P.src, bits, hist_p);
-            } else {
-                launch_hist<uint32_t>(B.src, bits, hist_b);
-                launch_hist<uint32_t>(P.src, bits, hist_p);
-            }
-        }
-        {
-            TimedScope ts("scan");
-            partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, hist_p, nparts, cap, a.slice, off_b,
-                                                                  off_p, cur_b, cur_p, items);
-            B200_LAUNCH_CHECK();
-        }
         const size_t tsz = key64 ? sizeof(Tup64) : sizeof(Tup32);
         tup_b            = dev_alloc((size_t)B.src.n * tsz);
         tup_p            = dev_alloc((size_t)P.src.n * tsz);
@@ -563,14 +583,59 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
                 ++npay;
             }
         }
-        {
-            TimedScope ts("scatter_b");
+        auto scatter_build = [&](uint32_t *cursor) {
             if (npay > 0)
-                launch_scatter_pay<uint32_t>(B.src, bits, cur_b, tup_b->ptr, pay, npay);
+                launch_scatter_pay<uint32_t>(B.src, bits, cursor, tup_b->ptr, pay, npay);
             else if (key64)
-                launch_scatter<uint64_t>(B.src, bits, cur_b, tup_b->ptr);
+                launch_scatter<uint64_t>(B.src, bits, cursor, tup_b->ptr);
             else
-                launch_scatter<uint32_t>(B.src, bits, cur_b, tup_b->ptr);
+                launch_scatter<uint32_t>(B.src, bits, cursor, tup_b->ptr);
+        };
+        // The build side is ready to scatter as soon as ITS histogram is scanned; that scatter (small,
+        // latency-bound) then runs on the side stream underneath the probe side's HBM-bound histogram.
+        // With per-kernel timing on, everything stays on one stream so the timers mean what they say.
+        const bool overlap = !profiling_enabled() && t.overlap;
+        {
+            TimedScope ts("hist_b");
+            if (key64)
+                launch_hist<uint64_t>(B.src, bits, hist_b);
+            else
+                launch_hist<uint32_t>(B.src, bits, hist_b);
+        }
+        if (overlap) {
+            // private cursors for the early build scatter (scratch outputs of this first scan are unused)
+            DevBufPtr early = dev_alloc(5 * (size_t)(nparts + 1) * sizeof(uint32_t));
+            uint32_t *e0 = early->as<uint32_t>(), *e1 = e0 + nparts + 1, *e2 = e1 + nparts + 1, *e3 = e2 + nparts + 1,
+                     *e4 = e3 + nparts + 1;
+            partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, hist_b, nparts, cap, a.slice, e0, e1, e2, e3,
+                                                                  e4);
+            B200_LAUNCH_CHECK();
+            B200_CUDA(cudaEventRecord(c.ev_fork, c.stream));
+            B200_CUDA(cudaStreamWaitEvent(c.side_stream, c.ev_fork, 0));
+            {
+                SideStreamScope side(c.side_stream);
+                scatter_build(e2);
+            }
+            B200_CUDA(cudaEventRecord(c.ev_join, c.side_stream));
+            keep_alive = early;
+        }
+        {
+            TimedScope ts("hist_p");
+            // 2 CTAs/SM leave thread slots for the build-side scatter running next to it
+            if (key64)
+                launch_hist<uint64_t>(P.src, bits, hist_p, overlap ? 2 : 4);
+            else
+                launch_hist<uint32_t>(P.src, bits, hist_p, overlap ? 2 : 4);
+        }
+        {
+            TimedScope ts("scan");
+            partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, hist_p, nparts, cap, a.slice, off_b,
+                                                                  off_p, cur_b, cur_p, items);
+            B200_LAUNCH_CHECK();
+        }
+        if (!overlap) {
+            TimedScope ts("scatter_b");
+            scatter_build(cur_b);
         }
         {
             TimedScope ts("scatter_p");
@@ -579,6 +644,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             else
                 launch_scatter<uint32_t>(P.src, bits, cur_p, tup_p->ptr);
         }
+        if (overlap) B200_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
         a.tup_b      = tup_b->ptr;
         a.tup_p      = tup_p->ptr;
         a.off_b      = off_b;
@@ -853,7 +919,7 @@ JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const v
     a.slots_log2 = tag_slots_log2_for(cap);
     a.radix_bits = (uint32_t)bits;
     a.slice      = t.slice;
-    B200_REQUIRE(bits + (int)a.slots_log2 >= 16, "radix bits too small for the tag table");
+    B200_REQUIRE(bits + (int)a.slots_log2 >= 17, "radix bits too small for the tag table");
     DevBufPtr ctrl = dev_alloc((64 + 5 * (size_t)(nparts + 1)) * sizeof(uint32_t) + 64 * sizeof(unsigned long long));
     B200_CUDA(cudaMemsetAsync(ctrl->ptr, 0, ctrl->bytes, c.stream));
     unsigned long long *d_u64 = ctrl->as<unsigned long long>();

@@ -961,7 +961,7 @@ hash_join_kernel(const JoinArgs a) {
 // This kernel makes a probe ONE 32-bit LDS:
 //   * y = mix(key >> radix_bits) is a bijection on the 32 - radix_bits bits
 //     that differ inside a partition; slot = low L bits of y, tag = the rest
-//     (<= 16 bits).  Slot and tag together identify the key exactly, so a tag
+//     (<= 15 bits).  Slot and tag together identify the key exactly, so a tag
 //     match IS a key match: no key array in shared memory, no verification;
 //   * a slot word is [tag | has_next | position of the build tuple in its
 //     chunk]; build tuples that collide in a slot are chained through a second
@@ -972,7 +972,8 @@ hash_join_kernel(const JoinArgs a) {
 //     time with every lane active (chain walks re-push the matches they find;
 //     payload gathers of a drain are all in flight together and are consumed
 //     by the next drain).
-// Used for partitioned joins with radix_bits >= 2 and keys below 2^32 - 1.
+// Used for partitioned joins of 32-bit keys with radix_bits + slots_log2 >= 17; a table holds up
+// to 32766 build tuples (2 CTAs/SM of 512 threads for small tables, 1 CTA of 1024 for large ones).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
     uint4 v;
@@ -1051,10 +1052,10 @@ __device__ __forceinline__ JoinItem fetch_join_item(const JoinArgs &a, int lane)
     return it;
 }
 
-constexpr uint32_t kTagShift  = 15;
-constexpr uint32_t kNextBit   = 0x4000u;
-constexpr uint32_t kIdxMask   = 0x3FFFu;
-constexpr uint32_t kEmptyWord = 0xFFFFBFFFu;   // tag all ones (never a real tag), no chain
+constexpr uint32_t kTagShift  = 16;            // word = [tag 16 | has_next 1 | position 15]
+constexpr uint32_t kNextBit   = 0x8000u;
+constexpr uint32_t kIdxMask   = 0x7FFFu;
+constexpr uint32_t kEmptyWord = 0xFFFF7FFFu;   // tag all ones (never a real tag: tags have <= 15 bits), no chain
 constexpr int      kTagQueue  = 96;            // entries per warp (<= 31 left + 64 pushed per probe)
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
@@ -1075,8 +1076,8 @@ __device__ __forceinline__ uint64_t ld_gather_u64(const uint64_t *p) {
     return v;
 }
 
-template <int NT, int G, int MODE, int NP>
-__global__ void __launch_bounds__(NT, 2)
+template <int NT, int MINB, int G, int MODE, int NP>
+__global__ void __launch_bounds__(NT, MINB)
 tag_join_kernel(const JoinArgs a) {
     constexpr int NW  = NT / 32;
     constexpr int NPA = NP > 0 ? NP : 1;
