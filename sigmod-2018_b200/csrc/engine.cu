@@ -66,7 +66,7 @@ static void init_device(int device) {
     if (const char *v = getenv("B200_DEBUG")) t.debug = atoi(v);
     if (const char *v = getenv("B200_SCATTER_CFG")) t.scatter_cfg = atoi(v);
     if (const char *v = getenv("B200_EARLY_MAT")) t.early_mat = atoi(v);
-    if (const char *v = getenv("B200_OVERLAP")) t.overlap = atoi(v);
+    if (const char *v = getenv("B200_OPT_PARTITION")) t.opt_partition = atoi(v);
     if (const char *v = getenv("B200_L2_FETCH")) {
         // granularity hint for L2 fills of the random payload gathers (32, 64 or 128)
         B200_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v)));
@@ -306,27 +306,33 @@ static void launch_hist(const KeySrc &src, int bits, uint32_t *ghist, int ctas_p
     B200_LAUNCH_CHECK();
 }
 
-template <typename KeyT, int CFG>
-static void launch_scatter_c(const KeySrc &src, int bits, uint32_t *cursor, void *out) {
+template <typename KeyT, int CFG, bool OPT>
+static void launch_scatter_c(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
     using TupT            = typename TupOf<KeyT>::type;
     constexpr int NT      = PartCfg<KeyT, CFG>::NT;
     constexpr int U       = PartCfg<KeyT, CFG>::U;
     constexpr int MINB    = PartCfg<KeyT, CFG>::MINB;
-    const size_t  smem    = (size_t)NT * U * sizeof(TupT) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
-    auto          k       = radix_scatter_kernel<NT, U, MINB, KeyT>;
+    const size_t  smem    = (size_t)NT * U * sizeof(TupT) + (OPT ? 4 : 3) * (size_t)(1u << bits) * sizeof(uint32_t);
+    auto          k       = radix_scatter_kernel<NT, U, MINB, KeyT, OPT>;
     allow_smem(k, smem);
     k<<<grid_for(src.n, NT * U, MINB), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor,
-                                                                 static_cast<TupT *>(out));
+                                                                 static_cast<TupT *>(out), opt);
     B200_LAUNCH_CHECK();
 }
 
 template <typename KeyT>
 static void launch_scatter(const KeySrc &src, int bits, uint32_t *cursor, void *out) {
+    const OptArgs none{0, nullptr, nullptr};
     switch (tuning().scatter_cfg) {
-        case 0: launch_scatter_c<KeyT, 0>(src, bits, cursor, out); break;
-        case 2: launch_scatter_c<KeyT, 2>(src, bits, cursor, out); break;
-        default: launch_scatter_c<KeyT, 1>(src, bits, cursor, out); break;
+        case 0: launch_scatter_c<KeyT, 0, false>(src, bits, cursor, out, none); break;
+        case 2: launch_scatter_c<KeyT, 2, false>(src, bits, cursor, out, none); break;
+        default: launch_scatter_c<KeyT, 1, false>(src, bits, cursor, out, none); break;
     }
+}
+
+// histogram-free probe-side scatter (32-bit keys): fixed regions of opt.opt_cap tuples + overflow
+static void launch_scatter_opt(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
+    launch_scatter_c<uint32_t, 1, true>(src, bits, cursor, out, opt);
 }
 
 // build-side scatter with early-materialised projections (radix_scatter_pay_kernel)
@@ -336,12 +342,25 @@ static void launch_scatter_pay_n(const KeySrc &src, int bits, uint32_t *cursor, 
     constexpr int NT   = 1024;   // 8192-tuple tiles, one CTA per SM
     constexpr int U    = 8;
     const size_t  smem = (size_t)NT * U * (sizeof(TupT) + 8 * NPAY) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
-    auto          k    = radix_scatter_pay_kernel<NT, U, KeyT, NPAY>;
+    auto          k    = radix_scatter_pay_kernel<NT, U, KeyT, NPAY, false>;
     allow_smem(k, smem);
     k<<<grid_for(src.n, NT * U, 1), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor, static_cast<TupT *>(out),
                                                                pay);
     B200_LAUNCH_CHECK();
 }
+// overflow tuples of an OPT scatter -> partition order (input = packed tuples, row id kept)
+static void launch_scatter_tuples(const uint64_t *tuples, uint32_t n, int bits, uint32_t *cursor, void *out) {
+    constexpr int NT   = 1024;
+    constexpr int U    = 8;
+    const size_t  smem = (size_t)NT * U * sizeof(Tup32) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
+    auto          k    = radix_scatter_pay_kernel<NT, U, uint32_t, 0, true>;
+    allow_smem(k, smem);
+    KeySrc  src{tuples, nullptr, n};
+    PayArgs pay{};
+    k<<<grid_for(n, NT * U, 1), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor, static_cast<Tup32 *>(out), pay);
+    B200_LAUNCH_CHECK();
+}
+
 template <typename KeyT>
 static void launch_scatter_pay(const KeySrc &src, int bits, uint32_t *cursor, void *out, const PayArgs &pay, int npay) {
     if (npay == 0)
@@ -469,7 +488,8 @@ PartitionOut run_partition(const KeyVec &kv, int bits) {
     else
         launch_hist<uint32_t>(kv.src, bits, o.hist->as<uint32_t>());
     partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(o.hist->as<uint32_t>(), zeros->as<uint32_t>(),
-                                                          nparts, 1u, 1u, off_b, off_p, cur_b, cur_p, items);
+                                                          nparts, 1u, 1u, off_b, off_p, cur_b, cur_p, items,
+                                                          zeros->as<uint32_t>(), 0u);
     B200_LAUNCH_CHECK();
     if (o.key64)
         launch_scatter<uint64_t>(kv.src, bits, cur_b, o.tuples->ptr);
@@ -528,7 +548,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
 
     // one allocation for the small control arrays
     const uint32_t nparts = 1u << bits;
-    DevBufPtr ctrl = dev_alloc((64 + 7 * (size_t)(nparts + 1)) * sizeof(uint32_t) + 64 * sizeof(unsigned long long));
+    DevBufPtr ctrl = dev_alloc((64 + 8 * (size_t)(nparts + 1)) * sizeof(uint32_t) + 64 * sizeof(unsigned long long));
     B200_CUDA(cudaMemsetAsync(ctrl->ptr, 0, ctrl->bytes, c.stream));
     unsigned long long *d_u64   = ctrl->as<unsigned long long>();   // [0] total, [1] out_cursor, [8..16) sums
     uint32_t           *d_u32   = reinterpret_cast<uint32_t *>(d_u64 + 64);
@@ -540,12 +560,16 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     uint32_t           *cur_b   = off_p + nparts + 1;
     uint32_t           *cur_p   = cur_b + nparts + 1;
     uint32_t           *items   = cur_p + nparts + 1;
+    uint32_t           *cnt_p   = items + nparts + 1;
+    uint32_t           *d_ovcnt = d_u32 + 1;   // overflow counter of the histogram-free scatter
     a.work_counter = d_work;
     a.total        = d_u64;
     a.out_cursor   = d_u64 + 1;
     a.sums         = d_u64 + 8;
 
-    DevBufPtr tup_b, tup_p, keep_alive;
+    DevBufPtr tup_b, tup_p, ov_tup;
+    bool      opt     = false;
+    uint32_t  opt_cap = 0;
     DevBufPtr part_vals[kMaxProj];
     uint64_t  n_items = 0;
     if (direct) {
@@ -566,8 +590,15 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     } else {
         a.slice = t.slice;
         const size_t tsz = key64 ? sizeof(Tup64) : sizeof(Tup32);
-        tup_b            = dev_alloc((size_t)B.src.n * tsz);
-        tup_p            = dev_alloc((size_t)P.src.n * tsz);
+        // Histogram-free probe side (fused SUM, 32-bit keys): every partition owns a region a few percent
+        // above the uniform expectation; what does not fit overflows and is partitioned exactly afterwards.
+        opt = mode == JoinOut::Sum && !key64 && t.opt_partition && P.src.n >= (1u << 20) && P.src.n <= (1u << 30);
+        if (opt) {
+            const uint64_t mean = (P.src.n + nparts - 1) / nparts;
+            opt_cap             = (uint32_t)((mean + mean / 32 + 6 * (uint64_t)sqrt((double)mean) + 64 + 3) & ~3ull);
+        }
+        tup_b = dev_alloc((size_t)B.src.n * tsz);
+        tup_p = dev_alloc(opt ? (size_t)opt_cap * nparts * tsz : (size_t)P.src.n * tsz);
         // early materialisation: the first two build-side projections of a fused
         // SUM travel with the build tuples into partition order (32-bit-key path)
         PayArgs pay{};
@@ -584,6 +615,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             }
         }
         auto scatter_build = [&](uint32_t *cursor) {
+            TimedScope ts("scatter_b");
             if (npay > 0)
                 launch_scatter_pay<uint32_t>(B.src, bits, cursor, tup_b->ptr, pay, npay);
             else if (key64)
@@ -591,10 +623,6 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             else
                 launch_scatter<uint32_t>(B.src, bits, cursor, tup_b->ptr);
         };
-        // The build side is ready to scatter as soon as ITS histogram is scanned; that scatter (small,
-        // latency-bound) then runs on the side stream underneath the probe side's HBM-bound histogram.
-        // With per-kernel timing on, everything stays on one stream so the timers mean what they say.
-        const bool overlap = !profiling_enabled() && t.overlap;
         {
             TimedScope ts("hist_b");
             if (key64)
@@ -602,53 +630,53 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             else
                 launch_hist<uint32_t>(B.src, bits, hist_b);
         }
-        if (overlap) {
-            // private cursors for the early build scatter (scratch outputs of this first scan are unused)
-            DevBufPtr early = dev_alloc(5 * (size_t)(nparts + 1) * sizeof(uint32_t));
-            uint32_t *e0 = early->as<uint32_t>(), *e1 = e0 + nparts + 1, *e2 = e1 + nparts + 1, *e3 = e2 + nparts + 1,
-                     *e4 = e3 + nparts + 1;
-            partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, hist_b, nparts, cap, a.slice, e0, e1, e2, e3,
-                                                                  e4);
+        if (opt) {
+            // build side: exact (its histogram is cheap); hist_p is still all zero here
+            partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, hist_p, nparts, cap, a.slice, off_b, off_p,
+                                                                  cur_b, cur_p, items, cnt_p, 0u);
             B200_LAUNCH_CHECK();
-            B200_CUDA(cudaEventRecord(c.ev_fork, c.stream));
-            B200_CUDA(cudaStreamWaitEvent(c.side_stream, c.ev_fork, 0));
-            {
-                SideStreamScope side(c.side_stream);
-                scatter_build(e2);
-            }
-            B200_CUDA(cudaEventRecord(c.ev_join, c.side_stream));
-            keep_alive = early;
-        }
-        {
-            TimedScope ts("hist_p");
-            // 2 CTAs/SM leave thread slots for the build-side scatter running next to it
-            if (key64)
-                launch_hist<uint64_t>(P.src, bits, hist_p, overlap ? 2 : 4);
-            else
-                launch_hist<uint32_t>(P.src, bits, hist_p, overlap ? 2 : 4);
-        }
-        {
-            TimedScope ts("scan");
-            partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, hist_p, nparts, cap, a.slice, off_b,
-                                                                  off_p, cur_b, cur_p, items);
-            B200_LAUNCH_CHECK();
-        }
-        if (!overlap) {
-            TimedScope ts("scatter_b");
             scatter_build(cur_b);
+            init_opt_cursors_kernel<<<(nparts + 255) / 256, 256, 0, c.stream>>>(cur_p, nparts, opt_cap);
+            B200_LAUNCH_CHECK();
+            ov_tup = dev_alloc((size_t)P.src.n * tsz);
+            {
+                TimedScope ts("scatter_p");
+                launch_scatter_opt(P.src, bits, cur_p, tup_p->ptr, OptArgs{opt_cap, d_ovcnt, ov_tup->ptr});
+            }
+            {
+                TimedScope ts("scan");
+                partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, cur_p, nparts, cap, a.slice, off_b,
+                                                                      off_p, cur_b, cur_p, items, cnt_p, opt_cap);
+                B200_LAUNCH_CHECK();
+            }
+        } else {
+            {
+                TimedScope ts("hist_p");
+                if (key64)
+                    launch_hist<uint64_t>(P.src, bits, hist_p);
+                else
+                    launch_hist<uint32_t>(P.src, bits, hist_p);
+            }
+            {
+                TimedScope ts("scan");
+                partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, hist_p, nparts, cap, a.slice, off_b,
+                                                                      off_p, cur_b, cur_p, items, cnt_p, 0u);
+                B200_LAUNCH_CHECK();
+            }
+            scatter_build(cur_b);
+            {
+                TimedScope ts("scatter_p");
+                if (key64)
+                    launch_scatter<uint64_t>(P.src, bits, cur_p, tup_p->ptr);
+                else
+                    launch_scatter<uint32_t>(P.src, bits, cur_p, tup_p->ptr);
+            }
         }
-        {
-            TimedScope ts("scatter_p");
-            if (key64)
-                launch_scatter<uint64_t>(P.src, bits, cur_p, tup_p->ptr);
-            else
-                launch_scatter<uint32_t>(P.src, bits, cur_p, tup_p->ptr);
-        }
-        if (overlap) B200_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
         a.tup_b      = tup_b->ptr;
         a.tup_p      = tup_p->ptr;
         a.off_b      = off_b;
         a.off_p      = off_p;
+        a.cnt_p      = cnt_p;
         a.item_start = items;
         a.nparts     = nparts;
     }
@@ -667,9 +695,31 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             TimedScope ts("join");
             launch_join(a, key64, direct, MODE_SUM);
         }
-        B200_CUDA(cudaMemcpyAsync(c.h_scratch, d_u64, 16 * sizeof(unsigned long long),
-                                  cudaMemcpyDeviceToHost, c.stream));
-        B200_CUDA(cudaStreamSynchronize(c.stream));
+        auto read_back = [&]() {
+            B200_CUDA(cudaMemcpyAsync(c.h_scratch, d_u64, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                      c.stream));
+            B200_CUDA(cudaMemcpyAsync(c.h_scratch + 16, d_ovcnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+            B200_CUDA(cudaStreamSynchronize(c.stream));
+        };
+        read_back();
+        const uint32_t n_over = opt ? *reinterpret_cast<uint32_t *>(c.h_scratch + 16) : 0u;
+        if (n_over) {
+            // second pass over the overflow only: exact histogram, scatter, join against the same build partitions
+            // (matches and sums keep accumulating in the same device counters)
+            TimedScope ts("overflow");
+            B200_CUDA(cudaMemsetAsync(hist_p, 0, (size_t)nparts * sizeof(uint32_t), c.stream));
+            KeySrc ov_src{ov_tup->as<uint64_t>(), nullptr, n_over};   // low half of a packed tuple is its key
+            launch_hist<uint32_t>(ov_src, bits, hist_p);
+            partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, hist_p, nparts, cap, a.slice, off_b, off_p,
+                                                                  cur_b, cur_p, items, cnt_p, 0u);
+            B200_LAUNCH_CHECK();
+            DevBufPtr ov_part = dev_alloc((size_t)n_over * sizeof(Tup32));
+            launch_scatter_tuples(ov_tup->as<uint64_t>(), n_over, bits, cur_p, ov_part->ptr);
+            B200_CUDA(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), c.stream));
+            a.tup_p = ov_part->ptr;
+            launch_join(a, key64, direct, MODE_SUM);
+            read_back();
+        }
         res.m = c.h_scratch[0];
         for (int k = 0; k < nproj; ++k) res.sums[k] = c.h_scratch[8 + k];
         return res;
@@ -861,7 +911,7 @@ void stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, 
     uint32_t *off_l = ctrl->as<uint32_t>(), *off_x = off_l + nparts + 1, *cur_l = off_x + nparts + 1,
              *cur_x = cur_l + nparts + 1, *items = cur_x + nparts + 1;
     partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_local, d_hist_local, nparts, 1u, 1u, off_l, off_x,
-                                                          cur_l, cur_x, items);
+                                                          cur_l, cur_x, items, items, 0u);
     B200_LAUNCH_CHECK();
     DevBufPtr stage_tup = dev_alloc(n * sizeof(Tup32));
     DevBufPtr stage_pay[2];
@@ -920,12 +970,12 @@ JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const v
     a.radix_bits = (uint32_t)bits;
     a.slice      = t.slice;
     B200_REQUIRE(bits + (int)a.slots_log2 >= 17, "radix bits too small for the tag table");
-    DevBufPtr ctrl = dev_alloc((64 + 5 * (size_t)(nparts + 1)) * sizeof(uint32_t) + 64 * sizeof(unsigned long long));
+    DevBufPtr ctrl = dev_alloc((64 + 6 * (size_t)(nparts + 1)) * sizeof(uint32_t) + 64 * sizeof(unsigned long long));
     B200_CUDA(cudaMemsetAsync(ctrl->ptr, 0, ctrl->bytes, c.stream));
     unsigned long long *d_u64 = ctrl->as<unsigned long long>();
     uint32_t           *d_u32 = reinterpret_cast<uint32_t *>(d_u64 + 64);
     uint32_t *off_b = d_u32 + 64, *off_p = off_b + nparts + 1, *cur_b = off_p + nparts + 1,
-             *cur_p = cur_b + nparts + 1, *items = cur_p + nparts + 1;
+             *cur_p = cur_b + nparts + 1, *items = cur_p + nparts + 1, *cnt_p = items + nparts + 1;
     a.work_counter = d_u32;
     a.total        = d_u64;
     a.out_cursor   = d_u64 + 1;
@@ -933,13 +983,14 @@ JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const v
     {
         TimedScope ts("scan");
         partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_b, d_hist_p, nparts, cap, a.slice, off_b, off_p,
-                                                              cur_b, cur_p, items);
+                                                              cur_b, cur_p, items, cnt_p, 0u);
         B200_LAUNCH_CHECK();
     }
     a.tup_b      = d_tup_b;
     a.tup_p      = d_tup_p;
     a.off_b      = off_b;
     a.off_p      = off_p;
+    a.cnt_p      = cnt_p;
     a.item_start = items;
     a.nparts     = nparts;
     a.nproj      = nproj;

@@ -39,7 +39,7 @@ struct Tuning {
     uint32_t cap32       = 17408;    // build tuples per shared-memory table, 32-bit keys
     uint32_t cap64       = 6144;     // ... 64-bit keys
     uint32_t slice       = 1u << 18; // probe tuples per work item
-    int      overlap     = 0;        // build-side scatter on a side stream under the probe-side histogram
+    int      opt_partition = 1;      // histogram-free probe-side scatter for the fused join -> SUM
     int      early_mat   = 1;        // carry build-side SUM projections through the scatter
     int      scatter_cfg = 1;        // see engine.cu PartCfg
     int      max_bits    = 12;

@@ -174,12 +174,21 @@ radix_hist_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ ghist)
 // contributes ceil(b_p/cap) * ceil(p_p/slice) items when both sides are
 // non-empty (rhjoin.c:31-34 counts the same bucket pairs).  One CTA.
 // ---------------------------------------------------------------------------
+// opt_cap > 0 selects the histogram-free probe side (see radix_scatter_kernel,
+// OPT): partition p owns the fixed region [p*opt_cap, (p+1)*opt_cap) and
+// `hist_p` is the cursor array the scatter left behind, so the number of tuples
+// that landed in the region is min(cursor - p*opt_cap, opt_cap).
+// cnt_p[p] always receives the probe-side count of partition p.
+__device__ __forceinline__ uint32_t probe_count(const uint32_t *hist_p, uint32_t b, uint32_t opt_cap) {
+    return opt_cap ? min(hist_p[b] - b * opt_cap, opt_cap) : hist_p[b];
+}
 template <int NT>
 __global__ void __launch_bounds__(NT)
 partition_plan_kernel(const uint32_t *__restrict__ hist_b, const uint32_t *__restrict__ hist_p,
                       uint32_t nparts, uint32_t cap, uint32_t slice, uint32_t *__restrict__ off_b,
                       uint32_t *__restrict__ off_p, uint32_t *__restrict__ cur_b,
-                      uint32_t *__restrict__ cur_p, uint32_t *__restrict__ item_start) {
+                      uint32_t *__restrict__ cur_p, uint32_t *__restrict__ item_start,
+                      uint32_t *__restrict__ cnt_p, uint32_t opt_cap) {
     __shared__ uint32_t warp_sums[NT / 32 + 1];
     const uint32_t      per   = (nparts + NT - 1) / NT;
     const uint32_t      first = threadIdx.x * per;
@@ -187,7 +196,7 @@ partition_plan_kernel(const uint32_t *__restrict__ hist_b, const uint32_t *__res
     for (uint32_t k = 0; k < per; ++k) {
         const uint32_t b = first + k;
         if (b < nparts) {
-            const uint32_t cb = hist_b[b], cp = hist_p[b];
+            const uint32_t cb = hist_b[b], cp = probe_count(hist_p, b, opt_cap);
             sb += cb;
             sp += cp;
             if (cb && cp) si += ((cb + cap - 1) / cap) * ((cp + slice - 1) / slice);
@@ -204,11 +213,12 @@ partition_plan_kernel(const uint32_t *__restrict__ hist_b, const uint32_t *__res
     for (uint32_t k = 0; k < per; ++k) {
         const uint32_t b = first + k;
         if (b < nparts) {
-            const uint32_t cb = hist_b[b], cp = hist_p[b];
+            const uint32_t cb = hist_b[b], cp = probe_count(hist_p, b, opt_cap);
             off_b[b] = eb;
             cur_b[b] = eb;
-            off_p[b] = ep;
-            cur_p[b] = ep;
+            off_p[b] = opt_cap ? b * opt_cap : ep;
+            if (!opt_cap) cur_p[b] = ep;   // in OPT mode hist_p may alias cur_p
+            cnt_p[b] = cp;
             item_start[b] = ei;
             eb += cb;
             ep += cp;
@@ -243,13 +253,26 @@ partition_plan_kernel(const uint32_t *__restrict__ hist_b, const uint32_t *__res
 // Order inside a partition is not the reference's (stable) order; only the
 // multiset matters downstream.
 // ---------------------------------------------------------------------------
-template <int NT, int U, typename KeyT, bool FULL>
+// OPT = histogram-free ("optimistic") partitioning of the probe side: partition
+// b owns the fixed region [b*opt_cap, (b+1)*opt_cap) of `out`, sized a few
+// percent above the uniform expectation, and its cursor starts at b*opt_cap.
+// Tuples whose position falls beyond the region are appended to `ov_out`
+// (one global counter) and are partitioned exactly, with a histogram, in a
+// second pass over that (normally empty) overflow only.  This removes the
+// histogram read of the whole probe column (8 B/row) from the common case.
+struct OptArgs {
+    uint32_t  opt_cap;
+    uint32_t *ov_cursor;
+    void     *ov_out;
+};
+template <int NT, int U, typename KeyT, bool FULL, bool OPT>
 __device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U], uint64_t base, uint32_t count,
                                              bool vec, uint64_t nbase, uint32_t ncount, bool nvec, bool has_next,
                                              uint32_t nbins, uint32_t mask, uint32_t per,
                                              typename TupOf<KeyT>::type *stage, uint32_t *cnt, uint32_t *loc,
                                              uint32_t *gdelta, uint32_t *warp_sums, uint32_t *__restrict__ cursor,
-                                             typename TupOf<KeyT>::type *__restrict__ out) {
+                                             typename TupOf<KeyT>::type *__restrict__ out, const OptArgs &opt,
+                                             uint32_t *ovdelta) {
     using TupT = typename TupOf<KeyT>::type;
     const uint32_t tid = threadIdx.x;
     uint32_t rank2[(U + 1) / 2];   // two 16-bit ranks per register
@@ -276,7 +299,18 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U],
             if (b < nbins) {
                 const uint32_t c = cnt[b];
                 loc[b]           = run;
-                if (c) gdelta[b] = atomicAdd(&cursor[b], c) - run;
+                if (c) {
+                    const uint32_t old = atomicAdd(&cursor[b], c);
+                    gdelta[b]          = old - run;
+                    if constexpr (OPT) {
+                        const uint32_t lim = (b + 1u) * opt.opt_cap;
+                        if (old + c > lim) {   // part of this run does not fit the region any more
+                            const uint32_t from = max(old, lim);
+                            const uint32_t ovd  = atomicAdd(opt.ov_cursor, old + c - from);
+                            ovdelta[b]          = ovd - (from - (old - run));   // overflow index = ovdelta + i
+                        }
+                    }
+                }
                 run += c;
                 cnt[b] = 0;   // ready for the next tile
             }
@@ -299,26 +333,31 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U],
     // keys[] and the ranks are dead: put the next tile's loads in flight before
     // the copy-out so their latency hides behind the stores
     if (has_next) load_tile_keys<NT, U, KeyT>(src, nbase, ncount, nvec, keys);
+    auto put = [&](uint32_t i) {
+        const TupT     t   = stage[i];
+        const uint32_t b   = (uint32_t)t.key & mask;
+        const uint32_t pos = gdelta[b] + i;
+        if constexpr (OPT) {
+            if (pos >= (b + 1u) * opt.opt_cap) {
+                static_cast<TupT *>(opt.ov_out)[ovdelta[b] + i] = t;
+                return;
+            }
+        }
+        out[pos] = t;
+    };
     if constexpr (FULL) {
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const uint32_t i = (uint32_t)(k * NT) + tid;
-            const TupT     t = stage[i];
-            out[gdelta[(uint32_t)t.key & mask] + i] = t;
-        }
+        for (int k = 0; k < U; ++k) put((uint32_t)(k * NT) + tid);
     } else {
-        for (uint32_t i = tid; i < count; i += NT) {
-            const TupT t = stage[i];
-            out[gdelta[(uint32_t)t.key & mask] + i] = t;
-        }
+        for (uint32_t i = tid; i < count; i += NT) put(i);
     }
     __syncthreads();
 }
 
-template <int NT, int U, int MINB, typename KeyT>
+template <int NT, int U, int MINB, typename KeyT, bool OPT>
 __global__ void __launch_bounds__(NT, MINB)
 radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cursor,
-                     typename TupOf<KeyT>::type *__restrict__ out) {
+                     typename TupOf<KeyT>::type *__restrict__ out, const OptArgs opt) {
     using TupT = typename TupOf<KeyT>::type;
     constexpr uint32_t TILE = NT * U;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -326,8 +365,9 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
     uint32_t *cnt    = reinterpret_cast<uint32_t *>(stage + TILE);
     const uint32_t nbins = 1u << radix_bits;
     const uint32_t mask  = nbins - 1u;
-    uint32_t *loc    = cnt + nbins;
-    uint32_t *gdelta = loc + nbins;
+    uint32_t *loc     = cnt + nbins;
+    uint32_t *gdelta  = loc + nbins;
+    uint32_t *ovdelta = gdelta + nbins;   // OPT only (the launch reserves 4 bin arrays then)
     __shared__ uint32_t warp_sums[NT / 32 + 1];
 
     // row ids are 32-bit: tile bases fit 32 bits as well
@@ -356,11 +396,13 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
         const uint32_t ncount   = has_next ? (uint32_t)min((uint64_t)TILE, n - nbase) : 0u;
         const bool     nvec     = vec_ok && ncount == TILE;
         if (vec)
-            scatter_tile<NT, U, KeyT, true>(src, keys, base, count, vec, nbase, ncount, nvec, has_next, nbins, mask,
-                                            per, stage, cnt, loc, gdelta, warp_sums, cursor, out);
+            scatter_tile<NT, U, KeyT, true, OPT>(src, keys, base, count, vec, nbase, ncount, nvec, has_next, nbins,
+                                                 mask, per, stage, cnt, loc, gdelta, warp_sums, cursor, out, opt,
+                                                 ovdelta);
         else
-            scatter_tile<NT, U, KeyT, false>(src, keys, base, count, vec, nbase, ncount, nvec, has_next, nbins, mask,
-                                             per, stage, cnt, loc, gdelta, warp_sums, cursor, out);
+            scatter_tile<NT, U, KeyT, false, OPT>(src, keys, base, count, vec, nbase, ncount, nvec, has_next, nbins,
+                                                  mask, per, stage, cnt, loc, gdelta, warp_sums, cursor, out, opt,
+                                                  ovdelta);
     }
 }
 
@@ -385,7 +427,9 @@ struct PayArgs {
     void     *tup_dst[kMaxPeers];
     uint64_t *pay_dst[2][kMaxPeers];
 };
-template <int NT, int U, typename KeyT, int NPAY>
+// TUPIN: the input "column" is an array of packed 32-bit-key tuples {key32, rid32}
+// (the overflow of an OPT scatter); the row id comes from the tuple, not the position.
+template <int NT, int U, typename KeyT, int NPAY, bool TUPIN>
 __global__ void __launch_bounds__(NT)
 radix_scatter_pay_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cursor,
                          typename TupOf<KeyT>::type *__restrict__ out, PayArgs pay) {
@@ -410,8 +454,19 @@ radix_scatter_pay_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__
         const uint64_t base  = tile * TILE;
         const uint32_t count = (uint32_t)min((uint64_t)TILE, n - base);
         KeyT     keys[U];
+        uint32_t in_rid[TUPIN ? U : 1];
         uint16_t rank[U];
-        load_tile_keys<NT, U, KeyT>(src, base, count, false, keys);
+        if constexpr (TUPIN) {
+            uint64_t raw[U];
+            load_tile_keys<NT, U, uint64_t>(src, base, count, false, raw);
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                keys[j]   = (KeyT)(uint32_t)raw[j];
+                in_rid[j] = (uint32_t)(raw[j] >> 32);
+            }
+        } else {
+            load_tile_keys<NT, U, KeyT>(src, base, count, false, keys);
+        }
 #pragma unroll
         for (int j = 0; j < U; ++j)
             if ((uint32_t)(j * NT) + threadIdx.x < count)
@@ -443,7 +498,8 @@ radix_scatter_pay_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__
                 const uint32_t pos = loc[(uint32_t)keys[j] & mask] + rank[j];
                 TupT           t;
                 t.key = keys[j];
-                t.rid = pay.rid_base + rid;
+                if constexpr (TUPIN) t.rid = in_rid[j];
+                else t.rid = pay.rid_base + rid;
                 if constexpr (sizeof(KeyT) == 8) t.pad = 0;
                 stage[pos] = t;
 #pragma unroll
@@ -531,7 +587,7 @@ constexpr int kWarpQueue = 64;   // entries per warp; drained when >= 32
 struct JoinArgs {
     KeySrc          src_b, src_p;   // DIRECT
     const void     *tup_b, *tup_p;  // partitioned
-    const uint32_t *off_b, *off_p, *item_start;
+    const uint32_t *off_b, *off_p, *cnt_p, *item_start;   // probe side of partition p: [off_p[p], off_p[p] + cnt_p[p])
     uint32_t        nparts, radix_bits, cap, slice, slots_log2;
     uint32_t        n_items_direct, sc_direct;
     uint32_t       *work_counter;
@@ -815,7 +871,7 @@ hash_join_kernel(const JoinArgs a) {
                     const uint32_t p   = lo;
                     const uint32_t k   = w - a.item_start[p];
                     const uint32_t b0  = a.off_b[p], b1 = a.off_b[p + 1];
-                    const uint32_t p0  = a.off_p[p], p1 = a.off_p[p + 1];
+                    const uint32_t p0  = a.off_p[p], p1 = p0 + a.cnt_p[p];
                     const uint32_t sc  = (p1 - p0 + a.slice - 1) / a.slice;
                     const uint32_t rch = k / sc, ssl = k % sc;
                     bs                 = b0 + rch * a.cap;
@@ -1040,7 +1096,7 @@ __device__ __forceinline__ JoinItem fetch_join_item(const JoinArgs &a, int lane)
             const uint32_t p   = lo;
             const uint32_t k   = w - a.item_start[p];
             const uint32_t b0  = a.off_b[p], b1 = a.off_b[p + 1];
-            const uint32_t p0  = a.off_p[p], p1 = a.off_p[p + 1];
+            const uint32_t p0  = a.off_p[p], p1 = p0 + a.cnt_p[p];
             const uint32_t sc  = (p1 - p0 + a.slice - 1) / a.slice;
             const uint32_t rch = k / sc, ssl = k % sc;
             it.b_start         = b0 + rch * a.cap;
@@ -1524,6 +1580,12 @@ column_max_kernel(const uint64_t *__restrict__ col, uint64_t n, unsigned long lo
         m                          = o > m ? o : m;
     }
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// cursors of the histogram-free probe-side scatter: partition p starts at p * opt_cap
+__global__ void init_opt_cursors_kernel(uint32_t *__restrict__ cursor, uint32_t nparts, uint32_t opt_cap) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nparts) cursor[b] = b * opt_cap;
 }
 
 // Synthetic columns of BASELINE.json's configs, generated in HBM
