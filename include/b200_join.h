@@ -231,17 +231,52 @@ int   b200_stage_scatter_build(const uint64_t *d_keys, uint64_t n,
                                const uint32_t *d_dst_start, int ndst,
                                void *const *tup_dst, int npay,
                                const uint64_t *const *pay_cols,
-                               uint64_t *const *pay_dst);
+                               uint64_t *const *pay_dst, int phase);
+/* phase 0 = partition + broadcast; 1 = only the local partition pass (staged
+ * inside the library); 2 = only the broadcast of what phase 1 staged, so that a
+ * caller can put other work (the probe-side scatter, on another stream)
+ * between the two. */
 int   b200_stage_scatter_probe(const uint64_t *d_keys, uint64_t n,
                                int radix_bits, uint32_t *d_cursor,
                                void *d_tup_out);
+/* Histogram-free probe side: 2^bits regions of b200_opt_region_cap() tuples in
+ * d_tup_out; what does not fit goes to d_ov (n tuples) / *d_ovcnt and is
+ * partitioned exactly inside b200_stage_join_sum. */
+uint32_t b200_opt_region_cap(uint64_t n_probe, int radix_bits);
+int   b200_stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n,
+                                   int radix_bits, uint32_t opt_cap,
+                                   uint32_t *d_cursor, void *d_tup_out,
+                                   void *d_ov, uint32_t *d_ovcnt);
+/* d_hist_p is the probe histogram (opt_cap == 0) or the cursor array that
+ * b200_stage_scatter_probe_opt left behind (opt_cap > 0, with d_ov/d_ovcnt). */
 int   b200_stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b,
                           const void *d_tup_p, const uint32_t *d_hist_p,
                           int radix_bits, int n_proj,
                           const uint64_t *const *proj_cols,
                           const int *proj_side,
                           const uint64_t *const *proj_part_vals,
+                          uint32_t opt_cap, const void *d_ov,
+                          const uint32_t *d_ovcnt,
                           uint64_t *out_sums, uint64_t *out_matches);
+
+/* From the all-gathered per-rank build histograms hist_all[world][2^bits]:
+ * the global histogram and this rank's start inside every partition. */
+int   b200_stage_build_cursors(const uint32_t *d_hist_all, int world, int rank,
+                               int radix_bits, uint32_t *d_total,
+                               uint32_t *d_my_start);
+/* b200_stage_join_sum without the host read-back: d_result (DEVICE, n_proj + 2
+ * u64) receives {matches, sums..., overflow count} on the stream, so the
+ * caller can all-reduce it in place.  A non-zero overflow count means the
+ * overflow of the histogram-free scatter still has to be joined: call
+ * b200_stage_join_sum (synchronous) instead for that step. */
+int   b200_stage_join_sum_async(const void *d_tup_b, const uint32_t *d_hist_b,
+                                const void *d_tup_p, const uint32_t *d_hist_p,
+                                int radix_bits, int n_proj,
+                                const uint64_t *const *proj_cols,
+                                const int *proj_side,
+                                const uint64_t *const *proj_part_vals,
+                                uint32_t opt_cap, const void *d_ov,
+                                const uint32_t *d_ovcnt, uint64_t *d_result);
 
 /* Per-kernel device times of the calling thread's last RadixHashJoin /
  * b200_join_sum, measured with CUDA events on its stream when profiling is

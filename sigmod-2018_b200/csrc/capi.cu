@@ -332,11 +332,12 @@ int b200_stage_hist(const uint64_t *d_keys, uint64_t n, int radix_bits, uint32_t
 int b200_stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int radix_bits,
                              const uint32_t *d_hist_local, const uint32_t *d_dst_start, int ndst,
                              void *const *tup_dst, int npay, const uint64_t *const *pay_cols,
-                             uint64_t *const *pay_dst) {
+                             uint64_t *const *pay_dst, int phase) {
     if (n > kMaxRows) return fail("more than 2^32-1 rows");
     if (ndst < 1 || ndst > 8 || npay < 0 || npay > 2) return fail("ndst must be 1..8 and npay 0..2");
+    if (phase < 0 || phase > 2) return fail("phase must be 0, 1 or 2");
     stage_scatter_build(d_keys, n, rid_base, radix_bits, d_hist_local, d_dst_start, ndst, tup_dst, npay, pay_cols,
-                        pay_dst);
+                        pay_dst, phase);
     return 0;
 }
 
@@ -346,14 +347,44 @@ int b200_stage_scatter_probe(const uint64_t *d_keys, uint64_t n, int radix_bits,
     return 0;
 }
 
-int b200_stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p, const uint32_t *d_hist_p,
-                        int radix_bits, int n_proj, const uint64_t *const *proj_cols, const int *proj_side,
-                        const uint64_t *const *proj_part_vals, uint64_t *out_sums, uint64_t *out_matches) {
+uint32_t b200_opt_region_cap(uint64_t n_probe, int radix_bits) { return opt_region_cap(n_probe, radix_bits); }
+
+int b200_stage_build_cursors(const uint32_t *d_hist_all, int world, int rank, int radix_bits, uint32_t *d_total,
+                             uint32_t *d_my_start) {
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail("bad world / rank");
+    stage_build_cursors(d_hist_all, world, rank, radix_bits, d_total, d_my_start);
+    return 0;
+}
+
+int b200_stage_join_sum_async(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p,
+                              const uint32_t *d_hist_p, int radix_bits, int n_proj, const uint64_t *const *proj_cols,
+                              const int *proj_side, const uint64_t *const *proj_part_vals, uint32_t opt_cap,
+                              const void *d_ov, const uint32_t *d_ovcnt, uint64_t *d_result) {
     if (n_proj < 0 || n_proj > kMaxProj) return fail("at most 8 fused projections");
     ProjDesc pd[kMaxProj];
     for (int k = 0; k < n_proj; ++k)
         pd[k] = ProjDesc{proj_cols[k], nullptr, proj_side[k], proj_part_vals ? proj_part_vals[k] : nullptr};
-    JoinResult j = stage_join_sum(d_tup_b, d_hist_b, d_tup_p, d_hist_p, radix_bits, n_proj, pd);
+    stage_join_sum(d_tup_b, d_hist_b, d_tup_p, d_hist_p, radix_bits, n_proj, pd, opt_cap, d_ov, d_ovcnt,
+                   reinterpret_cast<unsigned long long *>(d_result));
+    return 0;
+}
+
+int b200_stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int radix_bits, uint32_t opt_cap,
+                                 uint32_t *d_cursor, void *d_tup_out, void *d_ov, uint32_t *d_ovcnt) {
+    if (n > (1u << 30)) return fail("histogram-free scatter is limited to 2^30 probe rows");
+    stage_scatter_probe_opt(d_keys, n, radix_bits, opt_cap, d_cursor, d_tup_out, d_ov, d_ovcnt);
+    return 0;
+}
+
+int b200_stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p, const uint32_t *d_hist_p,
+                        int radix_bits, int n_proj, const uint64_t *const *proj_cols, const int *proj_side,
+                        const uint64_t *const *proj_part_vals, uint32_t opt_cap, const void *d_ov,
+                        const uint32_t *d_ovcnt, uint64_t *out_sums, uint64_t *out_matches) {
+    if (n_proj < 0 || n_proj > kMaxProj) return fail("at most 8 fused projections");
+    ProjDesc pd[kMaxProj];
+    for (int k = 0; k < n_proj; ++k)
+        pd[k] = ProjDesc{proj_cols[k], nullptr, proj_side[k], proj_part_vals ? proj_part_vals[k] : nullptr};
+    JoinResult j = stage_join_sum(d_tup_b, d_hist_b, d_tup_p, d_hist_p, radix_bits, n_proj, pd, opt_cap, d_ov, d_ovcnt);
     for (int k = 0; k < n_proj; ++k) out_sums[k] = j.sums[k];
     *out_matches = j.m;
     return 0;

@@ -459,6 +459,8 @@ static void launch_join(const JoinArgs &a, bool key64, bool direct, int mode) {
     }
 }
 
+uint32_t opt_region_cap(uint64_t n_probe, int bits);
+
 static uint32_t ceil_log2(uint64_t v) {
     uint32_t l = 0;
     while ((1ull << l) < v) ++l;
@@ -593,10 +595,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         // Histogram-free probe side (fused SUM, 32-bit keys): every partition owns a region a few percent
         // above the uniform expectation; what does not fit overflows and is partitioned exactly afterwards.
         opt = mode == JoinOut::Sum && !key64 && t.opt_partition && P.src.n >= (1u << 20) && P.src.n <= (1u << 30);
-        if (opt) {
-            const uint64_t mean = (P.src.n + nparts - 1) / nparts;
-            opt_cap             = (uint32_t)((mean + mean / 32 + 6 * (uint64_t)sqrt((double)mean) + 64 + 3) & ~3ull);
-        }
+        if (opt) opt_cap = opt_region_cap(P.src.n, bits);
         tup_b = dev_alloc((size_t)B.src.n * tsz);
         tup_p = dev_alloc(opt ? (size_t)opt_cap * nparts * tsz : (size_t)P.src.n * tsz);
         // early materialisation: the first two build-side projections of a fused
@@ -899,43 +898,60 @@ void stage_hist(const uint64_t *d_keys, uint64_t n, int bits, uint32_t *d_hist) 
     launch_hist<uint32_t>(src, bits, d_hist);
 }
 
+// phase 0: partition + broadcast; phase 1: only the local partition pass (the staging buffers stay alive
+// in the calling thread's context); phase 2: only the broadcast of what phase 1 staged.
+struct BuildStaging {
+    DevBufPtr ctrl, tup, pay[2];
+};
+static thread_local BuildStaging t_build_staging;
+
 void stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int bits, const uint32_t *d_hist_local,
                          const uint32_t *d_dst_start, int ndst, void *const *tup_dst, int npay,
-                         const uint64_t *const *pay_cols, uint64_t *const *pay_dst) {
+                         const uint64_t *const *pay_cols, uint64_t *const *pay_dst, int phase) {
     B200_REQUIRE(ndst >= 1 && ndst <= kMaxPeers && npay >= 0 && npay <= 2, "bad destination / payload count");
     if (n == 0) return;
     Context       &c      = ctx();
     const uint32_t nparts = 1u << bits;
+    BuildStaging  &st     = t_build_staging;
+    if (phase == 2) {
+        B200_REQUIRE(st.tup != nullptr, "broadcast phase without a staged partition pass");
+    } else {
     // 1. partition the local shard into a staging buffer (local offsets from the local histogram)
-    DevBufPtr ctrl = dev_alloc(5 * (size_t)(nparts + 1) * sizeof(uint32_t));
+    st.ctrl = dev_alloc(5 * (size_t)(nparts + 1) * sizeof(uint32_t));
+    DevBufPtr &ctrl = st.ctrl;
     uint32_t *off_l = ctrl->as<uint32_t>(), *off_x = off_l + nparts + 1, *cur_l = off_x + nparts + 1,
              *cur_x = cur_l + nparts + 1, *items = cur_x + nparts + 1;
     partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_local, d_hist_local, nparts, 1u, 1u, off_l, off_x,
                                                           cur_l, cur_x, items, items, 0u);
     B200_LAUNCH_CHECK();
-    DevBufPtr stage_tup = dev_alloc(n * sizeof(Tup32));
-    DevBufPtr stage_pay[2];
+    st.tup = dev_alloc(n * sizeof(Tup32));
     PayArgs   pay{};
     pay.ndst     = 0;
     pay.rid_base = rid_base;
     for (int k = 0; k < npay; ++k) {
-        stage_pay[k] = dev_alloc(n * sizeof(uint64_t));
-        pay.col[k]   = pay_cols[k];
-        pay.ids[k]   = nullptr;
-        pay.out[k]   = stage_pay[k]->as<uint64_t>();
+        st.pay[k]  = dev_alloc(n * sizeof(uint64_t));
+        pay.col[k] = pay_cols[k];
+        pay.ids[k] = nullptr;
+        pay.out[k] = st.pay[k]->as<uint64_t>();
     }
     KeySrc src{d_keys, nullptr, (uint32_t)n};
     {
         TimedScope ts("scatter_b");
-        launch_scatter_pay<uint32_t>(src, bits, cur_l, stage_tup->ptr, pay, npay);
+        launch_scatter_pay<uint32_t>(src, bits, cur_l, st.tup->ptr, pay, npay);
     }
+    }
+    if (phase == 1) return;
     // 2. copy every partition segment to its place in the global layout of all destinations
+    DevBufPtr stage_tup = st.tup;
+    DevBufPtr stage_pay[2] = {st.pay[0], st.pay[1]};
+    const uint32_t *off_l = st.ctrl->as<uint32_t>();
     SegCopyArgs s{};
     s.src_tup   = stage_tup->as<uint64_t>();
     s.src_off   = off_l;
     s.dst_start = d_dst_start;
     s.ndst      = ndst;
     s.npay      = npay;
+    s.first     = ndst > 1 ? (int)(rid_base / (uint32_t)n) % ndst : 0;   // = this rank (equal shards)
     for (int d = 0; d < ndst; ++d) s.dst_tup[d] = static_cast<uint64_t *>(tup_dst[d]);
     for (int k = 0; k < npay; ++k) {
         s.src_pay[k] = stage_pay[k]->as<uint64_t>();
@@ -946,6 +962,7 @@ void stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, 
         segment_broadcast_kernel<<<nparts, 256, 0, c.stream>>>(s);
         B200_LAUNCH_CHECK();
     }
+    st = BuildStaging{};   // released in stream order
 }
 
 void stage_scatter_probe(const uint64_t *d_keys, uint64_t n, int bits, uint32_t *d_cursor, void *d_tup_out) {
@@ -955,8 +972,42 @@ void stage_scatter_probe(const uint64_t *d_keys, uint64_t n, int bits, uint32_t 
     launch_scatter<uint32_t>(src, bits, d_cursor, d_tup_out);
 }
 
+void stage_build_cursors(const uint32_t *d_hist_all, int world, int rank, int bits, uint32_t *d_total,
+                         uint32_t *d_my_start) {
+    build_cursors_kernel<1024><<<1, 1024, 0, ctx().stream>>>(d_hist_all, (uint32_t)world, (uint32_t)rank, 1u << bits,
+                                                              d_total, d_my_start);
+    B200_LAUNCH_CHECK();
+}
+
+uint32_t opt_region_cap(uint64_t n_probe, int bits) {
+    const uint64_t nparts = 1ull << bits;
+    const uint64_t mean   = (n_probe + nparts - 1) / nparts;
+    return (uint32_t)((mean + mean / 32 + 6 * (uint64_t)sqrt((double)mean) + 64 + 3) & ~3ull);
+}
+
+// histogram-free probe-side scatter into caller-owned buffers: d_tup_out holds 2^bits regions of opt_cap tuples,
+// d_ov (n tuples) and d_ovcnt (one u32) receive what does not fit
+void stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint32_t opt_cap, uint32_t *d_cursor,
+                             void *d_tup_out, void *d_ov, uint32_t *d_ovcnt) {
+    Context       &c      = ctx();
+    const uint32_t nparts = 1u << bits;
+    B200_REQUIRE(n <= (1u << 30), "histogram-free scatter is limited to 2^30 probe rows");
+    init_opt_cursors_kernel<<<(nparts + 255) / 256, 256, 0, c.stream>>>(d_cursor, nparts, opt_cap);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cudaMemsetAsync(d_ovcnt, 0, sizeof(uint32_t), c.stream));
+    if (n == 0) return;
+    KeySrc src{d_keys, nullptr, (uint32_t)n};
+    TimedScope ts("scatter_p");
+    launch_scatter_opt(src, bits, d_cursor, d_tup_out, OptArgs{opt_cap, d_ovcnt, d_ov});
+}
+
+// d_hist_p: probe-side histogram (opt_cap == 0) or the cursor array stage_scatter_probe_opt left behind
+// d_result != nullptr: asynchronous — matches, the nproj sums and the overflow count are copied to
+// d_result[0], d_result[1..nproj], d_result[nproj + 1] (u64 each) on the stream and nothing is read back;
+// the caller runs stage_join_overflow when it later finds a non-zero overflow count.
 JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p, const uint32_t *d_hist_p,
-                          int bits, int nproj, const ProjDesc *proj) {
+                          int bits, int nproj, const ProjDesc *proj, uint32_t opt_cap, const void *d_ov,
+                          const uint32_t *d_ovcnt, unsigned long long *d_result) {
     Context   &c = ctx();
     Tuning    &t = tuning();
     JoinResult res;
@@ -983,7 +1034,7 @@ JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const v
     {
         TimedScope ts("scan");
         partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_b, d_hist_p, nparts, cap, a.slice, off_b, off_p,
-                                                              cur_b, cur_p, items, cnt_p, 0u);
+                                                              cur_b, cur_p, items, cnt_p, opt_cap);
         B200_LAUNCH_CHECK();
     }
     a.tup_b      = d_tup_b;
@@ -1003,8 +1054,43 @@ JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const v
         TimedScope ts("join");
         launch_join(a, false, false, MODE_SUM);
     }
-    B200_CUDA(cudaMemcpyAsync(c.h_scratch, d_u64, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
-    B200_CUDA(cudaStreamSynchronize(c.stream));
+    if (d_result) {
+        B200_CUDA(cudaMemcpyAsync(d_result, d_u64, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c.stream));
+        if (nproj)
+            B200_CUDA(cudaMemcpyAsync(d_result + 1, d_u64 + 8, (size_t)nproj * sizeof(unsigned long long),
+                                      cudaMemcpyDeviceToDevice, c.stream));
+        B200_CUDA(cudaMemsetAsync(d_result + nproj + 1, 0, sizeof(unsigned long long), c.stream));
+        if (opt_cap)
+            B200_CUDA(cudaMemcpyAsync(d_result + nproj + 1, d_ovcnt, sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                      c.stream));
+        return res;
+    }
+    auto read_back = [&]() {
+        B200_CUDA(cudaMemcpyAsync(c.h_scratch, d_u64, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                  c.stream));
+        if (opt_cap)
+            B200_CUDA(cudaMemcpyAsync(c.h_scratch + 16, d_ovcnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+        B200_CUDA(cudaStreamSynchronize(c.stream));
+    };
+    read_back();
+    const uint32_t n_over = opt_cap ? *reinterpret_cast<uint32_t *>(c.h_scratch + 16) : 0u;
+    if (n_over) {
+        // exact second pass over the overflow (see run_join)
+        TimedScope ts("overflow");
+        DevBufPtr hist_ov = dev_alloc((size_t)nparts * sizeof(uint32_t));
+        B200_CUDA(cudaMemsetAsync(hist_ov->ptr, 0, hist_ov->bytes, c.stream));
+        KeySrc ov_src{static_cast<const uint64_t *>(d_ov), nullptr, n_over};
+        launch_hist<uint32_t>(ov_src, bits, hist_ov->as<uint32_t>());
+        partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_b, hist_ov->as<uint32_t>(), nparts, cap, a.slice,
+                                                              off_b, off_p, cur_b, cur_p, items, cnt_p, 0u);
+        B200_LAUNCH_CHECK();
+        DevBufPtr ov_part = dev_alloc((size_t)n_over * sizeof(Tup32));
+        launch_scatter_tuples(static_cast<const uint64_t *>(d_ov), n_over, bits, cur_p, ov_part->ptr);
+        B200_CUDA(cudaMemsetAsync(d_u32, 0, sizeof(uint32_t), c.stream));
+        a.tup_p = ov_part->ptr;
+        launch_join(a, false, false, MODE_SUM);
+        read_back();
+    }
     res.m = c.h_scratch[0];
     for (int k = 0; k < nproj; ++k) res.sums[k] = c.h_scratch[8 + k];
     return res;

@@ -94,10 +94,16 @@ void       stage_hist(const uint64_t *d_keys, uint64_t n, int bits, uint32_t *d_
 void       stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int bits,
                                const uint32_t *d_hist_local, const uint32_t *d_dst_start, int ndst,
                                void *const *tup_dst, int npay, const uint64_t *const *pay_cols,
-                               uint64_t *const *pay_dst);
+                               uint64_t *const *pay_dst, int phase = 0);
 void       stage_scatter_probe(const uint64_t *d_keys, uint64_t n, int bits, uint32_t *d_cursor, void *d_tup_out);
+uint32_t   opt_region_cap(uint64_t n_probe, int bits);
+void       stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint32_t opt_cap, uint32_t *d_cursor,
+                                   void *d_tup_out, void *d_ov, uint32_t *d_ovcnt);
 JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p,
-                          const uint32_t *d_hist_p, int bits, int nproj, const ProjDesc *proj);
+                          const uint32_t *d_hist_p, int bits, int nproj, const ProjDesc *proj, uint32_t opt_cap,
+                          const void *d_ov, const uint32_t *d_ovcnt, unsigned long long *d_result = nullptr);
+void       stage_build_cursors(const uint32_t *d_hist_all, int world, int rank, int bits, uint32_t *d_total,
+                               uint32_t *d_my_start);
 
 // runtime control (engine.cu)
 void               request_device(int device);   // before the first use

@@ -540,6 +540,8 @@ struct SegCopyArgs {
     const uint32_t *src_off;       // [nparts + 1] local partition offsets
     const uint32_t *dst_start;     // [nparts] start of this GPU's segment in the global layout
     int             ndst, npay;
+    int             first;         // destinations are visited first+1, first+2, ... (mod ndst): every rank starts
+                                   // at a different peer, so no destination's NVLink ingress is hit by all at once
     uint64_t       *dst_tup[kMaxPeers];
     uint64_t       *dst_pay[2][kMaxPeers];
 };
@@ -548,10 +550,27 @@ __global__ void __launch_bounds__(256) segment_broadcast_kernel(const SegCopyArg
     const uint32_t first = s.src_off[p];
     const uint32_t count = s.src_off[p + 1] - first;
     const uint32_t dst   = s.dst_start[p];
-    for (int d = 0; d < s.ndst; ++d) {
-        for (uint32_t i = threadIdx.x; i < count; i += 256) s.dst_tup[d][dst + i] = s.src_tup[first + i];
-        for (int k = 0; k < s.npay; ++k)
-            for (uint32_t i = threadIdx.x; i < count; i += 256) s.dst_pay[k][d][dst + i] = s.src_pay[k][first + i];
+    constexpr int  UN    = 4;
+    // every element is loaded once and stored to all destinations; 4 elements per thread in flight
+    for (int a = 0; a <= s.npay; ++a) {
+        const uint64_t *src = a == 0 ? s.src_tup : s.src_pay[a - 1];
+        for (uint32_t i0 = threadIdx.x; i0 < count; i0 += 256 * UN) {
+            uint64_t v[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const uint32_t i = i0 + (uint32_t)u * 256;
+                v[u]             = i < count ? ld_stream_u64(src + first + i) : 0ull;
+            }
+            for (int j = 1; j <= s.ndst; ++j) {
+                const int d    = (s.first + j) % s.ndst;
+                uint64_t *out  = (a == 0 ? s.dst_tup[d] : s.dst_pay[a - 1][d]) + dst;
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const uint32_t i = i0 + (uint32_t)u * 256;
+                    if (i < count) out[i] = v[u];
+                }
+            }
+        }
     }
 }
 
@@ -1580,6 +1599,38 @@ column_max_kernel(const uint64_t *__restrict__ col, uint64_t n, unsigned long lo
         m                          = o > m ? o : m;
     }
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// multi-GPU build side: from the all-gathered per-rank histograms hist_all[world][nparts] compute the
+// global histogram and this rank's scatter start inside the global partition layout (one CTA)
+template <int NT>
+__global__ void __launch_bounds__(NT)
+build_cursors_kernel(const uint32_t *__restrict__ hist_all, uint32_t world, uint32_t rank, uint32_t nparts,
+                     uint32_t *__restrict__ total, uint32_t *__restrict__ my_start) {
+    __shared__ uint32_t warp_sums[NT / 32 + 1];
+    const uint32_t per   = (nparts + NT - 1) / NT;
+    const uint32_t first = threadIdx.x * per;
+    uint32_t       s     = 0;
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t b = first + k;
+        if (b < nparts)
+            for (uint32_t r = 0; r < world; ++r) s += hist_all[r * nparts + b];
+    }
+    uint32_t run = block_exclusive_scan<NT>(s, warp_sums);
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t b = first + k;
+        if (b < nparts) {
+            uint32_t tot = 0, before = 0;
+            for (uint32_t r = 0; r < world; ++r) {
+                const uint32_t c = hist_all[r * nparts + b];
+                if (r < rank) before += c;
+                tot += c;
+            }
+            total[b]    = tot;
+            my_start[b] = run + before;
+            run += tot;
+        }
+    }
 }
 
 // cursors of the histogram-free probe-side scatter: partition p starts at p * opt_cap

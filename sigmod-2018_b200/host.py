@@ -182,10 +182,19 @@ def _declare(L: C.CDLL) -> None:
         "b200_radix_bits_for": (C.c_int, [C.c_uint64]),
         "b200_stage_hist": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
         "b200_stage_scatter_build": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
-                                               C.c_int, P(C.c_void_p), C.c_int, P(C.c_void_p), P(C.c_void_p)]),
+                                               C.c_int, P(C.c_void_p), C.c_int, P(C.c_void_p), P(C.c_void_p),
+                                               C.c_int]),
         "b200_stage_scatter_probe": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
+        "b200_opt_region_cap": (C.c_uint32, [C.c_uint64, C.c_int]),
+        "b200_stage_build_cursors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+        "b200_stage_join_sum_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                P(C.c_void_p), P(C.c_int), P(C.c_void_p), C.c_uint32, C.c_void_p,
+                                                C.c_void_p, C.c_void_p]),
+        "b200_stage_scatter_probe_opt": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p]),
         "b200_stage_join_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
-                                          P(C.c_void_p), P(C.c_int), P(C.c_void_p), u64p, u64p]),
+                                          P(C.c_void_p), P(C.c_int), P(C.c_void_p), C.c_uint32, C.c_void_p,
+                                          C.c_void_p, u64p, u64p]),
         "b200_set_profiling": (C.c_int, [C.c_int]),
         "b200_last_kernel_ms": (C.c_double, [C.c_char_p]),
         "b200_kernel_launches": (C.c_uint64, [C.c_int]),

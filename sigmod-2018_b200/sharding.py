@@ -59,6 +59,9 @@ def allgather_column(shard, total_rows: int, dist, out=None):
     return torch.cat(parts)
 
 
+kMaxResult = 10   # matches + up to 8 sums + overflow count
+
+
 class BroadcastScatterJoin:
     """Config-2-shaped join over `world` GPUs, one process each (broadcast plan).
 
@@ -71,8 +74,9 @@ class BroadcastScatterJoin:
          CUDA-IPC mappings, the copy kernel's 256-byte stores travel over NVLink (no all-gather of
          raw columns, no second partition pass on the receivers); up to two build-side SUM
          columns travel with the tuples (early materialisation);
-      4. the probe shard is scattered locally; a stream-ordered all-reduce is the barrier that
-         tells every rank the peers' stores have landed;
+      4. the probe shard is partitioned locally (histogram-free regions + overflow) on a SIDE
+         stream, underneath steps 1-3; a stream-ordered all-reduce is the barrier that tells every
+         rank the peers' stores have landed;
       5. per-partition build + probe + SUM on local buffers, then the k checksums and the match
          count are all-reduced.
     The probe side never moves.  `dist` may be None (world = 1: the same phases, no exchange),
@@ -93,10 +97,22 @@ class BroadcastScatterJoin:
         # build-partition buffers live in cudaMalloc memory so they can be exported over CUDA IPC
         self.tup_b = b200.DeviceColumn(max(n_build_total, 1))
         self.pay_b = [b200.DeviceColumn(max(n_build_total, 1)) for _ in range(n_pay)]
-        self.tup_p = b200.DeviceColumn(max(n_probe_local, 1))
+        # histogram-free probe side: P fixed regions + an overflow array (host.py / DESIGN.md §4)
+        self.opt_cap = int(L.b200_opt_region_cap(n_probe_local, self.bits)) if n_probe_local >= (1 << 20) else 0
+        self.tup_p = b200.DeviceColumn(max(self.opt_cap * self.P if self.opt_cap else n_probe_local, 1))
+        self.ov_p = b200.DeviceColumn(max(n_probe_local, 1)) if self.opt_cap else None
+        self.ovcnt = torch.zeros(1, dtype=torch.int32, device=device)
+        import os
+        self.side = torch.cuda.Stream(device=device) if device is not None and getattr(device, "type", "") == "cuda" \
+            and not os.environ.get("B200_PLAN_SERIAL") else None
+        self.debug = bool(os.environ.get("B200_PLAN_DEBUG"))
+        self.marks = []
         self.hist = torch.zeros((2, self.P), dtype=torch.int32, device=device)      # [build, probe] local
         self.hist_all = torch.zeros((world, self.P), dtype=torch.int32, device=device)
         self.token = torch.zeros(1, dtype=torch.int32, device=device)
+        self.total_b = torch.zeros(self.P, dtype=torch.int32, device=device)
+        self.cur_b = torch.zeros(self.P, dtype=torch.int32, device=device)
+        self.result = torch.zeros(kMaxResult, dtype=torch.int64, device=device)
         self.peer_tup = [self.tup_b.ptr] * 1
         self.peer_pay = [[p.ptr] for p in self.pay_b]
         self._imported = []
@@ -135,49 +151,98 @@ class BroadcastScatterJoin:
         C, L, torch = self.C, self.L, self.torch
         P, bits, world, rank = self.P, self.bits, self.world, self.rank
         h_b, h_p = self.hist[0], self.hist[1]
+        main = torch.cuda.current_stream()
+        side = self.side if self.side is not None else main
+
+        def mark(name, stream=None):
+            if self.debug:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream or main)
+                self.marks.append((name, ev))
+
+        self.marks = []
+        mark("start")
+        # ---- build side: histogram, exchange of the counts, local partition pass ----
         assert L.b200_stage_hist(build_keys_ptr, self.n_build_local, bits, h_b.data_ptr()) == 0
-        assert L.b200_stage_hist(probe_keys_ptr, self.n_probe_local, bits, h_p.data_ptr()) == 0
         if world > 1:
             self.dist.all_gather_into_tensor(self.hist_all.view(-1), h_b)
-            total_b = self.hist_all.sum(0, dtype=torch.int32)
-            before_me = self.hist_all[:rank].sum(0, dtype=torch.int32) if rank else torch.zeros_like(total_b)
         else:
-            total_b, before_me = h_b.clone(), torch.zeros_like(h_b)
-        start_b = torch.cumsum(total_b, 0, dtype=torch.int32) - total_b          # partition starts, global layout
-        cur_b = (start_b + before_me).contiguous()
-        cur_p = (torch.cumsum(h_p, 0, dtype=torch.int32) - h_p).contiguous()
+            self.hist_all[0].copy_(h_b)
+        total_b, cur_b = self.total_b, self.cur_b
+        assert L.b200_stage_build_cursors(self.hist_all.data_ptr(), world, rank, bits, total_b.data_ptr(),
+                                          cur_b.data_ptr()) == 0
         ndst = len(self.peer_tup)
         tup_dst = (C.c_void_p * ndst)(*self.peer_tup)
         npay = self.n_pay
         pay_cols = (C.c_void_p * max(npay, 1))(*build_pay_ptrs[:npay])
         flat = [self.peer_pay[k][d] for k in range(npay) for d in range(ndst)]
         pay_dst = (C.c_void_p * max(len(flat), 1))(*flat)
+        # the local partition pass of the build shard and the probe-side scatter both want a whole SM's shared
+        # memory per CTA, so they run back to back; the NVLink-bound broadcast copy (tiny CTAs) then runs
+        # UNDER the probe-side scatter, which is issued on the side stream in between
         assert L.b200_stage_scatter_build(build_keys_ptr, self.n_build_local, rank * self.n_build_local, bits,
                                           h_b.data_ptr(), cur_b.data_ptr(), ndst, tup_dst, npay, pay_cols,
-                                          pay_dst) == 0
-        assert L.b200_stage_scatter_probe(probe_keys_ptr, self.n_probe_local, bits, cur_p.data_ptr(),
-                                          self.tup_p.ptr) == 0
+                                          pay_dst, 1) == 0
+        mark("build partitioned")
+        # ---- probe side: local, independent of the exchange -> side stream ----
+        side.wait_stream(main)
+        L.b200_set_stream(side.cuda_stream)
+        if self.opt_cap:
+            assert L.b200_stage_scatter_probe_opt(probe_keys_ptr, self.n_probe_local, bits, self.opt_cap,
+                                                  h_p.data_ptr(), self.tup_p.ptr, self.ov_p.ptr,
+                                                  self.ovcnt.data_ptr()) == 0
+        else:
+            assert L.b200_stage_hist(probe_keys_ptr, self.n_probe_local, bits, h_p.data_ptr()) == 0
+            with torch.cuda.stream(side):
+                cur_p = (torch.cumsum(h_p, 0, dtype=torch.int32) - h_p).contiguous()
+            assert L.b200_stage_scatter_probe(probe_keys_ptr, self.n_probe_local, bits, cur_p.data_ptr(),
+                                              self.tup_p.ptr) == 0
+            cur_p.record_stream(side)
+        mark("probe scattered (side)", side)
+        L.b200_set_stream(main.cuda_stream)
+        # ---- broadcast of the partitioned build shard (main stream, concurrent with the probe scatter) ----
+        assert L.b200_stage_scatter_build(build_keys_ptr, self.n_build_local, rank * self.n_build_local, bits,
+                                          h_b.data_ptr(), cur_b.data_ptr(), ndst, tup_dst, npay, pay_cols,
+                                          pay_dst, 2) == 0
+        mark("broadcast done")
         if world > 1:
-            self.dist.all_reduce(self.token)      # stream-ordered barrier: every peer's scatter has completed
+            self.dist.all_reduce(self.token)      # stream-ordered barrier: every peer's broadcast has landed
+        mark("barrier done")
+        main.wait_stream(side)
         k = len(proj_cols)
         cols = (C.c_void_p * max(k, 1))(*proj_cols)
         sides = (C.c_int * max(k, 1))(*proj_side)
         part = []
-        for col, side in zip(proj_cols, proj_side):
-            if side == 0:
+        for col, side_k in zip(proj_cols, proj_side):
+            if side_k == 0:
                 part.append(self.pay_b[build_pay_ptrs.index(col)].ptr)
             else:
                 part.append(None)
         part_vals = (C.c_void_p * max(k, 1))(*part)
-        sums = (C.c_uint64 * max(k, 1))()
-        m = C.c_uint64(0)
-        total_b = total_b.contiguous()
-        assert L.b200_stage_join_sum(self.tup_b.ptr, total_b.data_ptr(), self.tup_p.ptr, h_p.data_ptr(), bits, k, cols,
-                                     sides, part_vals, sums, C.byref(m)) == 0
-        # the all-reduce of the checksums also ends the step on every rank: no peer can start
-        # overwriting this rank's build buffers before its join has finished
-        return allreduce_checksums([int(s) for s in sums[:k]], int(m.value), self.dist if world > 1 else None,
-                                   self.device)
+        args = (self.tup_b.ptr, total_b.data_ptr(), self.tup_p.ptr, h_p.data_ptr(), bits, k, cols, sides, part_vals,
+                self.opt_cap, self.ov_p.ptr if self.opt_cap else None, self.ovcnt.data_ptr())
+        # asynchronous join: {matches, sums, overflow count} stay on the device and are all-reduced in place
+        # (u64 sums mod 2^64 == wrapping int64 sums); that all-reduce also ends the step on every rank, so no
+        # peer can start overwriting this rank's build buffers before its join has finished
+        res = self.result[: k + 2]
+        assert L.b200_stage_join_sum_async(*args, res.data_ptr()) == 0
+        if world > 1:
+            self.dist.all_reduce(res)
+        mark("join + all-reduce done")
+        host = res.cpu().tolist()
+        if self.debug and rank == 0:
+            t0 = self.marks[0][1]
+            print("plan timeline (ms): " + ", ".join(f"{n} {t0.elapsed_time(e):.3f}" for n, e in self.marks[1:]),
+                  file=__import__("sys").stderr)
+        if host[k + 1] != 0:
+            # some rank's histogram-free scatter overflowed (skewed keys): redo the join part of this step
+            # synchronously, overflow pass included, and reduce again
+            sums = (C.c_uint64 * max(k, 1))()
+            m = C.c_uint64(0)
+            assert L.b200_stage_join_sum(*args, sums, C.byref(m)) == 0
+            return allreduce_checksums([int(x) for x in sums[:k]], int(m.value), self.dist if world > 1 else None,
+                                       self.device)
+        return i64_to_u64(host[1: k + 1]), int(host[0])
 
     def close(self):
         for p in self._imported:

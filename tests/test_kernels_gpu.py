@@ -154,14 +154,15 @@ def test_join_sum_config2_shape_scaled_down(gpu, orc, kr_bits, ks_bits):
 
 
 # ---- staged join (the phases the multi-GPU plan drives), single GPU ----------
-@pytest.mark.parametrize("kr_bits,ks_bits", [(15, 18), (18, 21)])
-def test_staged_join_matches_fused_join(gpu, orc, kr_bits, ks_bits):
+@pytest.mark.parametrize("kr_bits,ks_bits,zipf", [(15, 18, False), (18, 21, False), (16, 21, True)])
+def test_staged_join_matches_fused_join(gpu, orc, kr_bits, ks_bits, zipf):
     """sharding.BroadcastScatterJoin with world = 1: hist -> cursors -> scatter (build side with an
     early-materialised payload, through the multi-destination path) -> join_sum, against the oracle."""
     torch = pytest.importorskip("torch")
     nr, ns = 1 << kr_bits, 1 << ks_bits
     kr = orc.synth_column(nr, 0, kr_bits, gpu.SEED_R)
-    ks = orc.synth_column(ns, 0, ks_bits, gpu.SEED_S)
+    # zipf: the histogram-free probe scatter overflows its regions -> exact second pass
+    ks = orc.synth_column(ns, 2, kr_bits, 77) if zipf else orc.synth_column(ns, 0, ks_bits, gpu.SEED_S)
     pr = orc.synth_column(nr, 1, 0, gpu.SEED_R + 1)
     ps = orc.synth_column(ns, 1, 0, gpu.SEED_S + 1)
     want, wm = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
