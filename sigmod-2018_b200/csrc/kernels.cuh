@@ -449,13 +449,15 @@ radix_scatter_pay_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__
     const uint64_t ntiles = (n + TILE - 1) / TILE;
     const uint32_t per    = (nbins + NT - 1) / NT;
     for (uint32_t b = threadIdx.x; b < nbins; b += NT) cnt[b] = 0;
-    __syncthreads();
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+
+    // keys (and payload values) of a tile live in registers; the next tile's are loaded while the
+    // current one is copied out
+    KeyT     keys[U];
+    uint32_t in_rid[TUPIN ? U : 1];
+    uint64_t pvals[NPAY > 0 ? NPAY : 1][U];
+    auto load_tile = [&](uint64_t tile) {
         const uint64_t base  = tile * TILE;
         const uint32_t count = (uint32_t)min((uint64_t)TILE, n - base);
-        KeyT     keys[U];
-        uint32_t in_rid[TUPIN ? U : 1];
-        uint16_t rank[U];
         if constexpr (TUPIN) {
             uint64_t raw[U];
             load_tile_keys<NT, U, uint64_t>(src, base, count, false, raw);
@@ -467,6 +469,23 @@ radix_scatter_pay_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__
         } else {
             load_tile_keys<NT, U, KeyT>(src, base, count, false, keys);
         }
+#pragma unroll
+        for (int k = 0; k < NPAY; ++k) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const uint32_t li  = (uint32_t)(j * NT) + threadIdx.x;
+                const uint32_t rid = (uint32_t)base + li;
+                pvals[k][j]        = li < count ? ld_stream_u64(pay.col[k] + (pay.ids[k] ? pay.ids[k][rid] : rid)) : 0ull;
+            }
+        }
+    };
+    uint64_t tile = blockIdx.x;
+    if (tile < ntiles) load_tile(tile);
+    __syncthreads();
+    for (; tile < ntiles; tile += gridDim.x) {
+        const uint64_t base  = tile * TILE;
+        const uint32_t count = (uint32_t)min((uint64_t)TILE, n - base);
+        uint16_t rank[U];
 #pragma unroll
         for (int j = 0; j < U; ++j)
             if ((uint32_t)(j * NT) + threadIdx.x < count)
@@ -503,11 +522,11 @@ radix_scatter_pay_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__
                 if constexpr (sizeof(KeyT) == 8) t.pad = 0;
                 stage[pos] = t;
 #pragma unroll
-                for (int k = 0; k < NPAY; ++k)
-                    pstage[(size_t)k * TILE + pos] = pay.col[k][pay.ids[k] ? pay.ids[k][rid] : rid];
+                for (int k = 0; k < NPAY; ++k) pstage[(size_t)k * TILE + pos] = pvals[k][j];
             }
         }
         __syncthreads();
+        if (tile + gridDim.x < ntiles) load_tile(tile + gridDim.x);
         for (uint32_t i = threadIdx.x; i < count; i += NT) {
             const TupT     t = stage[i];
             const uint32_t o = gdelta[(uint32_t)t.key & mask] + i;

@@ -20,7 +20,7 @@ import numpy as np
 
 __all__ = [
     "LIB_PATH", "load_library", "lib", "declared_symbols",
-    "RelationMapArray", "parse_query", "execute_query", "QueryResult",
+    "RelationMapArray", "parse_query", "execute_query", "execute_batch", "QueryResult",
     "scan_filter", "radix_partition", "hash_join_pairs", "gather_sum", "join_sum",
     "join_sum_device", "synth_column_device", "DeviceColumn", "kernel_launches", "last_kernel_ms",
     "SYNTH_PERM", "SYNTH_PAYLOAD", "SYNTH_ZIPF", "SYNTH_UNIFORM", "SYNTH_IOTA",
@@ -374,6 +374,21 @@ def execute_query(text: str, rel_map: RelationMapArray) -> QueryResult:
         return QueryResult([int(s) for s in sums], int(rows.value))
     finally:
         L.FreeInterResults(inter)
+
+
+def execute_batch(queries: list[str], rel_map: RelationMapArray, workers: int = 4) -> list[QueryResult]:
+    """A batch of queries on `workers` host threads (the reference's scheduler.c as a
+    stream scheduler).  The reference runs a batch sequentially on one thread (handler.c:78-89) and its
+    job queue cannot overlap two queries (one global barrier counter, structs.h:223).  Here a job is a
+    whole query: every worker thread owns a CUDA stream inside the library (thread-local context), ctypes
+    releases the GIL during the calls, and results come back in submission order so the output stays the
+    reference's."""
+    from concurrent.futures import ThreadPoolExecutor
+    rel_map.register()          # uploads happen once, before the workers start
+    if workers <= 1:
+        return [execute_query(q, rel_map) for q in queries]
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        return list(pool.map(lambda q: execute_query(q, rel_map), queries))
 
 
 # --------------------------------------------------------------------------
