@@ -49,9 +49,6 @@ struct KernelTimer {
 struct Context {
     cudaStream_t stream       = nullptr;
     bool         owns_stream  = false;
-    // second stream + events: the build-side scatter overlaps the probe-side histogram
-    cudaStream_t side_stream  = nullptr;
-    cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
     // pinned scratch for counters read back after a stream synchronise
     unsigned long long *h_scratch = nullptr;   // 64 x u64, pinned
     unsigned long long *d_scratch = nullptr;   // 64 x u64, device

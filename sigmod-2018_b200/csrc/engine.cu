@@ -130,9 +130,6 @@ Context::~Context() {
         if (kv.second.start) cudaEventDestroy(kv.second.start);
         if (kv.second.stop) cudaEventDestroy(kv.second.stop);
     }
-    if (ev_fork) cudaEventDestroy(ev_fork);
-    if (ev_join) cudaEventDestroy(ev_join);
-    if (side_stream) cudaStreamDestroy(side_stream);
     if (h_scratch) cudaFreeHost(h_scratch);
     if (d_scratch) cudaFree(d_scratch);
     if (owns_stream && stream) cudaStreamDestroy(stream);
@@ -149,9 +146,6 @@ Context &ctx() {
         c = new Context();
         B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->owns_stream = true;
-        B200_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-        B200_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        B200_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         B200_CUDA(cudaMallocHost(&c->h_scratch, 64 * sizeof(unsigned long long)));
         B200_CUDA(cudaMalloc(&c->d_scratch, 64 * sizeof(unsigned long long)));
     }
@@ -304,14 +298,8 @@ void unregister_all_columns() {
 // ---------------------------------------------------------------------------
 // kernel launch helpers
 // ---------------------------------------------------------------------------
-// stream the launch_* helpers enqueue on: the context stream unless a scope
-// redirects them to the side stream
-static thread_local cudaStream_t t_launch_override = nullptr;
-static cudaStream_t launch_stream() { return t_launch_override ? t_launch_override : ctx().stream; }
-struct SideStreamScope {
-    explicit SideStreamScope(cudaStream_t s) { t_launch_override = s; }
-    ~SideStreamScope() { t_launch_override = nullptr; }
-};
+static cudaStream_t launch_stream() { return ctx().stream; }
+
 template <typename KernelT>
 static void allow_smem(KernelT kernel, size_t bytes) {
     if (bytes > 48 * 1024)

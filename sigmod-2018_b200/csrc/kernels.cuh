@@ -654,54 +654,9 @@ template <typename KeyT> struct ProbeTup {
     uint32_t rid;
 };
 
-// Shared-memory table entry access.  32-bit keys: one 8-byte word per build
-// tuple {key, next} so a chain step is a single LDS.64; 64-bit keys: a key
-// array and a 16-bit link array.
+// Shared-memory bucket-chain table of hash_join_kernel (64-bit keys): a key array, a 16-bit link array
+// and 16-bit chain heads — rhjoin.c:219-273's bucket[]/chain[] in shared memory.
 template <typename KeyT> struct TableView;
-// 32-bit keys: bucketised open addressing.  A bucket is four key slots (one
-// LDS.128 per probe step, four compares), a parallel 16-bit array maps a slot
-// to the build tuple's position in its chunk.  Slots = 2^slots_log2 >= 1.75 x cap.
-// 0xFFFFFFFF marks an empty slot; the 32-bit-key kernels only run when the
-// column maxima are below it (engine.cu).  Duplicate build keys simply occupy
-// several slots; a probe walks on to the next bucket only while buckets are full.
-constexpr uint32_t kEmptyKey32 = 0xFFFFFFFFu;
-template <> struct TableView<uint32_t> {
-    uint4    *keys4;
-    uint16_t *idx;
-    uint32_t  bmask;   // number of buckets - 1
-    __device__ __forceinline__ TableView(unsigned char *smem, uint32_t cap, uint32_t slots_log2) {
-        keys4 = reinterpret_cast<uint4 *>(smem);
-        idx   = reinterpret_cast<uint16_t *>(smem + ((size_t)4 << slots_log2));
-        bmask = (1u << (slots_log2 - 2)) - 1u;
-    }
-    __device__ __forceinline__ void clear(uint32_t tid, uint32_t nt) {
-        for (uint32_t b = tid; b <= bmask; b += nt) keys4[b] = make_uint4(kEmptyKey32, kEmptyKey32, kEmptyKey32, kEmptyKey32);
-    }
-    __device__ __forceinline__ void insert(uint32_t i, uint32_t key, uint32_t hash_bucket) {
-        uint32_t *keys = reinterpret_cast<uint32_t *>(keys4);
-        uint32_t  b    = hash_bucket;
-        for (;;) {
-#pragma unroll
-            for (uint32_t s = 0; s < 4; ++s) {
-                const uint32_t slot = b * 4u + s;
-                if (keys[slot] == kEmptyKey32 && atomicCAS(&keys[slot], kEmptyKey32, key) == kEmptyKey32) {
-                    idx[slot] = (uint16_t)i;
-                    return;
-                }
-            }
-            b = (b + 1u) & bmask;
-        }
-    }
-    static __host__ __device__ uint32_t slots_log2_for(uint32_t cap) {
-        uint32_t l = 4;   // slots >= 1.75 x cap: load factor <= 0.57
-        while ((uint64_t)4 << l < (uint64_t)7 * cap) ++l;
-        return l;
-    }
-    static __host__ __device__ size_t bytes(uint32_t cap, uint32_t slots_log2) {
-        (void)cap;
-        return ((size_t)4 << slots_log2) + ((size_t)2 << slots_log2);
-    }
-};
 template <> struct TableView<uint64_t> {
     uint64_t *keys;
     uint16_t *next;
@@ -752,8 +707,7 @@ hash_join_kernel(const JoinArgs a) {
     constexpr int NPA = NP > 0 ? NP : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TableView<KeyT> tab(smem_raw, a.cap, a.slots_log2);
-    // 32-bit keys hash to a bucket of four slots, 64-bit keys to a chain head
-    const uint32_t hash_log2 = sizeof(KeyT) == 4 ? a.slots_log2 - 2 : a.slots_log2;
+    const uint32_t hash_log2 = a.slots_log2;
 
     __shared__ uint32_t           s_item[6];   // valid, b_start, b_count, p_start, p_count, w
     __shared__ uint32_t           s_cursor;
@@ -842,22 +796,7 @@ hash_join_kernel(const JoinArgs a) {
     // one probe tuple through the table; returns the number of matches pushed or counted
     auto probe_one = [&](KeyT key, uint32_t prid) -> uint32_t {
         uint32_t nh = 0;
-        if constexpr (sizeof(KeyT) == 4) {
-            uint32_t b = table_hash<KeyT>(key, a.radix_bits, hash_log2);
-            for (;;) {
-                const uint4 k = tab.keys4[b];
-                uint32_t    m = (k.x == key ? 1u : 0u) | (k.y == key ? 2u : 0u) | (k.z == key ? 4u : 0u) |
-                             (k.w == key ? 8u : 0u);
-                while (m) {
-                    const uint32_t s = __ffs(m) - 1;
-                    m &= m - 1u;
-                    ++nh;
-                    on_match(tab.idx[b * 4u + s], prid);
-                }
-                if (k.x == kEmptyKey32 || k.y == kEmptyKey32 || k.z == kEmptyKey32 || k.w == kEmptyKey32) break;
-                b = (b + 1u) & tab.bmask;
-            }
-        } else {
+        {
             uint32_t idx = tab.heads[table_hash<KeyT>(key, a.radix_bits, hash_log2)];
             while (idx != kEmpty16) {
                 KeyT     k;
@@ -1069,16 +1008,6 @@ hash_join_kernel(const JoinArgs a) {
 // Used for partitioned joins of 32-bit keys with radix_bits + slots_log2 >= 17; a table holds up
 // to 32766 build tuples (2 CTAs/SM of 512 threads for small tables, 1 CTA of 1024 for large ones).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
-    uint16_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
-    return v;
-}
 __device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t x, uint32_t y) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(x), "r"(y) : "memory");
 }
@@ -1086,13 +1015,6 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t saddr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
     return v;
-}
-__device__ __forceinline__ uint32_t match4(const uint4 &k, uint32_t key) {
-    return (k.x == key ? 1u : 0u) | (k.y == key ? 2u : 0u) | (k.z == key ? 4u : 0u) | (k.w == key ? 8u : 0u);
-}
-__device__ __forceinline__ uint32_t used4(const uint4 &k) {
-    return (k.x != kEmptyKey32 ? 1u : 0u) | (k.y != kEmptyKey32 ? 2u : 0u) | (k.z != kEmptyKey32 ? 4u : 0u) |
-           (k.w != kEmptyKey32 ? 8u : 0u);
 }
 
 // work item of the join kernels: (build chunk, probe slice)
@@ -1150,19 +1072,20 @@ constexpr uint32_t kTagShift  = 16;            // word = [tag 16 | has_next 1 | 
 constexpr uint32_t kNextBit   = 0x8000u;
 constexpr uint32_t kIdxMask   = 0x7FFFu;
 constexpr uint32_t kEmptyWord = 0xFFFF7FFFu;   // tag all ones (never a real tag: tags have <= 15 bits), no chain
-constexpr int      kTagQueue  = 96;            // entries per warp (<= 31 left + 64 pushed per probe)
+constexpr int      kTagQueue  = 64;            // entries per warp (<= 31 left + 32 pushed per probe)
+// queue entry word: [31] match at position | [30:16] tag of the probe key | [15] walk the chain behind position | [14:0] position
+constexpr uint32_t kQMatch    = 0x80000000u;
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
-// invertible on the low nb bits: odd multiply, xor-shift by >= nb/2, odd multiply
-__device__ __forceinline__ uint32_t mix_bijective(uint32_t x, uint32_t nb_mask, uint32_t half) {
-    x = (x * 0x9E3779B1u) & nb_mask;
-    x ^= x >> half;
-    x = (x * 0x85EBCA6Bu) & nb_mask;
-    return x;
+// x = key >> radix_bits.  tag = x >> L, slot = (low L bits of x) ^ hash(tag): given slot and tag the low bits of
+// x are slot ^ hash(tag), so (slot, tag) <-> x is a bijection and equal (slot, tag) means equal keys.
+__device__ __forceinline__ void slot_and_tag(uint32_t x, uint32_t L, uint32_t smask, uint32_t &slot, uint32_t &tag) {
+    tag  = x >> L;
+    slot = (x ^ (tag * 0x9E3779B1u)) & smask;
 }
 __device__ __forceinline__ uint64_t ld_gather_u64(const uint64_t *p) {
     uint64_t v;   // random 8-byte gather: fetch 64 B from DRAM, not the default 128 B
@@ -1180,9 +1103,6 @@ tag_join_kernel(const JoinArgs a) {
     // layout: slots [4 << L bytes] | tagnext [4 * cap bytes] | queues [NW * QN * 8 bytes]
     const uint32_t L       = a.slots_log2;
     const uint32_t smask   = (1u << L) - 1u;
-    const uint32_t nb      = 32u - a.radix_bits;
-    const uint32_t nb_mask = 0xFFFFFFFFu >> a.radix_bits;
-    const uint32_t half    = (nb + 1u) / 2u;
     const uint32_t s_slots = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t s_next  = s_slots + (4u << L);
     const uint32_t s_queue = s_next + 4u * a.cap;
@@ -1241,9 +1161,9 @@ tag_join_kernel(const JoinArgs a) {
         queued -= take;
         const bool  mine = lane < take;
         const uint2 e    = lds_v2(my_q + (queued + (mine ? lane : 0u)) * 8u);
-        const uint32_t t = e.x >> kTagShift;
+        const uint32_t t = (e.x >> 16) & 0x7FFFu;
         // ---- match entries ----
-        const bool is_match = mine && (e.x & kNextBit) == 0u;
+        const bool is_match = mine && (e.x & kQMatch) != 0u;
         if constexpr (MODE == MODE_SUM) {
             const uint32_t bpos = b_start + (e.x & kIdxMask);
             uint32_t       brid = 0;
@@ -1286,7 +1206,7 @@ tag_join_kernel(const JoinArgs a) {
             const uint32_t bal = __ballot_sync(kFullMask, hit);
             if (hit) {
                 const uint32_t slot = queued + __popc(bal & lt);
-                if (slot < (uint32_t)QN) sts_v2(my_q + slot * 8u, (t << kTagShift) | (w & kIdxMask), e.y);
+                if (slot < (uint32_t)QN) sts_v2(my_q + slot * 8u, kQMatch | (t << 16) | (w & kIdxMask), e.y);
                 else handle_inline(w & kIdxMask, e.y);
             }
             queued  = min(queued + (uint32_t)__popc(bal), (uint32_t)QN);
@@ -1339,9 +1259,8 @@ tag_join_kernel(const JoinArgs a) {
         __syncthreads();
         for (uint32_t i = tid; i < b_count; i += NT) {
             const uint32_t key = tup_b[b_start + i].key;
-            const uint32_t y   = mix_bijective(key >> a.radix_bits, nb_mask, half);
-            const uint32_t h   = y & smask;
-            const uint32_t t   = y >> L;
+            uint32_t       h, t;
+            slot_and_tag(key >> a.radix_bits, L, smask, h, t);
             uint32_t       old = slots[h], assumed;
             do {
                 assumed            = old;
@@ -1353,42 +1272,40 @@ tag_join_kernel(const JoinArgs a) {
         __syncthreads();
 
         // ---- probe (K7) ---------------------------------------------------
-        for (uint32_t off = 0; off < p_count; off += NT * G) {
-#pragma unroll
-            for (int j = 0; j < G; ++j) load_probe(off + (uint32_t)(NT * G + j * NT) + tid, nkey[j], nrid[j]);
+        // groups of G probes, ping-pong between two register sets: while one group is probed the next one's
+        // tuples are in flight
+        auto probe_group = [&](const uint32_t (&key)[G], const uint32_t (&rid)[G]) {
             uint32_t w[G], t[G];
 #pragma unroll
             for (int j = 0; j < G; ++j) {
-                const uint32_t y = mix_bijective(ckey[j] >> a.radix_bits, nb_mask, half);
-                t[j]             = y >> L;
-                w[j]             = lds_u32(s_slots + (y & smask) * 4u);
+                uint32_t h;
+                slot_and_tag(key[j] >> a.radix_bits, L, smask, h, t[j]);
+                w[j] = lds_u32(s_slots + h * 4u);
             }
 #pragma unroll
             for (int j = 0; j < G; ++j) {
-                const bool     ok    = crid[j] != 0xFFFFFFFFu;
-                const bool     is_m  = ok && (w[j] >> kTagShift) == t[j];
-                const bool     has_n = ok && (w[j] & kNextBit) != 0u;
-                const uint32_t act_m = __ballot_sync(kFullMask, is_m);
-                const uint32_t act_c = __ballot_sync(kFullMask, has_n);
-                if (act_m | act_c) {
-                    // queued <= 31 here and a probe adds <= 64 entries: no overflow (QN = 96)
-                    if (is_m)
-                        sts_v2(my_q + (queued + __popc(act_m & lt)) * 8u, (t[j] << kTagShift) | (w[j] & kIdxMask),
-                               crid[j]);
-                    queued += __popc(act_m);
-                    if (has_n)
-                        sts_v2(my_q + (queued + __popc(act_c & lt)) * 8u,
-                               (t[j] << kTagShift) | kNextBit | (w[j] & kIdxMask), crid[j]);
-                    queued += __popc(act_c);
+                const bool     ok   = rid[j] != 0xFFFFFFFFu;
+                const bool     is_m = (w[j] >> kTagShift) == t[j];
+                const bool     need = ok && (is_m || (w[j] & kNextBit) != 0u);
+                const uint32_t act  = __ballot_sync(kFullMask, need);
+                if (act) {
+                    // queued <= 31 here and a probe adds <= 32 entries: no overflow (QN = 64)
+                    if (need)
+                        sts_v2(my_q + (queued + __popc(act & lt)) * 8u,
+                               (is_m ? kQMatch : 0u) | (t[j] << 16) | (w[j] & 0xFFFFu), rid[j]);
+                    queued += __popc(act);
                     __syncwarp();
                     while (queued >= 32u) drain(32u);
                 }
             }
+        };
+        for (uint32_t off = 0; off < p_count; off += 2 * NT * G) {
 #pragma unroll
-            for (int j = 0; j < G; ++j) {
-                ckey[j] = nkey[j];
-                crid[j] = nrid[j];
-            }
+            for (int j = 0; j < G; ++j) load_probe(off + (uint32_t)(NT * G + j * NT) + tid, nkey[j], nrid[j]);
+            probe_group(ckey, crid);
+#pragma unroll
+            for (int j = 0; j < G; ++j) load_probe(off + (uint32_t)(2 * NT * G + j * NT) + tid, ckey[j], crid[j]);
+            if (off + NT * G < p_count) probe_group(nkey, nrid);
         }
         // leftovers of this item (queue entries are relative to this item's build chunk)
         __syncwarp();
