@@ -162,7 +162,7 @@ def test_config3_chain_join_matches_the_reference(gpu, orc, f, d1, d2, d3):
     if not ref_driver.exists():
         pytest.skip("oracle/_ref/ref_driver not built")
     specs = [s.format(f=f, d1=d1, d2=d2, d3=d3) for s in CONFIG3_SPECS]
-    want = subprocess.run([str(ref_driver), "-t", "8", *specs, "--", CONFIG3_QUERY], capture_output=True, text=True,
+    want = subprocess.run([str(ref_driver), "-t", "4", *specs, "--", CONFIG3_QUERY], capture_output=True, text=True,
                           timeout=600)
     assert want.returncode == 0, want.stderr[-1000:]
     want_line = want.stdout.splitlines()[0]
