@@ -64,8 +64,8 @@ def test_join_pairs_match_reference_in_order(orc, ref, seed, nr, ns, domain, thr
 
 def test_reference_loses_pairs_at_16_threads(orc, ref):
     """Reference defect that bounds the CPU baseline's thread count: with 16 scheduler threads (= 2^N_LSB
-    buckets, structs.h:11) ReorderArray/PartitionJob (preprocess.c:134-165, 222-299) drops about one bucket's
-    worth of tuples and RadixHashJoin returns ~15/16 of the pairs; 2, 4 and 8 threads are exact.  (Found at
+    buckets, structs.h:11) RadixHashJoin intermittently returns ~15/16 of the pairs (about one bucket's worth
+    is missing); 2, 4 and 8 threads were exact in every run.  (Found at
     BASELINE config 3 full size, where the 16-thread reference disagrees with an independent numpy evaluation
     that the 4/8-thread reference and the GPU library both match; scripts/run_config3.sh.)  bench.py therefore
     times the reference with at most 8 threads."""
@@ -76,9 +76,11 @@ def test_reference_loses_pairs_at_16_threads(orc, ref):
     for threads in (2, 4, 8):
         r = ref.radix_hash_join(kr, ks, threads)
         assert np.array_equal(r[0], want[0]) and np.array_equal(r[1], want[1])
-    r16 = ref.radix_hash_join(kr, ks, 16)
-    assert len(r16[0]) < len(want[0])          # the defect
-    assert len(r16[0]) > 0.9 * len(want[0])
+    # 16 threads: intermittent (a race: the unsynchronised answers_waiting store, preprocess.c:21/131) — the
+    # result is the full pair list or one with roughly a bucket missing, never anything else
+    for _ in range(3):
+        r16 = ref.radix_hash_join(kr, ks, 16)
+        assert 0.9 * len(want[0]) < len(r16[0]) <= len(want[0])
 
 
 def test_join_no_match_is_empty_not_null(orc, ref):
