@@ -229,9 +229,18 @@ def run_b200_arm(args):
     r1 = synth(nr_loc, r_first, b200.SYNTH_PAYLOAD, 0, b200.SEED_R + 1)
     s0 = synth(ns_loc, s_first, b200.SYNTH_PERM, KS_BITS, b200.SEED_S)
     s1 = synth(ns_loc, s_first, b200.SYNTH_PAYLOAD, 0, b200.SEED_S + 1)
+    # the build-side SUM column's maximum is a column statistic (relation_map.c:53-61 keeps min/max per column); the
+    # library uses it to carry 32-bit values inside the build tuples
+    r1_max = int(r1.max().item())
+    if world > 1:
+        t_max = torch.tensor([r1_max], dtype=torch.int64, device=dev)
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        r1_max = int(t_max.item())
+    L.b200_register_device_column(r1.data_ptr(), r1.data_ptr(), nr_loc, r1_max)
     plan = None
     if world > 1:
-        plan = b200.sharding.BroadcastScatterJoin(b200, torch, dist, rank, world, nr, nr_loc, ns_loc, 1, dev)
+        plan = b200.sharding.BroadcastScatterJoin(b200, torch, dist, rank, world, nr, nr_loc, ns_loc, 1, dev,
+                                                  carry32=r1_max < (1 << 32))
     torch.cuda.synchronize()
 
     def step(kr=None, pr=None, ks=None, ps=None):

@@ -232,7 +232,10 @@ int   b200_stage_scatter_build(const uint64_t *d_keys, uint64_t n,
                                void *const *tup_dst, int npay,
                                const uint64_t *const *pay_cols,
                                uint64_t *const *pay_dst, int phase);
-/* phase 0 = partition + broadcast; 1 = only the local partition pass (staged
+/* npay == 1 with pay_dst == NULL: the one payload column holds 32-bit values
+ * and travels in the row-id slot of the build tuples (no payload buffers; pass
+ * (const uint64_t *)1 as that projection's proj_part_vals to the join).
+ * phase 0 = partition + broadcast; 1 = only the local partition pass (staged
  * inside the library); 2 = only the broadcast of what phase 1 staged, so that a
  * caller can put other work (the probe-side scatter, on another stream)
  * between the two. */

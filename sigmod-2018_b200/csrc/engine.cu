@@ -69,6 +69,7 @@ static void init_device(int device) {
     if (const char *v = getenv("B200_SCATTER_CFG")) t.scatter_cfg = atoi(v);
     if (const char *v = getenv("B200_EARLY_MAT")) t.early_mat = atoi(v);
     if (const char *v = getenv("B200_OPT_PARTITION")) t.opt_partition = atoi(v);
+    if (const char *v = getenv("B200_CARRY32")) t.carry32 = atoi(v);
     if (const char *v = getenv("B200_L2_FETCH")) {
         // granularity hint for L2 fills of the random payload gathers (32, 64 or 128)
         B200_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v)));
@@ -288,6 +289,14 @@ DevColumn lookup_column(const uint64_t *host_col, uint64_t n) {
     return g_columns[host_col].col;
 }
 
+// largest value of a column registered under this DEVICE pointer, or UINT64_MAX when unknown
+uint64_t known_column_max(const uint64_t *dev_ptr) {
+    std::lock_guard<std::mutex> lk(g_col_mu);
+    for (const auto &kv : g_columns)
+        if (kv.second.col.d == dev_ptr) return kv.second.col.max_val;
+    return UINT64_MAX;
+}
+
 void unregister_all_columns() {
     std::lock_guard<std::mutex> lk(g_col_mu);
     for (auto &kv : g_columns)
@@ -385,8 +394,24 @@ static void launch_scatter_tuples(const uint64_t *tuples, uint32_t n, int bits, 
     B200_LAUNCH_CHECK();
 }
 
+// build-side scatter whose tuples carry a 32-bit payload in the row-id slot
+static void launch_scatter_carry(const KeySrc &src, int bits, uint32_t *cursor, void *out, const PayArgs &pay) {
+    constexpr int NT   = 1024;
+    constexpr int U    = 8;
+    const size_t  smem = (size_t)NT * U * sizeof(Tup32) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
+    auto          k    = radix_scatter_pay_kernel<NT, U, uint32_t, 0, false, true>;
+    allow_smem(k, smem);
+    k<<<grid_for(src.n, NT * U, 1), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor, static_cast<Tup32 *>(out),
+                                                                pay);
+    B200_LAUNCH_CHECK();
+}
+
 template <typename KeyT>
 static void launch_scatter_pay(const KeySrc &src, int bits, uint32_t *cursor, void *out, const PayArgs &pay, int npay) {
+    if (pay.carry32) {
+        launch_scatter_carry(src, bits, cursor, out, pay);
+        return;
+    }
     if (npay == 0)
         launch_scatter_pay_n<KeyT, 0>(src, bits, cursor, out, pay);
     else if (npay == 1)
@@ -597,6 +622,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     bool      opt     = false;
     uint32_t  opt_cap = 0;
     DevBufPtr part_vals[kMaxProj];
+    int       carry_k = -1;
     uint64_t  n_items = 0;
     if (direct) {
         a.src_b = B.src;
@@ -627,14 +653,30 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         PayArgs pay{};
         int     npay = 0;
         if (mode == JoinOut::Sum && !key64 && t.early_mat) {
-            for (int k = 0; k < nproj && npay < 2; ++k) {
-                const int side_b = swapped ? 1 : 0;   // proj[].side is relative to (R, S)
-                if (proj[k].side != side_b) continue;
-                part_vals[k]  = dev_alloc((size_t)B.src.n * sizeof(uint64_t));
-                pay.col[npay] = proj[k].col;
-                pay.ids[npay] = proj[k].ids;
-                pay.out[npay] = part_vals[k]->as<uint64_t>();
-                ++npay;
+            const int side_b  = swapped ? 1 : 0;   // proj[].side is relative to (R, S)
+            int       n_build = 0, first = -1;
+            for (int k = 0; k < nproj; ++k)
+                if (proj[k].side == side_b) {
+                    if (first < 0) first = k;
+                    ++n_build;
+                }
+            // one build-side projection whose column is known to hold 32-bit values: carry it in the row-id slot
+            // (no other projection reads the build row id then)
+            if (n_build == 1 && t.carry32 && known_column_max(proj[first].col) <= 0xFFFFFFFFull) {
+                carry_k      = first;
+                pay.carry32  = 1;
+                pay.col[0]   = proj[first].col;
+                pay.ids[0]   = proj[first].ids;
+                npay         = 1;   // selects the payload-aware scatter
+            } else {
+                for (int k = 0; k < nproj && npay < 2; ++k) {
+                    if (proj[k].side != side_b) continue;
+                    part_vals[k]  = dev_alloc((size_t)B.src.n * sizeof(uint64_t));
+                    pay.col[npay] = proj[k].col;
+                    pay.ids[npay] = proj[k].ids;
+                    pay.out[npay] = part_vals[k]->as<uint64_t>();
+                    ++npay;
+                }
             }
         }
         auto scatter_build = [&](uint32_t *cursor) {
@@ -711,8 +753,8 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             a.proj[k] = proj[k];
             // sides are given relative to (R, S); the kernel wants (build, probe)
             a.proj[k].side      = swapped ? 1 - proj[k].side : proj[k].side;
-            a.proj[k].part_vals = part_vals[k] ? part_vals[k]->as<uint64_t>() : nullptr;
-            if (a.proj[k].side == 0 && !a.proj[k].part_vals) a.need_brid = 1;
+            a.proj[k].part_vals = k == carry_k ? B200_PROJ_IN_RID : part_vals[k] ? part_vals[k]->as<uint64_t>() : nullptr;
+            if (a.proj[k].side == 0 && (!a.proj[k].part_vals || k == carry_k)) a.need_brid = 1;
         }
         {
             TimedScope ts("join");
@@ -952,7 +994,13 @@ void stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, 
     PayArgs   pay{};
     pay.ndst     = 0;
     pay.rid_base = rid_base;
-    for (int k = 0; k < npay; ++k) {
+    const bool carry = npay == 1 && pay_dst == nullptr;   // the one payload column travels in the row-id slot
+    if (carry) {
+        pay.carry32 = 1;
+        pay.col[0]  = pay_cols[0];
+        pay.ids[0]  = nullptr;
+    }
+    for (int k = 0; k < (carry ? 0 : npay); ++k) {
         st.pay[k]  = dev_alloc(n * sizeof(uint64_t));
         pay.col[k] = pay_cols[k];
         pay.ids[k] = nullptr;
@@ -974,10 +1022,10 @@ void stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, 
     s.src_off   = off_l;
     s.dst_start = d_dst_start;
     s.ndst      = ndst;
-    s.npay      = npay;
+    s.npay      = pay_dst == nullptr ? 0 : npay;
     s.first     = ndst > 1 ? (int)(rid_base / (uint32_t)n) % ndst : 0;   // = this rank (equal shards)
     for (int d = 0; d < ndst; ++d) s.dst_tup[d] = static_cast<uint64_t *>(tup_dst[d]);
-    for (int k = 0; k < npay; ++k) {
+    for (int k = 0; k < s.npay; ++k) {
         s.src_pay[k] = stage_pay[k]->as<uint64_t>();
         for (int d = 0; d < ndst; ++d) s.dst_pay[k][d] = pay_dst[k * ndst + d];
     }
@@ -1072,7 +1120,7 @@ JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const v
     a.need_brid  = 0;
     for (int k = 0; k < nproj; ++k) {
         a.proj[k] = proj[k];
-        if (a.proj[k].side == 0 && !a.proj[k].part_vals) a.need_brid = 1;
+        if (a.proj[k].side == 0 && (!a.proj[k].part_vals || a.proj[k].part_vals == B200_PROJ_IN_RID)) a.need_brid = 1;
     }
     {
         TimedScope ts("join");

@@ -24,6 +24,7 @@ void      register_host_column(const uint64_t *host_col, uint64_t n, bool replac
 void      register_device_column(const uint64_t *host_key, const uint64_t *dev, uint64_t n,
                                  uint64_t max_val);
 void      unregister_all_columns();
+uint64_t  known_column_max(const uint64_t *dev_ptr);
 void      unregister_column(const uint64_t *host_col);
 
 // Lazy key vector with ownership of the row-id list it reads through.
@@ -39,6 +40,7 @@ struct Tuning {
     uint32_t cap32       = 17408;    // build tuples per shared-memory table, 32-bit keys
     uint32_t cap64       = 6144;     // ... 64-bit keys
     uint32_t slice       = 1u << 18; // probe tuples per work item
+    int      carry32     = 1;        // a single 32-bit build-side SUM column travels in the tuple's row-id slot
     int      opt_partition = 1;      // histogram-free probe-side scatter for the fused join -> SUM
     int      early_mat   = 1;        // carry build-side SUM projections through the scatter
     int      scatter_cfg = 1;        // see engine.cu PartCfg

@@ -423,13 +423,16 @@ struct PayArgs {
     // own and its peers' (CUDA IPC mappings, written over NVLink) — instead of
     // `out`; row ids are rid_base + position so they stay global
     int       ndst;
+    int       carry32;   // store (uint32)col[0][row] in the tuple's row-id slot instead of the row id
     uint32_t  rid_base;
     void     *tup_dst[kMaxPeers];
     uint64_t *pay_dst[2][kMaxPeers];
 };
 // TUPIN: the input "column" is an array of packed 32-bit-key tuples {key32, rid32}
 // (the overflow of an OPT scatter); the row id comes from the tuple, not the position.
-template <int NT, int U, typename KeyT, int NPAY, bool TUPIN>
+// CARRY: the tuple's row-id slot carries (uint32)pay.col[0][row] — one build-side SUM column whose values fit 32
+// bits needs no separate payload array at all (and half the bytes on the wire in the multi-GPU broadcast).
+template <int NT, int U, typename KeyT, int NPAY, bool TUPIN, bool CARRY = false>
 __global__ void __launch_bounds__(NT)
 radix_scatter_pay_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cursor,
                          typename TupOf<KeyT>::type *__restrict__ out, PayArgs pay) {
@@ -455,6 +458,7 @@ radix_scatter_pay_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__
     KeyT     keys[U];
     uint32_t in_rid[TUPIN ? U : 1];
     uint64_t pvals[NPAY > 0 ? NPAY : 1][U];
+    uint32_t cvals[CARRY ? U : 1];
     auto load_tile = [&](uint64_t tile) {
         const uint64_t base  = tile * TILE;
         const uint32_t count = (uint32_t)min((uint64_t)TILE, n - base);
@@ -476,6 +480,14 @@ radix_scatter_pay_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__
                 const uint32_t li  = (uint32_t)(j * NT) + threadIdx.x;
                 const uint32_t rid = (uint32_t)base + li;
                 pvals[k][j]        = li < count ? ld_stream_u64(pay.col[k] + (pay.ids[k] ? pay.ids[k][rid] : rid)) : 0ull;
+            }
+        }
+        if constexpr (CARRY) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const uint32_t li  = (uint32_t)(j * NT) + threadIdx.x;
+                const uint32_t rid = (uint32_t)base + li;
+                cvals[j] = li < count ? (uint32_t)ld_stream_u64(pay.col[0] + (pay.ids[0] ? pay.ids[0][rid] : rid)) : 0u;
             }
         }
     };
@@ -518,6 +530,7 @@ radix_scatter_pay_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__
                 TupT           t;
                 t.key = keys[j];
                 if constexpr (TUPIN) t.rid = in_rid[j];
+                else if constexpr (CARRY) t.rid = cvals[j];
                 else t.rid = pay.rid_base + rid;
                 if constexpr (sizeof(KeyT) == 8) t.pad = 0;
                 stage[pos] = t;
@@ -1138,7 +1151,9 @@ tag_join_kernel(const JoinArgs a) {
 #pragma unroll
                 for (int k = 0; k < NPA; ++k) {
                     if (k < a.nproj) {
-                        if (a.proj[k].part_vals) {
+                        if (a.proj[k].part_vals == B200_PROJ_IN_RID) {
+                            my_sum[k] += brid;   // the slot carries the value
+                        } else if (a.proj[k].part_vals) {
                             my_sum[k] += a.proj[k].part_vals[b_start + pos];
                         } else {
                             const uint32_t r  = a.proj[k].side == 0 ? brid : prid;
@@ -1173,7 +1188,9 @@ tag_join_kernel(const JoinArgs a) {
                 my_sum[k] += pend[k];
                 pend[k] = 0;
                 if (k < a.nproj && is_match) {
-                    if (a.proj[k].part_vals) {
+                    if (a.proj[k].part_vals == B200_PROJ_IN_RID) {
+                        pend[k] = brid;                         // the row-id slot carries the value
+                    } else if (a.proj[k].part_vals) {
                         pend[k] = a.proj[k].part_vals[bpos];   // dense window of this partition, L2-resident
                     } else {
                         const uint32_t r  = a.proj[k].side == 0 ? brid : e.y;

@@ -41,6 +41,8 @@ struct ProjDesc {
     // partition order by the scatter (value of build tuple i of the partition
     // buffer), or nullptr when the value is gathered through the row id
     const uint64_t *part_vals;
+    // kInRid: the (32-bit) value travels in the row-id slot of the build tuple itself
 };
+#define B200_PROJ_IN_RID (reinterpret_cast<const uint64_t *>(1))
 
 }  // namespace b200

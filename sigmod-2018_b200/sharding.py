@@ -83,7 +83,10 @@ class BroadcastScatterJoin:
     which is how the single-GPU test drives the staged C-ABI.
     """
 
-    def __init__(self, b200, torch, dist, rank, world, n_build_total, n_build_local, n_probe_local, n_pay, device):
+    def __init__(self, b200, torch, dist, rank, world, n_build_total, n_build_local, n_probe_local, n_pay, device,
+                 carry32=False):
+        """carry32: the single build-side SUM column (n_pay == 1) holds 32-bit values and travels in the row-id
+        slot of the build tuples: no payload buffers, half the bytes in the NVLink broadcast."""
         import ctypes as C
         self.b, self.torch, self.dist, self.rank, self.world = b200, torch, dist, rank, world
         self.C = C
@@ -91,12 +94,13 @@ class BroadcastScatterJoin:
         self.L = L
         self.n_build_total, self.n_build_local, self.n_probe_local = n_build_total, n_build_local, n_probe_local
         self.n_pay = n_pay
+        self.carry32 = bool(carry32) and n_pay == 1
         self.bits = int(L.b200_radix_bits_for(n_build_total))
         self.P = 1 << self.bits
         self.device = device
         # build-partition buffers live in cudaMalloc memory so they can be exported over CUDA IPC
         self.tup_b = b200.DeviceColumn(max(n_build_total, 1))
-        self.pay_b = [b200.DeviceColumn(max(n_build_total, 1)) for _ in range(n_pay)]
+        self.pay_b = [] if self.carry32 else [b200.DeviceColumn(max(n_build_total, 1)) for _ in range(n_pay)]
         # histogram-free probe side: P fixed regions + an overflow array (host.py / DESIGN.md §4)
         self.opt_cap = int(L.b200_opt_region_cap(n_probe_local, self.bits)) if n_probe_local >= (1 << 20) else 0
         self.tup_p = b200.DeviceColumn(max(self.opt_cap * self.P if self.opt_cap else n_probe_local, 1))
@@ -120,15 +124,15 @@ class BroadcastScatterJoin:
             handles = [self._export(self.tup_b.ptr)] + [self._export(p.ptr) for p in self.pay_b]
             gathered = [None] * world
             dist.all_gather_object(gathered, handles)
-            self.peer_tup, self.peer_pay = [], [[] for _ in range(n_pay)]
+            self.peer_tup, self.peer_pay = [], [[] for _ in self.pay_b]
             for r in range(world):
                 if r == rank:
                     self.peer_tup.append(self.tup_b.ptr)
-                    for k in range(n_pay):
+                    for k in range(len(self.pay_b)):
                         self.peer_pay[k].append(self.pay_b[k].ptr)
                 else:
                     self.peer_tup.append(self._import(gathered[r][0]))
-                    for k in range(n_pay):
+                    for k in range(len(self.pay_b)):
                         self.peer_pay[k].append(self._import(gathered[r][1 + k]))
 
     def _export(self, ptr):
@@ -175,8 +179,8 @@ class BroadcastScatterJoin:
         tup_dst = (C.c_void_p * ndst)(*self.peer_tup)
         npay = self.n_pay
         pay_cols = (C.c_void_p * max(npay, 1))(*build_pay_ptrs[:npay])
-        flat = [self.peer_pay[k][d] for k in range(npay) for d in range(ndst)]
-        pay_dst = (C.c_void_p * max(len(flat), 1))(*flat)
+        flat = [self.peer_pay[k][d] for k in range(len(self.pay_b)) for d in range(ndst)]
+        pay_dst = None if self.carry32 else (C.c_void_p * max(len(flat), 1))(*flat)
         # the local partition pass of the build shard and the probe-side scatter both want a whole SM's shared
         # memory per CTA, so they run back to back; the NVLink-bound broadcast copy (tiny CTAs) then runs
         # UNDER the probe-side scatter, which is issued on the side stream in between
@@ -215,7 +219,7 @@ class BroadcastScatterJoin:
         part = []
         for col, side_k in zip(proj_cols, proj_side):
             if side_k == 0:
-                part.append(self.pay_b[build_pay_ptrs.index(col)].ptr)
+                part.append(1 if self.carry32 else self.pay_b[build_pay_ptrs.index(col)].ptr)
             else:
                 part.append(None)
         part_vals = (C.c_void_p * max(k, 1))(*part)

@@ -139,6 +139,30 @@ def test_join_sum_golden(gpu, i):
     assert m == case["m"] and sums == [case["sum_r"], case["sum_s"]]
 
 
+def test_join_sum_device_carries_registered_32bit_payload(gpu, orc):
+    """A build-side SUM column registered with a maximum below 2^32 travels in the row-id slot of the build
+    tuples; a wider one (or an unregistered pointer) takes the payload-array path.  Same checksums."""
+    kr_bits, ks_bits = 18, 21
+    nr, ns = 1 << kr_bits, 1 << ks_bits
+    kr = orc.synth_column(nr, 0, kr_bits, gpu.SEED_R)
+    ks = orc.synth_column(ns, 0, ks_bits, gpu.SEED_S)
+    ps = orc.synth_column(ns, 1, 0, 8)
+    for wide in (False, True):
+        pr = orc.synth_column(nr, 1, 0, 7) * np.uint64((1 << 40) + 1 if wide else 1)
+        want, wm = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
+        cols = [gpu.DeviceColumn(len(a)) for a in (kr, ks, pr, ps)]
+        for c, a in zip(cols, (kr, ks, pr, ps)):
+            gpu.lib().b200_copy_to_device(c.ptr, a.ctypes.data, 8 * len(a))
+        gpu.lib().b200_register_device_column(cols[2].ptr, cols[2].ptr, nr, int(pr.max()))
+        got, m = gpu.join_sum_device(cols[0].ptr, nr, cols[1].ptr, ns, [cols[2].ptr, cols[3].ptr], [0, 1], ns - 1)
+        assert m == wm and got == want
+        got, m = gpu.join_sum_device(cols[1].ptr, ns, cols[0].ptr, nr, [cols[3].ptr, cols[2].ptr], [0, 1], ns - 1)
+        assert m == wm and got == [want[1], want[0]]
+        gpu.lib().b200_unregister_all()
+        for c in cols:
+            c.free()
+
+
 @pytest.mark.parametrize("kr_bits,ks_bits", [(12, 16), (16, 20), (20, 22)])
 def test_join_sum_config2_shape_scaled_down(gpu, orc, kr_bits, ks_bits):
     """BASELINE config 2 at reduced size: unique permutation keys, probe
@@ -154,8 +178,9 @@ def test_join_sum_config2_shape_scaled_down(gpu, orc, kr_bits, ks_bits):
 
 
 # ---- staged join (the phases the multi-GPU plan drives), single GPU ----------
-@pytest.mark.parametrize("kr_bits,ks_bits,zipf", [(15, 18, False), (18, 21, False), (16, 21, True)])
-def test_staged_join_matches_fused_join(gpu, orc, kr_bits, ks_bits, zipf):
+@pytest.mark.parametrize("kr_bits,ks_bits,zipf,carry", [(15, 18, False, False), (18, 21, False, False),
+                                                        (16, 21, True, False), (18, 21, False, True)])
+def test_staged_join_matches_fused_join(gpu, orc, kr_bits, ks_bits, zipf, carry):
     """sharding.BroadcastScatterJoin with world = 1: hist -> cursors -> scatter (build side with an
     early-materialised payload, through the multi-destination path) -> join_sum, against the oracle."""
     torch = pytest.importorskip("torch")
@@ -171,7 +196,7 @@ def test_staged_join_matches_fused_join(gpu, orc, kr_bits, ks_bits, zipf):
     try:
         t = {n: torch.from_numpy(a.view(np.int64).copy()).to(dev) for n, a in
              [("kr", kr), ("ks", ks), ("pr", pr), ("ps", ps)]}
-        plan = gpu.sharding.BroadcastScatterJoin(gpu, torch, None, 0, 1, nr, nr, ns, 1, dev)
+        plan = gpu.sharding.BroadcastScatterJoin(gpu, torch, None, 0, 1, nr, nr, ns, 1, dev, carry32=carry)
         for _ in range(2):     # buffers are reused across steps
             got, m = plan.step(t["kr"].data_ptr(), [t["pr"].data_ptr()], t["ks"].data_ptr(),
                                [t["pr"].data_ptr(), t["ps"].data_ptr()], [0, 1])
