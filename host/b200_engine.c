@@ -1,0 +1,237 @@
+/*
+ * b200_engine.c — a stand-alone C host for libb200join.so with the reference's process protocol.
+ *
+ * The reference's host side (handler.c, query.c, best_tree.c, stats.c, relation_map.c, scheduler.c) links
+ * against the library unchanged.  This file is the same thing written from scratch, for
+ * boxes that do not have the reference: it speaks the contest protocol of handler.c:17-105 — relation file
+ * names until `Done`, then query lines, `F` ends a batch, one result line per query — loads relations the
+ * way relation_map.c:13-88 does (mmap, header [rows][cols], column-major uint64; files larger than 2 GiB
+ * are fine here), parses queries with the semantics of query.c:44-249, and runs them through the operator
+ * API in ExecuteQuery's order (query.c:325-467).
+ *
+ * Two things differ from the reference on purpose:
+ *   - scheduler (scheduler.c:9-132): the reference's jobs are slices of ONE join and a batch runs query by
+ *     query (handler.c:78-89).  Here a job is a whole query: a batch is handed to a pool of worker threads,
+ *     each of which owns a CUDA stream inside the library (thread-local context), and the result lines are
+ *     printed in submission order when the batch ends — config 5's "concurrent queries on GPU streams".
+ *   - join order: textual order with one rule, "start from a filtered binding if there is one"; the
+ *     reference's JoinEnum DP (best_tree.c:105-223) only changes cost, never results.
+ *
+ * usage: b200_engine [-w workers]      (default 4; B200_WORKERS overrides)
+ */
+#define _GNU_SOURCE
+#include <fcntl.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "../include/b200_join.h"
+
+#define MAX_BINDINGS 16
+#define MAX_PREDS 32
+#define MAX_VIEWS 16
+
+typedef struct {
+    int  nrel, rel[MAX_BINDINGS];
+    int  nfilter;
+    filter_pred filters[MAX_PREDS];
+    int  njoin;
+    join_pred joins[MAX_PREDS];
+    int  nview, view_b[MAX_VIEWS], view_c[MAX_VIEWS];
+    char line[256];      /* result */
+} query_t;
+
+static relation_map *g_map   = NULL;
+static int           g_nrel  = 0;
+
+/* ---- relation loading (relation_map.c:13-88) ------------------------------------------------------ */
+static int load_relation(const char *path, relation_map *rm) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { perror(path); return 1; }
+    struct stat sb;
+    if (fstat(fd, &sb) < 0) { perror("fstat"); return 1; }
+    uint64_t *base = mmap(NULL, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (base == MAP_FAILED) { perror("mmap"); return 1; }
+    rm->num_tuples  = base[0];
+    rm->num_columns = base[1];
+    rm->columns     = malloc(rm->num_columns * sizeof(uint64_t *));
+    rm->col_stats   = calloc(rm->num_columns, sizeof(column_stats));
+    for (uint64_t j = 0; j < rm->num_columns; ++j) rm->columns[j] = base + 2 + j * rm->num_tuples;
+    return 0;
+}
+
+/* ---- query parsing (query.c:44-249) ----------------------------------------------------------------- */
+static int parse_query(const char *text, query_t *q) {
+    char buf[256];
+    strncpy(buf, text, sizeof buf - 1);
+    buf[sizeof buf - 1] = 0;
+    char *save = NULL;
+    char *rels = strtok_r(buf, "|", &save), *preds = strtok_r(NULL, "|", &save), *views = strtok_r(NULL, "|\n", &save);
+    if (!rels || !preds || !views) return 1;
+    memset(q, 0, sizeof *q);
+    char *s2 = NULL;
+    for (char *t = strtok_r(rels, " ", &s2); t; t = strtok_r(NULL, " ", &s2)) q->rel[q->nrel++] = atoi(t);
+    for (char *p = strtok_r(preds, "&", &s2); p; p = strtok_r(NULL, "&", &s2)) {
+        int b1, c1, b2, c2, k;
+        char op;
+        if (sscanf(p, "%d.%d=%d.%d", &b1, &c1, &b2, &c2) == 4) {
+            q->joins[q->njoin++] = (join_pred){b1, b2, c1, c2};          /* tail of the list: textual order */
+        } else if (sscanf(p, "%d.%d%c%d", &b1, &c1, &op, &k) == 4 && (op == '<' || op == '>' || op == '=')) {
+            /* filters go to the list head => they run in reverse textual order (query.c:150-157) */
+            memmove(q->filters + 1, q->filters, (size_t)q->nfilter * sizeof(filter_pred));
+            q->filters[0] = (filter_pred){b1, c1, k, op};
+            q->nfilter++;
+        } else {
+            return 1;
+        }
+    }
+    for (char *v = strtok_r(views, " \n", &s2); v; v = strtok_r(NULL, " \n", &s2)) {
+        q->view_b[q->nview] = v[0] - '0';       /* single digits, inter_res.c:325-327 */
+        q->view_c[q->nview] = v[2] - '0';
+        q->nview++;
+    }
+    return 0;
+}
+
+static void null_line(query_t *q) {
+    char *p = q->line;
+    for (int i = 0; i < q->nview; ++i) p += sprintf(p, "%sNULL", i ? " " : "");
+}
+
+/* ---- ExecuteQuery (query.c:325-467) over the operator API ------------------------------------------- */
+static void execute_query(query_t *q) {
+    inter_res *inter = NULL;
+    InitInterResults(&inter, q->nrel);
+    for (int i = 0; i < q->nfilter; ++i) {
+        result *res = Filter(inter, &q->filters[i], g_map, q->rel);
+        if (!res) { null_line(q); FreeInterResults(inter); return; }           /* query.c:360-369 */
+        InsertSingleRowIdsToInterResult(&inter, q->filters[i].relation, res);
+        FreeResult(res);
+    }
+    /* joins: a predicate whose two bindings already share a node is a filter on the intermediate */
+    int done[MAX_PREDS] = {0}, left = q->njoin;
+    while (left) {
+        int pick = -1;
+        /* prefer a predicate connected to what has been joined/filtered so far (keeps intermediates small) */
+        for (int i = 0; i < q->njoin && pick < 0; ++i) {
+            if (done[i]) continue;
+            for (inter_res *n = inter; n; n = n->next)
+                if (n->data->num_tuples && (n->data->table[q->joins[i].relation1] || n->data->table[q->joins[i].relation2]))
+                    pick = i;
+        }
+        for (int i = 0; i < q->njoin && pick < 0; ++i)
+            if (!done[i]) pick = i;
+        join_pred *j = &q->joins[pick];
+        done[pick]   = 1;
+        --left;
+        if (j->relation1 == j->relation2) {
+            result *res = SelfJoin(j->relation1, j->column1, j->column2, &inter, g_map, q->rel);
+            if (!res) { null_line(q); FreeInterResults(inter); return; }
+            InsertSingleRowIdsToInterResult(&inter, j->relation1, res);
+            FreeResult(res);
+            continue;
+        }
+        if (AreActiveInInter(inter, j->relation1, j->relation2)) {
+            JoinInterNode(&inter, g_map, j->relation1, j->column1, j->relation2, j->column2, q->rel);
+            continue;
+        }
+        relation *r1 = GetRelation(j->relation1, j->column1, inter, g_map, q->rel);
+        relation *r2 = GetRelation(j->relation2, j->column2, inter, g_map, q->rel);
+        result   *res = RadixHashJoin(r1, r2, NULL);
+        FreeRelation(r1);
+        FreeRelation(r2);
+        if (!res) { null_line(q); FreeInterResults(inter); return; }           /* query.c:439-449 */
+        InsertJoinToInterResults(inter, j->relation1, j->relation2, res);
+        FreeResult(res);
+        if (inter->next) MergeInterNodes(&inter);
+    }
+    if (inter->next) CartesianInterResults(&inter);
+    /* CalculateQueryResults without the printf: lines are printed in order when the batch ends */
+    char               v0[MAX_VIEWS][4];
+    char              *vp[MAX_VIEWS];
+    query_string_array views = {vp, q->nview};
+    for (int i = 0; i < q->nview; ++i) {
+        snprintf(v0[i], sizeof v0[i], "%d.%d", q->view_b[i], q->view_c[i]);
+        vp[i] = v0[i];
+    }
+    batch_listnode node = {q->nrel, q->rel, NULL, &views, NULL};
+    uint64_t       sums[MAX_VIEWS], rows = 0;
+    b200_calculate_sums(inter, g_map, &node, sums, &rows);
+    char *p = q->line;
+    for (int i = 0; i < q->nview; ++i) p += sprintf(p, "%s%lu", i ? " " : "", (unsigned long)sums[i]);
+    FreeInterResults(inter);
+}
+
+/* ---- the scheduler: jobs = whole queries, workers = threads that own a CUDA stream ------------------- */
+typedef struct {
+    query_t        *queries;
+    int             n, next;
+    pthread_mutex_t mu;
+} batch_t;
+
+static void *worker(void *arg) {
+    batch_t *b = arg;
+    for (;;) {
+        pthread_mutex_lock(&b->mu);
+        int i = b->next < b->n ? b->next++ : -1;
+        pthread_mutex_unlock(&b->mu);
+        if (i < 0) break;
+        execute_query(&b->queries[i]);
+    }
+    return NULL;
+}
+
+static void run_batch(query_t *queries, int n, int workers) {
+    batch_t b = {queries, n, 0, PTHREAD_MUTEX_INITIALIZER};
+    if (workers > n) workers = n;
+    if (workers <= 1) {
+        worker(&b);
+    } else {
+        pthread_t th[64];
+        for (int w = 0; w < workers; ++w) pthread_create(&th[w], NULL, worker, &b);
+        for (int w = 0; w < workers; ++w) pthread_join(th[w], NULL);
+    }
+    for (int i = 0; i < n; ++i) puts(queries[i].line);      /* submission order, like the reference */
+    fflush(stdout);
+}
+
+int main(int argc, char **argv) {
+    int workers = 4;
+    if (getenv("B200_WORKERS")) workers = atoi(getenv("B200_WORKERS"));
+    if (argc == 3 && !strcmp(argv[1], "-w")) workers = atoi(argv[2]);
+    if (workers < 1) workers = 1;
+    if (workers > 64) workers = 64;
+
+    char buff[256];
+    int  cap = 16;
+    g_map    = malloc((size_t)cap * sizeof(relation_map));
+    while (scanf("%255s", buff) == 1 && strcmp(buff, "Done")) {            /* handler.c:27-48 */
+        if (g_nrel == cap) g_map = realloc(g_map, (size_t)(cap *= 2) * sizeof(relation_map));
+        if (load_relation(buff, &g_map[g_nrel])) return 1;
+        ++g_nrel;
+    }
+    b200_init(-1);
+    b200_register_relations(g_map, g_nrel);     /* the untimed preparation phase: columns go to HBM once */
+
+    query_t *batch = NULL;
+    int      nq = 0, qcap = 0;
+    while (fgets(buff, sizeof buff, stdin)) {                              /* handler.c:66-96 */
+        if (strlen(buff) < 2) continue;
+        if (!strcmp(buff, "Exit\n")) break;
+        if (!strcmp(buff, "F\n")) {
+            run_batch(batch, nq, workers);
+            nq = 0;
+            continue;
+        }
+        if (nq == qcap) batch = realloc(batch, (size_t)(qcap = qcap ? 2 * qcap : 64) * sizeof(query_t));
+        if (parse_query(buff, &batch[nq])) { fprintf(stderr, "cannot parse query: %s", buff); return 2; }
+        ++nq;
+    }
+    if (nq) run_batch(batch, nq, workers);
+    b200_shutdown();
+    return 0;
+}

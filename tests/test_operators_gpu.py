@@ -107,6 +107,22 @@ def test_small_workload_concurrent_queries_on_streams(gpu, workers):
     assert [r.line() for r in got] == golden * 2
 
 
+@pytest.mark.parametrize("workers", [1, 4])
+def test_small_workload_standalone_c_host(workers):
+    """BASELINE config 1 through host/b200_engine.c — our own C host (protocol of handler.c, loader of
+    relation_map.c, parser of query.c, a scheduler whose jobs are whole queries on per-thread CUDA streams) —
+    fed the harness protocol on stdin; output must equal the reference's small.result."""
+    exe = ROOT / "host" / "b200_engine"
+    small = ROOT / "oracle" / "_ref" / "small"
+    if not exe.exists() or not (small / "r0").exists():
+        pytest.skip("host/b200_engine or the small workload data not present")
+    stdin = (small / "small.init").read_text() + "Done\n" + (small / "small.work").read_text()
+    out = subprocess.run([str(exe), "-w", str(workers)], input=stdin, capture_output=True, text=True, cwd=small,
+                         timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout == (small / "small.result").read_text()
+
+
 def test_small_workload_dropin_binary():
     """BASELINE config 1 through the link-time drop-in: the reference's own
     handler.o/query.o/best_tree.o/stats.o/relation_map.o over libb200join.so,
