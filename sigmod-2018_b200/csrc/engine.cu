@@ -365,7 +365,11 @@ static void launch_scatter(const KeySrc &src, int bits, uint32_t *cursor, void *
 
 // histogram-free probe-side scatter (32-bit keys): fixed regions of opt.opt_cap tuples + overflow
 static void launch_scatter_opt(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
-    launch_scatter_c<uint32_t, 1, true>(src, bits, cursor, out, opt);
+    switch (tuning().scatter_cfg) {
+        case 0: launch_scatter_c<uint32_t, 0, true>(src, bits, cursor, out, opt); break;
+        case 2: launch_scatter_c<uint32_t, 2, true>(src, bits, cursor, out, opt); break;
+        default: launch_scatter_c<uint32_t, 1, true>(src, bits, cursor, out, opt); break;
+    }
 }
 
 // build-side scatter with early-materialised projections (radix_scatter_pay_kernel)

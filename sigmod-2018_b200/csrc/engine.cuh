@@ -38,7 +38,7 @@ struct Tuning {
     int      radix_bits  = 0;   // 0 = automatic
     int      force_key64 = 0;
     uint32_t cap32       = 17408;    // build tuples per shared-memory table, 32-bit keys
-    uint32_t cap64       = 6144;     // ... 64-bit keys
+    uint32_t cap64       = 12288;    // ... 64-bit keys
     uint32_t slice       = 1u << 18; // probe tuples per work item
     int      carry32     = 1;        // a single 32-bit build-side SUM column travels in the tuple's row-id slot
     int      opt_partition = 1;      // histogram-free probe-side scatter for the fused join -> SUM
