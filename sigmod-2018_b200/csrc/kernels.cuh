@@ -6,17 +6,23 @@
 //                                      row-id list) view, never an AoS copy
 //   K3  preprocess.c:189-192        -> radix_hist_kernel
 //   K4  preprocess.c:83-102         -> partition_plan_kernel
-//   K5  preprocess.c:262-296,350-359-> radix_scatter_kernel
-//   K6  rhjoin.c:227-248,270-271    -> hash_join_kernel, build phase
-//   K7  rhjoin.c:154-216            -> hash_join_kernel, probe phase
+//   K5  preprocess.c:262-296,350-359-> radix_scatter_kernel (+ its histogram-free
+//                                      OPT instance), radix_scatter_pay_kernel
+//   K6  rhjoin.c:227-248,270-271    -> tag_join_kernel (32-bit keys) /
+//   K7  rhjoin.c:154-216               hash_join_kernel (64-bit keys, small
+//                                      unpartitioned builds): build, probe
 //   K8  inter_res.c:79-98,119-137;
 //       filter.c:60-76; inter_res.c:304-313 -> gather_columns_kernel
-//   K9  inter_res.c:332-333         -> checksum_kernel / hash_join_kernel<SUM>
+//   K9  inter_res.c:332-333         -> checksum_kernel / the MODE_SUM instances
+//                                      of the join kernels
 //   K11 inter_res.c:376-385         -> inter_equal_kernel
+//   multi-GPU (absent in the reference): build_cursors_kernel,
+//                                      segment_broadcast_kernel
 //
-// Everything is HBM-bound integer work: no tensor cores.  Row ids and
-// positions are 32-bit on the device; keys are 32-bit when the column maximum
-// allows it (8-byte partition tuples) and 64-bit otherwise (16-byte tuples).
+// Integer/byte work only: no tensor cores.  Row ids and positions are 32-bit
+// on the device; keys are 32-bit when the column maxima allow it (8-byte
+// partition tuples) and 64-bit otherwise (16-byte tuples).  What bounds each
+// kernel (HBM, or the SM's L1/shared-memory pipe) is in DESIGN.md §4-5.
 #pragma once
 
 #include "types.cuh"
