@@ -233,3 +233,26 @@ def test_join_skewed_build_side_duplicates(gpu, orc):
     r, s, mp = gpu.hash_join_pairs(kr[:20000], ks[:20000])
     o_r, o_s = orc.radix_hash_join(kr[:20000], ks[:20000], 4)
     assert mp == len(o_r) and orc.checksum(pr, r) == orc.checksum(pr, o_r) and orc.checksum(ps, s) == orc.checksum(ps, o_s)
+
+
+# ---- differential fuzz of the fused join -> SUM over sizes, key widths, radix bits and table capacities ----
+@pytest.mark.parametrize("seed", range(10))
+def test_join_sum_fuzz(gpu, orc, seed):
+    g = np.random.default_rng(500 + seed)
+    nr = int(g.integers(1, 400_000))
+    ns = int(g.integers(1, 3_000_000))
+    wide = bool(g.integers(0, 4) == 0)                                   # one in four: keys above 2^32
+    domain = int(g.integers(max(2, nr // 4), 4 * nr + 4))                # <= ~4 matches per probe on average
+    kr = col(nr, domain, 9000 + seed)
+    ks = col(ns, domain, 9100 + seed)
+    if wide:
+        kr, ks = kr * np.uint64(0x100000001), ks * np.uint64(0x100000001)
+    pr, ps = col(nr, 1 << 40, 9200 + seed), col(ns, 1 << 62, 9300 + seed)
+    want, wm = orc.join_sum(kr, ks, [pr, ps, ps], [0, 1, 1], 4)
+    bits = int(g.choice([0, 0, 3, 6, 9, 12]))                            # 0 = automatic
+    gpu.lib().b200_set_tuning(bits, 0)
+    try:
+        got, m = gpu.join_sum(kr, ks, [pr, ps, ps], [0, 1, 1])
+    finally:
+        gpu.lib().b200_set_tuning(0, 0)
+    assert m == wm and got == want, (nr, ns, domain, wide, bits)

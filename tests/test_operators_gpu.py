@@ -194,3 +194,37 @@ def test_config3_chain_join_matches_the_reference(gpu, orc, f, d1, d2, d3):
                              timeout=600)
         assert got.returncode == 0, got.stderr[-1000:]
         assert got.stdout.splitlines()[0] == want_line
+
+
+# ---- differential fuzz: random conjunctive queries over random relations, GPU operators vs the oracle ----
+def _random_query(g, nrel, ncols):
+    nb = int(g.integers(2, 5))                                  # bindings
+    rels = [int(g.integers(0, nrel)) for _ in range(nb)]
+    preds, joined = [], {0}
+    order = list(range(1, nb))
+    g.shuffle(order)
+    for b in order:                                              # a spanning tree keeps the query connected
+        a = int(g.choice(sorted(joined)))
+        preds.append(f"{a}.{int(g.integers(0, ncols))}={b}.{int(g.integers(0, ncols))}")
+        joined.add(b)
+    for _ in range(int(g.integers(0, 3))):                       # extra edges: cycles / duplicate pairs / self joins
+        a, b = int(g.integers(0, nb)), int(g.integers(0, nb))
+        preds.append(f"{a}.{int(g.integers(0, ncols))}={b}.{int(g.integers(0, ncols))}")
+    for _ in range(int(g.integers(0, 3))):                       # filters, possibly on several bindings
+        op = "<>="[int(g.integers(0, 3))]
+        preds.append(f"{int(g.integers(0, nb))}.{int(g.integers(0, ncols))}{op}{int(g.integers(0, 400))}")
+    g.shuffle(preds)
+    views = " ".join(f"{int(g.integers(0, nb))}.{int(g.integers(0, ncols))}" for _ in range(int(g.integers(1, 4))))
+    return " ".join(map(str, rels)) + "|" + "&".join(preds) + "|" + views
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_queries_against_the_oracle(gpu, orc, seed):
+    g = np.random.default_rng(1000 + seed)
+    sizes = [int(x) for x in g.integers(1, 300, 4)]           # fan-out per join <= 6: results stay small
+    rels = [[col(n, int(g.integers(50, 400)), 7000 + 100 * seed + 10 * r + c) for c in range(3)]
+            for r, n in enumerate(sizes)]
+    rm = gpu.RelationMapArray(rels)
+    for _ in range(25):
+        q = _random_query(g, len(rels), 3)
+        assert gpu.execute_query(q, rm).line() == orc.execute_query(q, rels), q
