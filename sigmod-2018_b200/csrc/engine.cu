@@ -648,7 +648,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         const size_t tsz = key64 ? sizeof(Tup64) : sizeof(Tup32);
         // Histogram-free probe side (fused SUM, 32-bit keys): every partition owns a region a few percent
         // above the uniform expectation; what does not fit overflows and is partitioned exactly afterwards.
-        opt = mode == JoinOut::Sum && !key64 && t.opt_partition && P.src.n >= (1u << 20) && P.src.n <= (1u << 30);
+        opt = !key64 && t.opt_partition && P.src.n >= (1u << 20) && P.src.n <= (1u << 30);
         if (opt) opt_cap = opt_region_cap(P.src.n, bits);
         tup_b = dev_alloc((size_t)B.src.n * tsz);
         tup_p = dev_alloc(opt ? (size_t)opt_cap * nparts * tsz : (size_t)P.src.n * tsz);
@@ -796,10 +796,31 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
 
     // Pairs: count pass sizes the output exactly, write pass fills it.
     if (!direct) {
-        B200_CUDA(cudaMemcpyAsync(c.h_scratch, items + nparts, sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                  c.stream));
-        B200_CUDA(cudaStreamSynchronize(c.stream));
-        n_items = *reinterpret_cast<uint32_t *>(c.h_scratch);
+        auto read_items = [&]() {
+            B200_CUDA(cudaMemcpyAsync(c.h_scratch, items + nparts, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                      c.stream));
+            B200_CUDA(cudaMemcpyAsync(c.h_scratch + 1, d_ovcnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+            B200_CUDA(cudaStreamSynchronize(c.stream));
+            n_items = *reinterpret_cast<uint32_t *>(c.h_scratch);
+        };
+        read_items();
+        if (opt && *reinterpret_cast<uint32_t *>(c.h_scratch + 1) != 0) {
+            // the histogram-free scatter overflowed its regions (skewed keys): the pair-materialising path
+            // simply partitions the probe side again, exactly
+            TimedScope ts("overflow");
+            const size_t tsz = sizeof(Tup32);
+            B200_CUDA(cudaMemsetAsync(hist_p, 0, (size_t)nparts * sizeof(uint32_t), c.stream));
+            B200_CUDA(cudaMemsetAsync(d_ovcnt, 0, sizeof(uint32_t), c.stream));
+            launch_hist<uint32_t>(P.src, bits, hist_p);
+            partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, hist_p, nparts, cap, a.slice, off_b, off_p,
+                                                                  cur_b, cur_p, items, cnt_p, 0u);
+            B200_LAUNCH_CHECK();
+            tup_p = dev_alloc((size_t)P.src.n * tsz);
+            launch_scatter<uint32_t>(P.src, bits, cur_p, tup_p->ptr);
+            a.tup_p = tup_p->ptr;
+            opt     = false;
+            read_items();
+        }
     }
     DevBufPtr item_count = dev_alloc((n_items + 1) * sizeof(unsigned long long));
     a.item_count         = item_count->as<unsigned long long>();

@@ -256,3 +256,18 @@ def test_join_sum_fuzz(gpu, orc, seed):
     finally:
         gpu.lib().b200_set_tuning(0, 0)
     assert m == wm and got == want, (nr, ns, domain, wide, bits)
+
+
+def test_join_pairs_zipf_probe_side_overflows_the_regions(gpu, orc):
+    """Pair-materialising join with 2^21 Zipf probe keys: the histogram-free scatter overflows and the
+    probe side is partitioned again exactly; the pairs must still be the oracle's multiset."""
+    kr_bits, ns = 16, 1 << 21
+    kr = orc.synth_column(1 << kr_bits, 0, kr_bits, gpu.SEED_R)
+    ks = orc.synth_column(ns, 2, kr_bits, 31)
+    r, s, m = gpu.hash_join_pairs(kr, ks)
+    o_r, o_s = orc.radix_hash_join(kr, ks, 4)
+    assert m == ns == len(o_r)
+    assert np.array_equal(kr[r.astype(np.int64)], ks[s.astype(np.int64)])
+    assert np.array_equal(np.sort(s), np.arange(ns, dtype=np.uint64))          # every probe row exactly once
+    pr = orc.synth_column(1 << kr_bits, 1, 0, 5)
+    assert orc.checksum(pr, r) == orc.checksum(pr, o_r)
