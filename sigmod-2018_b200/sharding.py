@@ -148,8 +148,8 @@ class BroadcastScatterJoin:
         self._imported.append(p)
         return p
 
-    def step(self, build_keys_ptr, build_pay_ptrs, probe_keys_ptr, proj_cols, proj_side):
-        """proj_cols[k]: device pointer of projection k — for a build-side projection (side 0) it must be
+    def step(self, build_keys_ptr, build_pay_ptrs, probe_keys_ptr, proj_cols, proj_side, finish=True):
+        """One join: enqueue() then finish().  proj_cols[k]: device pointer of projection k — for a build-side projection (side 0) it must be
         one of build_pay_ptrs (it is read through the early-materialised copy); a probe-side projection
         (side 1) is this rank's local column, indexed by the local probe row id."""
         C, L, torch = self.C, self.L, self.torch
@@ -159,7 +159,7 @@ class BroadcastScatterJoin:
         side = self.side if self.side is not None else main
 
         def mark(name, stream=None):
-            if self.debug:
+            if self.debug and not torch.cuda.is_current_stream_capturing():
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record(stream or main)
                 self.marks.append((name, ev))
@@ -233,8 +233,23 @@ class BroadcastScatterJoin:
         if world > 1:
             self.dist.all_reduce(res)
         mark("join + all-reduce done")
+        self._pending = (args, k)
+        if not finish:
+            return None
+        return self.finish()
+
+    def enqueue(self, *a):
+        """Everything of a step that runs on the device, without any host read-back: capturable in a CUDA
+        graph (bench.py does, for N > 1, to take the per-step launch and collective set-up latency out)."""
+        return self.step(*a, finish=False)
+
+    def finish(self):
+        """Read {matches, sums, overflow count} back; run the exact overflow pass when it is needed."""
+        C, L, world, rank = self.C, self.L, self.world, self.rank
+        args, k = self._pending
+        res = self.result[: k + 2]
         host = res.cpu().tolist()
-        if self.debug and rank == 0:
+        if self.debug and rank == 0 and self.marks:
             t0 = self.marks[0][1]
             print("plan timeline (ms): " + ", ".join(f"{n} {t0.elapsed_time(e):.3f}" for n, e in self.marks[1:]),
                   file=__import__("sys").stderr)
