@@ -392,16 +392,7 @@ int b200_stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const voi
 
 int b200_radix_bits_for(uint64_t n_build) {
     // the library's automatic choice for a 32-bit-key build side of n_build rows
-    const Tuning  &t    = tuning();
-    const uint32_t L    = 14;
-    int            bits = 2;
-    (void)L;
-    auto fits = [&](int b) {
-        const double mean = (double)n_build / (double)(1ull << b);
-        return mean + 5.0 * sqrt(mean) <= (double)t.cap32;
-    };
-    while (bits < t.max_bits && !fits(bits)) ++bits;
-    return bits;
+    return auto_radix_bits(n_build, false);
 }
 
 }  // extern "C"

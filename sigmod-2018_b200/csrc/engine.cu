@@ -553,6 +553,24 @@ PartitionOut run_partition(const KeyVec &kv, int bits) {
     return o;
 }
 
+// Radix bits of a partitioned join: the fewest partitions whose build side — expected largest partition under a
+// uniform split, mean + 5 sigma; a larger one is split into build chunks — fits one shared-memory table.  Fewer
+// partitions mean longer runs per scatter tile.  The tag table (32-bit keys) needs radix_bits + slots_log2 >= 17.
+int auto_radix_bits(uint64_t n_build, bool key64) {
+    const Tuning  &t          = tuning();
+    const uint32_t cap        = key64 ? t.cap64 : t.cap32;
+    const uint32_t slots_log2 = key64 ? TableView<uint64_t>::slots_log2_for(cap) : tag_slots_log2_for(cap);
+    const int      min_bits   = key64 ? 1 : std::max(2, 17 - (int)slots_log2);
+    if (t.radix_bits > 0) return std::max(min_bits, std::min(t.radix_bits, t.max_bits));
+    auto fits = [&](int b) {
+        const double mean = (double)n_build / (double)(1ull << b);
+        return mean + 5.0 * sqrt(mean) <= (double)cap;
+    };
+    int bits = min_bits;
+    while (bits < t.max_bits && !fits(bits)) ++bits;
+    return bits;
+}
+
 // ---------------------------------------------------------------------------
 // the join: RadixHashJoin (rhjoin.c:13-111) + optional fused SUM
 // ---------------------------------------------------------------------------
@@ -576,24 +594,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     const uint32_t cap = key64 ? t.cap64 : t.cap32;
     B200_REQUIRE(cap >= 32 && cap <= (key64 ? 65534u : 32766u), "table capacity out of range");
     const uint32_t slots_log2 = key64 ? TableView<uint64_t>::slots_log2_for(cap) : tag_slots_log2_for(cap);
-    // expected largest partition under a uniform split: mean + 5 sigma (a larger one is split into build chunks)
-    auto fits = [&](int b) {
-        const double mean = (double)B.src.n / (double)(1ull << b);
-        return mean + 5.0 * sqrt(mean) <= (double)cap;
-    };
-
-    int bits = 0;
-    if (!direct) {
-        // the tag table needs radix_bits + slots_log2 >= 17 (tag <= 15 bits)
-        const int min_bits = key64 ? 1 : std::max(2, 17 - (int)slots_log2);
-        if (t.radix_bits > 0) {
-            bits = std::max(min_bits, std::min(t.radix_bits, t.max_bits));
-        } else {
-            // fewest partitions whose build side fits one table (longer runs per scatter tile)
-            bits = min_bits;
-            while (bits < t.max_bits && !fits(bits)) ++bits;
-        }
-    }
+    const int bits = direct ? 0 : auto_radix_bits(B.src.n, key64);
 
     JoinArgs a;
     memset(&a, 0, sizeof(a));

@@ -99,6 +99,7 @@ void       stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_
                                uint64_t *const *pay_dst, int phase = 0);
 void       stage_scatter_probe(const uint64_t *d_keys, uint64_t n, int bits, uint32_t *d_cursor, void *d_tup_out);
 uint32_t   opt_region_cap(uint64_t n_probe, int bits);
+int        auto_radix_bits(uint64_t n_build, bool key64);
 void       stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint32_t opt_cap, uint32_t *d_cursor,
                                    void *d_tup_out, void *d_ov, uint32_t *d_ovcnt);
 JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p,
