@@ -263,7 +263,8 @@ def run_b200_arm(args):
     plan = None
     if world > 1:
         plan = b200.sharding.BroadcastScatterJoin(b200, torch, dist, rank, world, nr, nr_loc, ns_loc, 1, dev,
-                                                  carry32=r1_max < (1 << 32))
+                                                  carry32=r1_max < (1 << 32),
+                                                  rank_major=os.environ.get("B200_PLAN", "copy") == "copy")
     torch.cuda.synchronize()
 
     def step(kr=None, pr=None, ks=None, ps=None):

@@ -281,6 +281,32 @@ int   b200_stage_join_sum_async(const void *d_tup_b, const uint32_t *d_hist_b,
                                 uint32_t opt_cap, const void *d_ov,
                                 const uint32_t *d_ovcnt, uint64_t *d_result);
 
+/* Rank-major build layout (the broadcast runs on the copy engines): every rank
+ * partitions its build shard straight into region `rank` of its own build
+ * buffer (b200_stage_scatter_build_local), copies that region verbatim into the
+ * same region of every peer's buffer (b200_copy_device_async on IPC-mapped
+ * pointers: one large copy per peer), and the join reads partition p as nseg
+ * runs: d_hist_all[nseg][2^bits] are the all-gathered histograms, region r
+ * starts at r * seg_rows.  d_result != NULL: asynchronous, {matches, sums...,
+ * overflow count} written to that DEVICE buffer; else synchronous into
+ * out_sums / out_matches (overflow pass included). */
+int   b200_stage_scatter_build_local(const uint64_t *d_keys, uint64_t n,
+                                     uint32_t rid_base, int radix_bits,
+                                     const uint32_t *d_hist_local,
+                                     void *d_tup_out, int npay,
+                                     const uint64_t *const *pay_cols,
+                                     uint64_t *const *pay_out);
+int   b200_copy_device_async(void *dst, const void *src, uint64_t bytes);
+int   b200_stage_join_sum_seg(const void *d_tup_b, const uint32_t *d_hist_all,
+                              int nseg, uint32_t seg_rows, const void *d_tup_p,
+                              const uint32_t *d_hist_p, int radix_bits,
+                              int n_proj, const uint64_t *const *proj_cols,
+                              const int *proj_side,
+                              const uint64_t *const *proj_part_vals,
+                              uint32_t opt_cap, const void *d_ov,
+                              const uint32_t *d_ovcnt, uint64_t *d_result,
+                              uint64_t *out_sums, uint64_t *out_matches);
+
 /* Per-kernel device times of the calling thread's last RadixHashJoin /
  * b200_join_sum, measured with CUDA events on its stream when profiling is
  * enabled with b200_set_profiling(1).  Names: "hist_b", "hist_p", "scan",

@@ -390,6 +390,39 @@ int b200_stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const voi
     return 0;
 }
 
+int b200_stage_scatter_build_local(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int radix_bits,
+                                   const uint32_t *d_hist_local, void *d_tup_out, int npay,
+                                   const uint64_t *const *pay_cols, uint64_t *const *pay_out) {
+    if (n > kMaxRows) return fail("more than 2^32-1 rows");
+    if (npay < 0 || npay > 2) return fail("npay must be 0..2");
+    stage_scatter_build_local(d_keys, n, rid_base, radix_bits, d_hist_local, d_tup_out, npay, pay_cols, pay_out);
+    return 0;
+}
+
+int b200_copy_device_async(void *dst, const void *src, uint64_t bytes) {
+    B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx().stream));
+    return 0;
+}
+
+int b200_stage_join_sum_seg(const void *d_tup_b, const uint32_t *d_hist_all, int nseg, uint32_t seg_rows,
+                            const void *d_tup_p, const uint32_t *d_hist_p, int radix_bits, int n_proj,
+                            const uint64_t *const *proj_cols, const int *proj_side,
+                            const uint64_t *const *proj_part_vals, uint32_t opt_cap, const void *d_ov,
+                            const uint32_t *d_ovcnt, uint64_t *d_result, uint64_t *out_sums, uint64_t *out_matches) {
+    if (n_proj < 0 || n_proj > kMaxProj) return fail("at most 8 fused projections");
+    if (nseg < 1 || nseg > 8) return fail("nseg must be 1..8");
+    ProjDesc pd[kMaxProj];
+    for (int k = 0; k < n_proj; ++k)
+        pd[k] = ProjDesc{proj_cols[k], nullptr, proj_side[k], proj_part_vals ? proj_part_vals[k] : nullptr};
+    JoinResult j = stage_join_sum(d_tup_b, d_hist_all, d_tup_p, d_hist_p, radix_bits, n_proj, pd, opt_cap, d_ov, d_ovcnt,
+                                  reinterpret_cast<unsigned long long *>(d_result), nseg, seg_rows);
+    if (!d_result) {
+        for (int k = 0; k < n_proj; ++k) out_sums[k] = j.sums[k];
+        *out_matches = j.m;
+    }
+    return 0;
+}
+
 int b200_radix_bits_for(uint64_t n_build) {
     // the library's automatic choice for a 32-bit-key build side of n_build rows
     return auto_radix_bits(n_build, false);

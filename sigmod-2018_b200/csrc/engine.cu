@@ -492,7 +492,25 @@ static size_t tag_join_smem(uint32_t cap, uint32_t slots_log2) {
     const int nw = tag_join_big(cap, slots_log2) ? 32 : 16;
     return ((size_t)4 << slots_log2) + (size_t)4 * cap + (size_t)8 * kTagQueue * nw;
 }
+// segmented build side (multi-GPU rank-major layout): fused SUM only
+template <int NT, int MINB>
+static void launch_join32_seg(const JoinArgs &a, size_t smem) {
+    if (a.nproj <= 2)
+        launch_persistent_join_nt(tag_join_kernel<NT, MINB, kJoinG, MODE_SUM, 2, true>, a, smem, NT);
+    else if (a.nproj <= 4)
+        launch_persistent_join_nt(tag_join_kernel<NT, MINB, kJoinG, MODE_SUM, 4, true>, a, smem, NT);
+    else
+        launch_persistent_join_nt(tag_join_kernel<NT, MINB, kJoinG, MODE_SUM, kMaxProj, true>, a, smem, NT);
+}
 static void launch_join32(const JoinArgs &a, int mode, size_t smem) {
+    if (a.nseg > 0) {
+        B200_REQUIRE(mode == MODE_SUM, "a segmented build side is only joined into SUMs");
+        if (tag_join_big(a.cap, a.slots_log2))
+            launch_join32_seg<1024, 1>(a, smem);
+        else
+            launch_join32_seg<512, 2>(a, smem);
+        return;
+    }
     if (tag_join_big(a.cap, a.slots_log2))
         launch_join32_cfg<1024, 1>(a, mode, smem);
     else
@@ -1063,6 +1081,37 @@ void stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, 
     st = BuildStaging{};   // released in stream order
 }
 
+// partition the local build shard straight into a caller-owned region (rank-major layout): tuples, and either
+// up to two payload columns (pay_out) or one 32-bit payload carried in the row-id slot (npay == 1, pay_out == NULL)
+void stage_scatter_build_local(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int bits,
+                               const uint32_t *d_hist_local, void *d_tup_out, int npay, const uint64_t *const *pay_cols,
+                               uint64_t *const *pay_out) {
+    B200_REQUIRE(npay >= 0 && npay <= 2, "bad payload count");
+    if (n == 0) return;
+    Context       &c      = ctx();
+    const uint32_t nparts = 1u << bits;
+    DevBufPtr ctrl = dev_alloc(5 * (size_t)(nparts + 1) * sizeof(uint32_t));
+    uint32_t *off_l = ctrl->as<uint32_t>(), *off_x = off_l + nparts + 1, *cur_l = off_x + nparts + 1,
+             *cur_x = cur_l + nparts + 1, *items = cur_x + nparts + 1;
+    partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_local, d_hist_local, nparts, 1u, 1u, off_l, off_x,
+                                                          cur_l, cur_x, items, items, 0u);
+    B200_LAUNCH_CHECK();
+    PayArgs pay{};
+    pay.rid_base = rid_base;
+    const bool carry = npay == 1 && pay_out == nullptr;
+    if (carry) {
+        pay.carry32 = 1;
+        pay.col[0]  = pay_cols[0];
+    }
+    for (int k = 0; k < (carry ? 0 : npay); ++k) {
+        pay.col[k] = pay_cols[k];
+        pay.out[k] = pay_out[k];
+    }
+    KeySrc src{d_keys, nullptr, (uint32_t)n};
+    TimedScope ts("scatter_b");
+    launch_scatter_pay<uint32_t>(src, bits, cur_l, d_tup_out, pay, npay);
+}
+
 void stage_scatter_probe(const uint64_t *d_keys, uint64_t n, int bits, uint32_t *d_cursor, void *d_tup_out) {
     if (n == 0) return;
     KeySrc src{d_keys, nullptr, (uint32_t)n};
@@ -1103,9 +1152,11 @@ void stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint3
 // d_result != nullptr: asynchronous — matches, the nproj sums and the overflow count are copied to
 // d_result[0], d_result[1..nproj], d_result[nproj + 1] (u64 each) on the stream and nothing is read back;
 // the caller runs stage_join_overflow when it later finds a non-zero overflow count.
+// nseg > 0: rank-major build layout — d_hist_b is then hist_all[nseg][2^bits] and region r of d_tup_b (and of the
+// part_vals arrays) starts at r * seg_rows and holds rank r's shard in partition order.
 JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p, const uint32_t *d_hist_p,
                           int bits, int nproj, const ProjDesc *proj, uint32_t opt_cap, const void *d_ov,
-                          const uint32_t *d_ovcnt, unsigned long long *d_result) {
+                          const uint32_t *d_ovcnt, unsigned long long *d_result, int nseg, uint32_t seg_rows) {
     Context   &c = ctx();
     Tuning    &t = tuning();
     JoinResult res;
@@ -1129,6 +1180,19 @@ JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const v
     a.total        = d_u64;
     a.out_cursor   = d_u64 + 1;
     a.sums         = d_u64 + 8;
+    DevBufPtr seg;
+    if (nseg > 0) {
+        B200_REQUIRE(nseg <= kMaxPeers, "at most 8 build segments");
+        seg                = dev_alloc(((size_t)nseg + 1) * nparts * sizeof(uint32_t));
+        uint32_t *seg_off  = seg->as<uint32_t>(), *total = seg_off + (size_t)nseg * nparts;
+        segment_offsets_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_b, (uint32_t)nseg, nparts, seg_rows, seg_off,
+                                                                total);
+        B200_LAUNCH_CHECK();
+        a.nseg    = nseg;
+        a.seg_off = seg_off;
+        a.seg_cnt = d_hist_b;
+        d_hist_b  = total;   // the plan works on the global histogram (virtual concatenation of the runs)
+    }
     {
         TimedScope ts("scan");
         partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_b, d_hist_p, nparts, cap, a.slice, off_b, off_p,

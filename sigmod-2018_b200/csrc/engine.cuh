@@ -104,7 +104,11 @@ void       stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits,
                                    void *d_tup_out, void *d_ov, uint32_t *d_ovcnt);
 JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p,
                           const uint32_t *d_hist_p, int bits, int nproj, const ProjDesc *proj, uint32_t opt_cap,
-                          const void *d_ov, const uint32_t *d_ovcnt, unsigned long long *d_result = nullptr);
+                          const void *d_ov, const uint32_t *d_ovcnt, unsigned long long *d_result = nullptr,
+                          int nseg = 0, uint32_t seg_rows = 0);
+void       stage_scatter_build_local(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int bits,
+                                     const uint32_t *d_hist_local, void *d_tup_out, int npay,
+                                     const uint64_t *const *pay_cols, uint64_t *const *pay_out);
 void       stage_build_cursors(const uint32_t *d_hist_all, int world, int rank, int bits, uint32_t *d_total,
                                uint32_t *d_my_start);
 

@@ -652,6 +652,11 @@ struct JoinArgs {
     unsigned long long *item_count;   // per item: written by COUNT, read by WRITE
     unsigned long long *out_cursor;   // WRITE
     uint32_t       *out_b, *out_p;    // WRITE
+    // segmented build side (multi-GPU, rank-major layout): the build tuples of partition p are nseg runs, run r
+    // holding seg_cnt[r * nparts + p] tuples from physical position seg_off[r * nparts + p]; off_b[] then
+    // describes the VIRTUAL concatenation of the runs (tag_join_kernel<SEG = true>)
+    int             nseg;
+    const uint32_t *seg_off, *seg_cnt;
     int             nproj;            // SUM
     int             need_brid;        // SUM: some build-side projection is gathered through the row id
     ProjDesc        proj[kMaxProj];
@@ -1038,12 +1043,12 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t saddr) {
 
 // work item of the join kernels: (build chunk, probe slice)
 struct JoinItem {
-    uint32_t valid, b_start, b_count, p_start, p_count, w;
+    uint32_t valid, b_start, b_count, p_start, p_count, w, part;
 };
 
 template <bool DIRECT>
 __device__ __forceinline__ JoinItem fetch_join_item(const JoinArgs &a, int lane) {
-    JoinItem it{0, 0, 0, 0, 0, 0};
+    JoinItem it{0, 0, 0, 0, 0, 0, 0};
     uint32_t w = 0;
     if (lane == 0) w = atomicAdd(a.work_counter, 1u);
     w    = __shfl_sync(kFullMask, w, 0);
@@ -1073,6 +1078,7 @@ __device__ __forceinline__ JoinItem fetch_join_item(const JoinArgs &a, int lane)
                 lo                  = nlo;
             }
             const uint32_t p   = lo;
+            it.part            = p;
             const uint32_t k   = w - a.item_start[p];
             const uint32_t b0  = a.off_b[p], b1 = a.off_b[p + 1];
             const uint32_t p0  = a.off_p[p], p1 = p0 + a.cnt_p[p];
@@ -1112,7 +1118,7 @@ __device__ __forceinline__ uint64_t ld_gather_u64(const uint64_t *p) {
     return v;
 }
 
-template <int NT, int MINB, int G, int MODE, int NP>
+template <int NT, int MINB, int G, int MODE, int NP, bool SEG = false>
 __global__ void __launch_bounds__(NT, MINB)
 tag_join_kernel(const JoinArgs a) {
     constexpr int NW  = NT / 32;
@@ -1132,12 +1138,23 @@ tag_join_kernel(const JoinArgs a) {
     __shared__ uint32_t           s_cursor;
     __shared__ unsigned long long s_base;
     __shared__ unsigned long long s_cnt;
+    __shared__ uint32_t           s_seg_vend[kMaxPeers], s_seg_delta[kMaxPeers];   // SEG: see bphys()
 
     const uint32_t tid  = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t wid  = tid >> 5;
     const uint32_t lt   = (1u << lane) - 1u;
     const uint32_t my_q = s_queue + wid * (uint32_t)(QN * 8);
+    // virtual build position (off_b space) -> physical index in tup_b / part_vals
+    auto bphys = [&](uint32_t v) -> uint32_t {
+        if constexpr (SEG) {
+            int r = 0;
+            while (r + 1 < a.nseg && v >= s_seg_vend[r]) ++r;
+            return v + s_seg_delta[r];
+        } else {
+            return v;
+        }
+    };
     const Tup32 *tup_b = static_cast<const Tup32 *>(a.tup_b);
     const Tup32 *tup_p = static_cast<const Tup32 *>(a.tup_p);
 
@@ -1152,7 +1169,7 @@ tag_join_kernel(const JoinArgs a) {
     auto handle_inline = [&](uint32_t pos, uint32_t prid) {
         ++my_matches;
         if constexpr (MODE != MODE_COUNT) {
-            const uint32_t brid = tup_b[b_start + pos].rid;
+            const uint32_t brid = tup_b[bphys(b_start + pos)].rid;
             if constexpr (MODE == MODE_SUM) {
 #pragma unroll
                 for (int k = 0; k < NPA; ++k) {
@@ -1160,7 +1177,7 @@ tag_join_kernel(const JoinArgs a) {
                         if (a.proj[k].part_vals == B200_PROJ_IN_RID) {
                             my_sum[k] += brid;   // the slot carries the value
                         } else if (a.proj[k].part_vals) {
-                            my_sum[k] += a.proj[k].part_vals[b_start + pos];
+                            my_sum[k] += a.proj[k].part_vals[bphys(b_start + pos)];
                         } else {
                             const uint32_t r  = a.proj[k].side == 0 ? brid : prid;
                             const uint32_t rr = a.proj[k].ids ? __ldg(a.proj[k].ids + r) : r;
@@ -1186,7 +1203,7 @@ tag_join_kernel(const JoinArgs a) {
         // ---- match entries ----
         const bool is_match = mine && (e.x & kQMatch) != 0u;
         if constexpr (MODE == MODE_SUM) {
-            const uint32_t bpos = b_start + (e.x & kIdxMask);
+            const uint32_t bpos = bphys(b_start + (e.x & kIdxMask));
             uint32_t       brid = 0;
             if (is_match && a.need_brid) brid = tup_b[bpos].rid;
 #pragma unroll
@@ -1213,7 +1230,7 @@ tag_join_kernel(const JoinArgs a) {
             pos = __shfl_sync(kFullMask, pos, 0);
             if (is_match) {
                 const uint32_t o  = pos + __popc(bal & lt);
-                a.out_b[s_base + o] = tup_b[b_start + (e.x & kIdxMask)].rid;
+                a.out_b[s_base + o] = tup_b[bphys(b_start + (e.x & kIdxMask))].rid;
                 a.out_p[s_base + o] = e.y;
             }
         } else {
@@ -1242,6 +1259,23 @@ tag_join_kernel(const JoinArgs a) {
     for (;;) {
         if (tid < 32) {
             const JoinItem it = fetch_join_item<false>(a, (int)lane);
+            if constexpr (SEG) {
+                if (it.valid) {
+                    // lane r owns run r of this partition: inclusive scan of the run lengths over the lanes
+                    const uint32_t cnt = (int)lane < a.nseg ? a.seg_cnt[lane * a.nparts + it.part] : 0u;
+                    uint32_t       inc = cnt;
+#pragma unroll
+                    for (int d = 1; d < kMaxPeers; d <<= 1) {
+                        const uint32_t up = __shfl_up_sync(kFullMask, inc, d);
+                        if ((int)lane >= d) inc += up;
+                    }
+                    if ((int)lane < a.nseg) {
+                        const uint32_t vstart = a.off_b[it.part] + inc - cnt;
+                        s_seg_vend[lane]      = a.off_b[it.part] + inc;
+                        s_seg_delta[lane]     = a.seg_off[lane * a.nparts + it.part] - vstart;
+                    }
+                }
+            }
             if (lane == 0) {
                 s_item[0] = it.valid;
                 s_item[1] = it.b_start;
@@ -1288,7 +1322,7 @@ tag_join_kernel(const JoinArgs a) {
 #pragma unroll
             for (int u = 0; u < KB; ++u) {
                 const uint32_t i = i0 + (uint32_t)u * NT;
-                bk[u]            = i < b_count ? ld_stream_u32(&tup_b[b_start + i].key) : 0u;
+                bk[u]            = i < b_count ? ld_stream_u32(&tup_b[bphys(b_start + i)].key) : 0u;
             }
 #pragma unroll
             for (int u = 0; u < KB; ++u) {
@@ -1603,6 +1637,37 @@ build_cursors_kernel(const uint32_t *__restrict__ hist_all, uint32_t world, uint
             my_start[b] = run + before;
             run += tot;
         }
+    }
+}
+
+// rank-major build layout: region r of the build buffer holds rank r's shard in partition order.  From the
+// all-gathered histograms: seg_off[r][p] = r * seg_rows + (exclusive scan of hist_all[r] over p) and the global
+// histogram total[p].  One CTA; rank r is scanned by warp... simply one rank after the other.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+segment_offsets_kernel(const uint32_t *__restrict__ hist_all, uint32_t world, uint32_t nparts, uint32_t seg_rows,
+                       uint32_t *__restrict__ seg_off, uint32_t *__restrict__ total) {
+    __shared__ uint32_t warp_sums[NT / 32 + 1];
+    const uint32_t per   = (nparts + NT - 1) / NT;
+    const uint32_t first = threadIdx.x * per;
+    for (uint32_t r = 0; r < world; ++r) {
+        uint32_t s = 0;
+        for (uint32_t k = 0; k < per; ++k)
+            if (first + k < nparts) s += hist_all[r * nparts + first + k];
+        uint32_t run = block_exclusive_scan<NT>(s, warp_sums);
+        for (uint32_t k = 0; k < per; ++k) {
+            const uint32_t b = first + k;
+            if (b < nparts) {
+                seg_off[r * nparts + b] = r * seg_rows + run;
+                run += hist_all[r * nparts + b];
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t b = threadIdx.x; b < nparts; b += NT) {
+        uint32_t t = 0;
+        for (uint32_t r = 0; r < world; ++r) t += hist_all[r * nparts + b];
+        total[b] = t;
     }
 }
 

@@ -186,6 +186,12 @@ def _declare(L: C.CDLL) -> None:
                                                C.c_int]),
         "b200_stage_scatter_probe": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
         "b200_opt_region_cap": (C.c_uint32, [C.c_uint64, C.c_int]),
+        "b200_stage_scatter_build_local": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p,
+                                                     C.c_void_p, C.c_int, P(C.c_void_p), P(C.c_void_p)]),
+        "b200_copy_device_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+        "b200_stage_join_sum_seg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p,
+                                              C.c_int, C.c_int, P(C.c_void_p), P(C.c_int), P(C.c_void_p), C.c_uint32,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, u64p, u64p]),
         "b200_stage_build_cursors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
         "b200_stage_join_sum_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                 P(C.c_void_p), P(C.c_int), P(C.c_void_p), C.c_uint32, C.c_void_p,

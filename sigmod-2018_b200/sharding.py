@@ -84,7 +84,7 @@ class BroadcastScatterJoin:
     """
 
     def __init__(self, b200, torch, dist, rank, world, n_build_total, n_build_local, n_probe_local, n_pay, device,
-                 carry32=False):
+                 carry32=False, rank_major=False):
         """carry32: the single build-side SUM column (n_pay == 1) holds 32-bit values and travels in the row-id
         slot of the build tuples: no payload buffers, half the bytes in the NVLink broadcast."""
         import ctypes as C
@@ -95,6 +95,11 @@ class BroadcastScatterJoin:
         self.n_build_total, self.n_build_local, self.n_probe_local = n_build_total, n_build_local, n_probe_local
         self.n_pay = n_pay
         self.carry32 = bool(carry32) and n_pay == 1
+        # rank_major: region r of every build buffer holds rank r's shard in partition order; the broadcast is
+        # then ONE contiguous copy per peer on the copy engines (no SM kernel), and the join reads a partition
+        # as `world` runs (b200_stage_join_sum_seg).  Needs equal build shards.
+        self.rank_major = bool(rank_major) and n_build_local * world == n_build_total
+        self.copy_streams = []
         self.bits = int(L.b200_radix_bits_for(n_build_total))
         self.P = 1 << self.bits
         self.device = device
@@ -107,8 +112,10 @@ class BroadcastScatterJoin:
         self.ov_p = b200.DeviceColumn(max(n_probe_local, 1)) if self.opt_cap else None
         self.ovcnt = torch.zeros(1, dtype=torch.int32, device=device)
         import os
-        self.side = torch.cuda.Stream(device=device) if device is not None and getattr(device, "type", "") == "cuda" \
-            and not os.environ.get("B200_PLAN_SERIAL") else None
+        on_gpu = device is not None and getattr(device, "type", "") == "cuda"
+        self.side = torch.cuda.Stream(device=device) if on_gpu and not os.environ.get("B200_PLAN_SERIAL") else None
+        if self.rank_major and on_gpu:
+            self.copy_streams = [torch.cuda.Stream(device=device) for _ in range(min(4, max(world - 1, 1)))]
         self.debug = bool(os.environ.get("B200_PLAN_DEBUG"))
         self.marks = []
         self.hist = torch.zeros((2, self.P), dtype=torch.int32, device=device)      # [build, probe] local
@@ -172,21 +179,29 @@ class BroadcastScatterJoin:
             self.dist.all_gather_into_tensor(self.hist_all.view(-1), h_b)
         else:
             self.hist_all[0].copy_(h_b)
-        total_b, cur_b = self.total_b, self.cur_b
-        assert L.b200_stage_build_cursors(self.hist_all.data_ptr(), world, rank, bits, total_b.data_ptr(),
-                                          cur_b.data_ptr()) == 0
-        ndst = len(self.peer_tup)
-        tup_dst = (C.c_void_p * ndst)(*self.peer_tup)
         npay = self.n_pay
         pay_cols = (C.c_void_p * max(npay, 1))(*build_pay_ptrs[:npay])
-        flat = [self.peer_pay[k][d] for k in range(len(self.pay_b)) for d in range(ndst)]
-        pay_dst = None if self.carry32 else (C.c_void_p * max(len(flat), 1))(*flat)
-        # the local partition pass of the build shard and the probe-side scatter both want a whole SM's shared
-        # memory per CTA, so they run back to back; the NVLink-bound broadcast copy (tiny CTAs) then runs
-        # UNDER the probe-side scatter, which is issued on the side stream in between
-        assert L.b200_stage_scatter_build(build_keys_ptr, self.n_build_local, rank * self.n_build_local, bits,
-                                          h_b.data_ptr(), cur_b.data_ptr(), ndst, tup_dst, npay, pay_cols,
-                                          pay_dst, 1) == 0
+        total_b, cur_b = self.total_b, self.cur_b
+        ndst = len(self.peer_tup)
+        region = 8 * rank * self.n_build_local          # byte offset of this rank's region (8-byte tuples / values)
+        if self.rank_major:
+            # partition the local shard straight into this rank's region of its own build buffer
+            outs = None if self.carry32 else (C.c_void_p * max(npay, 1))(*[pb.ptr + region for pb in self.pay_b])
+            assert L.b200_stage_scatter_build_local(build_keys_ptr, self.n_build_local, rank * self.n_build_local,
+                                                    bits, h_b.data_ptr(), self.tup_b.ptr + region, npay, pay_cols,
+                                                    outs) == 0
+        else:
+            assert L.b200_stage_build_cursors(self.hist_all.data_ptr(), world, rank, bits, total_b.data_ptr(),
+                                              cur_b.data_ptr()) == 0
+            tup_dst = (C.c_void_p * ndst)(*self.peer_tup)
+            flat = [self.peer_pay[k][d] for k in range(len(self.pay_b)) for d in range(ndst)]
+            pay_dst = None if self.carry32 else (C.c_void_p * max(len(flat), 1))(*flat)
+            # the local partition pass of the build shard and the probe-side scatter both want a whole SM's shared
+            # memory per CTA, so they run back to back; the NVLink-bound broadcast copy (tiny CTAs) then runs
+            # UNDER the probe-side scatter, which is issued on the side stream in between
+            assert L.b200_stage_scatter_build(build_keys_ptr, self.n_build_local, rank * self.n_build_local, bits,
+                                              h_b.data_ptr(), cur_b.data_ptr(), ndst, tup_dst, npay, pay_cols,
+                                              pay_dst, 1) == 0
         mark("build partitioned")
         # ---- probe side: local, independent of the exchange -> side stream ----
         side.wait_stream(main)
@@ -204,10 +219,26 @@ class BroadcastScatterJoin:
             cur_p.record_stream(side)
         mark("probe scattered (side)", side)
         L.b200_set_stream(main.cuda_stream)
-        # ---- broadcast of the partitioned build shard (main stream, concurrent with the probe scatter) ----
-        assert L.b200_stage_scatter_build(build_keys_ptr, self.n_build_local, rank * self.n_build_local, bits,
-                                          h_b.data_ptr(), cur_b.data_ptr(), ndst, tup_dst, npay, pay_cols,
-                                          pay_dst, 2) == 0
+        # ---- broadcast of the partitioned build shard, concurrent with the probe scatter ----
+        if self.rank_major:
+            # one contiguous peer copy per destination (copy engines, NVLink), every rank starting at a different peer
+            nbytes = 8 * self.n_build_local
+            for j in range(1, world):
+                dpeer = (rank + j) % world
+                cs = self.copy_streams[(j - 1) % len(self.copy_streams)] if self.copy_streams else main
+                cs.wait_stream(main)
+                L.b200_set_stream(cs.cuda_stream)
+                assert L.b200_copy_device_async(self.peer_tup[dpeer] + region, self.tup_b.ptr + region, nbytes) == 0
+                for k in range(len(self.pay_b)):
+                    assert L.b200_copy_device_async(self.peer_pay[k][dpeer] + region, self.pay_b[k].ptr + region,
+                                                    nbytes) == 0
+            L.b200_set_stream(main.cuda_stream)
+            for cs in self.copy_streams:
+                main.wait_stream(cs)
+        else:
+            assert L.b200_stage_scatter_build(build_keys_ptr, self.n_build_local, rank * self.n_build_local, bits,
+                                              h_b.data_ptr(), cur_b.data_ptr(), ndst, tup_dst, npay, pay_cols,
+                                              pay_dst, 2) == 0
         mark("broadcast done")
         if world > 1:
             self.dist.all_reduce(self.token)      # stream-ordered barrier: every peer's broadcast has landed
@@ -223,13 +254,21 @@ class BroadcastScatterJoin:
             else:
                 part.append(None)
         part_vals = (C.c_void_p * max(k, 1))(*part)
-        args = (self.tup_b.ptr, total_b.data_ptr(), self.tup_p.ptr, h_p.data_ptr(), bits, k, cols, sides, part_vals,
-                self.opt_cap, self.ov_p.ptr if self.opt_cap else None, self.ovcnt.data_ptr())
+        if self.rank_major:
+            args = (self.tup_b.ptr, self.hist_all.data_ptr(), world, self.n_build_local, self.tup_p.ptr, h_p.data_ptr(),
+                    bits, k, cols, sides, part_vals, self.opt_cap, self.ov_p.ptr if self.opt_cap else None,
+                    self.ovcnt.data_ptr())
+        else:
+            args = (self.tup_b.ptr, total_b.data_ptr(), self.tup_p.ptr, h_p.data_ptr(), bits, k, cols, sides,
+                    part_vals, self.opt_cap, self.ov_p.ptr if self.opt_cap else None, self.ovcnt.data_ptr())
         # asynchronous join: {matches, sums, overflow count} stay on the device and are all-reduced in place
         # (u64 sums mod 2^64 == wrapping int64 sums); that all-reduce also ends the step on every rank, so no
         # peer can start overwriting this rank's build buffers before its join has finished
         res = self.result[: k + 2]
-        assert L.b200_stage_join_sum_async(*args, res.data_ptr()) == 0
+        if self.rank_major:
+            assert L.b200_stage_join_sum_seg(*args, res.data_ptr(), None, None) == 0
+        else:
+            assert L.b200_stage_join_sum_async(*args, res.data_ptr()) == 0
         if world > 1:
             self.dist.all_reduce(res)
         mark("join + all-reduce done")
@@ -258,7 +297,10 @@ class BroadcastScatterJoin:
             # synchronously, overflow pass included, and reduce again
             sums = (C.c_uint64 * max(k, 1))()
             m = C.c_uint64(0)
-            assert L.b200_stage_join_sum(*args, sums, C.byref(m)) == 0
+            if self.rank_major:
+                assert L.b200_stage_join_sum_seg(*args, None, sums, C.byref(m)) == 0
+            else:
+                assert L.b200_stage_join_sum(*args, sums, C.byref(m)) == 0
             return allreduce_checksums([int(x) for x in sums[:k]], int(m.value), self.dist if world > 1 else None,
                                        self.device)
         return i64_to_u64(host[1: k + 1]), int(host[0])

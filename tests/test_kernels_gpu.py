@@ -178,9 +178,10 @@ def test_join_sum_config2_shape_scaled_down(gpu, orc, kr_bits, ks_bits):
 
 
 # ---- staged join (the phases the multi-GPU plan drives), single GPU ----------
-@pytest.mark.parametrize("kr_bits,ks_bits,zipf,carry", [(15, 18, False, False), (18, 21, False, False),
-                                                        (16, 21, True, False), (18, 21, False, True)])
-def test_staged_join_matches_fused_join(gpu, orc, kr_bits, ks_bits, zipf, carry):
+@pytest.mark.parametrize("kr_bits,ks_bits,zipf,carry,rank_major", [
+    (15, 18, False, False, False), (18, 21, False, False, False), (16, 21, True, False, False),
+    (18, 21, False, True, False), (18, 21, False, True, True), (16, 21, True, False, True)])
+def test_staged_join_matches_fused_join(gpu, orc, kr_bits, ks_bits, zipf, carry, rank_major):
     """sharding.BroadcastScatterJoin with world = 1: hist -> cursors -> scatter (build side with an
     early-materialised payload, through the multi-destination path) -> join_sum, against the oracle."""
     torch = pytest.importorskip("torch")
@@ -196,7 +197,8 @@ def test_staged_join_matches_fused_join(gpu, orc, kr_bits, ks_bits, zipf, carry)
     try:
         t = {n: torch.from_numpy(a.view(np.int64).copy()).to(dev) for n, a in
              [("kr", kr), ("ks", ks), ("pr", pr), ("ps", ps)]}
-        plan = gpu.sharding.BroadcastScatterJoin(gpu, torch, None, 0, 1, nr, nr, ns, 1, dev, carry32=carry)
+        plan = gpu.sharding.BroadcastScatterJoin(gpu, torch, None, 0, 1, nr, nr, ns, 1, dev, carry32=carry,
+                                                 rank_major=rank_major)
         for _ in range(2):     # buffers are reused across steps
             got, m = plan.step(t["kr"].data_ptr(), [t["pr"].data_ptr()], t["ks"].data_ptr(),
                                [t["pr"].data_ptr(), t["ps"].data_ptr()], [0, 1])
@@ -271,3 +273,51 @@ def test_join_pairs_zipf_probe_side_overflows_the_regions(gpu, orc):
     assert np.array_equal(np.sort(s), np.arange(ns, dtype=np.uint64))          # every probe row exactly once
     pr = orc.synth_column(1 << kr_bits, 1, 0, 5)
     assert orc.checksum(pr, r) == orc.checksum(pr, o_r)
+
+
+# ---- rank-major (segmented) build side: several "ranks" emulated on one GPU ----------------------------------
+@pytest.mark.parametrize("world,carry", [(2, False), (3, False), (4, True)])
+def test_segmented_build_side_join(gpu, orc, world, carry):
+    """Every emulated rank partitions its build shard into its own region of ONE build buffer (what the
+    copy-engine broadcast produces on every GPU); the join then reads each partition as `world` runs."""
+    import ctypes as C
+    L = gpu.lib()
+    kr_bits, ks_bits = 17, 20
+    nr, ns = (1 << kr_bits) - 5, 1 << ks_bits
+    kr = orc.synth_column(1 << kr_bits, 0, kr_bits, gpu.SEED_R)[:nr]
+    ks = orc.synth_column(ns, 0, ks_bits, gpu.SEED_S) % np.uint64(1 << kr_bits)     # ~8 probes per build key
+    pr = orc.synth_column(nr, 1, 0, 3)
+    ps = orc.synth_column(ns, 1, 0, 4)
+    want, wm = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
+    bits = int(L.b200_radix_bits_for(nr))
+    P = 1 << bits
+    seg_rows = (nr + world - 1) // world
+    d = {k: gpu.DeviceColumn(len(a)) for k, a in (("kr", kr), ("ks", ks), ("pr", pr), ("ps", ps))}
+    for k, a in (("kr", kr), ("ks", ks), ("pr", pr), ("ps", ps)):
+        L.b200_copy_to_device(d[k].ptr, a.ctypes.data, 8 * len(a))
+    tup_b, pay_b, tup_p = gpu.DeviceColumn(world * seg_rows), gpu.DeviceColumn(world * seg_rows), gpu.DeviceColumn(ns)
+    hist_all = gpu.DeviceColumn(world * P)           # u32[world][P] inside a u64 buffer
+    hist_p, cur_p = gpu.DeviceColumn(P), gpu.DeviceColumn(P)
+    for r in range(world):
+        first = r * seg_rows
+        cnt = min(seg_rows, nr - first)
+        h_r = hist_all.ptr + 4 * r * P
+        assert L.b200_stage_hist(d["kr"].ptr + 8 * first, cnt, bits, h_r) == 0
+        cols = (C.c_void_p * 1)(d["pr"].ptr + 8 * first)
+        outs = None if carry else (C.c_void_p * 1)(pay_b.ptr + 8 * first)
+        assert L.b200_stage_scatter_build_local(d["kr"].ptr + 8 * first, cnt, first, bits, h_r, tup_b.ptr + 8 * first, 1,
+                                                cols, outs) == 0
+    assert L.b200_stage_hist(d["ks"].ptr, ns, bits, hist_p.ptr) == 0
+    h = np.empty(P, np.uint32)
+    L.b200_copy_to_host(h.ctypes.data, hist_p.ptr, 4 * P)
+    cur = (np.cumsum(h, dtype=np.uint64) - h).astype(np.uint32)
+    L.b200_copy_to_device(cur_p.ptr, cur.ctypes.data, 4 * P)
+    assert L.b200_stage_scatter_probe(d["ks"].ptr, ns, bits, cur_p.ptr, tup_p.ptr) == 0
+    pc = (C.c_void_p * 2)(d["pr"].ptr, d["ps"].ptr)
+    sides = (C.c_int * 2)(0, 1)
+    part = (C.c_void_p * 2)(1 if carry else pay_b.ptr, None)
+    sums = (C.c_uint64 * 2)()
+    m = C.c_uint64(0)
+    assert L.b200_stage_join_sum_seg(tup_b.ptr, hist_all.ptr, world, seg_rows, tup_p.ptr, hist_p.ptr, bits, 2, pc, sides,
+                                     part, 0, None, None, None, sums, C.byref(m)) == 0
+    assert int(m.value) == wm and [int(sums[0]), int(sums[1])] == want
