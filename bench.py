@@ -261,10 +261,20 @@ def run_b200_arm(args):
         r1_max = int(t_max.item())
     L.b200_register_device_column(r1.data_ptr(), r1.data_ptr(), nr_loc, r1_max)
     plan = None
-    if world > 1:
+    # B200_PLAN: "copy" (default) / "scatter" = the two broadcast plans (small build side: config 2's shape);
+    # "exchange" = radix-sharded all-to-all of both sides (config 4's plan), here for comparison
+    plan_kind = os.environ.get("B200_PLAN", "copy")
+    if world > 1 and plan_kind == "exchange":
+        s1_max = int(s1.max().item())
+        t_max = torch.tensor([s1_max], dtype=torch.int64, device=dev)
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        plan = b200.sharding.ShardedExchangeJoin(b200, torch, dist, rank, world, nr, nr_loc, ns_loc, 1, 1, dev,
+                                                 size_from=(r0.data_ptr(), s0.data_ptr()),
+                                                 carry_build=r1_max < (1 << 32),
+                                                 carry_probe=int(t_max.item()) < (1 << 32))
+    elif world > 1:
         plan = b200.sharding.BroadcastScatterJoin(b200, torch, dist, rank, world, nr, nr_loc, ns_loc, 1, dev,
-                                                  carry32=r1_max < (1 << 32),
-                                                  rank_major=os.environ.get("B200_PLAN", "copy") == "copy")
+                                                  carry32=r1_max < (1 << 32), rank_major=plan_kind == "copy")
     torch.cuda.synchronize()
 
     def step(kr=None, pr=None, ks=None, ps=None):
@@ -272,6 +282,8 @@ def run_b200_arm(args):
         all-reduced result at N > 1 (sharding.BroadcastScatterJoin)."""
         kr, pr = (r0 if kr is None else kr), (r1 if pr is None else pr)
         ks, ps = (s0 if ks is None else ks), (s1 if ps is None else ps)
+        if world > 1 and plan_kind == "exchange":
+            return plan.step(kr.data_ptr(), [pr.data_ptr()], ks.data_ptr(), [ps.data_ptr()])
         if world > 1:
             return plan.step(kr.data_ptr(), [pr.data_ptr()], ks.data_ptr(), [pr.data_ptr(), ps.data_ptr()], [0, 1])
         return b200.join_sum_device(kr.data_ptr(), nr, ks.data_ptr(), ns_loc, [pr.data_ptr(), ps.data_ptr()], [0, 1],
@@ -326,7 +338,7 @@ def run_b200_arm(args):
     for _ in range(9):
         step()
         torch.cuda.synchronize()
-        for name in ("hist", "hist_b", "hist_p", "scan", "scatter_b", "broadcast", "scatter_p", "join"):
+        for name in ("hist", "hist_b", "hist_p", "scan", "scatter_b", "broadcast", "exchange", "scatter_p", "join"):
             v = b200.last_kernel_ms(name)
             if v >= 0:
                 per_kernel.setdefault(name, []).append(v)
@@ -428,6 +440,9 @@ def run_b200_arm(args):
                    "matches": nr, "seeds": [hex(b200.SEED_R), hex(b200.SEED_S)],
                    "l2": "inputs (4.6 GB) larger than L2; no flush",
                    "parallelism": "single GPU" if world == 1 else
+                   f"R and S position-sharded x{world}; both sides radix-partitioned locally, every partition stored "
+                   "into its owner rank's buffers over NVLink (CUDA IPC; all-to-all), owners join, u64 all-reduce "
+                   "of sums" if plan_kind == "exchange" else
                    f"R and S position-sharded x{world}; build shard scattered into every rank's partition buffers "
                    "by P2P stores over NVLink (CUDA IPC), probe shard partitioned locally, u64 all-reduce of sums"},
         "hbm": {"canonical_bytes_per_step": canon_bytes, "achieved_gbs": canon_bytes / t_s / 1e9 / world,

@@ -307,10 +307,40 @@ int   b200_stage_join_sum_seg(const void *d_tup_b, const uint32_t *d_hist_all,
                               const uint32_t *d_ovcnt, uint64_t *d_result,
                               uint64_t *out_sums, uint64_t *out_matches);
 
+/* Radix-sharded exchange (the all-to-all plan of SURVEY 8e; absent in the
+ * reference, which is single-process): rank g owns the partitions p with
+ * (p * world) >> radix_bits == g and receives every rank's segment of them;
+ * an owner's receive buffer is partition-major, source-rank-minor.
+ * b200_stage_exchange_cursors: from the all-gathered histograms
+ * d_hist_all[world][2^bits], d_src_off[2^bits + 1] = offsets of this rank's
+ * locally partitioned shard (b200_stage_scatter_build_local), d_dst_start[p] =
+ * where its segment of p starts in the owner's buffer, d_own_total[p] = global
+ * size of p if this rank owns it else 0 (the histogram the local join runs
+ * on), d_need[0] = rows this rank receives, d_need[1] = 1 if that exceeds cap.
+ * b200_stage_exchange_segments: copies every staged tuple (and up to two
+ * payload columns, pay_dst[k * world + d]) to tup_dst[owner] with stores of
+ * 256 contiguous bytes per warp (peer buffers are CUDA-IPC mappings: NVLink);
+ * positions >= cap are dropped.  rewrite_rid: the row-id slot of a tuple
+ * becomes its position in the receive buffer, so that payload columns copied
+ * alongside are addressed by it.  A projection whose 32-bit value travels in
+ * the row-id slot is passed to the join with proj_part_vals = (uint64_t*)1 on
+ * either side. */
+int   b200_stage_exchange_cursors(const uint32_t *d_hist_all, int world,
+                                  int rank, int radix_bits, uint32_t cap,
+                                  uint32_t *d_src_off, uint32_t *d_dst_start,
+                                  uint32_t *d_own_total, uint32_t *d_need);
+int   b200_stage_exchange_segments(const void *d_src_tup, int npay,
+                                   const uint64_t *const *src_pay, uint64_t n,
+                                   int radix_bits, int world,
+                                   const uint32_t *d_src_off,
+                                   const uint32_t *d_dst_start, uint32_t cap,
+                                   int rewrite_rid, void *const *tup_dst,
+                                   uint64_t *const *pay_dst);
+
 /* Per-kernel device times of the calling thread's last RadixHashJoin /
  * b200_join_sum, measured with CUDA events on its stream when profiling is
  * enabled with b200_set_profiling(1).  Names: "hist_b", "hist_p", "scan",
- * "scatter_b", "scatter_p", "join" (b = build side, p = probe side).  Returns milliseconds, or a negative value if the
+ * "scatter_b", "scatter_p", "join", "exchange" (b = build side, p = probe side).  Returns milliseconds, or a negative value if the
  * kernel did not run. */
 int    b200_set_profiling(int on);
 double b200_last_kernel_ms(const char *name);

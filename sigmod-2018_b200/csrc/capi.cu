@@ -423,6 +423,25 @@ int b200_stage_join_sum_seg(const void *d_tup_b, const uint32_t *d_hist_all, int
     return 0;
 }
 
+int b200_stage_exchange_cursors(const uint32_t *d_hist_all, int world, int rank, int radix_bits, uint32_t cap,
+                                uint32_t *d_src_off, uint32_t *d_dst_start, uint32_t *d_own_total, uint32_t *d_need) {
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail("bad world / rank");
+    if (radix_bits < 3 || (1u << radix_bits) < (uint32_t)world) return fail("fewer partitions than ranks");
+    stage_exchange_cursors(d_hist_all, world, rank, radix_bits, cap, d_src_off, d_dst_start, d_own_total, d_need);
+    return 0;
+}
+
+int b200_stage_exchange_segments(const void *d_src_tup, int npay, const uint64_t *const *src_pay, uint64_t n,
+                                 int radix_bits, int world, const uint32_t *d_src_off, const uint32_t *d_dst_start,
+                                 uint32_t cap, int rewrite_rid, void *const *tup_dst, uint64_t *const *pay_dst) {
+    if (world < 1 || world > 8) return fail("bad world");
+    if (npay < 0 || npay > 2) return fail("npay must be 0..2");
+    if (n > kMaxRows) return fail("more than 2^32-1 rows");
+    stage_exchange_segments(d_src_tup, npay, src_pay, n, radix_bits, world, d_src_off, d_dst_start, cap, rewrite_rid,
+                            tup_dst, pay_dst);
+    return 0;
+}
+
 int b200_radix_bits_for(uint64_t n_build) {
     // the library's automatic choice for a 32-bit-key build side of n_build rows
     return auto_radix_bits(n_build, false);

@@ -1126,6 +1126,43 @@ void stage_build_cursors(const uint32_t *d_hist_all, int world, int rank, int bi
     B200_LAUNCH_CHECK();
 }
 
+// Radix-sharded exchange (SURVEY §8e all-to-all): layout of the exchange from the all-gathered histograms
+void stage_exchange_cursors(const uint32_t *d_hist_all, int world, int rank, int bits, uint32_t cap,
+                            uint32_t *d_src_off, uint32_t *d_dst_start, uint32_t *d_own_total, uint32_t *d_need) {
+    B200_REQUIRE(world >= 1 && world <= kMaxPeers && (1u << bits) >= (uint32_t)world, "bad world for the exchange");
+    exchange_cursors_kernel<1024><<<1, 1024, 0, ctx().stream>>>(d_hist_all, (uint32_t)world, (uint32_t)rank,
+                                                                (uint32_t)bits, cap, d_src_off, d_dst_start,
+                                                                d_own_total, d_need);
+    B200_LAUNCH_CHECK();
+}
+
+// ... and the exchange: every staged tuple (and payload value) goes to the owner of its partition
+void stage_exchange_segments(const void *d_src_tup, int npay, const uint64_t *const *src_pay, uint64_t n, int bits,
+                             int world, const uint32_t *d_src_off, const uint32_t *d_dst_start, uint32_t cap,
+                             int rewrite_rid, void *const *tup_dst, uint64_t *const *pay_dst) {
+    B200_REQUIRE(world >= 1 && world <= kMaxPeers && npay >= 0 && npay <= 2, "bad destination / payload count");
+    if (n == 0) return;
+    ExchangeArgs x{};
+    x.src_tup     = static_cast<const uint64_t *>(d_src_tup);
+    x.src_off     = d_src_off;
+    x.dst_start   = d_dst_start;
+    x.n           = (uint32_t)n;
+    x.radix_bits  = (uint32_t)bits;
+    x.world       = (uint32_t)world;
+    x.cap         = cap;
+    x.npay        = npay;
+    x.rewrite_rid = rewrite_rid;
+    for (int d = 0; d < world; ++d) x.dst_tup[d] = static_cast<uint64_t *>(tup_dst[d]);
+    for (int k = 0; k < npay; ++k) {
+        x.src_pay[k] = src_pay[k];
+        for (int d = 0; d < world; ++d) x.dst_pay[k][d] = pay_dst[k * world + d];
+    }
+    TimedScope ts("exchange");
+    const uint32_t blocks = (uint32_t)((n + 1023) / 1024);
+    segment_exchange_kernel<<<blocks, 256, 0, ctx().stream>>>(x);
+    B200_LAUNCH_CHECK();
+}
+
 uint32_t opt_region_cap(uint64_t n_probe, int bits) {
     const uint64_t nparts = 1ull << bits;
     const uint64_t mean   = (n_probe + nparts - 1) / nparts;

@@ -111,6 +111,11 @@ void       stage_scatter_build_local(const uint64_t *d_keys, uint64_t n, uint32_
                                      const uint64_t *const *pay_cols, uint64_t *const *pay_out);
 void       stage_build_cursors(const uint32_t *d_hist_all, int world, int rank, int bits, uint32_t *d_total,
                                uint32_t *d_my_start);
+void       stage_exchange_cursors(const uint32_t *d_hist_all, int world, int rank, int bits, uint32_t cap,
+                                  uint32_t *d_src_off, uint32_t *d_dst_start, uint32_t *d_own_total, uint32_t *d_need);
+void       stage_exchange_segments(const void *d_src_tup, int npay, const uint64_t *const *src_pay, uint64_t n,
+                                   int bits, int world, const uint32_t *d_src_off, const uint32_t *d_dst_start,
+                                   uint32_t cap, int rewrite_rid, void *const *tup_dst, uint64_t *const *pay_dst);
 
 // runtime control (engine.cu)
 void               request_device(int device);   // before the first use

@@ -17,7 +17,9 @@
 //                                      of the join kernels
 //   K11 inter_res.c:376-385         -> inter_equal_kernel
 //   multi-GPU (absent in the reference): build_cursors_kernel,
-//                                      segment_broadcast_kernel
+//                                      segment_broadcast_kernel,
+//                                      exchange_cursors_kernel,
+//                                      segment_exchange_kernel
 //
 // Integer/byte work only: no tensor cores.  Row ids and positions are 32-bit
 // on the device; keys are 32-bit when the column maxima allow it (8-byte
@@ -1175,7 +1177,7 @@ tag_join_kernel(const JoinArgs a) {
                 for (int k = 0; k < NPA; ++k) {
                     if (k < a.nproj) {
                         if (a.proj[k].part_vals == B200_PROJ_IN_RID) {
-                            my_sum[k] += brid;   // the slot carries the value
+                            my_sum[k] += a.proj[k].side == 0 ? brid : prid;   // the slot carries the value
                         } else if (a.proj[k].part_vals) {
                             my_sum[k] += a.proj[k].part_vals[bphys(b_start + pos)];
                         } else {
@@ -1212,7 +1214,7 @@ tag_join_kernel(const JoinArgs a) {
                 pend[k] = 0;
                 if (k < a.nproj && is_match) {
                     if (a.proj[k].part_vals == B200_PROJ_IN_RID) {
-                        pend[k] = brid;                         // the row-id slot carries the value
+                        pend[k] = a.proj[k].side == 0 ? brid : e.y;   // the row-id slot carries the value
                     } else if (a.proj[k].part_vals) {
                         pend[k] = a.proj[k].part_vals[bpos];   // dense window of this partition, L2-resident
                     } else {
@@ -1668,6 +1670,138 @@ segment_offsets_kernel(const uint32_t *__restrict__ hist_all, uint32_t world, ui
         uint32_t t = 0;
         for (uint32_t r = 0; r < world; ++r) t += hist_all[r * nparts + b];
         total[b] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Radix-sharded exchange ("all-to-all" row; K10).  Rank g owns the
+// partitions p with owner(p) = (p * world) >> radix_bits — a contiguous range,
+// i.e. the TOP bits of the partition id — and receives, from every rank, that
+// rank's segment of each owned partition.  The receive buffer of an owner is
+// partition-major, source-rank-minor, so each owned partition is contiguous
+// and the local join runs on it with the masked histogram `own_total`.
+//
+// exchange_cursors_kernel (one CTA), from the all-gathered histograms
+// hist_all[world][nparts]:
+//   src_off[p]   exclusive scan of hist_all[rank]  (+ src_off[nparts] = n local)
+//   dst_start[p] where this rank's segment of p starts in owner(p)'s buffer
+//   own_total[p] global size of p if this rank owns it, else 0
+//   need[0]      rows this rank receives (capacity check), need[1] = 1 if that
+//                exceeds `cap` (the copy kernel then drops what does not fit
+//                and the caller must fail the step)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t partition_owner(uint32_t p, uint32_t world, uint32_t radix_bits) {
+    return (uint32_t)(((uint64_t)p * world) >> radix_bits);
+}
+template <int NT>
+__global__ void __launch_bounds__(NT)
+exchange_cursors_kernel(const uint32_t *__restrict__ hist_all, uint32_t world, uint32_t rank, uint32_t radix_bits,
+                        uint32_t cap, uint32_t *__restrict__ src_off, uint32_t *__restrict__ dst_start,
+                        uint32_t *__restrict__ own_total, uint32_t *__restrict__ need) {
+    __shared__ uint32_t warp_sums[NT / 32 + 1];
+    __shared__ uint32_t owner_base[kMaxPeers + 1];   // global prefix at the first partition of every owner
+    const uint32_t nparts = 1u << radix_bits;
+    const uint32_t per    = (nparts + NT - 1) / NT;
+    const uint32_t first  = threadIdx.x * per;
+    // pass 1: local offsets of this rank's staging buffer
+    uint32_t s = 0;
+    for (uint32_t k = 0; k < per; ++k)
+        if (first + k < nparts) s += hist_all[rank * nparts + first + k];
+    uint32_t run = block_exclusive_scan<NT>(s, warp_sums);
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t b = first + k;
+        if (b < nparts) {
+            src_off[b] = run;
+            run += hist_all[rank * nparts + b];
+            if (b == nparts - 1) src_off[nparts] = run;
+        }
+    }
+    // pass 2: global prefix of the partition totals; an owner's buffer starts at its first partition
+    s = 0;
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t b = first + k;
+        if (b < nparts)
+            for (uint32_t r = 0; r < world; ++r) s += hist_all[r * nparts + b];
+    }
+    const uint32_t start = block_exclusive_scan<NT>(s, warp_sums);
+    const uint32_t grand = warp_sums[NT / 32];
+    run = start;
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t b = first + k;
+        if (b < nparts) {
+            if (b == 0 || partition_owner(b, world, radix_bits) != partition_owner(b - 1, world, radix_bits))
+                owner_base[partition_owner(b, world, radix_bits)] = run;
+            for (uint32_t r = 0; r < world; ++r) run += hist_all[r * nparts + b];
+        }
+    }
+    if (threadIdx.x == 0) owner_base[world] = grand;
+    __syncthreads();
+    run = start;
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t b = first + k;
+        if (b < nparts) {
+            uint32_t tot = 0, before = 0;
+            for (uint32_t r = 0; r < world; ++r) {
+                const uint32_t c = hist_all[r * nparts + b];
+                if (r < rank) before += c;
+                tot += c;
+            }
+            const uint32_t o = partition_owner(b, world, radix_bits);
+            dst_start[b]     = run - owner_base[o] + before;
+            own_total[b]     = o == rank ? tot : 0u;
+            run += tot;
+        }
+    }
+    if (threadIdx.x == 0) {
+        // owners whose range is empty (world > nparts) never set their base; world <= nparts is required
+        const uint32_t mine = owner_base[rank + 1] - owner_base[rank];
+        need[0]             = mine;
+        need[1]             = mine > cap ? 1u : 0u;
+    }
+}
+
+// The exchange itself: the staging buffer holds this rank's shard in partition order (src_off); element e of
+// partition p goes to owner(p)'s receive buffer at dst_start[p] + (e - src_off[p]).  Flat decomposition (a
+// thread block takes 1024 consecutive staged elements whatever partition they belong to), so a skewed
+// partition is copied by as many CTAs as it has kilo-elements.  Consecutive lanes copy consecutive elements:
+// a warp's stores are 256 contiguous bytes in the peer's memory (full NVLink packets) except where a
+// partition ends.  REWRITE: the row-id slot of a tuple is replaced by its position in the receive buffer, so
+// that payload columns copied alongside (same index) can be read through the "row id" after the exchange.
+struct ExchangeArgs {
+    const uint64_t *src_tup;
+    const uint64_t *src_pay[2];
+    const uint32_t *src_off;     // [nparts + 1]
+    const uint32_t *dst_start;   // [nparts]
+    uint32_t        n, radix_bits, world, cap;
+    int             npay, rewrite_rid;
+    uint64_t       *dst_tup[kMaxPeers];
+    uint64_t       *dst_pay[2][kMaxPeers];
+};
+__global__ void __launch_bounds__(256) segment_exchange_kernel(const ExchangeArgs x) {
+    constexpr int  UN     = 4;
+    const uint32_t nparts = 1u << x.radix_bits;
+    const uint32_t base   = blockIdx.x * (256u * UN);
+    // partition of this thread's first element: last p with src_off[p] <= e
+    uint32_t e = base + threadIdx.x;
+    uint32_t lo = 0, hi = nparts;   // invariant: src_off[lo] <= e < src_off[hi] (src_off[nparts] = n > e)
+    if (e < x.n) {
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(x.src_off + mid) <= e) lo = mid; else hi = mid;
+        }
+    }
+    uint32_t p = lo;
+#pragma unroll
+    for (int u = 0; u < UN; ++u, e += 256u) {
+        if (e >= x.n) break;
+        while (__ldg(x.src_off + p + 1) <= e) ++p;   // empty partitions are skipped as well
+        const uint32_t d   = partition_owner(p, x.world, x.radix_bits);
+        const uint32_t pos = __ldg(x.dst_start + p) + (e - __ldg(x.src_off + p));
+        if (pos >= x.cap) continue;                  // receive buffer too small: flagged by exchange_cursors_kernel
+        uint64_t t = ld_stream_u64(x.src_tup + e);
+        if (x.rewrite_rid) t = (t & 0xFFFFFFFFull) | ((uint64_t)pos << 32);
+        x.dst_tup[d][pos] = t;
+        for (int k = 0; k < x.npay; ++k) x.dst_pay[k][d][pos] = ld_stream_u64(x.src_pay[k] + e);
     }
 }
 

@@ -193,6 +193,11 @@ def _declare(L: C.CDLL) -> None:
                                               C.c_int, C.c_int, P(C.c_void_p), P(C.c_int), P(C.c_void_p), C.c_uint32,
                                               C.c_void_p, C.c_void_p, C.c_void_p, u64p, u64p]),
         "b200_stage_build_cursors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+        "b200_stage_exchange_cursors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+        "b200_stage_exchange_segments": (C.c_int, [C.c_void_p, C.c_int, P(C.c_void_p), C.c_uint64, C.c_int, C.c_int,
+                                                   C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, P(C.c_void_p),
+                                                   P(C.c_void_p)]),
         "b200_stage_join_sum_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                 P(C.c_void_p), P(C.c_int), P(C.c_void_p), C.c_uint32, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]),

@@ -6,6 +6,11 @@ side with its probe shard, and the k u64 checksums plus the match count are
 all-reduced.  u64 sums mod 2^64 are reduced as wrapping int64 sums (NCCL and
 gloo have no uint64 SUM).  Works on any torch.distributed backend; the CPU
 tests run it under gloo with the oracle as the local join.
+
+Exchange plan (large build side, SURVEY §8e "all-to-all"): both relations are
+radix-partitioned locally and every partition travels to its owner rank
+(`partition_owner`); `exchange_layout` is the host restatement of the layout
+the device computes (exchange_cursors_kernel), `ShardedExchangeJoin` the plan.
 """
 from __future__ import annotations
 
@@ -303,6 +308,233 @@ class BroadcastScatterJoin:
                 assert L.b200_stage_join_sum(*args, sums, C.byref(m)) == 0
             return allreduce_checksums([int(x) for x in sums[:k]], int(m.value), self.dist if world > 1 else None,
                                        self.device)
+        return i64_to_u64(host[1: k + 1]), int(host[0])
+
+    def close(self):
+        for p in self._imported:
+            self.L.b200_ipc_close(p)
+        self._imported = []
+
+
+def partition_owner(p, world: int, bits: int):
+    """Rank that owns radix partition p (scalar or numpy array): the top bits of the partition id, so every
+    rank owns a contiguous range of the 2^bits partitions."""
+    return (np.asarray(p, dtype=np.uint64) * np.uint64(world)) >> np.uint64(bits)
+
+
+def exchange_layout(hist_all, rank: int, bits: int):
+    """Layout of the radix-sharded exchange from the all-gathered histograms hist_all[world][2^bits]:
+    (src_off[P+1], dst_start[P], own_total[P], rows_received) for `rank` — the host restatement of
+    exchange_cursors_kernel.  An owner's receive buffer is partition-major, source-rank-minor."""
+    h = np.asarray(hist_all, dtype=np.uint64)
+    world, P = h.shape
+    assert P == 1 << bits and world <= P
+    src_off = np.concatenate([[0], np.cumsum(h[rank])]).astype(np.uint64)
+    total = h.sum(axis=0)
+    prefix = np.concatenate([[0], np.cumsum(total)]).astype(np.uint64)       # global exclusive prefix, P + 1
+    owner = partition_owner(np.arange(P), world, bits).astype(np.int64)
+    first_of_owner = np.searchsorted(owner, np.arange(world), side="left")   # owner ranges are contiguous
+    base = prefix[first_of_owner][owner]
+    before = h[:rank].sum(axis=0) if rank else np.zeros(P, dtype=np.uint64)
+    dst_start = prefix[:-1] - base + before
+    own_total = np.where(owner == rank, total, 0).astype(np.uint64)
+    return src_off, dst_start.astype(np.uint64), own_total, int(own_total.sum())
+
+
+class ShardedExchangeJoin:
+    """Radix-sharded join over `world` GPUs, one process each (all-to-all plan; config 4's shape).
+
+    Relations start position-sharded.  Per step and rank:
+      1. histograms of the local build and probe shards over 2^bits radix partitions; ONE all-gather of both;
+      2. exchange_cursors_kernel turns them into the exchange layout (exchange_layout above);
+      3. both shards are partitioned locally into staging buffers (the probe side on a side stream, under the
+         all-gather), SUM columns travelling with the tuples: one column per side whose values fit 32 bits
+         rides in the row-id slot (8 bytes per row on the wire); otherwise up to two 8-byte payload columns
+         per side are exchanged alongside and the probe tuples' row ids are rewritten to receive positions;
+      4. segment_exchange_kernel stores every staged row into the receive buffer of the partition's owner —
+         peers' buffers are CUDA-IPC mappings, a warp stores 256 contiguous bytes over NVLink; a
+         stream-ordered all-reduce of a token is the barrier that says every peer's rows have landed;
+      5. the owner joins its partitions (masked histograms) and the checksums are all-reduced.
+    Receive buffers are sized by `recv_rows_*`; `measure_capacity` returns what a given input needs (skewed
+    probe keys make owners uneven).  A step that would overflow them is detected on the device and raises.
+    """
+
+    def __init__(self, b200, torch, dist, rank, world, n_build_total, n_build_local, n_probe_local,
+                 n_pay_build, n_pay_probe, device, recv_rows_build=None, recv_rows_probe=None, size_from=None,
+                 carry_build=False, carry_probe=False, bits=None):
+        """recv_rows_*: capacity of this rank's receive buffers in rows; None = measure it from the key columns
+        `size_from = (build_keys_ptr, probe_keys_ptr)` (one histogram pass + all-gather at construction)."""
+        import ctypes as C
+        import os
+        self.b, self.torch, self.dist, self.rank, self.world, self.C = b200, torch, dist, rank, world, C
+        L = self.L = b200.lib()
+        self.n_build_local, self.n_probe_local = n_build_local, n_probe_local
+        self.npb, self.npp = n_pay_build, n_pay_probe
+        assert 0 <= n_pay_build <= 2 and 0 <= n_pay_probe <= 2
+        self.carry_b = bool(carry_build) and n_pay_build == 1
+        self.carry_p = bool(carry_probe) and n_pay_probe == 1
+        # partitions are sized for the per-partition table exactly as on one GPU: by the GLOBAL build side
+        self.bits = int(bits) if bits else int(L.b200_radix_bits_for(n_build_total))
+        self.P = 1 << self.bits
+        assert self.P >= world
+        self.device = device
+        i32 = dict(dtype=torch.int32, device=device)
+        P = self.P
+        self.hist = torch.zeros((2, P), **i32)                # [build, probe] local
+        self.hist_all = torch.zeros((world, 2, P), **i32)
+        if recv_rows_build is None or recv_rows_probe is None:
+            assert size_from is not None, "give recv_rows_build / recv_rows_probe or size_from"
+            recv_rows_build, recv_rows_probe = self.measure_capacity(*size_from)
+        self.cap_b, self.cap_p = max(int(recv_rows_build), 1), max(int(recv_rows_probe), 1)
+        col = b200.DeviceColumn
+        self.stage_b, self.stage_p = col(max(n_build_local, 1)), col(max(n_probe_local, 1))
+        self.stage_pay_b = [] if self.carry_b else [col(max(n_build_local, 1)) for _ in range(n_pay_build)]
+        self.stage_pay_p = [] if self.carry_p else [col(max(n_probe_local, 1)) for _ in range(n_pay_probe)]
+        self.recv_b, self.recv_p = col(self.cap_b), col(self.cap_p)
+        self.recv_pay_b = [] if self.carry_b else [col(self.cap_b) for _ in range(n_pay_build)]
+        self.recv_pay_p = [] if self.carry_p else [col(self.cap_p) for _ in range(n_pay_probe)]
+        on_gpu = device is not None and getattr(device, "type", "") == "cuda"
+        self.side = torch.cuda.Stream(device=device) if on_gpu and not os.environ.get("B200_PLAN_SERIAL") else None
+        self.debug = bool(os.environ.get("B200_PLAN_DEBUG"))
+        self.marks = []
+        self.src_off = torch.zeros((2, P + 1), **i32)
+        self.dst_start = torch.zeros((2, P), **i32)
+        self.own_total = torch.zeros((2, P), **i32)
+        self.need = torch.zeros((2, 2), **i32)                # [side][rows received, overflow flag]
+        self.token = torch.zeros(1, **i32)
+        self.result = torch.zeros(kMaxResult, dtype=torch.int64, device=device)
+        self._imported = []
+        mine = [self.recv_b.ptr, self.recv_p.ptr] + [c.ptr for c in self.recv_pay_b + self.recv_pay_p]
+        self.peers = [mine]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, [self._export(p) for p in mine])
+            self.peers = [mine if r == rank else [self._import(h) for h in gathered[r]] for r in range(world)]
+
+    _export = BroadcastScatterJoin._export
+    _import = BroadcastScatterJoin._import
+
+    def measure_capacity(self, build_keys_ptr, probe_keys_ptr):
+        """(rows, rows) the receive buffers of the most loaded rank must hold for these inputs."""
+        L, torch = self.L, self.torch
+        assert L.b200_stage_hist(build_keys_ptr, self.n_build_local, self.bits, self.hist[0].data_ptr()) == 0
+        assert L.b200_stage_hist(probe_keys_ptr, self.n_probe_local, self.bits, self.hist[1].data_ptr()) == 0
+        return self._capacity_from_hist()
+
+    def _capacity_from_hist(self):
+        torch, world = self.torch, self.world
+        if world > 1:
+            self.dist.all_gather_into_tensor(self.hist_all.view(-1), self.hist.view(-1))
+        else:
+            self.hist_all[0].copy_(self.hist)
+        h = self.hist_all.cpu().numpy().astype(np.uint64)
+        need = [max(exchange_layout(h[:, s, :], r, self.bits)[3] for r in range(world)) for s in (0, 1)]
+        return need[0], need[1]
+
+    def step(self, build_keys_ptr, build_pay_ptrs, probe_keys_ptr, probe_pay_ptrs, finish=True):
+        """One join; returns ([Σ build_pay..., Σ probe_pay...], matches) over all ranks."""
+        C, L, torch = self.C, self.L, self.torch
+        P, bits, world, rank = self.P, self.bits, self.world, self.rank
+        main = torch.cuda.current_stream()
+        side = self.side if self.side is not None else main
+        vp = C.c_void_p
+
+        def mark(name, stream=None):
+            if self.debug:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream or main)
+                self.marks.append((name, ev))
+
+        def arr(ptrs):
+            return (vp * max(len(ptrs), 1))(*ptrs)
+
+        self.marks = []
+        mark("start")
+        h_b, h_p = self.hist[0], self.hist[1]
+        assert L.b200_stage_hist(build_keys_ptr, self.n_build_local, bits, h_b.data_ptr()) == 0
+        assert L.b200_stage_hist(probe_keys_ptr, self.n_probe_local, bits, h_p.data_ptr()) == 0
+        mark("histograms")
+        # ---- probe side: the local partition pass needs only the local histogram -> side stream ----
+        side.wait_stream(main)
+        L.b200_set_stream(side.cuda_stream)
+        outs = None if self.carry_p else arr([c.ptr for c in self.stage_pay_p])
+        assert L.b200_stage_scatter_build_local(probe_keys_ptr, self.n_probe_local, 0, bits, h_p.data_ptr(),
+                                                self.stage_p.ptr, self.npp, arr(probe_pay_ptrs[:self.npp]),
+                                                outs) == 0
+        mark("probe partitioned (side)", side)
+        L.b200_set_stream(main.cuda_stream)
+        # ---- exchange layout ----
+        if world > 1:
+            self.dist.all_gather_into_tensor(self.hist_all.view(-1), self.hist.view(-1))
+        else:
+            self.hist_all[0].copy_(self.hist)
+        by_side = self.hist_all.permute(1, 0, 2).contiguous()          # [side][world][P]
+        for s, cap in ((0, self.cap_b), (1, self.cap_p)):
+            assert L.b200_stage_exchange_cursors(by_side[s].data_ptr(), world, rank, bits, cap,
+                                                 self.src_off[s].data_ptr(), self.dst_start[s].data_ptr(),
+                                                 self.own_total[s].data_ptr(), self.need[s].data_ptr()) == 0
+        # ---- build side: partition, exchange ----
+        outs = None if self.carry_b else arr([c.ptr for c in self.stage_pay_b])
+        assert L.b200_stage_scatter_build_local(build_keys_ptr, self.n_build_local, 0, bits, h_b.data_ptr(),
+                                                self.stage_b.ptr, self.npb, arr(build_pay_ptrs[:self.npb]),
+                                                outs) == 0
+        nb, npp = len(self.recv_pay_b), len(self.recv_pay_p)
+        tup_dst_b = arr([self.peers[d][0] for d in range(world)])
+        tup_dst_p = arr([self.peers[d][1] for d in range(world)])
+        pay_dst_b = arr([self.peers[d][2 + k] for k in range(nb) for d in range(world)])
+        pay_dst_p = arr([self.peers[d][2 + nb + k] for k in range(npp) for d in range(world)])
+        assert L.b200_stage_exchange_segments(self.stage_b.ptr, nb, arr([c.ptr for c in self.stage_pay_b]),
+                                              self.n_build_local, bits, world, self.src_off[0].data_ptr(),
+                                              self.dst_start[0].data_ptr(), self.cap_b, 0, tup_dst_b,
+                                              pay_dst_b) == 0
+        mark("build exchanged")
+        main.wait_stream(side)
+        assert L.b200_stage_exchange_segments(self.stage_p.ptr, npp, arr([c.ptr for c in self.stage_pay_p]),
+                                              self.n_probe_local, bits, world, self.src_off[1].data_ptr(),
+                                              self.dst_start[1].data_ptr(), self.cap_p, 0 if self.carry_p else 1,
+                                              tup_dst_p, pay_dst_p) == 0
+        mark("probe exchanged")
+        if world > 1:
+            self.dist.all_reduce(self.token)      # stream-ordered barrier: every peer's rows have landed
+        mark("barrier done")
+        # ---- local join of the owned partitions ----
+        k = self.npb + self.npp
+        in_rid = 1
+        cols, sides, part = [], [], []
+        for j in range(self.npb):
+            cols.append(build_pay_ptrs[j]); sides.append(0)
+            part.append(in_rid if self.carry_b else self.recv_pay_b[j].ptr)
+        for j in range(self.npp):
+            # carried: the probe tuple's row-id slot is the value; else the row id is the receive position
+            cols.append(probe_pay_ptrs[j] if self.carry_p else self.recv_pay_p[j].ptr); sides.append(1)
+            part.append(in_rid if self.carry_p else None)
+        res = self.result[: k + 2]
+        assert L.b200_stage_join_sum_async(self.recv_b.ptr, self.own_total[0].data_ptr(), self.recv_p.ptr,
+                                           self.own_total[1].data_ptr(), bits, k, arr(cols),
+                                           (C.c_int * max(k, 1))(*sides), arr(part), 0, None, None,
+                                           res.data_ptr()) == 0
+        res[k + 1: k + 2].add_(self.need[:, 1].sum())       # receive-buffer overflow flags of this rank
+        if world > 1:
+            self.dist.all_reduce(res)     # also ends the step: no peer overwrites buffers still being joined
+        mark("join + all-reduce done")
+        self._k = k
+        return self.finish() if finish else None
+
+    def enqueue(self, *a):
+        return self.step(*a, finish=False)
+
+    def finish(self):
+        k = self._k
+        host = self.result[: k + 2].cpu().tolist()
+        if self.debug and self.rank == 0 and self.marks:
+            t0 = self.marks[0][1]
+            print("exchange plan timeline (ms): " + ", ".join(f"{n} {t0.elapsed_time(e):.3f}"
+                                                               for n, e in self.marks[1:]),
+                  file=__import__("sys").stderr)
+        if host[k + 1] != 0:
+            need = self.need.cpu().tolist()
+            raise RuntimeError(f"exchange receive buffers too small on {host[k + 1]} (rank, side) pairs; this rank "
+                               f"needs build {need[0][0]} / probe {need[1][0]} rows, has {self.cap_b} / {self.cap_p}")
         return i64_to_u64(host[1: k + 1]), int(host[0])
 
     def close(self):

@@ -321,3 +321,147 @@ def test_segmented_build_side_join(gpu, orc, world, carry):
     assert L.b200_stage_join_sum_seg(tup_b.ptr, hist_all.ptr, world, seg_rows, tup_p.ptr, hist_p.ptr, bits, 2, pc, sides,
                                      part, 0, None, None, None, sums, C.byref(m)) == 0
     assert int(m.value) == wm and [int(sums[0]), int(sums[1])] == want
+
+
+# ---- radix-sharded exchange (all-to-all plan): several "ranks" emulated on one GPU ----------------------------
+def _to_dev(gpu, a):
+    d = gpu.DeviceColumn(max(len(a), 1))
+    if len(a):
+        gpu.lib().b200_copy_to_device(d.ptr, a.ctypes.data, a.nbytes)
+    return d
+
+
+def _from_dev(gpu, ptr, n, dtype):
+    out = np.empty(n, dtype)
+    gpu.lib().b200_copy_to_host(out.ctypes.data, ptr, out.nbytes)
+    return out
+
+
+@pytest.mark.parametrize("world,bits", [(1, 3), (2, 5), (3, 6), (5, 10), (8, 12)])
+def test_exchange_cursors_match_host_layout(gpu, world, bits):
+    """exchange_cursors_kernel against sharding.exchange_layout on random histograms with empty partitions."""
+    L = gpu.lib()
+    P = 1 << bits
+    g = np.random.default_rng(world * 100 + bits)
+    hist = g.integers(0, 5000, size=(world, P)).astype(np.uint32)
+    hist[:, g.integers(0, P, size=max(P // 8, 1))] = 0
+    hist[g.integers(0, world), :] //= 3
+    d_hist = _to_dev(gpu, hist.reshape(-1))
+    src_off, dst_start, own, need = (gpu.DeviceColumn(P + 1) for _ in range(4))
+    for rank in range(world):
+        w_src, w_dst, w_own, w_need = gpu.sharding.exchange_layout(hist, rank, bits)
+        for cap in (w_need, max(w_need - 1, 0)):
+            assert L.b200_stage_exchange_cursors(d_hist.ptr, world, rank, bits, cap, src_off.ptr, dst_start.ptr,
+                                                 own.ptr, need.ptr) == 0
+            assert np.array_equal(_from_dev(gpu, src_off.ptr, P + 1, np.uint32), w_src.astype(np.uint32))
+            assert np.array_equal(_from_dev(gpu, dst_start.ptr, P, np.uint32), w_dst.astype(np.uint32))
+            assert np.array_equal(_from_dev(gpu, own.ptr, P, np.uint32), w_own.astype(np.uint32))
+            assert _from_dev(gpu, need.ptr, 2, np.uint32).tolist() == [w_need, 1 if w_need > cap else 0]
+
+
+@pytest.mark.parametrize("world,carry,npay,zipf,bits", [
+    (1, True, 1, False, 0), (2, True, 1, False, 0), (3, False, 1, False, 0), (4, False, 2, True, 0),
+    (8, True, 1, True, 0), (8, False, 2, False, 7), (2, False, 0, False, 0)])
+def test_exchange_plan_emulated_ranks(gpu, orc, world, carry, npay, zipf, bits):
+    """The whole data path of sharding.ShardedExchangeJoin with `world` ranks emulated on one GPU (the peers'
+    receive buffers are ordinary local buffers): per rank hist -> cursors -> local partition pass -> exchange
+    kernel; per owner the join of its partitions; the sums over owners must equal the oracle's single join."""
+    import ctypes as C
+    L = gpu.lib()
+    kr_bits, ns = 17, (1 << 20) + 77
+    nr = (1 << kr_bits) - 9
+    kr = orc.synth_column(1 << kr_bits, 0, kr_bits, gpu.SEED_R)[:nr]
+    ks = (orc.synth_column(ns, 2, kr_bits, 41) if zipf
+          else orc.synth_column(ns, 0, 20, gpu.SEED_S) % np.uint64(1 << kr_bits))
+    wide = np.uint64(1) if carry else np.uint64(0x10000000001)          # payload values beyond 32 bits unless carried
+    pays_r = [orc.synth_column(nr, 1, 0, 3 + k) * wide for k in range(npay)]
+    pays_s = [orc.synth_column(ns, 1, 0, 13 + k) * wide for k in range(npay)]
+    want, wm = orc.join_sum(kr, ks, pays_r + pays_s, [0] * npay + [1] * npay, 4)
+    bits = bits or int(L.b200_radix_bits_for(nr))
+    P = 1 << bits
+    sh = gpu.sharding
+    d_kr, d_ks = _to_dev(gpu, kr), _to_dev(gpu, ks)
+    d_pr, d_ps = [_to_dev(gpu, p) for p in pays_r], [_to_dev(gpu, p) for p in pays_s]
+    spans = [[sh.shard_bounds(n, r, world) for r in range(world)] for n in (nr, ns)]
+    hist = np.zeros((2, world, P), np.uint32)
+    d_hist = gpu.DeviceColumn(2 * world * P)
+    for s, d_keys in ((0, d_kr), (1, d_ks)):
+        for r, (first, cnt) in enumerate(spans[s]):
+            assert L.b200_stage_hist(d_keys.ptr + 8 * first, cnt, bits, d_hist.ptr + 4 * (s * world + r) * P) == 0
+    hist = _from_dev(gpu, d_hist.ptr, 2 * world * P, np.uint32).reshape(2, world, P)
+    cap = [max(sh.exchange_layout(hist[s], r, bits)[3] for r in range(world)) for s in (0, 1)]
+    npay_x = 0 if carry else npay                                        # payload arrays that travel separately
+    recv = [[gpu.DeviceColumn(max(cap[s], 1)) for _ in range(world)] for s in (0, 1)]
+    recv_pay = [[[gpu.DeviceColumn(max(cap[s], 1)) for _ in range(world)] for _ in range(npay_x)] for s in (0, 1)]
+    own = [[gpu.DeviceColumn(P) for _ in range(world)] for s in (0, 1)]
+    src_off, dst_start, need = gpu.DeviceColumn(P + 1), gpu.DeviceColumn(P), gpu.DeviceColumn(2)
+    arr = lambda ptrs: (C.c_void_p * max(len(ptrs), 1))(*ptrs)
+    for s, d_keys, d_pays, n_tot in ((0, d_kr, d_pr, nr), (1, d_ks, d_ps, ns)):
+        stage = gpu.DeviceColumn(max(c for _, c in spans[s]))
+        stage_pay = [gpu.DeviceColumn(max(c for _, c in spans[s])) for _ in range(npay_x)]
+        for r, (first, cnt) in enumerate(spans[s]):
+            h_all = d_hist.ptr + 4 * s * world * P
+            assert L.b200_stage_exchange_cursors(h_all, world, r, bits, cap[s], src_off.ptr, dst_start.ptr,
+                                                 own[s][r].ptr, need.ptr) == 0
+            assert _from_dev(gpu, need.ptr, 2, np.uint32)[1] == 0
+            cols = arr([p.ptr + 8 * first for p in d_pays])
+            outs = None if carry else arr([p.ptr for p in stage_pay])
+            assert L.b200_stage_scatter_build_local(d_keys.ptr + 8 * first, cnt, 0, bits, h_all + 4 * r * P, stage.ptr,
+                                                    npay, cols, outs) == 0
+            pay_dst = arr([recv_pay[s][k][d].ptr for k in range(npay_x) for d in range(world)])
+            assert L.b200_stage_exchange_segments(stage.ptr, npay_x, arr([p.ptr for p in stage_pay]), cnt, bits, world,
+                                                  src_off.ptr, dst_start.ptr, cap[s], 0 if (carry or s == 0) else 1,
+                                                  arr([recv[s][d].ptr for d in range(world)]), pay_dst) == 0
+        L.b200_synchronize()
+    sums_all, m_all = [0] * (2 * npay), 0
+    for r in range(world):
+        cols, sides, part = [], [], []
+        for k in range(npay):
+            cols.append(d_pr[k].ptr); sides.append(0)
+            part.append(1 if carry else recv_pay[0][k][r].ptr)
+        for k in range(npay):
+            cols.append(d_ps[k].ptr if carry else recv_pay[1][k][r].ptr); sides.append(1)
+            part.append(1 if carry else None)
+        k2 = 2 * npay
+        sums = (C.c_uint64 * max(k2, 1))()
+        m = C.c_uint64(0)
+        assert L.b200_stage_join_sum(recv[0][r].ptr, own[0][r].ptr, recv[1][r].ptr, own[1][r].ptr, bits, k2, arr(cols),
+                                     (C.c_int * max(k2, 1))(*sides), arr(part), 0, None, None, sums, C.byref(m)) == 0
+        m_all += int(m.value)
+        sums_all = [(a + int(b)) % (1 << 64) for a, b in zip(sums_all, sums[:k2])]
+    assert m_all == wm and sums_all == want
+
+
+def test_exchange_overflow_is_flagged_not_written(gpu, orc):
+    """A receive buffer that is too small: the cursors kernel raises the flag and the exchange kernel drops the
+    rows beyond the capacity instead of writing past the buffer."""
+    import ctypes as C
+    L = gpu.lib()
+    n, bits, world = 50_000, 6, 2
+    P = 1 << bits
+    keys = orc.synth_column(n, 0, 20, 5)
+    d_keys = _to_dev(gpu, keys)
+    d_hist = gpu.DeviceColumn(world * P)
+    L.b200_copy_to_device(d_hist.ptr, np.zeros(world * P, np.uint32).ctypes.data, 4 * world * P)
+    assert L.b200_stage_hist(d_keys.ptr, n, bits, d_hist.ptr) == 0           # rank 0 holds everything, rank 1 nothing
+    hist = _from_dev(gpu, d_hist.ptr, world * P, np.uint32).reshape(world, P)
+    need0 = gpu.sharding.exchange_layout(hist, 0, bits)[3]
+    cap = need0 - 100
+    guard = 4096
+    recv = [gpu.DeviceColumn(cap + guard) for _ in range(world)]
+    sentinel = np.full(cap + guard, 0xABCDABCDABCDABCD, np.uint64)
+    for r in recv:
+        L.b200_copy_to_device(r.ptr, sentinel.ctypes.data, sentinel.nbytes)
+    src_off, dst_start, own, need = (gpu.DeviceColumn(P + 1) for _ in range(4))
+    assert L.b200_stage_exchange_cursors(d_hist.ptr, world, 0, bits, cap, src_off.ptr, dst_start.ptr, own.ptr,
+                                         need.ptr) == 0
+    assert _from_dev(gpu, need.ptr, 2, np.uint32).tolist() == [need0, 1]
+    stage = gpu.DeviceColumn(n)
+    assert L.b200_stage_scatter_build_local(d_keys.ptr, n, 0, bits, d_hist.ptr, stage.ptr, 0, None, None) == 0
+    tup_dst = (C.c_void_p * world)(*[r.ptr for r in recv])
+    assert L.b200_stage_exchange_segments(stage.ptr, 0, None, n, bits, world, src_off.ptr, dst_start.ptr, cap, 0,
+                                          tup_dst, None) == 0
+    L.b200_synchronize()
+    for r in recv:
+        tail = _from_dev(gpu, r.ptr + 8 * cap, guard, np.uint64)
+        assert np.all(tail == np.uint64(0xABCDABCDABCDABCD))
