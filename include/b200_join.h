@@ -316,7 +316,8 @@ int   b200_stage_join_sum_seg(const void *d_tup_b, const uint32_t *d_hist_all,
  * locally partitioned shard (b200_stage_scatter_build_local), d_dst_start[p] =
  * where its segment of p starts in the owner's buffer, d_own_total[p] = global
  * size of p if this rank owns it else 0 (the histogram the local join runs
- * on), d_need[0] = rows this rank receives, d_need[1] = 1 if that exceeds cap.
+ * on; all zero when the capacity is exceeded), d_need[0] = rows this rank
+ * receives, d_need[1] = 1 if that exceeds cap (the caller must fail the step).
  * b200_stage_exchange_segments: copies every staged tuple (and up to two
  * payload columns, pay_dst[k * world + d]) to tup_dst[owner] with stores of
  * 256 contiguous bytes per warp (peer buffers are CUDA-IPC mappings: NVLink);

@@ -426,7 +426,7 @@ int b200_stage_join_sum_seg(const void *d_tup_b, const uint32_t *d_hist_all, int
 int b200_stage_exchange_cursors(const uint32_t *d_hist_all, int world, int rank, int radix_bits, uint32_t cap,
                                 uint32_t *d_src_off, uint32_t *d_dst_start, uint32_t *d_own_total, uint32_t *d_need) {
     if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail("bad world / rank");
-    if (radix_bits < 3 || (1u << radix_bits) < (uint32_t)world) return fail("fewer partitions than ranks");
+    if (radix_bits < 2 || (1u << radix_bits) < (uint32_t)world) return fail("fewer partitions than ranks");
     stage_exchange_cursors(d_hist_all, world, rank, radix_bits, cap, d_src_off, d_dst_start, d_own_total, d_need);
     return 0;
 }

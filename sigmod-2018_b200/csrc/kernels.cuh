@@ -1687,8 +1687,9 @@ segment_offsets_kernel(const uint32_t *__restrict__ hist_all, uint32_t world, ui
 //   dst_start[p] where this rank's segment of p starts in owner(p)'s buffer
 //   own_total[p] global size of p if this rank owns it, else 0
 //   need[0]      rows this rank receives (capacity check), need[1] = 1 if that
-//                exceeds `cap` (the copy kernel then drops what does not fit
-//                and the caller must fail the step)
+//                exceeds `cap`: the copy kernel then drops what does not fit,
+//                own_total is all zero (the join reads nothing) and the
+//                caller must fail the step
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t partition_owner(uint32_t p, uint32_t world, uint32_t radix_bits) {
     return (uint32_t)(((uint64_t)p * world) >> radix_bits);
@@ -1736,6 +1737,9 @@ exchange_cursors_kernel(const uint32_t *__restrict__ hist_all, uint32_t world, u
     }
     if (threadIdx.x == 0) owner_base[world] = grand;
     __syncthreads();
+    // (world <= nparts, so every owner has at least one partition and has set its base)
+    const uint32_t mine = owner_base[rank + 1] - owner_base[rank];
+    const bool     over = mine > cap;   // the join must not read past the receive buffer: it gets nothing
     run = start;
     for (uint32_t k = 0; k < per; ++k) {
         const uint32_t b = first + k;
@@ -1748,15 +1752,13 @@ exchange_cursors_kernel(const uint32_t *__restrict__ hist_all, uint32_t world, u
             }
             const uint32_t o = partition_owner(b, world, radix_bits);
             dst_start[b]     = run - owner_base[o] + before;
-            own_total[b]     = o == rank ? tot : 0u;
+            own_total[b]     = (o == rank && !over) ? tot : 0u;
             run += tot;
         }
     }
     if (threadIdx.x == 0) {
-        // owners whose range is empty (world > nparts) never set their base; world <= nparts is required
-        const uint32_t mine = owner_base[rank + 1] - owner_base[rank];
-        need[0]             = mine;
-        need[1]             = mine > cap ? 1u : 0u;
+        need[0] = mine;
+        need[1] = over ? 1u : 0u;
     }
 }
 

@@ -374,7 +374,8 @@ class ShardedExchangeJoin:
         self.carry_b = bool(carry_build) and n_pay_build == 1
         self.carry_p = bool(carry_probe) and n_pay_probe == 1
         # partitions are sized for the per-partition table exactly as on one GPU: by the GLOBAL build side
-        self.bits = int(bits) if bits else int(L.b200_radix_bits_for(n_build_total))
+        # (and at least four partitions per rank, so that owners of a tiny build side stay balanced)
+        self.bits = int(bits) if bits else max(int(L.b200_radix_bits_for(n_build_total)), (world - 1).bit_length() + 2)
         self.P = 1 << self.bits
         assert self.P >= world
         self.device = device
