@@ -355,12 +355,27 @@ static void launch_scatter_c(const KeySrc &src, int bits, uint32_t *cursor, void
 
 template <typename KeyT>
 static void launch_scatter(const KeySrc &src, int bits, uint32_t *cursor, void *out) {
-    const OptArgs none{0, nullptr, nullptr};
+    const OptArgs none{0, nullptr, nullptr, nullptr};
     switch (tuning().scatter_cfg) {
         case 0: launch_scatter_c<KeyT, 0, false>(src, bits, cursor, out, none); break;
         case 2: launch_scatter_c<KeyT, 2, false>(src, bits, cursor, out, none); break;
         default: launch_scatter_c<KeyT, 1, false>(src, bits, cursor, out, none); break;
     }
+}
+
+// the tuned scatter with a 32-bit payload column carried in the row-id slot (base columns only)
+static void launch_scatter_carry_tuned(const KeySrc &src, int bits, uint32_t *cursor, void *out,
+                                       const uint64_t *carry_col) {
+    constexpr int NT   = PartCfg<uint32_t, 1>::NT;
+    constexpr int U    = PartCfg<uint32_t, 1>::U;
+    constexpr int MINB = PartCfg<uint32_t, 1>::MINB;
+    const size_t  smem = (size_t)NT * U * sizeof(Tup32) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
+    auto          k    = radix_scatter_kernel<NT, U, MINB, uint32_t, false, true>;
+    allow_smem(k, smem);
+    const OptArgs carry{0, nullptr, nullptr, carry_col};
+    k<<<grid_for(src.n, NT * U, MINB), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor,
+                                                                 static_cast<Tup32 *>(out), carry);
+    B200_LAUNCH_CHECK();
 }
 
 // histogram-free probe-side scatter (32-bit keys): fixed regions of opt.opt_cap tuples + overflow
@@ -1109,7 +1124,11 @@ void stage_scatter_build_local(const uint64_t *d_keys, uint64_t n, uint32_t rid_
     }
     KeySrc src{d_keys, nullptr, (uint32_t)n};
     TimedScope ts("scatter_b");
-    launch_scatter_pay<uint32_t>(src, bits, cur_l, d_tup_out, pay, npay);
+    // large shards with a carried payload (the probe side of the exchange plan) take the tuned scatter instance
+    if (carry && n >= (1u << 18))
+        launch_scatter_carry_tuned(src, bits, cur_l, d_tup_out, pay_cols[0]);
+    else
+        launch_scatter_pay<uint32_t>(src, bits, cur_l, d_tup_out, pay, npay);
 }
 
 void stage_scatter_probe(const uint64_t *d_keys, uint64_t n, int bits, uint32_t *d_cursor, void *d_tup_out) {
@@ -1182,7 +1201,7 @@ void stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint3
     if (n == 0) return;
     KeySrc src{d_keys, nullptr, (uint32_t)n};
     TimedScope ts("scatter_p");
-    launch_scatter_opt(src, bits, d_cursor, d_tup_out, OptArgs{opt_cap, d_ovcnt, d_ov});
+    launch_scatter_opt(src, bits, d_cursor, d_tup_out, OptArgs{opt_cap, d_ovcnt, d_ov, nullptr});
 }
 
 // d_hist_p: probe-side histogram (opt_cap == 0) or the cursor array stage_scatter_probe_opt left behind

@@ -109,7 +109,8 @@ __device__ __forceinline__ uint32_t tile_local_index(int j, bool vec) {
                : (uint32_t)(j * NT + (int)threadIdx.x);
 }
 
-template <int NT, int U, typename KeyT>
+// FOLD (32-bit-key instances over a genuine column, never over packed tuples): see below.
+template <int NT, int U, typename KeyT, bool FOLD = false>
 __device__ __forceinline__ void load_tile_keys(const KeySrc &src, uint64_t base, uint32_t count,
                                                bool vec, KeyT (&keys)[U]) {
     if (vec) {
@@ -117,8 +118,16 @@ __device__ __forceinline__ void load_tile_keys(const KeySrc &src, uint64_t base,
         for (int j = 0; j < U; j += 2) {
             const uint32_t li = ((uint32_t)((j >> 1) * NT + (int)threadIdx.x)) * 2u;
             ulonglong2     v  = ld_stream_u64x2(src.col + base + li);
-            keys[j]           = (KeyT)v.x;
-            keys[j + 1]       = (KeyT)v.y;
+            if constexpr (sizeof(KeyT) == 4 && FOLD) {
+                // 32-bit-key instances run only on columns whose maximum is < 2^32, so the high halves are zero;
+                // folding them in keeps ptxas from narrowing the 128-bit load into two 32-bit loads (which costs
+                // twice the L1 wavefronts in kernels bound by that pipe)
+                keys[j]     = (KeyT)v.x ^ (KeyT)(v.x >> 32);
+                keys[j + 1] = (KeyT)v.y ^ (KeyT)(v.y >> 32);
+            } else {
+                keys[j]     = (KeyT)v.x;
+                keys[j + 1] = (KeyT)v.y;
+            }
         }
     } else if (src.ids == nullptr) {
 #pragma unroll
@@ -269,11 +278,21 @@ partition_plan_kernel(const uint32_t *__restrict__ hist_b, const uint32_t *__res
 // second pass over that (normally empty) overflow only.  This removes the
 // histogram read of the whole probe column (8 B/row) from the common case.
 struct OptArgs {
-    uint32_t  opt_cap;
-    uint32_t *ov_cursor;
-    void     *ov_out;
+    uint32_t        opt_cap;
+    uint32_t       *ov_cursor;
+    void           *ov_out;
+    const uint64_t *carry_col;   // CARRY instances only
 };
-template <int NT, int U, typename KeyT, bool FULL, bool OPT>
+// CARRY: the row-id slot of a tuple carries (uint32)carry_col[row] instead of the row id (a SUM column whose
+// values fit 32 bits travels inside the tuple: the probe side of the multi-GPU exchange plan).  The column is
+// read where the tuples are staged; its tile was pulled into L2 (prefetch.global.L2, one 128-byte line per
+// thread) while the previous tile was processed, so those loads do not wait on DRAM.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int NT, int U>
+__device__ __forceinline__ void prefetch_carry_tile(const uint64_t *col, uint64_t base, uint32_t count) {
+    for (uint32_t e = threadIdx.x * 16u; e < count; e += NT * 16u) prefetch_l2(col + base + e);
+}
+template <int NT, int U, typename KeyT, bool FULL, bool OPT, bool CARRY = false>
 __device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U], uint64_t base, uint32_t count,
                                              bool vec, uint64_t nbase, uint32_t ncount, bool nvec, bool has_next,
                                              uint32_t nbins, uint32_t mask, uint32_t per,
@@ -325,6 +344,7 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U],
         }
     }
     __syncthreads();
+    [[maybe_unused]] uint32_t carry_lo = 0, carry_hi = 0;
 #pragma unroll
     for (int j = 0; j < U; ++j) {
         const uint32_t li = FULL ? ((uint32_t)((j >> 1) * NT) + tid) * 2u + (uint32_t)(j & 1)
@@ -332,7 +352,21 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U],
         if (FULL || li < count) {
             TupT t;
             t.key = keys[j];
-            t.rid = (uint32_t)base + li;
+            if constexpr (CARRY) {
+                if constexpr (FULL) {
+                    // registers j, j+1 hold two consecutive rows: one 128-bit load for both
+                    if ((j & 1) == 0) {
+                        const ulonglong2 v = ld_stream_u64x2(opt.carry_col + base + li);
+                        carry_lo           = (uint32_t)v.x;
+                        carry_hi           = (uint32_t)v.y;
+                    }
+                    t.rid = (j & 1) ? carry_hi : carry_lo;
+                } else {
+                    t.rid = (uint32_t)ld_stream_u64(opt.carry_col + base + li);
+                }
+            } else {
+                t.rid = (uint32_t)base + li;
+            }
             if constexpr (sizeof(KeyT) == 8) t.pad = 0;
             stage[loc[(uint32_t)keys[j] & mask] + ((rank2[j >> 1] >> (16 * (j & 1))) & 0xFFFFu)] = t;
         }
@@ -340,7 +374,10 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U],
     __syncthreads();
     // keys[] and the ranks are dead: put the next tile's loads in flight before
     // the copy-out so their latency hides behind the stores
-    if (has_next) load_tile_keys<NT, U, KeyT>(src, nbase, ncount, nvec, keys);
+    if (has_next) {
+        load_tile_keys<NT, U, KeyT, true>(src, nbase, ncount, nvec, keys);
+        if constexpr (CARRY) prefetch_carry_tile<NT, U>(opt.carry_col, nbase, ncount);
+    }
     auto put = [&](uint32_t i) {
         const TupT     t   = stage[i];
         const uint32_t b   = (uint32_t)t.key & mask;
@@ -362,7 +399,7 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U],
     __syncthreads();
 }
 
-template <int NT, int U, int MINB, typename KeyT, bool OPT>
+template <int NT, int U, int MINB, typename KeyT, bool OPT, bool CARRY = false>
 __global__ void __launch_bounds__(NT, MINB)
 radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cursor,
                      typename TupOf<KeyT>::type *__restrict__ out, const OptArgs opt) {
@@ -381,7 +418,8 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
     // row ids are 32-bit: tile bases fit 32 bits as well
     const uint64_t n      = src.n;
     const uint64_t ntiles = (n + TILE - 1) / TILE;
-    const bool     vec_ok = src.ids == nullptr && ((reinterpret_cast<uintptr_t>(src.col) & 15) == 0);
+    const bool     vec_ok = src.ids == nullptr && ((reinterpret_cast<uintptr_t>(src.col) & 15) == 0) &&
+                        (!CARRY || (reinterpret_cast<uintptr_t>(opt.carry_col) & 15) == 0);
     const uint32_t per    = (nbins + NT - 1) / NT;
 
     for (uint32_t b = threadIdx.x; b < nbins; b += NT) cnt[b] = 0;
@@ -390,7 +428,8 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
     if (tile < ntiles) {
         const uint64_t base  = tile * TILE;
         const uint32_t count = (uint32_t)min((uint64_t)TILE, n - base);
-        load_tile_keys<NT, U, KeyT>(src, base, count, vec_ok && count == TILE, keys);
+        load_tile_keys<NT, U, KeyT, true>(src, base, count, vec_ok && count == TILE, keys);
+        if constexpr (CARRY) prefetch_carry_tile<NT, U>(opt.carry_col, base, count);
     }
     __syncthreads();
 
@@ -404,13 +443,13 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
         const uint32_t ncount   = has_next ? (uint32_t)min((uint64_t)TILE, n - nbase) : 0u;
         const bool     nvec     = vec_ok && ncount == TILE;
         if (vec)
-            scatter_tile<NT, U, KeyT, true, OPT>(src, keys, base, count, vec, nbase, ncount, nvec, has_next, nbins,
-                                                 mask, per, stage, cnt, loc, gdelta, warp_sums, cursor, out, opt,
-                                                 ovdelta);
+            scatter_tile<NT, U, KeyT, true, OPT, CARRY>(src, keys, base, count, vec, nbase, ncount, nvec, has_next,
+                                                        nbins, mask, per, stage, cnt, loc, gdelta, warp_sums, cursor,
+                                                        out, opt, ovdelta);
         else
-            scatter_tile<NT, U, KeyT, false, OPT>(src, keys, base, count, vec, nbase, ncount, nvec, has_next, nbins,
-                                                  mask, per, stage, cnt, loc, gdelta, warp_sums, cursor, out, opt,
-                                                  ovdelta);
+            scatter_tile<NT, U, KeyT, false, OPT, CARRY>(src, keys, base, count, vec, nbase, ncount, nvec, has_next,
+                                                         nbins, mask, per, stage, cnt, loc, gdelta, warp_sums, cursor,
+                                                         out, opt, ovdelta);
     }
 }
 

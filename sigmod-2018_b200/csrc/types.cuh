@@ -18,7 +18,7 @@ struct KeySrc {
     uint32_t        n;
 };
 
-struct Tup32 {
+struct alignas(8) Tup32 {
     uint32_t key;
     uint32_t rid;
 };
