@@ -260,21 +260,28 @@ def run_b200_arm(args):
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
         r1_max = int(t_max.item())
     L.b200_register_device_column(r1.data_ptr(), r1.data_ptr(), nr_loc, r1_max)
+    # ... and the probe-side SUM column's: with it the library may stream that column into the probe tuples instead
+    # of gathering it per match
+    s1_max = int(s1.max().item())
+    L.b200_register_device_column(s1.data_ptr(), s1.data_ptr(), ns_loc, s1_max)
     plan = None
     # B200_PLAN: "copy" (default) / "scatter" = the two broadcast plans (small build side: config 2's shape);
     # "exchange" = radix-sharded all-to-all of both sides (config 4's plan), here for comparison
     plan_kind = os.environ.get("B200_PLAN", "copy")
-    if world > 1 and plan_kind == "exchange":
-        s1_max = int(s1.max().item())
+    s1_max_all = s1_max
+    if world > 1:
         t_max = torch.tensor([s1_max], dtype=torch.int64, device=dev)
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        s1_max_all = int(t_max.item())
+    if world > 1 and plan_kind == "exchange":
         plan = b200.sharding.ShardedExchangeJoin(b200, torch, dist, rank, world, nr, nr_loc, ns_loc, 1, 1, dev,
                                                  size_from=(r0.data_ptr(), s0.data_ptr()),
                                                  carry_build=r1_max < (1 << 32),
-                                                 carry_probe=int(t_max.item()) < (1 << 32))
+                                                 carry_probe=s1_max_all < (1 << 32))
     elif world > 1:
         plan = b200.sharding.BroadcastScatterJoin(b200, torch, dist, rank, world, nr, nr_loc, ns_loc, 1, dev,
-                                                  carry32=r1_max < (1 << 32), rank_major=plan_kind == "copy")
+                                                  carry32=r1_max < (1 << 32), rank_major=plan_kind == "copy",
+                                                  carry_probe=s1_max_all < (1 << 32))   # matches per probe row: 1/16
     torch.cuda.synchronize()
 
     def step(kr=None, pr=None, ks=None, ps=None):

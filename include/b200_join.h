@@ -250,6 +250,15 @@ int   b200_stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n,
                                    int radix_bits, uint32_t opt_cap,
                                    uint32_t *d_cursor, void *d_tup_out,
                                    void *d_ov, uint32_t *d_ovcnt);
+/* The same with a probe-side SUM column whose values fit 32 bits carried in
+ * the row-id slot of the probe tuples (streamed by the scatter instead of
+ * gathered per match by the join): pass that projection to the join with
+ * proj_part_vals = (uint64_t*)1. */
+int   b200_stage_scatter_probe_opt_carry(const uint64_t *d_keys, uint64_t n,
+                                         int radix_bits, uint32_t opt_cap,
+                                         uint32_t *d_cursor, void *d_tup_out,
+                                         void *d_ov, uint32_t *d_ovcnt,
+                                         const uint64_t *d_carry_col);
 /* d_hist_p is the probe histogram (opt_cap == 0) or the cursor array that
  * b200_stage_scatter_probe_opt left behind (opt_cap > 0, with d_ov/d_ovcnt). */
 int   b200_stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b,

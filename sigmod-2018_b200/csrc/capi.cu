@@ -376,6 +376,15 @@ int b200_stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int radix_b
     return 0;
 }
 
+int b200_stage_scatter_probe_opt_carry(const uint64_t *d_keys, uint64_t n, int radix_bits, uint32_t opt_cap,
+                                       uint32_t *d_cursor, void *d_tup_out, void *d_ov, uint32_t *d_ovcnt,
+                                       const uint64_t *d_carry_col) {
+    if (n > (1u << 30)) return fail("histogram-free scatter is limited to 2^30 probe rows");
+    if (!d_carry_col || (reinterpret_cast<uintptr_t>(d_carry_col) & 7)) return fail("bad carried column");
+    stage_scatter_probe_opt(d_keys, n, radix_bits, opt_cap, d_cursor, d_tup_out, d_ov, d_ovcnt, d_carry_col);
+    return 0;
+}
+
 int b200_stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p, const uint32_t *d_hist_p,
                         int radix_bits, int n_proj, const uint64_t *const *proj_cols, const int *proj_side,
                         const uint64_t *const *proj_part_vals, uint32_t opt_cap, const void *d_ov,

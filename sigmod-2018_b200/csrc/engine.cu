@@ -70,6 +70,7 @@ static void init_device(int device) {
     if (const char *v = getenv("B200_EARLY_MAT")) t.early_mat = atoi(v);
     if (const char *v = getenv("B200_OPT_PARTITION")) t.opt_partition = atoi(v);
     if (const char *v = getenv("B200_CARRY32")) t.carry32 = atoi(v);
+    if (const char *v = getenv("B200_CARRY_PROBE")) t.carry_probe = atoi(v);
     if (const char *v = getenv("B200_L2_FETCH")) {
         // granularity hint for L2 fills of the random payload gathers (32, 64 or 128)
         B200_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v)));
@@ -387,6 +388,26 @@ static void launch_scatter_opt(const KeySrc &src, int bits, uint32_t *cursor, vo
     }
 }
 
+// ... the same with a 32-bit probe-side SUM column carried in the row-id slot of the probe tuples
+template <int CFG>
+static void launch_scatter_opt_carry_c(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
+    constexpr int NT   = PartCfg<uint32_t, CFG>::NT;
+    constexpr int U    = PartCfg<uint32_t, CFG>::U;
+    constexpr int MINB = PartCfg<uint32_t, CFG>::MINB;
+    const size_t  smem = (size_t)NT * U * sizeof(Tup32) + 4 * (size_t)(1u << bits) * sizeof(uint32_t);
+    auto          k    = radix_scatter_kernel<NT, U, MINB, uint32_t, true, true>;
+    allow_smem(k, smem);
+    k<<<grid_for(src.n, NT * U, MINB), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor,
+                                                                 static_cast<Tup32 *>(out), opt);
+    B200_LAUNCH_CHECK();
+}
+static void launch_scatter_opt_carry(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
+    if (tuning().scatter_cfg == 2)
+        launch_scatter_opt_carry_c<2>(src, bits, cursor, out, opt);
+    else
+        launch_scatter_opt_carry_c<1>(src, bits, cursor, out, opt);
+}
+
 // build-side scatter with early-materialised projections (radix_scatter_pay_kernel)
 template <typename KeyT, int NPAY>
 static void launch_scatter_pay_n(const KeySrc &src, int bits, uint32_t *cursor, void *out, const PayArgs &pay) {
@@ -660,7 +681,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     bool      opt     = false;
     uint32_t  opt_cap = 0;
     DevBufPtr part_vals[kMaxProj];
-    int       carry_k = -1;
+    int       carry_k = -1, carry_p = -1;
     uint64_t  n_items = 0;
     if (direct) {
         a.src_b = B.src;
@@ -717,6 +738,28 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
                 }
             }
         }
+        // Probe-side early materialisation: ONE probe-side SUM column over the base relation whose values fit
+        // 32 bits rides in the row-id slot of the probe tuples (nothing else reads the probe row id in a fused
+        // SUM).  The scatter then streams that column (8 B per probe row, hidden under its L1-bound phases)
+        // instead of the join gathering it at random (8 B per MATCH at ~38 G gathers/s), which pays
+        // when matches are not rare: expected matches per probe row = build rows / key domain for a unique
+        // build side (stats.c estimates join cardinalities the same way from the column ranges).
+        if (mode == JoinOut::Sum && opt && t.carry32 && t.carry_probe && P.src.ids == nullptr) {
+            const int side_p  = swapped ? 0 : 1;
+            int       n_probe = 0, first = -1;
+            for (int k = 0; k < nproj; ++k)
+                if (proj[k].side == side_p) {
+                    if (first < 0) first = k;
+                    ++n_probe;
+                }
+            const double domain = (double)std::max(B.max_val, P.max_val) + 1.0;
+            const double sel    = std::min(1.0, (double)B.src.n / domain);
+            if (n_probe == 1 && proj[first].ids == nullptr && sel >= 1.0 / 24.0 &&
+                (reinterpret_cast<uintptr_t>(proj[first].col) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(P.src.col) & 15) == 0 &&
+                known_column_max(proj[first].col) <= 0xFFFFFFFFull)
+                carry_p = first;
+        }
         auto scatter_build = [&](uint32_t *cursor) {
             TimedScope ts("scatter_b");
             if (npay > 0)
@@ -744,7 +787,11 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             ov_tup = dev_alloc((size_t)P.src.n * tsz);
             {
                 TimedScope ts("scatter_p");
-                launch_scatter_opt(P.src, bits, cur_p, tup_p->ptr, OptArgs{opt_cap, d_ovcnt, ov_tup->ptr});
+                if (carry_p >= 0)
+                    launch_scatter_opt_carry(P.src, bits, cur_p, tup_p->ptr,
+                                             OptArgs{opt_cap, d_ovcnt, ov_tup->ptr, proj[carry_p].col});
+                else
+                    launch_scatter_opt(P.src, bits, cur_p, tup_p->ptr, OptArgs{opt_cap, d_ovcnt, ov_tup->ptr, nullptr});
             }
             {
                 TimedScope ts("scan");
@@ -791,7 +838,9 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             a.proj[k] = proj[k];
             // sides are given relative to (R, S); the kernel wants (build, probe)
             a.proj[k].side      = swapped ? 1 - proj[k].side : proj[k].side;
-            a.proj[k].part_vals = k == carry_k ? B200_PROJ_IN_RID : part_vals[k] ? part_vals[k]->as<uint64_t>() : nullptr;
+            a.proj[k].part_vals = (k == carry_k || k == carry_p) ? B200_PROJ_IN_RID
+                                  : part_vals[k]                 ? part_vals[k]->as<uint64_t>()
+                                                                 : nullptr;
             if (a.proj[k].side == 0 && (!a.proj[k].part_vals || k == carry_k)) a.need_brid = 1;
         }
         {
@@ -1190,8 +1239,10 @@ uint32_t opt_region_cap(uint64_t n_probe, int bits) {
 
 // histogram-free probe-side scatter into caller-owned buffers: d_tup_out holds 2^bits regions of opt_cap tuples,
 // d_ov (n tuples) and d_ovcnt (one u32) receive what does not fit
+// carry_col != nullptr: the row-id slot of every probe tuple carries (uint32)carry_col[row] (a probe-side SUM column
+// with 32-bit values; pass that projection to the join with part_vals = B200_PROJ_IN_RID)
 void stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint32_t opt_cap, uint32_t *d_cursor,
-                             void *d_tup_out, void *d_ov, uint32_t *d_ovcnt) {
+                             void *d_tup_out, void *d_ov, uint32_t *d_ovcnt, const uint64_t *carry_col) {
     Context       &c      = ctx();
     const uint32_t nparts = 1u << bits;
     B200_REQUIRE(n <= (1u << 30), "histogram-free scatter is limited to 2^30 probe rows");
@@ -1201,7 +1252,10 @@ void stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint3
     if (n == 0) return;
     KeySrc src{d_keys, nullptr, (uint32_t)n};
     TimedScope ts("scatter_p");
-    launch_scatter_opt(src, bits, d_cursor, d_tup_out, OptArgs{opt_cap, d_ovcnt, d_ov, nullptr});
+    if (carry_col)
+        launch_scatter_opt_carry(src, bits, d_cursor, d_tup_out, OptArgs{opt_cap, d_ovcnt, d_ov, carry_col});
+    else
+        launch_scatter_opt(src, bits, d_cursor, d_tup_out, OptArgs{opt_cap, d_ovcnt, d_ov, nullptr});
 }
 
 // d_hist_p: probe-side histogram (opt_cap == 0) or the cursor array stage_scatter_probe_opt left behind

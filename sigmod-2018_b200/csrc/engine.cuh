@@ -41,6 +41,8 @@ struct Tuning {
     uint32_t cap64       = 12288;    // ... 64-bit keys
     uint32_t slice       = 1u << 18; // probe tuples per work item
     int      carry32     = 1;        // a single 32-bit build-side SUM column travels in the tuple's row-id slot
+    int      carry_probe = 1;        // ... and a single 32-bit probe-side SUM column in the probe tuples', when the
+                                     // expected matches make streaming it cheaper than gathering it (run_join)
     int      opt_partition = 1;      // histogram-free probe-side scatter for the fused join -> SUM
     int      early_mat   = 1;        // carry build-side SUM projections through the scatter
     int      scatter_cfg = 1;        // see engine.cu PartCfg
@@ -101,7 +103,8 @@ void       stage_scatter_probe(const uint64_t *d_keys, uint64_t n, int bits, uin
 uint32_t   opt_region_cap(uint64_t n_probe, int bits);
 int        auto_radix_bits(uint64_t n_build, bool key64);
 void       stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint32_t opt_cap, uint32_t *d_cursor,
-                                   void *d_tup_out, void *d_ov, uint32_t *d_ovcnt);
+                                   void *d_tup_out, void *d_ov, uint32_t *d_ovcnt,
+                                   const uint64_t *carry_col = nullptr);
 JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p,
                           const uint32_t *d_hist_p, int bits, int nproj, const ProjDesc *proj, uint32_t opt_cap,
                           const void *d_ov, const uint32_t *d_ovcnt, unsigned long long *d_result = nullptr,

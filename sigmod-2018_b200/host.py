@@ -203,6 +203,8 @@ def _declare(L: C.CDLL) -> None:
                                                 C.c_void_p, C.c_void_p]),
         "b200_stage_scatter_probe_opt": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p,
                                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+        "b200_stage_scatter_probe_opt_carry": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p,
+                                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "b200_stage_join_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                           P(C.c_void_p), P(C.c_int), P(C.c_void_p), C.c_uint32, C.c_void_p,
                                           C.c_void_p, u64p, u64p]),

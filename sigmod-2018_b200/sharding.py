@@ -89,9 +89,12 @@ class BroadcastScatterJoin:
     """
 
     def __init__(self, b200, torch, dist, rank, world, n_build_total, n_build_local, n_probe_local, n_pay, device,
-                 carry32=False, rank_major=False):
+                 carry32=False, rank_major=False, carry_probe=False):
         """carry32: the single build-side SUM column (n_pay == 1) holds 32-bit values and travels in the row-id
-        slot of the build tuples: no payload buffers, half the bytes in the NVLink broadcast."""
+        slot of the build tuples: no payload buffers, half the bytes in the NVLink broadcast.
+        carry_probe: the single probe-side SUM column holds 32-bit values and is streamed into the row-id slot of
+        the probe tuples by the (histogram-free) scatter instead of being gathered per match by the join; worth
+        it when matches are not rare (see run_join in engine.cu)."""
         import ctypes as C
         self.b, self.torch, self.dist, self.rank, self.world = b200, torch, dist, rank, world
         self.C = C
@@ -100,6 +103,7 @@ class BroadcastScatterJoin:
         self.n_build_total, self.n_build_local, self.n_probe_local = n_build_total, n_build_local, n_probe_local
         self.n_pay = n_pay
         self.carry32 = bool(carry32) and n_pay == 1
+        self.carry_probe = bool(carry_probe)
         # rank_major: region r of every build buffer holds rank r's shard in partition order; the broadcast is
         # then ONE contiguous copy per peer on the copy engines (no SM kernel), and the join reads a partition
         # as `world` runs (b200_stage_join_sum_seg).  Needs equal build shards.
@@ -211,7 +215,13 @@ class BroadcastScatterJoin:
         # ---- probe side: local, independent of the exchange -> side stream ----
         side.wait_stream(main)
         L.b200_set_stream(side.cuda_stream)
-        if self.opt_cap:
+        probe_projs = [kk for kk, sd in enumerate(proj_side) if sd == 1]
+        carried = probe_projs[0] if (self.carry_probe and self.opt_cap and len(probe_projs) == 1) else -1
+        if carried >= 0:
+            assert L.b200_stage_scatter_probe_opt_carry(probe_keys_ptr, self.n_probe_local, bits, self.opt_cap,
+                                                        h_p.data_ptr(), self.tup_p.ptr, self.ov_p.ptr,
+                                                        self.ovcnt.data_ptr(), proj_cols[carried]) == 0
+        elif self.opt_cap:
             assert L.b200_stage_scatter_probe_opt(probe_keys_ptr, self.n_probe_local, bits, self.opt_cap,
                                                   h_p.data_ptr(), self.tup_p.ptr, self.ov_p.ptr,
                                                   self.ovcnt.data_ptr()) == 0
@@ -253,11 +263,11 @@ class BroadcastScatterJoin:
         cols = (C.c_void_p * max(k, 1))(*proj_cols)
         sides = (C.c_int * max(k, 1))(*proj_side)
         part = []
-        for col, side_k in zip(proj_cols, proj_side):
+        for kk, (col, side_k) in enumerate(zip(proj_cols, proj_side)):
             if side_k == 0:
                 part.append(1 if self.carry32 else self.pay_b[build_pay_ptrs.index(col)].ptr)
             else:
-                part.append(None)
+                part.append(1 if kk == carried else None)
         part_vals = (C.c_void_p * max(k, 1))(*part)
         if self.rank_major:
             args = (self.tup_b.ptr, self.hist_all.data_ptr(), world, self.n_build_local, self.tup_p.ptr, h_p.data_ptr(),

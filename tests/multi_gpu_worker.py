@@ -74,13 +74,14 @@ def main():
     pr, ps = orc.synth_column(nr, 1, 0, 3), orc.synth_column(ns, 1, 0, 4)
     want, wm = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
     d_kr, d_ks, d_pr, d_ps = shard(kr, nr), shard(ks, ns), shard(pr, nr), shard(ps, ns)
-    for carry, rank_major in ((False, False), (True, False), (True, True)):
+    for carry, rank_major, carry_probe in ((False, False, False), (True, False, False), (True, True, False),
+                                           (True, True, True), (False, False, True)):
         plan = sh.BroadcastScatterJoin(b200, torch, dist, rank, world, nr, d_kr.numel(), d_ks.numel(), 1, dev,
-                                       carry32=carry, rank_major=rank_major)
+                                       carry32=carry, rank_major=rank_major, carry_probe=carry_probe)
         for _ in range(2):
             got, m = plan.step(d_kr.data_ptr(), [d_pr.data_ptr()], d_ks.data_ptr(),
                                [d_pr.data_ptr(), d_ps.data_ptr()], [0, 1])
-            assert m == wm and got == want, ("broadcast", carry, rank_major, got, m, want, wm)
+            assert m == wm and got == want, ("broadcast", carry, rank_major, carry_probe, got, m, want, wm)
         plan.close()
         cases += 1
     torch.cuda.synchronize()

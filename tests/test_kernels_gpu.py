@@ -163,6 +163,42 @@ def test_join_sum_device_carries_registered_32bit_payload(gpu, orc):
             c.free()
 
 
+@pytest.mark.parametrize("kr_bits,ks_bits,zipf,wide", [(18, 21, False, False), (18, 21, False, True),
+                                                       (16, 21, False, False), (16, 21, True, False),
+                                                       (17, 20, True, False)])
+def test_join_sum_device_carries_registered_probe_payload(gpu, orc, kr_bits, ks_bits, zipf, wide):
+    """A probe-side SUM column registered with a maximum below 2^32 is streamed into the row-id slot of the probe
+    tuples by the histogram-free scatter when matches are not rare (build rows / key domain >= 1/24: 1/8 and, with
+    Zipf keys over the build domain, 1 — there the overflow pass carries the values too); a wider column, an
+    unregistered one or a sparser join (1/32) gathers per match.  Same checksums, both argument orders."""
+    nr, ns = 1 << kr_bits, 1 << ks_bits
+    kr = orc.synth_column(nr, 0, kr_bits, gpu.SEED_R)
+    ks = orc.synth_column(ns, 2, kr_bits, 21) if zipf else orc.synth_column(ns, 0, ks_bits, gpu.SEED_S)
+    max_key = nr - 1 if zipf else ns - 1
+    pr = orc.synth_column(nr, 1, 0, 7)
+    ps = orc.synth_column(ns, 1, 0, 8) * np.uint64((1 << 40) + 1 if wide else 1)
+    want, wm = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
+    cols = [gpu.DeviceColumn(len(a)) for a in (kr, ks, pr, ps)]
+    try:
+        for c, a in zip(cols, (kr, ks, pr, ps)):
+            gpu.lib().b200_copy_to_device(c.ptr, a.ctypes.data, 8 * len(a))
+        for register in (False, True):
+            if register:
+                gpu.lib().b200_register_device_column(cols[2].ptr, cols[2].ptr, nr, int(pr.max()))
+                gpu.lib().b200_register_device_column(cols[3].ptr, cols[3].ptr, ns, int(ps.max()))
+            got, m = gpu.join_sum_device(cols[0].ptr, nr, cols[1].ptr, ns, [cols[2].ptr, cols[3].ptr], [0, 1], max_key)
+            assert m == wm and got == want
+            got, m = gpu.join_sum_device(cols[1].ptr, ns, cols[0].ptr, nr, [cols[3].ptr, cols[2].ptr, cols[3].ptr],
+                                         [0, 1, 0], max_key)          # two probe-side projections: no carrying
+            assert m == wm and got == [want[1], want[0], want[1]]
+            got, m = gpu.join_sum_device(cols[1].ptr, ns, cols[0].ptr, nr, [cols[3].ptr], [0], max_key)
+            assert m == wm and got == [want[1]]
+    finally:
+        gpu.lib().b200_unregister_all()
+        for c in cols:
+            c.free()
+
+
 @pytest.mark.parametrize("kr_bits,ks_bits", [(12, 16), (16, 20), (20, 22)])
 def test_join_sum_config2_shape_scaled_down(gpu, orc, kr_bits, ks_bits):
     """BASELINE config 2 at reduced size: unique permutation keys, probe
@@ -178,10 +214,11 @@ def test_join_sum_config2_shape_scaled_down(gpu, orc, kr_bits, ks_bits):
 
 
 # ---- staged join (the phases the multi-GPU plan drives), single GPU ----------
-@pytest.mark.parametrize("kr_bits,ks_bits,zipf,carry,rank_major", [
-    (15, 18, False, False, False), (18, 21, False, False, False), (16, 21, True, False, False),
-    (18, 21, False, True, False), (18, 21, False, True, True), (16, 21, True, False, True)])
-def test_staged_join_matches_fused_join(gpu, orc, kr_bits, ks_bits, zipf, carry, rank_major):
+@pytest.mark.parametrize("kr_bits,ks_bits,zipf,carry,rank_major,carry_probe", [
+    (15, 18, False, False, False, False), (18, 21, False, False, False, False), (16, 21, True, False, False, False),
+    (18, 21, False, True, False, False), (18, 21, False, True, True, False), (16, 21, True, False, True, False),
+    (18, 21, False, True, True, True), (16, 21, True, False, False, True), (15, 18, False, True, False, True)])
+def test_staged_join_matches_fused_join(gpu, orc, kr_bits, ks_bits, zipf, carry, rank_major, carry_probe):
     """sharding.BroadcastScatterJoin with world = 1: hist -> cursors -> scatter (build side with an
     early-materialised payload, through the multi-destination path) -> join_sum, against the oracle."""
     torch = pytest.importorskip("torch")
@@ -198,7 +235,7 @@ def test_staged_join_matches_fused_join(gpu, orc, kr_bits, ks_bits, zipf, carry,
         t = {n: torch.from_numpy(a.view(np.int64).copy()).to(dev) for n, a in
              [("kr", kr), ("ks", ks), ("pr", pr), ("ps", ps)]}
         plan = gpu.sharding.BroadcastScatterJoin(gpu, torch, None, 0, 1, nr, nr, ns, 1, dev, carry32=carry,
-                                                 rank_major=rank_major)
+                                                 rank_major=rank_major, carry_probe=carry_probe)
         for _ in range(2):     # buffers are reused across steps
             got, m = plan.step(t["kr"].data_ptr(), [t["pr"].data_ptr()], t["ks"].data_ptr(),
                                [t["pr"].data_ptr(), t["ps"].data_ptr()], [0, 1])
