@@ -345,7 +345,8 @@ def run_b200_arm(args):
     for _ in range(9):
         step()
         torch.cuda.synchronize()
-        for name in ("hist", "hist_b", "hist_p", "scan", "scatter_b", "broadcast", "exchange", "scatter_p", "join"):
+        for name in ("hist", "hist_b", "hist_p", "scan", "scatter_b", "broadcast", "exchange", "scatter_p",
+                     "scatter_pc", "join"):
             v = b200.last_kernel_ms(name)
             if v >= 0:
                 per_kernel.setdefault(name, []).append(v)
@@ -414,6 +415,12 @@ def run_b200_arm(args):
         "scatter_b": ((8 + 16) * n_b, (8 + 8) * n_b),
         "join": (16 * (n_p + n_b) + 16 * nr // world, 8 * (n_p + n_b) + 16 * nr // world),
     }
+    if "scatter_pc" in per_kernel:
+        # the probe scatter streamed S.c1 into the tuples (early materialisation): it reads 8 B per row more, and the
+        # canonical bytes of that projection (8 B per match) are served by it instead of by the join
+        m_loc = nr // world
+        kernel_bytes["scatter_pc"] = ((8 + 16) * n_p + 8 * m_loc, (8 + 8 + 8) * n_p)
+        kernel_bytes["join"] = (16 * (n_p + n_b) + 8 * m_loc, 8 * (n_p + n_b))
     traffic = {}
     tpath = ROOT / "profiles" / "r1_traffic.json"
     if tpath.exists():

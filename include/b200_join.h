@@ -350,7 +350,8 @@ int   b200_stage_exchange_segments(const void *d_src_tup, int npay,
 /* Per-kernel device times of the calling thread's last RadixHashJoin /
  * b200_join_sum, measured with CUDA events on its stream when profiling is
  * enabled with b200_set_profiling(1).  Names: "hist_b", "hist_p", "scan",
- * "scatter_b", "scatter_p", "join", "exchange" (b = build side, p = probe side).  Returns milliseconds, or a negative value if the
+ * "scatter_b", "scatter_p", "scatter_pc" (the probe scatter when it also carries a
+ * SUM column), "join", "exchange" (b = build side, p = probe side).  Returns milliseconds, or a negative value if the
  * kernel did not run. */
 int    b200_set_profiling(int on);
 double b200_last_kernel_ms(const char *name);

@@ -402,10 +402,11 @@ static void launch_scatter_opt_carry_c(const KeySrc &src, int bits, uint32_t *cu
     B200_LAUNCH_CHECK();
 }
 static void launch_scatter_opt_carry(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
-    if (tuning().scatter_cfg == 2)
-        launch_scatter_opt_carry_c<2>(src, bits, cursor, out, opt);
-    else
-        launch_scatter_opt_carry_c<1>(src, bits, cursor, out, opt);
+    switch (tuning().scatter_cfg) {
+        case 0: launch_scatter_opt_carry_c<0>(src, bits, cursor, out, opt); break;
+        case 2: launch_scatter_opt_carry_c<2>(src, bits, cursor, out, opt); break;
+        default: launch_scatter_opt_carry_c<1>(src, bits, cursor, out, opt); break;
+    }
 }
 
 // build-side scatter with early-materialised projections (radix_scatter_pay_kernel)
@@ -786,7 +787,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             B200_LAUNCH_CHECK();
             ov_tup = dev_alloc((size_t)P.src.n * tsz);
             {
-                TimedScope ts("scatter_p");
+                TimedScope ts(carry_p >= 0 ? "scatter_pc" : "scatter_p");   // pc: with the carried SUM column
                 if (carry_p >= 0)
                     launch_scatter_opt_carry(P.src, bits, cur_p, tup_p->ptr,
                                              OptArgs{opt_cap, d_ovcnt, ov_tup->ptr, proj[carry_p].col});
@@ -1251,7 +1252,7 @@ void stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint3
     B200_CUDA(cudaMemsetAsync(d_ovcnt, 0, sizeof(uint32_t), c.stream));
     if (n == 0) return;
     KeySrc src{d_keys, nullptr, (uint32_t)n};
-    TimedScope ts("scatter_p");
+    TimedScope ts(carry_col ? "scatter_pc" : "scatter_p");
     if (carry_col)
         launch_scatter_opt_carry(src, bits, d_cursor, d_tup_out, OptArgs{opt_cap, d_ovcnt, d_ov, carry_col});
     else

@@ -356,9 +356,10 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U],
                 if constexpr (FULL) {
                     // registers j, j+1 hold two consecutive rows: one 128-bit load for both
                     if ((j & 1) == 0) {
+                        // (high halves are zero by contract; folded in so the load stays 128-bit, see load_tile_keys)
                         const ulonglong2 v = ld_stream_u64x2(opt.carry_col + base + li);
-                        carry_lo           = (uint32_t)v.x;
-                        carry_hi           = (uint32_t)v.y;
+                        carry_lo           = (uint32_t)v.x ^ (uint32_t)(v.x >> 32);
+                        carry_hi           = (uint32_t)v.y ^ (uint32_t)(v.y >> 32);
                     }
                     t.rid = (j & 1) ? carry_hi : carry_lo;
                 } else {
