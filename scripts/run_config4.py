@@ -22,6 +22,10 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 
 def main():
+    # ONE JSON line on stdout: libraries (NCCL prints its version there) get stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--build-bits", type=int, default=27)
     ap.add_argument("--probe-rows", type=int, default=2_000_000_000)
