@@ -151,6 +151,17 @@ int  b200_calculate_sums(inter_res *inter, relation_map *map,
                          batch_listnode *query, uint64_t *sums,
                          uint64_t *num_rows);
 
+/* Lazy last join (default on; B200_LAZY_JOIN=0 or b200_set_lazy_join(0) turns
+ * it off; returns the previous setting): RadixHashJoin returns a deferred
+ * result, InsertJoinToInterResults parks it on the intermediate, any operator
+ * that looks at the intermediate next materialises it exactly as the eager
+ * path would, and CalculateQueryResults / b200_calculate_sums run a join that
+ * is still parked fused with the SUMs, so the pairs of a query's last join
+ * are never written (query.c:408-461 is unchanged: it only reads
+ * inter_res::next).  result::current_load of a deferred result is 0 until one
+ * of the read-back calls below has materialised it. */
+int  b200_set_lazy_join(int on);
+
 /* Read-back for tests: copy a result (row ids, or pairs as r[],s[]) and one
  * intermediate column to host as uint64. */
 int  b200_result_kind(const result *res);               /* 1 row ids, 2 pairs */

@@ -7,6 +7,7 @@
 #include "../../include/b200_join.h"
 #include "engine.cuh"
 
+#include <atomic>
 #include <cstring>
 #include <vector>
 
@@ -18,16 +19,46 @@ struct B200Relation : relation {
     KeyVec kv;
 };
 
-enum ResultKind { kRowIds = 1, kPairs = 2 };
+enum ResultKind { kRowIds = 1, kPairs = 2, kDeferredJoin = 3 };
 struct B200Result : result {
     int       kind = 0;
     DevBufPtr a, b;   // row ids / (R ids, S ids)
     uint64_t  n = 0;
+    KeyVec    kr, ks;   // kDeferredJoin: the two inputs of a join that has not run yet
+};
+
+// Lazy last join ("fold the last join into the SUM"; query.c:408-461 runs the joins one after
+// the other and only then CalculateQueryResults).  Unless B200_LAZY_JOIN=0, RadixHashJoin returns a DEFERRED
+// result and InsertJoinToInterResults parks it on the node it belongs to.  Whatever operator looks at the
+// intermediate next materialises it first (resolve_all: the pairs are produced and inserted exactly as the
+// eager path does), so every join but the last behaves as before; when the next operator is
+// CalculateQueryResults the join runs fused with the SUMs (run_join(..., JoinOut::Sum)) and its pairs are never
+// written.  The caller cannot tell the difference: it only reads inter_res::next (query.c:453, 462), and
+// AreActiveInInter sees non-NULL placeholders for the parked bindings.
+struct PendingJoin {
+    bool   active = false;
+    KeyVec kr, ks;
+    int    rel1 = -1, rel2 = -1;
+    int    active_side = -1;   // -1: both bindings are new to the node; 0 / 1: rel1 / rel2 was already in it
 };
 
 struct B200InterData : inter_data {
     std::vector<DevBufPtr> bufs;
+    PendingJoin            pending;
 };
+
+uint64_t *const kParked = reinterpret_cast<uint64_t *>(8);   // table[] entry of a binding whose join is parked
+
+std::atomic<int> g_lazy_join{-1};   // -1: B200_LAZY_JOIN from the environment (default on)
+bool lazy_join_enabled() {
+    int v = g_lazy_join.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = getenv("B200_LAZY_JOIN");
+        v             = e ? (atoi(e) != 0) : 1;
+        g_lazy_join.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
 
 B200InterData *idata(const inter_res *node) { return static_cast<B200InterData *>(node->data); }
 
@@ -100,6 +131,53 @@ DevColumn binding_column(relation_map *map, int *query_relations, int binding, i
     return lookup_column(rm.columns[column], rm.num_tuples);
 }
 
+// pairs (position in R's key vector, position in S's) into the node: inter_res.c:39-62 when both bindings are
+// new to it, 64-141 when one of them is active (every active column is gathered through its positions)
+void insert_pairs(inter_res *node, int rel1, int rel2, int active_side, uint64_t m, DevBufPtr r_ids, DevBufPtr s_ids) {
+    if (active_side < 0) {
+        B200InterData *d = idata(node);
+        d->num_tuples    = m;
+        set_column(d, rel1, std::move(r_ids));
+        set_column(d, rel2, std::move(s_ids));
+        return;
+    }
+    const bool      has1    = active_side == 0;
+    DevBufPtr       pos     = has1 ? r_ids : s_ids;
+    DevBufPtr       fresh   = has1 ? s_ids : r_ids;
+    const int       new_rel = has1 ? rel2 : rel1;
+    compact_node(node, pos->as<uint32_t>(), m);
+    set_column(idata(node), new_rel, fresh);
+}
+
+// run the parked join of `node`, if any, and insert its pairs
+void resolve(inter_res *node) {
+    B200InterData *d = idata(node);
+    if (!d->pending.active) return;
+    PendingJoin pj    = std::move(d->pending);
+    d->pending        = PendingJoin{};
+    // the placeholders go first: compact_node gathers every non-NULL column
+    if (pj.active_side != 0) d->table[pj.rel1] = nullptr;
+    if (pj.active_side != 1) d->table[pj.rel2] = nullptr;
+    if (pj.active_side < 0) d->num_tuples = 0;
+    JoinResult j = run_join(pj.kr, pj.ks, JoinOut::Pairs, 0, nullptr);
+    insert_pairs(node, pj.rel1, pj.rel2, pj.active_side, j.m, j.r_ids, j.s_ids);
+}
+void resolve_all(inter_res *head) {
+    for (; head; head = head->next) resolve(head);
+}
+
+// a deferred join result that is looked at directly (tests) turns into its pairs
+void materialise(B200Result *r) {
+    if (!r || r->kind != kDeferredJoin) return;
+    JoinResult j    = run_join(r->kr, r->ks, JoinOut::Pairs, 0, nullptr);
+    r->kind         = kPairs;
+    r->n            = j.m;
+    r->current_load = j.m;
+    r->a            = j.r_ids;
+    r->b            = j.s_ids;
+    r->kr = r->ks = KeyVec{};
+}
+
 }  // namespace
 
 extern "C" {
@@ -123,6 +201,7 @@ void FreeInterResults(inter_res *var) {
 
 // filter.c:92-190
 result *Filter(inter_res *head, filter_pred *filter_p, relation_map *map, int *query_relations) {
+    resolve_all(head);
     const int  rel  = filter_p->relation;
     DevColumn  col  = binding_column(map, query_relations, rel, filter_p->column);
     inter_res *node = find_node(head, rel);
@@ -148,6 +227,7 @@ result *Filter(inter_res *head, filter_pred *filter_p, relation_map *map, int *q
 int InsertSingleRowIdsToInterResult(inter_res **head, int relation_num, result *res) {
     B200Result *r = static_cast<B200Result *>(res);
     B200_REQUIRE(r && r->kind == kRowIds, "InsertSingleRowIdsToInterResult needs a row-id result");
+    resolve_all(*head);
     inter_res *node = *head, *last = nullptr;
     for (; node; last = node, node = node->next) {
         if (node->data->num_tuples == 0) {   // filter.c:19-40: first instance of the node
@@ -169,6 +249,7 @@ int InsertSingleRowIdsToInterResult(inter_res **head, int relation_num, result *
 // (column, row-id list) view and is read by the partition / join kernels.
 relation *GetRelation(int given_rel, int column, inter_res *inter, relation_map *map, int *query_relations) {
     DevColumn  col  = binding_column(map, query_relations, given_rel, column);
+    resolve_all(inter);
     inter_res *node = inter ? find_node(inter, given_rel) : nullptr;
     auto      *rel  = new B200Relation();
     rel->tuples     = nullptr;
@@ -194,6 +275,13 @@ result *RadixHashJoin(relation *relR, relation *relS, scheduler *sched) {
     if (relR->num_tuples == 0 || relS->num_tuples == 0) return nullptr;   // rhjoin.c:15-16
     B200Relation *r = static_cast<B200Relation *>(relR);
     B200Relation *s = static_cast<B200Relation *>(relS);
+    if (lazy_join_enabled()) {
+        // deferred: the key vectors keep their row-id lists alive (ids_owner) after the caller frees relR / relS
+        B200Result *d = new_result(kDeferredJoin, 0, nullptr, nullptr);
+        d->kr         = r->kv;
+        d->ks         = s->kv;
+        return d;
+    }
     JoinResult    j = run_join(r->kv, s->kv, JoinOut::Pairs, 0, nullptr);
     // an empty join is a non-NULL result with zero pairs (rhjoin.c:356-359)
     return new_result(kPairs, j.m, j.r_ids, j.s_ids);
@@ -202,25 +290,31 @@ result *RadixHashJoin(relation *relR, relation *relS, scheduler *sched) {
 // inter_res.c:34-152
 int InsertJoinToInterResults(inter_res *head, int rel1, int rel2, result *res) {
     B200Result *r = static_cast<B200Result *>(res);
-    B200_REQUIRE(r && r->kind == kPairs, "InsertJoinToInterResults needs a pair result");
+    B200_REQUIRE(r && (r->kind == kPairs || r->kind == kDeferredJoin), "InsertJoinToInterResults needs a join result");
+    resolve_all(head);
     inter_res *node = head, *last = nullptr;
     for (; node; last = node, node = node->next) {
-        B200InterData *d = idata(node);
-        if (d->num_tuples == 0) {   // inter_res.c:39-62
-            d->num_tuples = r->n;
-            set_column(d, rel1, r->a);
-            set_column(d, rel2, r->b);
+        B200InterData *d    = idata(node);
+        const bool     none = d->num_tuples == 0;   // inter_res.c:39-62
+        const bool     has1 = d->table[rel1] != nullptr, has2 = d->table[rel2] != nullptr;
+        if (!none && has1 == has2) continue;
+        // inter_res.c:64-102 (rel1 active) / 104-141 (rel2 active)
+        const int active_side = none ? -1 : has1 ? 0 : 1;
+        if (r->kind == kDeferredJoin) {
+            // park the join on this node; its bindings read as active from now on
+            d->pending.active      = true;
+            d->pending.kr          = r->kr;
+            d->pending.ks          = r->ks;
+            d->pending.rel1        = rel1;
+            d->pending.rel2        = rel2;
+            d->pending.active_side = active_side;
+            if (active_side != 0) d->table[rel1] = kParked;
+            if (active_side != 1) d->table[rel2] = kParked;
+            if (none) d->num_tuples = 1;   // "not an empty node"; the real count exists once the join has run
             return 1;
         }
-        const bool has1 = d->table[rel1] != nullptr, has2 = d->table[rel2] != nullptr;
-        if (has1 != has2) {   // inter_res.c:64-102 (rel1 active) / 104-141 (rel2 active)
-            const uint32_t *pos     = has1 ? r->a->as<uint32_t>() : r->b->as<uint32_t>();
-            DevBufPtr       fresh   = has1 ? r->b : r->a;
-            const int       new_rel = has1 ? rel2 : rel1;
-            compact_node(node, pos, r->n);
-            set_column(idata(node), new_rel, fresh);
-            return 1;
-        }
+        insert_pairs(node, rel1, rel2, active_side, r->n, r->a, r->b);
+        return 1;
     }
     // inter_res.c:147-151: neither side lives in a node yet
     last->next = new_node(last->num_of_relations);
@@ -238,6 +332,7 @@ int AreActiveInInter(inter_res *inter, int rel1, int rel2) {
 // inter_res.c:363-389
 int JoinInterNode(inter_res **inter, relation_map *rel_map, int rel1, int col1, int rel2, int col2,
                   int *relations) {
+    resolve_all(*inter);
     inter_res *node = *inter;
     for (; node; node = node->next)
         if (node->data->table[rel1] != nullptr && node->data->table[rel2] != nullptr) break;
@@ -255,6 +350,7 @@ int JoinInterNode(inter_res **inter, relation_map *rel_map, int rel1, int col1, 
 // inter_res.c:265-318: a later node that shares an active binding with an
 // earlier one is folded into it through that binding's positions.
 void MergeInterNodes(inter_res **inter) {
+    resolve_all(*inter);
     for (inter_res *head = *inter; head; head = head->next) {
         bool merged = true;
         while (merged) {
@@ -290,6 +386,7 @@ void MergeInterNodes(inter_res **inter) {
 void CartesianInterResults(inter_res **inter) {
     inter_res *cur = *inter;
     if (cur->next == nullptr) return;
+    resolve_all(cur);
     CartesianInterResults(&cur->next);
     inter_res     *nxt = cur->next;
     B200InterData *a = idata(cur), *b = idata(nxt);
@@ -319,6 +416,47 @@ int b200_calculate_sums(inter_res *inter, relation_map *map, batch_listnode *que
     std::vector<const uint64_t *>  cols((size_t)nv);
     std::vector<const uint32_t *>  ids((size_t)nv);
     B200InterData                 *d = idata(inter);
+    if (d->pending.active) {
+        // the last join is still parked on the node: run it fused with the SUMs.  A projection on a binding that
+        // was in the node before the join reads through that binding's row ids at the position the join reports
+        // for the node's side; one on a binding the join brings in reads the base row of the other side.
+        const PendingJoin &pj = d->pending;
+        ProjDesc           pd[kMaxProj];
+        bool               fusable = nv <= kMaxProj;
+        for (int i = 0; i < nv && fusable; ++i) {
+            const int index  = query->views->data[i][0] - '0';
+            const int column = query->views->data[i][2] - '0';
+            if (index < 0 || index >= inter->num_of_relations || d->table[index] == nullptr) {
+                fusable = false;
+                break;
+            }
+            DevColumn col = binding_column(map, query->relations, index, column);
+            int       side;
+            const uint32_t *through = nullptr;
+            if (pj.active_side < 0) {
+                if (index != pj.rel1 && index != pj.rel2) { fusable = false; break; }
+                side = index == pj.rel1 ? 0 : 1;
+                if (pj.rel1 == pj.rel2) fusable = false;
+            } else {
+                const int new_rel = pj.active_side == 0 ? pj.rel2 : pj.rel1;
+                if (index == new_rel) {
+                    side = 1 - pj.active_side;
+                } else {
+                    side    = pj.active_side;
+                    through = column_ids(d, index);
+                }
+            }
+            pd[i] = ProjDesc{col.d, through, side, nullptr};
+        }
+        if (fusable) {
+            JoinResult j = run_join(pj.kr, pj.ks, JoinOut::Sum, nv, pd);
+            for (int i = 0; i < nv; ++i) sums[i] = j.sums[i];
+            if (num_rows) *num_rows = j.m;
+            return 0;
+        }
+        resolve(inter);
+        d = idata(inter);
+    }
     for (int i = 0; i < nv; ++i) {
         // single-digit binding and column, as in inter_res.c:325-327
         const int index  = query->views->data[i][0] - '0';
@@ -360,6 +498,7 @@ result *SelfJoin(int given_rel, int column1, int column2, inter_res **inter, rel
                  int *query_relations) {
     DevColumn  c1   = binding_column(map, query_relations, given_rel, column1);
     DevColumn  c2   = binding_column(map, query_relations, given_rel, column2);
+    resolve_all(*inter);
     inter_res *node = find_node(*inter, given_rel);
     IdList     l;
     if (node) {
@@ -383,7 +522,16 @@ void FreeRelation(relation *rel) {
 }
 
 // ---- read-back helpers for tests (Part 2) ---------------------------------
-int b200_result_kind(const result *res) { return res ? static_cast<const B200Result *>(res)->kind : 0; }
+int b200_set_lazy_join(int on) {
+    const int before = lazy_join_enabled() ? 1 : 0;
+    g_lazy_join.store(on ? 1 : 0, std::memory_order_relaxed);
+    return before;
+}
+
+int b200_result_kind(const result *res) {
+    materialise(static_cast<B200Result *>(const_cast<result *>(res)));   // a deferred join shows up as its pairs
+    return res ? static_cast<const B200Result *>(res)->kind : 0;
+}
 
 static int ids_to_host(const uint32_t *d, uint64_t n, uint64_t *out) {
     if (n == 0) return 0;
@@ -402,6 +550,7 @@ int b200_result_rowids_to_host(const result *res, uint64_t *out) {
 }
 
 int b200_result_pairs_to_host(const result *res, uint64_t *out_r, uint64_t *out_s) {
+    materialise(static_cast<B200Result *>(const_cast<result *>(res)));
     const B200Result *r = static_cast<const B200Result *>(res);
     if (!r || r->kind != kPairs) return 1;
     ids_to_host(r->a->as<uint32_t>(), r->n, out_r);
@@ -409,6 +558,7 @@ int b200_result_pairs_to_host(const result *res, uint64_t *out_r, uint64_t *out_
 }
 
 int b200_inter_column_to_host(const inter_res *node, int binding, uint64_t *out) {
+    resolve(const_cast<inter_res *>(node));
     const B200InterData *d = idata(node);
     if (!d->table[binding]) return 1;
     return ids_to_host(column_ids(d, binding), d->num_tuples, out);

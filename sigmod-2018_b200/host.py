@@ -164,6 +164,7 @@ def _declare(L: C.CDLL) -> None:
         "b200_set_stream": (C.c_int, [C.c_void_p]),
         "b200_synchronize": (C.c_int, []),
         "b200_calculate_sums": (C.c_int, [P(CInterRes), P(CRelationMap), P(CBatchListnode), u64p, u64p]),
+        "b200_set_lazy_join": (C.c_int, [C.c_int]),
         "b200_result_kind": (C.c_int, [P(CResult)]),
         "b200_result_rowids_to_host": (C.c_int, [P(CResult), u64p]),
         "b200_result_pairs_to_host": (C.c_int, [P(CResult), u64p, u64p]),
