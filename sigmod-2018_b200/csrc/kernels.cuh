@@ -7,7 +7,8 @@
 //   K3  preprocess.c:189-192        -> radix_hist_kernel
 //   K4  preprocess.c:83-102         -> partition_plan_kernel
 //   K5  preprocess.c:262-296,350-359-> radix_scatter_kernel (+ its histogram-free
-//                                      OPT instance), radix_scatter_pay_kernel
+//                                      OPT and payload-carrying CARRY instances),
+//                                      radix_scatter_pay_kernel
 //   K6  rhjoin.c:227-248,270-271    -> tag_join_kernel (32-bit keys) /
 //   K7  rhjoin.c:154-216               hash_join_kernel (64-bit keys, small
 //                                      unpartitioned builds): build, probe
