@@ -322,6 +322,8 @@ constexpr int kPartNT = 512;
 //   0: 512 x 16 (32-bit keys) / 512 x 8 (64-bit), 2 CTAs/SM  -> 64 KB stage each
 //   1: 512 x 32 / 512 x 16, 1 CTA/SM                          -> 128 KB stage
 //   2: 1024 x 16 / 1024 x 8, 1 CTA/SM                         -> 128 KB stage, 32 warps
+//   3: 256 x 48 / 256 x 24, 2 CTAs/SM                         -> 96 KB stage each: two independent phase streams
+//      per SM (one CTA copies out while the other ranks/stages) with tiles of 12 K tuples; not yet measured
 template <typename KeyT, int CFG> struct PartCfg;
 template <> struct PartCfg<uint32_t, 0> { static constexpr int NT = 512, U = 16, MINB = 2; };
 template <> struct PartCfg<uint64_t, 0> { static constexpr int NT = 512, U = 8, MINB = 2; };
@@ -329,6 +331,8 @@ template <> struct PartCfg<uint32_t, 1> { static constexpr int NT = 512, U = 32,
 template <> struct PartCfg<uint64_t, 1> { static constexpr int NT = 512, U = 16, MINB = 1; };
 template <> struct PartCfg<uint32_t, 2> { static constexpr int NT = 1024, U = 16, MINB = 1; };
 template <> struct PartCfg<uint64_t, 2> { static constexpr int NT = 1024, U = 8, MINB = 1; };
+template <> struct PartCfg<uint32_t, 3> { static constexpr int NT = 256, U = 48, MINB = 2; };
+template <> struct PartCfg<uint64_t, 3> { static constexpr int NT = 256, U = 24, MINB = 2; };
 
 template <typename KeyT>
 static void launch_hist(const KeySrc &src, int bits, uint32_t *ghist, int ctas_per_sm = 4) {
@@ -360,6 +364,7 @@ static void launch_scatter(const KeySrc &src, int bits, uint32_t *cursor, void *
     switch (tuning().scatter_cfg) {
         case 0: launch_scatter_c<KeyT, 0, false>(src, bits, cursor, out, none); break;
         case 2: launch_scatter_c<KeyT, 2, false>(src, bits, cursor, out, none); break;
+        case 3: launch_scatter_c<KeyT, 3, false>(src, bits, cursor, out, none); break;
         default: launch_scatter_c<KeyT, 1, false>(src, bits, cursor, out, none); break;
     }
 }
@@ -384,6 +389,7 @@ static void launch_scatter_opt(const KeySrc &src, int bits, uint32_t *cursor, vo
     switch (tuning().scatter_cfg) {
         case 0: launch_scatter_c<uint32_t, 0, true>(src, bits, cursor, out, opt); break;
         case 2: launch_scatter_c<uint32_t, 2, true>(src, bits, cursor, out, opt); break;
+        case 3: launch_scatter_c<uint32_t, 3, true>(src, bits, cursor, out, opt); break;
         default: launch_scatter_c<uint32_t, 1, true>(src, bits, cursor, out, opt); break;
     }
 }
@@ -405,6 +411,7 @@ static void launch_scatter_opt_carry(const KeySrc &src, int bits, uint32_t *curs
     switch (tuning().scatter_cfg) {
         case 0: launch_scatter_opt_carry_c<0>(src, bits, cursor, out, opt); break;
         case 2: launch_scatter_opt_carry_c<2>(src, bits, cursor, out, opt); break;
+        case 3: launch_scatter_opt_carry_c<3>(src, bits, cursor, out, opt); break;
         default: launch_scatter_opt_carry_c<1>(src, bits, cursor, out, opt); break;
     }
 }
