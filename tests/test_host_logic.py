@@ -32,3 +32,18 @@ def test_relation_map_layout(b200):
 def test_null_line(b200):
     assert b200.QueryResult(None, 3).line() == "NULL NULL NULL"
     assert b200.QueryResult([1, 2], 5).line() == "1 2"
+
+
+def test_scripts_and_entry_points_compile():
+    """Every Python entry point of the repo (bench, graft entry, scripts, the multi-GPU worker) byte-compiles and
+    every shell script parses: they only run on GPU boxes, where a syntax error would cost GPU minutes."""
+    import py_compile
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    files = [root / "bench.py", root / "__graft_entry__.py", root / "tests" / "multi_gpu_worker.py"]
+    files += sorted((root / "scripts").glob("*.py")) + sorted((root / "profiles").glob("*.py"))
+    for f in files:
+        py_compile.compile(str(f), doraise=True)
+    for sh in sorted((root / "scripts").glob("*.sh")):
+        assert subprocess.run(["bash", "-n", str(sh)]).returncode == 0, sh
