@@ -51,6 +51,12 @@ UNIT = "probe tuples/s"
 CANON_PER_INPUT, CANON_PER_MATCH = 40, 16
 
 
+def _ck(L, rc):
+    """Raise when a C-ABI call failed (never `assert call(...) == 0`: python -O strips asserts and with them the call)."""
+    if rc != 0:
+        raise RuntimeError("libb200join: " + (L.b200_last_error() or b"error").decode())
+
+
 def load_package():
     name = "sigmod2018_b200"
     pkg_dir = ROOT / "sigmod-2018_b200"
@@ -233,7 +239,7 @@ def run_b200_arm(args):
 
     b200 = load_package()
     L = b200.lib()
-    assert L.b200_init(local) == 0
+    _ck(L, L.b200_init(local))
     stream = torch.cuda.current_stream()
     L.b200_set_stream(stream.cuda_stream)        # kernels run on torch's current stream: torch events see them
 
@@ -376,7 +382,7 @@ def run_b200_arm(args):
             mm = C.c_uint64(0)
             rc = L.b200_join_sum(host["r0"].data_ptr(), nr, host["s0"].data_ptr(), ns_loc, max_key, 2, ptrs, sides, 0,
                                  out, C.byref(mm))
-            assert rc == 0
+            _ck(L, rc)
             return [int(out[0]), int(out[1])], int(mm.value)
 
         e2e_step()

@@ -43,7 +43,7 @@ typedef struct {
     int  njoin;
     join_pred joins[MAX_PREDS];
     int  nview, view_b[MAX_VIEWS], view_c[MAX_VIEWS];
-    char line[256];      /* result */
+    char line[MAX_VIEWS * 21 + 8];      /* result: up to MAX_VIEWS 20-digit sums */
 } query_t;
 
 static double now_s(void) {
@@ -74,7 +74,7 @@ static int load_relation(const char *path, relation_map *rm) {
 
 /* ---- query parsing (query.c:44-249) ----------------------------------------------------------------- */
 static int parse_query(const char *text, query_t *q) {
-    char buf[256];
+    char buf[1024];
     strncpy(buf, text, sizeof buf - 1);
     buf[sizeof buf - 1] = 0;
     char *save = NULL;
@@ -82,13 +82,24 @@ static int parse_query(const char *text, query_t *q) {
     if (!rels || !preds || !views) return 1;
     memset(q, 0, sizeof *q);
     char *s2 = NULL;
-    for (char *t = strtok_r(rels, " ", &s2); t; t = strtok_r(NULL, " ", &s2)) q->rel[q->nrel++] = atoi(t);
+    for (char *t = strtok_r(rels, " ", &s2); t; t = strtok_r(NULL, " ", &s2)) {
+        if (q->nrel == MAX_BINDINGS) return 1;
+        const int r = atoi(t);
+        if (r < 0 || r >= g_nrel) return 1;
+        q->rel[q->nrel++] = r;
+    }
     for (char *p = strtok_r(preds, "&", &s2); p; p = strtok_r(NULL, "&", &s2)) {
         int b1, c1, b2, c2, k;
         char op;
         if (sscanf(p, "%d.%d=%d.%d", &b1, &c1, &b2, &c2) == 4) {
+            if (q->njoin == MAX_PREDS || b1 < 0 || b1 >= q->nrel || b2 < 0 || b2 >= q->nrel) return 1;
+            if (c1 < 0 || (uint64_t)c1 >= g_map[q->rel[b1]].num_columns || c2 < 0 ||
+                (uint64_t)c2 >= g_map[q->rel[b2]].num_columns)
+                return 1;
             q->joins[q->njoin++] = (join_pred){b1, b2, c1, c2};          /* tail of the list: textual order */
         } else if (sscanf(p, "%d.%d%c%d", &b1, &c1, &op, &k) == 4 && (op == '<' || op == '>' || op == '=')) {
+            if (q->nfilter == MAX_PREDS || b1 < 0 || b1 >= q->nrel) return 1;
+            if (c1 < 0 || (uint64_t)c1 >= g_map[q->rel[b1]].num_columns) return 1;
             /* filters go to the list head => they run in reverse textual order (query.c:150-157) */
             memmove(q->filters + 1, q->filters, (size_t)q->nfilter * sizeof(filter_pred));
             q->filters[0] = (filter_pred){b1, c1, k, op};
@@ -98,11 +109,14 @@ static int parse_query(const char *text, query_t *q) {
         }
     }
     for (char *v = strtok_r(views, " \n", &s2); v; v = strtok_r(NULL, " \n", &s2)) {
-        q->view_b[q->nview] = v[0] - '0';       /* single digits, inter_res.c:325-327 */
-        q->view_c[q->nview] = v[2] - '0';
+        if (q->nview == MAX_VIEWS || strlen(v) != 3 || v[1] != '.') return 1;
+        const int b = v[0] - '0', c = v[2] - '0';  /* single digits, inter_res.c:325-327 */
+        if (b < 0 || b >= q->nrel || c < 0 || (uint64_t)c >= g_map[q->rel[b]].num_columns) return 1;
+        q->view_b[q->nview] = b;
+        q->view_c[q->nview] = c;
         q->nview++;
     }
-    return 0;
+    return q->nrel == 0 || q->nview == 0 || q->njoin + q->nfilter == 0;
 }
 
 static void null_line(query_t *q) {
@@ -174,34 +188,64 @@ static void execute_query(query_t *q) {
     FreeInterResults(inter);
 }
 
-/* ---- the scheduler: jobs = whole queries, workers = threads that own a CUDA stream ------------------- */
+/* ---- the scheduler: jobs = whole queries, workers = threads that own a CUDA stream -------------------
+ * scheduler.c:9-132 keeps a pool of pthreads alive for the whole process (SchedulerInit once, handler.c:61-63)
+ * and feeds it jobs; so does this one: the workers are created once, every batch is published under the
+ * mutex, and the main thread waits until the batch's last query has been answered (Barrier, scheduler.c:76-86).
+ * A worker keeps its library context (CUDA stream, pinned scratch) across batches. */
 typedef struct {
-    query_t        *queries;
-    int             n, next;
     pthread_mutex_t mu;
-} batch_t;
+    pthread_cond_t  work, done;
+    query_t        *queries;
+    int             n, next, finished, stop;
+    int             nworkers;
+    pthread_t       th[64];
+} pool_t;
+static pool_t g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER,
+                        NULL, 0, 0, 0, 0, 0, {0}};
 
 static void *worker(void *arg) {
-    batch_t *b = arg;
+    pool_t *p = arg;
+    pthread_mutex_lock(&p->mu);
     for (;;) {
-        pthread_mutex_lock(&b->mu);
-        int i = b->next < b->n ? b->next++ : -1;
-        pthread_mutex_unlock(&b->mu);
-        if (i < 0) break;
-        execute_query(&b->queries[i]);
+        while (!p->stop && p->next >= p->n) pthread_cond_wait(&p->work, &p->mu);
+        if (p->stop) break;
+        const int i = p->next++;
+        pthread_mutex_unlock(&p->mu);
+        execute_query(&p->queries[i]);
+        pthread_mutex_lock(&p->mu);
+        if (++p->finished == p->n) pthread_cond_signal(&p->done);
     }
+    pthread_mutex_unlock(&p->mu);
     return NULL;
 }
 
-static void run_batch(query_t *queries, int n, int workers) {
-    batch_t b = {queries, n, 0, PTHREAD_MUTEX_INITIALIZER};
-    if (workers > n) workers = n;
-    if (workers <= 1) {
-        worker(&b);
-    } else {
-        pthread_t th[64];
-        for (int w = 0; w < workers; ++w) pthread_create(&th[w], NULL, worker, &b);
-        for (int w = 0; w < workers; ++w) pthread_join(th[w], NULL);
+static void pool_start(int workers) {
+    g_pool.nworkers = workers;
+    for (int w = 0; w < workers; ++w) pthread_create(&g_pool.th[w], NULL, worker, &g_pool);
+}
+
+static void pool_stop(void) {
+    pthread_mutex_lock(&g_pool.mu);
+    g_pool.stop = 1;
+    pthread_cond_broadcast(&g_pool.work);
+    pthread_mutex_unlock(&g_pool.mu);
+    for (int w = 0; w < g_pool.nworkers; ++w) pthread_join(g_pool.th[w], NULL);
+}
+
+static void run_batch(query_t *queries, int n) {
+    if (g_pool.nworkers <= 1) {
+        for (int i = 0; i < n; ++i) execute_query(&queries[i]);
+    } else if (n > 0) {
+        pthread_mutex_lock(&g_pool.mu);
+        g_pool.queries  = queries;
+        g_pool.n        = n;
+        g_pool.next     = 0;
+        g_pool.finished = 0;
+        pthread_cond_broadcast(&g_pool.work);
+        while (g_pool.finished < n) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+        g_pool.n = g_pool.next = 0;
+        pthread_mutex_unlock(&g_pool.mu);
     }
     for (int i = 0; i < n; ++i) puts(queries[i].line);      /* submission order, like the reference */
     fflush(stdout);
@@ -214,10 +258,10 @@ int main(int argc, char **argv) {
     if (workers < 1) workers = 1;
     if (workers > 64) workers = 64;
 
-    char buff[256];
+    char buff[1024];
     int  cap = 16;
     g_map    = malloc((size_t)cap * sizeof(relation_map));
-    while (scanf("%255s", buff) == 1 && strcmp(buff, "Done")) {            /* handler.c:27-48 */
+    while (scanf("%1023s", buff) == 1 && strcmp(buff, "Done")) {            /* handler.c:27-48 */
         if (g_nrel == cap) g_map = realloc(g_map, (size_t)(cap *= 2) * sizeof(relation_map));
         if (load_relation(buff, &g_map[g_nrel])) return 1;
         ++g_nrel;
@@ -229,6 +273,7 @@ int main(int argc, char **argv) {
     b200_register_relations(g_map, g_nrel);     /* the untimed preparation phase: columns go to HBM once */
     if (g_timing) fprintf(stderr, "b200_engine: CUDA start-up %.3f s, upload of %d relations %.3f s\n", t1 - t0, g_nrel, now_s() - t1);
 
+    if (workers > 1) pool_start(workers);
     query_t *batch = NULL;
     int      nq = 0, qcap = 0;
     while (fgets(buff, sizeof buff, stdin)) {                              /* handler.c:66-96 */
@@ -236,7 +281,7 @@ int main(int argc, char **argv) {
         if (!strcmp(buff, "Exit\n")) break;
         if (!strcmp(buff, "F\n")) {
             double tb = now_s();
-            run_batch(batch, nq, workers);
+            run_batch(batch, nq);
             if (g_timing) fprintf(stderr, "b200_engine: batch of %d queries on %d workers: %.3f s\n", nq, workers, now_s() - tb);
             nq = 0;
             continue;
@@ -245,7 +290,8 @@ int main(int argc, char **argv) {
         if (parse_query(buff, &batch[nq])) { fprintf(stderr, "cannot parse query: %s", buff); return 2; }
         ++nq;
     }
-    if (nq) run_batch(batch, nq, workers);
+    if (nq) run_batch(batch, nq);
+    pool_stop();
     b200_shutdown();
     return 0;
 }

@@ -21,6 +21,12 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "tests"))
 
 
+def _ck(L, rc):
+    """Raise when a C-ABI call failed (never `assert call(...) == 0`: python -O strips asserts and with them the call)."""
+    if rc != 0:
+        raise RuntimeError("libb200join: " + (L.b200_last_error() or b"error").decode())
+
+
 def main():
     # ONE JSON line on stdout: libraries (NCCL prints its version there) get stderr
     real_stdout = os.dup(1)
@@ -48,7 +54,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     b200 = load_package()
     L = b200.lib()
-    assert L.b200_init(local) == 0
+    _ck(L, L.b200_init(local))
     stream = torch.cuda.current_stream()
     L.b200_set_stream(stream.cuda_stream)
     sh = b200.sharding

@@ -47,8 +47,9 @@ struct KernelTimer {
 // (scheduler.c); here every calling thread owns a CUDA stream and all of an
 // operator's kernels are enqueued on it in order.
 struct Context {
-    cudaStream_t stream       = nullptr;
-    bool         owns_stream  = false;
+    cudaStream_t stream       = nullptr;   // the stream operators run on: own_stream, or one adopted by b200_set_stream
+    cudaStream_t own_stream   = nullptr;   // created with the context, never destroyed while the process lives
+    int          device       = 0;
     // pinned scratch for counters read back after a stream synchronise
     unsigned long long *h_scratch = nullptr;   // 64 x u64, pinned
     unsigned long long *d_scratch = nullptr;   // 64 x u64, device
@@ -56,7 +57,9 @@ struct Context {
     ~Context();
 };
 
-Context &ctx();                 // thread-local, created on first use
+Context &ctx();                 // thread-local, created on first use (pooled across threads)
+void     set_thread_device(int device);   // device the calling thread's context lives on (-1 = process default)
+int      thread_device();
 void     ensure_init();         // device + pool, idempotent
 int      sm_count();
 bool     profiling_enabled();

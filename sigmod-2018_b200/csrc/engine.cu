@@ -11,6 +11,7 @@
 #include <mutex>
 #include <thread>
 #include <unordered_map>
+#include <vector>
 
 namespace b200 {
 
@@ -38,6 +39,14 @@ static int            g_sm_count = 0;
 static bool           g_profiling = false;
 std::atomic<uint64_t> g_launches{0};
 
+// keep freed blocks in the stream-ordered pool instead of returning them
+static void configure_device_pool(int device) {
+    cudaMemPool_t pool;
+    B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t threshold = UINT64_MAX;
+    B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+}
+
 static void init_device(int device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -54,11 +63,7 @@ static void init_device(int device) {
     B200_CUDA(cudaGetDeviceProperties(&prop, device));
     g_sm_count = prop.multiProcessorCount;
     g_device   = device;
-    // keep freed blocks in the stream-ordered pool instead of returning them
-    cudaMemPool_t pool;
-    B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t threshold = UINT64_MAX;
-    B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    configure_device_pool(device);
     Tuning &t = tuning();
     if (const char *v = getenv("B200_RADIX_BITS")) t.radix_bits = atoi(v);
     if (const char *v = getenv("B200_FORCE_KEY64")) t.force_key64 = atoi(v);
@@ -134,24 +139,65 @@ Context::~Context() {
     }
     if (h_scratch) cudaFreeHost(h_scratch);
     if (d_scratch) cudaFree(d_scratch);
-    if (owns_stream && stream) cudaStreamDestroy(stream);
+    if (own_stream) cudaStreamDestroy(own_stream);
 }
 
+// Contexts are pooled: a host that creates fresh worker threads for every batch (host/b200_engine.c before its
+// persistent pool, a ThreadPoolExecutor per execute_batch call) would otherwise leak a stream plus pinned and
+// device scratch per thread, and pay their (device-synchronising) allocation inside the batch.  A thread takes a
+// context of its device from the free list and hands it back when it exits; no CUDA call is made at thread exit
+// (destroying CUDA objects from a thread_local destructor races with runtime teardown).
+static std::mutex              g_ctx_mu;
+static std::vector<Context *>  g_ctx_free;
+static thread_local int        t_device = -1;   // device this thread works on (-1: the process default)
+
+struct ContextHolder {
+    Context *c = nullptr;
+    ~ContextHolder() {
+        if (!c) return;
+        c->stream = c->own_stream;   // an adopted caller stream is not ours to keep
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        g_ctx_free.push_back(c);
+    }
+};
+
+void set_thread_device(int device) { t_device = device; }
+int  thread_device() { return t_device >= 0 ? t_device : g_device; }
+
 Context &ctx() {
-    static thread_local Context *c = nullptr;
-    if (!c) {
-        join_warmup();
-        ensure_init();
-        B200_CUDA(cudaSetDevice(g_device));
-        // leaked on purpose at thread exit of the main thread: destroying CUDA
-        // objects from a thread_local destructor races with runtime teardown
-        c = new Context();
-        B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        c->owns_stream = true;
+    static thread_local ContextHolder h;
+    const int want = t_device;
+    if (h.c && (want < 0 || h.c->device == want)) return *h.c;
+    join_warmup();
+    ensure_init();
+    const int device = want >= 0 ? want : g_device;
+    B200_CUDA(cudaSetDevice(device));
+    if (h.c) {   // the thread moved to another device: hand the old context back
+        h.c->stream = h.c->own_stream;
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        g_ctx_free.push_back(h.c);
+        h.c = nullptr;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        for (size_t i = 0; i < g_ctx_free.size(); ++i)
+            if (g_ctx_free[i]->device == device) {
+                h.c = g_ctx_free[i];
+                g_ctx_free.erase(g_ctx_free.begin() + (long)i);
+                break;
+            }
+    }
+    if (!h.c) {
+        Context *c = new Context();
+        c->device  = device;
+        if (device != g_device) configure_device_pool(device);
+        B200_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        c->stream = c->own_stream;
         B200_CUDA(cudaMallocHost(&c->h_scratch, 64 * sizeof(unsigned long long)));
         B200_CUDA(cudaMalloc(&c->d_scratch, 64 * sizeof(unsigned long long)));
+        h.c = c;
     }
-    return *c;
+    return *h.c;
 }
 
 TimedScope::TimedScope(const char *name) {
@@ -230,16 +276,21 @@ static ColumnEntry upload_entry(const uint64_t *host_col, uint64_t n) {
 void register_host_column(const uint64_t *host_col, uint64_t n, bool replace) {
     ensure_init();
     {
-        std::lock_guard<std::mutex> lk(g_col_mu);
+        std::unique_lock<std::mutex> lk(g_col_mu);
         auto it = g_columns.find(host_col);
         if (it != g_columns.end()) {
             if (!replace) return;
             if (it->second.owned && it->second.col.n == n) {
-                // refresh in place: the end-to-end bench arm re-uploads every step
+                // refresh in place (synchronous): new data may exceed the old maximum, which selects the 32-bit
+                // kernels and the carried payloads — recompute it; device_column_max also synchronises the copy
+                uint64_t *dst = it->second.owned;
+                lk.unlock();
                 Context &c = ctx();
-                if (n)
-                    B200_CUDA(cudaMemcpyAsync(it->second.owned, host_col, n * sizeof(uint64_t),
-                                              cudaMemcpyHostToDevice, c.stream));
+                if (n) B200_CUDA(cudaMemcpyAsync(dst, host_col, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
+                const uint64_t mx = device_column_max(dst, n);
+                lk.lock();
+                auto again = g_columns.find(host_col);
+                if (again != g_columns.end() && again->second.owned == dst) again->second.col.max_val = mx;
                 return;
             }
             if (it->second.owned) cudaFree(it->second.owned);
@@ -248,7 +299,17 @@ void register_host_column(const uint64_t *host_col, uint64_t n, bool replace) {
     }
     ColumnEntry e = upload_entry(host_col, n);
     std::lock_guard<std::mutex> lk(g_col_mu);
-    g_columns[host_col] = e;
+    // two threads may have uploaded the same column concurrently (first use from worker threads): keep the
+    // entry that is already in the map and free the loser's copy
+    auto ins = g_columns.emplace(host_col, e);
+    if (!ins.second) {
+        if (replace || ins.first->second.col.n != n) {
+            if (ins.first->second.owned) cudaFree(ins.first->second.owned);
+            ins.first->second = e;
+        } else if (e.owned) {
+            cudaFree(e.owned);
+        }
+    }
 }
 
 void register_device_column(const uint64_t *host_key, const uint64_t *dev, uint64_t n, uint64_t max_val) {

@@ -1340,9 +1340,11 @@ tag_join_kernel(const JoinArgs a) {
         const uint32_t p_start = s_item[3], p_count = s_item[4];
         const uint32_t item_w  = s_item[5];
 
+        // (a padding lane of the last round is recognised by its index, never by a row-id sentinel: the row-id slot
+        // may carry an arbitrary 32-bit SUM value)
         auto load_probe = [&](uint32_t li, uint32_t &key, uint32_t &rid) {
             key = 0;
-            rid = 0xFFFFFFFFu;   // padding lane of the last round
+            rid = 0;
             if (li < p_count) {
                 const uint64_t v = ld_stream_u64(reinterpret_cast<const uint64_t *>(tup_p + p_start + li));
                 key              = (uint32_t)v;
@@ -1388,7 +1390,7 @@ tag_join_kernel(const JoinArgs a) {
         // ---- probe (K7) ---------------------------------------------------
         // groups of G probes, ping-pong between two register sets: while one group is probed the next one's
         // tuples are in flight
-        auto probe_group = [&](const uint32_t (&key)[G], const uint32_t (&rid)[G]) {
+        auto probe_group = [&](const uint32_t (&key)[G], const uint32_t (&rid)[G], uint32_t first) {
             uint32_t w[G], t[G];
 #pragma unroll
             for (int j = 0; j < G; ++j) {
@@ -1398,7 +1400,7 @@ tag_join_kernel(const JoinArgs a) {
             }
 #pragma unroll
             for (int j = 0; j < G; ++j) {
-                const bool     ok   = rid[j] != 0xFFFFFFFFu;
+                const bool     ok   = first + (uint32_t)(j * NT) + tid < p_count;
                 const bool     is_m = (w[j] >> kTagShift) == t[j];
                 const bool     need = ok && (is_m || (w[j] & kNextBit) != 0u);
                 const uint32_t act  = __ballot_sync(kFullMask, need);
@@ -1416,10 +1418,10 @@ tag_join_kernel(const JoinArgs a) {
         for (uint32_t off = 0; off < p_count; off += 2 * NT * G) {
 #pragma unroll
             for (int j = 0; j < G; ++j) load_probe(off + (uint32_t)(NT * G + j * NT) + tid, nkey[j], nrid[j]);
-            probe_group(ckey, crid);
+            probe_group(ckey, crid, off);
 #pragma unroll
             for (int j = 0; j < G; ++j) load_probe(off + (uint32_t)(2 * NT * G + j * NT) + tid, ckey[j], crid[j]);
-            if (off + NT * G < p_count) probe_group(nkey, nrid);
+            if (off + NT * G < p_count) probe_group(nkey, nrid, off + (uint32_t)(NT * G));
         }
         // leftovers of this item (queue entries are relative to this item's build chunk)
         __syncwarp();

@@ -17,6 +17,12 @@ from __future__ import annotations
 import numpy as np
 
 
+def _ck(L, rc):
+    """Raise when a C-ABI call failed (never `assert call(...) == 0`: python -O strips asserts and with them the call)."""
+    if rc != 0:
+        raise RuntimeError("libb200join: " + (L.b200_last_error() or b"error").decode())
+
+
 def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
     """[first, first + count) of `n` rows for `rank`; the last rank takes the remainder."""
     per = n // world
@@ -183,7 +189,7 @@ class BroadcastScatterJoin:
         self.marks = []
         mark("start")
         # ---- build side: histogram, exchange of the counts, local partition pass ----
-        assert L.b200_stage_hist(build_keys_ptr, self.n_build_local, bits, h_b.data_ptr()) == 0
+        _ck(L, L.b200_stage_hist(build_keys_ptr, self.n_build_local, bits, h_b.data_ptr()))
         if world > 1:
             self.dist.all_gather_into_tensor(self.hist_all.view(-1), h_b)
         else:
@@ -196,21 +202,21 @@ class BroadcastScatterJoin:
         if self.rank_major:
             # partition the local shard straight into this rank's region of its own build buffer
             outs = None if self.carry32 else (C.c_void_p * max(npay, 1))(*[pb.ptr + region for pb in self.pay_b])
-            assert L.b200_stage_scatter_build_local(build_keys_ptr, self.n_build_local, rank * self.n_build_local,
+            _ck(L, L.b200_stage_scatter_build_local(build_keys_ptr, self.n_build_local, rank * self.n_build_local,
                                                     bits, h_b.data_ptr(), self.tup_b.ptr + region, npay, pay_cols,
-                                                    outs) == 0
+                                                    outs))
         else:
-            assert L.b200_stage_build_cursors(self.hist_all.data_ptr(), world, rank, bits, total_b.data_ptr(),
-                                              cur_b.data_ptr()) == 0
+            _ck(L, L.b200_stage_build_cursors(self.hist_all.data_ptr(), world, rank, bits, total_b.data_ptr(),
+                                              cur_b.data_ptr()))
             tup_dst = (C.c_void_p * ndst)(*self.peer_tup)
             flat = [self.peer_pay[k][d] for k in range(len(self.pay_b)) for d in range(ndst)]
             pay_dst = None if self.carry32 else (C.c_void_p * max(len(flat), 1))(*flat)
             # the local partition pass of the build shard and the probe-side scatter both want a whole SM's shared
             # memory per CTA, so they run back to back; the NVLink-bound broadcast copy (tiny CTAs) then runs
             # UNDER the probe-side scatter, which is issued on the side stream in between
-            assert L.b200_stage_scatter_build(build_keys_ptr, self.n_build_local, rank * self.n_build_local, bits,
+            _ck(L, L.b200_stage_scatter_build(build_keys_ptr, self.n_build_local, rank * self.n_build_local, bits,
                                               h_b.data_ptr(), cur_b.data_ptr(), ndst, tup_dst, npay, pay_cols,
-                                              pay_dst, 1) == 0
+                                              pay_dst, 1))
         mark("build partitioned")
         # ---- probe side: local, independent of the exchange -> side stream ----
         side.wait_stream(main)
@@ -218,19 +224,19 @@ class BroadcastScatterJoin:
         probe_projs = [kk for kk, sd in enumerate(proj_side) if sd == 1]
         carried = probe_projs[0] if (self.carry_probe and self.opt_cap and len(probe_projs) == 1) else -1
         if carried >= 0:
-            assert L.b200_stage_scatter_probe_opt_carry(probe_keys_ptr, self.n_probe_local, bits, self.opt_cap,
+            _ck(L, L.b200_stage_scatter_probe_opt_carry(probe_keys_ptr, self.n_probe_local, bits, self.opt_cap,
                                                         h_p.data_ptr(), self.tup_p.ptr, self.ov_p.ptr,
-                                                        self.ovcnt.data_ptr(), proj_cols[carried]) == 0
+                                                        self.ovcnt.data_ptr(), proj_cols[carried]))
         elif self.opt_cap:
-            assert L.b200_stage_scatter_probe_opt(probe_keys_ptr, self.n_probe_local, bits, self.opt_cap,
+            _ck(L, L.b200_stage_scatter_probe_opt(probe_keys_ptr, self.n_probe_local, bits, self.opt_cap,
                                                   h_p.data_ptr(), self.tup_p.ptr, self.ov_p.ptr,
-                                                  self.ovcnt.data_ptr()) == 0
+                                                  self.ovcnt.data_ptr()))
         else:
-            assert L.b200_stage_hist(probe_keys_ptr, self.n_probe_local, bits, h_p.data_ptr()) == 0
+            _ck(L, L.b200_stage_hist(probe_keys_ptr, self.n_probe_local, bits, h_p.data_ptr()))
             with torch.cuda.stream(side):
                 cur_p = (torch.cumsum(h_p, 0, dtype=torch.int32) - h_p).contiguous()
-            assert L.b200_stage_scatter_probe(probe_keys_ptr, self.n_probe_local, bits, cur_p.data_ptr(),
-                                              self.tup_p.ptr) == 0
+            _ck(L, L.b200_stage_scatter_probe(probe_keys_ptr, self.n_probe_local, bits, cur_p.data_ptr(),
+                                              self.tup_p.ptr))
             cur_p.record_stream(side)
         mark("probe scattered (side)", side)
         L.b200_set_stream(main.cuda_stream)
@@ -243,17 +249,17 @@ class BroadcastScatterJoin:
                 cs = self.copy_streams[(j - 1) % len(self.copy_streams)] if self.copy_streams else main
                 cs.wait_stream(main)
                 L.b200_set_stream(cs.cuda_stream)
-                assert L.b200_copy_device_async(self.peer_tup[dpeer] + region, self.tup_b.ptr + region, nbytes) == 0
+                _ck(L, L.b200_copy_device_async(self.peer_tup[dpeer] + region, self.tup_b.ptr + region, nbytes))
                 for k in range(len(self.pay_b)):
-                    assert L.b200_copy_device_async(self.peer_pay[k][dpeer] + region, self.pay_b[k].ptr + region,
-                                                    nbytes) == 0
+                    _ck(L, L.b200_copy_device_async(self.peer_pay[k][dpeer] + region, self.pay_b[k].ptr + region,
+                                                    nbytes))
             L.b200_set_stream(main.cuda_stream)
             for cs in self.copy_streams:
                 main.wait_stream(cs)
         else:
-            assert L.b200_stage_scatter_build(build_keys_ptr, self.n_build_local, rank * self.n_build_local, bits,
+            _ck(L, L.b200_stage_scatter_build(build_keys_ptr, self.n_build_local, rank * self.n_build_local, bits,
                                               h_b.data_ptr(), cur_b.data_ptr(), ndst, tup_dst, npay, pay_cols,
-                                              pay_dst, 2) == 0
+                                              pay_dst, 2))
         mark("broadcast done")
         if world > 1:
             self.dist.all_reduce(self.token)      # stream-ordered barrier: every peer's broadcast has landed
@@ -281,9 +287,9 @@ class BroadcastScatterJoin:
         # peer can start overwriting this rank's build buffers before its join has finished
         res = self.result[: k + 2]
         if self.rank_major:
-            assert L.b200_stage_join_sum_seg(*args, res.data_ptr(), None, None) == 0
+            _ck(L, L.b200_stage_join_sum_seg(*args, res.data_ptr(), None, None))
         else:
-            assert L.b200_stage_join_sum_async(*args, res.data_ptr()) == 0
+            _ck(L, L.b200_stage_join_sum_async(*args, res.data_ptr()))
         if world > 1:
             self.dist.all_reduce(res)
         mark("join + all-reduce done")
@@ -313,9 +319,9 @@ class BroadcastScatterJoin:
             sums = (C.c_uint64 * max(k, 1))()
             m = C.c_uint64(0)
             if self.rank_major:
-                assert L.b200_stage_join_sum_seg(*args, None, sums, C.byref(m)) == 0
+                _ck(L, L.b200_stage_join_sum_seg(*args, None, sums, C.byref(m)))
             else:
-                assert L.b200_stage_join_sum(*args, sums, C.byref(m)) == 0
+                _ck(L, L.b200_stage_join_sum(*args, sums, C.byref(m)))
             return allreduce_checksums([int(x) for x in sums[:k]], int(m.value), self.dist if world > 1 else None,
                                        self.device)
         return i64_to_u64(host[1: k + 1]), int(host[0])
@@ -428,8 +434,8 @@ class ShardedExchangeJoin:
     def measure_capacity(self, build_keys_ptr, probe_keys_ptr):
         """(rows, rows) the receive buffers of the most loaded rank must hold for these inputs."""
         L, torch = self.L, self.torch
-        assert L.b200_stage_hist(build_keys_ptr, self.n_build_local, self.bits, self.hist[0].data_ptr()) == 0
-        assert L.b200_stage_hist(probe_keys_ptr, self.n_probe_local, self.bits, self.hist[1].data_ptr()) == 0
+        _ck(L, L.b200_stage_hist(build_keys_ptr, self.n_build_local, self.bits, self.hist[0].data_ptr()))
+        _ck(L, L.b200_stage_hist(probe_keys_ptr, self.n_probe_local, self.bits, self.hist[1].data_ptr()))
         return self._capacity_from_hist()
 
     def _capacity_from_hist(self):
@@ -462,16 +468,16 @@ class ShardedExchangeJoin:
         self.marks = []
         mark("start")
         h_b, h_p = self.hist[0], self.hist[1]
-        assert L.b200_stage_hist(build_keys_ptr, self.n_build_local, bits, h_b.data_ptr()) == 0
-        assert L.b200_stage_hist(probe_keys_ptr, self.n_probe_local, bits, h_p.data_ptr()) == 0
+        _ck(L, L.b200_stage_hist(build_keys_ptr, self.n_build_local, bits, h_b.data_ptr()))
+        _ck(L, L.b200_stage_hist(probe_keys_ptr, self.n_probe_local, bits, h_p.data_ptr()))
         mark("histograms")
         # ---- probe side: the local partition pass needs only the local histogram -> side stream ----
         side.wait_stream(main)
         L.b200_set_stream(side.cuda_stream)
         outs = None if self.carry_p else arr([c.ptr for c in self.stage_pay_p])
-        assert L.b200_stage_scatter_build_local(probe_keys_ptr, self.n_probe_local, 0, bits, h_p.data_ptr(),
+        _ck(L, L.b200_stage_scatter_build_local(probe_keys_ptr, self.n_probe_local, 0, bits, h_p.data_ptr(),
                                                 self.stage_p.ptr, self.npp, arr(probe_pay_ptrs[:self.npp]),
-                                                outs) == 0
+                                                outs))
         mark("probe partitioned (side)", side)
         L.b200_set_stream(main.cuda_stream)
         # ---- exchange layout ----
@@ -481,29 +487,29 @@ class ShardedExchangeJoin:
             self.hist_all[0].copy_(self.hist)
         by_side = self.hist_all.permute(1, 0, 2).contiguous()          # [side][world][P]
         for s, cap in ((0, self.cap_b), (1, self.cap_p)):
-            assert L.b200_stage_exchange_cursors(by_side[s].data_ptr(), world, rank, bits, cap,
+            _ck(L, L.b200_stage_exchange_cursors(by_side[s].data_ptr(), world, rank, bits, cap,
                                                  self.src_off[s].data_ptr(), self.dst_start[s].data_ptr(),
-                                                 self.own_total[s].data_ptr(), self.need[s].data_ptr()) == 0
+                                                 self.own_total[s].data_ptr(), self.need[s].data_ptr()))
         # ---- build side: partition, exchange ----
         outs = None if self.carry_b else arr([c.ptr for c in self.stage_pay_b])
-        assert L.b200_stage_scatter_build_local(build_keys_ptr, self.n_build_local, 0, bits, h_b.data_ptr(),
+        _ck(L, L.b200_stage_scatter_build_local(build_keys_ptr, self.n_build_local, 0, bits, h_b.data_ptr(),
                                                 self.stage_b.ptr, self.npb, arr(build_pay_ptrs[:self.npb]),
-                                                outs) == 0
+                                                outs))
         nb, npp = len(self.recv_pay_b), len(self.recv_pay_p)
         tup_dst_b = arr([self.peers[d][0] for d in range(world)])
         tup_dst_p = arr([self.peers[d][1] for d in range(world)])
         pay_dst_b = arr([self.peers[d][2 + k] for k in range(nb) for d in range(world)])
         pay_dst_p = arr([self.peers[d][2 + nb + k] for k in range(npp) for d in range(world)])
-        assert L.b200_stage_exchange_segments(self.stage_b.ptr, nb, arr([c.ptr for c in self.stage_pay_b]),
+        _ck(L, L.b200_stage_exchange_segments(self.stage_b.ptr, nb, arr([c.ptr for c in self.stage_pay_b]),
                                               self.n_build_local, bits, world, self.src_off[0].data_ptr(),
                                               self.dst_start[0].data_ptr(), self.cap_b, 0, tup_dst_b,
-                                              pay_dst_b) == 0
+                                              pay_dst_b))
         mark("build exchanged")
         main.wait_stream(side)
-        assert L.b200_stage_exchange_segments(self.stage_p.ptr, npp, arr([c.ptr for c in self.stage_pay_p]),
+        _ck(L, L.b200_stage_exchange_segments(self.stage_p.ptr, npp, arr([c.ptr for c in self.stage_pay_p]),
                                               self.n_probe_local, bits, world, self.src_off[1].data_ptr(),
                                               self.dst_start[1].data_ptr(), self.cap_p, 0 if self.carry_p else 1,
-                                              tup_dst_p, pay_dst_p) == 0
+                                              tup_dst_p, pay_dst_p))
         mark("probe exchanged")
         if world > 1:
             self.dist.all_reduce(self.token)      # stream-ordered barrier: every peer's rows have landed
@@ -520,10 +526,10 @@ class ShardedExchangeJoin:
             cols.append(probe_pay_ptrs[j] if self.carry_p else self.recv_pay_p[j].ptr); sides.append(1)
             part.append(in_rid if self.carry_p else None)
         res = self.result[: k + 2]
-        assert L.b200_stage_join_sum_async(self.recv_b.ptr, self.own_total[0].data_ptr(), self.recv_p.ptr,
+        _ck(L, L.b200_stage_join_sum_async(self.recv_b.ptr, self.own_total[0].data_ptr(), self.recv_p.ptr,
                                            self.own_total[1].data_ptr(), bits, k, arr(cols),
                                            (C.c_int * max(k, 1))(*sides), arr(part), 0, None, None,
-                                           res.data_ptr()) == 0
+                                           res.data_ptr()))
         res[k + 1: k + 2].add_(self.need[:, 1].sum())       # receive-buffer overflow flags of this rank
         if world > 1:
             self.dist.all_reduce(res)     # also ends the step: no peer overwrites buffers still being joined

@@ -199,6 +199,32 @@ def test_join_sum_device_carries_registered_probe_payload(gpu, orc, kr_bits, ks_
             c.free()
 
 
+def test_carried_payload_may_hold_all_ones(gpu, orc):
+    """A carried SUM value of exactly 2^32 - 1 is data, not a padding marker: the join recognises padding lanes by
+    their index (round-1 advisor finding: rows carrying 0xFFFFFFFF were dropped)."""
+    kr_bits, ks_bits = 17, 20
+    nr, ns = 1 << kr_bits, 1 << ks_bits
+    kr = orc.synth_column(nr, 0, kr_bits, gpu.SEED_R)
+    ks = orc.synth_column(ns, 2, kr_bits, 31)                  # every probe row matches
+    pr = orc.synth_column(nr, 1, 0, 7)
+    ps = orc.synth_column(ns, 1, 0, 8)
+    pr[::3] = np.uint64(0xFFFFFFFF)
+    ps[::2] = np.uint64(0xFFFFFFFF)
+    want, wm = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
+    cols = [gpu.DeviceColumn(len(a)) for a in (kr, ks, pr, ps)]
+    try:
+        for c, a in zip(cols, (kr, ks, pr, ps)):
+            gpu.lib().b200_copy_to_device(c.ptr, a.ctypes.data, 8 * len(a))
+        gpu.lib().b200_register_device_column(cols[2].ptr, cols[2].ptr, nr, 0xFFFFFFFF)
+        gpu.lib().b200_register_device_column(cols[3].ptr, cols[3].ptr, ns, 0xFFFFFFFF)
+        got, m = gpu.join_sum_device(cols[0].ptr, nr, cols[1].ptr, ns, [cols[2].ptr, cols[3].ptr], [0, 1], nr - 1)
+        assert m == wm == ns and got == want
+    finally:
+        gpu.lib().b200_unregister_all()
+        for c in cols:
+            c.free()
+
+
 @pytest.mark.parametrize("kr_bits,ks_bits", [(12, 16), (16, 20), (20, 22)])
 def test_join_sum_config2_shape_scaled_down(gpu, orc, kr_bits, ks_bits):
     """BASELINE config 2 at reduced size: unique permutation keys, probe
