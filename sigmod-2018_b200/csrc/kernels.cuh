@@ -293,19 +293,70 @@ template <int NT, int U>
 __device__ __forceinline__ void prefetch_carry_tile(const uint64_t *col, uint64_t base, uint32_t count) {
     for (uint32_t e = threadIdx.x * 16u; e < count; e += NT * 16u) prefetch_l2(col + base + e);
 }
+// Raw tile loads of the scatter: 64-bit values exactly as the column holds them (two per 128-bit load on the vector
+// path).  They stay raw in registers across the copy-out of the previous tile and are narrowed to KeyT only at the
+// top of their own tile: ncu (profiles/r1_g_probe_carry_summary.txt, source page) showed 11 % of all warp samples
+// on the narrowing XOR that round 1 placed right behind the loads — every warp sat on the DRAM latency of the NEXT
+// tile before it stored a single tuple of the current one.
+template <int NT, int U>
+__device__ __forceinline__ void load_tile_raw(const KeySrc &src, uint64_t base, uint32_t count, bool vec,
+                                              uint64_t (&raw)[U]) {
+    if (vec) {
+#pragma unroll
+        for (int j = 0; j < U; j += 2) {
+            const uint32_t   li = ((uint32_t)((j >> 1) * NT + (int)threadIdx.x)) * 2u;
+            const ulonglong2 v  = ld_stream_u64x2(src.col + base + li);
+            raw[j]              = v.x;
+            raw[j + 1]          = v.y;
+        }
+    } else if (src.ids == nullptr) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const uint32_t li = (uint32_t)(j * NT + (int)threadIdx.x);
+            raw[j]            = li < count ? ld_stream_u64(src.col + base + li) : 0ull;
+        }
+    } else {
+        uint32_t id[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const uint32_t li = (uint32_t)(j * NT + (int)threadIdx.x);
+            id[j]             = li < count ? ld_stream_u32(src.ids + base + li) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const uint32_t li = (uint32_t)(j * NT + (int)threadIdx.x);
+            raw[j]            = li < count ? __ldg(src.col + id[j]) : 0ull;
+        }
+    }
+}
+// 32-bit-key instances run only on columns whose maximum is < 2^32, so the high halves are zero; folding them in
+// keeps ptxas from narrowing the 128-bit loads into two 32-bit loads (twice the L1 wavefronts, r1 finding)
+template <typename KeyT>
+__device__ __forceinline__ KeyT narrow_key(uint64_t v) {
+    if constexpr (sizeof(KeyT) == 4) return (KeyT)((uint32_t)v ^ (uint32_t)(v >> 32));
+    else return (KeyT)v;
+}
+
 template <int NT, int U, typename KeyT, bool FULL, bool OPT, bool CARRY = false>
-__device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U], uint64_t base, uint32_t count,
+__device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[U], uint64_t base, uint32_t count,
                                              bool vec, uint64_t nbase, uint32_t ncount, bool nvec, bool has_next,
                                              uint32_t nbins, uint32_t mask, uint32_t per,
                                              typename TupOf<KeyT>::type *stage, uint32_t *cnt, uint32_t *loc,
                                              uint32_t *gdelta, uint32_t *warp_sums, uint32_t *__restrict__ cursor,
                                              typename TupOf<KeyT>::type *__restrict__ out, const OptArgs &opt,
-                                             uint32_t *ovdelta) {
+                                             uint32_t *ovdelta, uint32_t *s_over) {
     using TupT = typename TupOf<KeyT>::type;
-    const uint32_t tid = threadIdx.x;
+    constexpr int  NW   = NT / 32;
+    constexpr int  PER  = 2;   // bins per thread whose reservation stays in flight across the staging phase
+    const uint32_t tid  = threadIdx.x;
+    const uint32_t lane = tid & 31u, wid = tid >> 5;
+    KeyT           keys[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) keys[j] = narrow_key<KeyT>(raw[j]);
     uint32_t rank2[(U + 1) / 2];   // two 16-bit ranks per register
 #pragma unroll
     for (int j = 0; j < (U + 1) / 2; ++j) rank2[j] = 0;
+    // ---- (1) rank of every tuple inside its partition: shared-memory atomics ----
 #pragma unroll
     for (int j = 0; j < U; ++j) {
         const uint32_t li = FULL ? ((uint32_t)((j >> 1) * NT) + tid) * 2u + (uint32_t)(j & 1)
@@ -315,36 +366,73 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U],
             rank2[j >> 1] |= r << (16 * (j & 1));
         }
     }
-    __syncthreads();
+    __syncthreads();   // (A) tile histogram complete
+    // ---- (2) block scan of the tile histogram with ONE barrier; the tile's run in every partition is reserved
+    //          with one global atomic per non-empty partition whose result is only consumed after the staging
+    //          phase (round 1 waited for it here: 10 % of the warp samples) ----
+    const uint32_t first = tid * per;
+    uint32_t       s = 0;
+    for (uint32_t k = 0; k < per; ++k)
+        if (first + k < nbins) s += cnt[first + k];
+    uint32_t incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    if (OPT && tid == 0) *s_over = 0u;
+    __syncthreads();   // (B) warp totals visible (every warp scans them redundantly: no second barrier)
+    uint32_t wbase = 0;
     {
-        const uint32_t first = tid * per;
-        uint32_t       s     = 0;
-        for (uint32_t k = 0; k < per; ++k)
-            if (first + k < nbins) s += cnt[first + k];
-        uint32_t run = block_exclusive_scan<NT>(s, warp_sums);
-        for (uint32_t k = 0; k < per; ++k) {
-            const uint32_t b = first + k;
-            if (b < nbins) {
-                const uint32_t c = cnt[b];
-                loc[b]           = run;
-                if (c) {
-                    const uint32_t old = atomicAdd(&cursor[b], c);
-                    gdelta[b]          = old - run;
-                    if constexpr (OPT) {
-                        const uint32_t lim = (b + 1u) * opt.opt_cap;
-                        if (old + c > lim) {   // part of this run does not fit the region any more
-                            const uint32_t from = max(old, lim);
-                            const uint32_t ovd  = atomicAdd(opt.ov_cursor, old + c - from);
-                            ovdelta[b]          = ovd - (from - (old - run));   // overflow index = ovdelta + i
-                        }
-                    }
-                }
-                run += c;
-                cnt[b] = 0;   // ready for the next tile
+        const uint32_t w = lane < (uint32_t)NW ? warp_sums[lane] : 0u;
+        uint32_t       wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFullMask, wi, d);
+            if (lane >= (uint32_t)d) wi += t;
+        }
+        wbase = __shfl_sync(kFullMask, wi - w, (int)wid);
+    }
+    // global position of stage slot i of partition b is gdelta[b] + i; a run that leaves its OPT region goes to
+    // the overflow array at ovdelta[b] + i
+    auto finalize = [&](uint32_t b, uint32_t cb, uint32_t oldv, uint32_t runv) {
+        gdelta[b] = oldv - runv;
+        if constexpr (OPT) {
+            const uint32_t lim = (b + 1u) * opt.opt_cap;
+            if (oldv + cb > lim) {   // part of this run does not fit the region any more
+                const uint32_t from = max(oldv, lim);
+                const uint32_t ovd  = atomicAdd(opt.ov_cursor, oldv + cb - from);
+                ovdelta[b]          = ovd - (from - (oldv - runv));
+                *s_over             = 1u;
             }
         }
+    };
+    const uint32_t run0 = wbase + incl - s;
+    uint32_t       run  = run0;
+    uint32_t       old[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {   // the first PER bins of the thread: reservation in flight across the staging
+        old[k] = 0;
+        if ((uint32_t)k < per && first + k < nbins) {
+            const uint32_t cb = cnt[first + k];
+            loc[first + k]    = run;
+            if (cb) old[k] = atomicAdd(&cursor[first + k], cb);
+            run += cb;
+        }
     }
-    __syncthreads();
+    for (uint32_t k = PER; k < per; ++k) {   // more than PER * NT partitions: the rest synchronously
+        const uint32_t b = first + k;
+        if (b < nbins) {
+            const uint32_t cb = cnt[b];
+            loc[b]            = run;
+            if (cb) finalize(b, cb, atomicAdd(&cursor[b], cb), run);
+            run += cb;
+            cnt[b] = 0;
+        }
+    }
+    __syncthreads();   // (C) local offsets visible
+    // ---- (3) tuples into shared memory in partition order ----
     [[maybe_unused]] uint32_t carry_lo = 0, carry_hi = 0;
 #pragma unroll
     for (int j = 0; j < U; ++j) {
@@ -357,10 +445,9 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U],
                 if constexpr (FULL) {
                     // registers j, j+1 hold two consecutive rows: one 128-bit load for both
                     if ((j & 1) == 0) {
-                        // (high halves are zero by contract; folded in so the load stays 128-bit, see load_tile_keys)
                         const ulonglong2 v = ld_stream_u64x2(opt.carry_col + base + li);
-                        carry_lo           = (uint32_t)v.x ^ (uint32_t)(v.x >> 32);
-                        carry_hi           = (uint32_t)v.y ^ (uint32_t)(v.y >> 32);
+                        carry_lo           = narrow_key<uint32_t>(v.x);
+                        carry_hi           = narrow_key<uint32_t>(v.y);
                     }
                     t.rid = (j & 1) ? carry_hi : carry_lo;
                 } else {
@@ -373,32 +460,50 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, KeyT (&keys)[U],
             stage[loc[(uint32_t)keys[j] & mask] + ((rank2[j >> 1] >> (16 * (j & 1))) & 0xFFFFu)] = t;
         }
     }
-    __syncthreads();
-    // keys[] and the ranks are dead: put the next tile's loads in flight before
-    // the copy-out so their latency hides behind the stores
+    // ---- (4) the reservations have arrived by now ----
+    run = run0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        if ((uint32_t)k < per && first + k < nbins) {
+            const uint32_t cb = cnt[first + k];
+            if (cb) finalize(first + k, cb, old[k], run);
+            run += cb;
+            cnt[first + k] = 0;   // ready for the next tile
+        }
+    }
+    __syncthreads();   // (D) stage, gdelta (and the overflow flag) visible
+    // keys and ranks are dead: put the next tile's loads in flight before the copy-out so that their latency hides
+    // behind the stores (they are narrowed at the top of the next tile, not here)
     if (has_next) {
-        load_tile_keys<NT, U, KeyT, true>(src, nbase, ncount, nvec, keys);
+        load_tile_raw<NT, U>(src, nbase, ncount, nvec, raw);
         if constexpr (CARRY) prefetch_carry_tile<NT, U>(opt.carry_col, nbase, ncount);
     }
-    auto put = [&](uint32_t i) {
-        const TupT     t   = stage[i];
-        const uint32_t b   = (uint32_t)t.key & mask;
-        const uint32_t pos = gdelta[b] + i;
+    // ---- (5) copy-out: a warp stores consecutive addresses inside each run ----
+    bool over = false;
+    if constexpr (OPT) over = *s_over != 0u;
+    if (!over) {
+        auto put = [&](uint32_t i) {
+            const TupT t = stage[i];
+            out[gdelta[(uint32_t)t.key & mask] + i] = t;
+        };
+        if constexpr (FULL) {
+#pragma unroll
+            for (int k = 0; k < U; ++k) put((uint32_t)(k * NT) + tid);
+        } else {
+            for (uint32_t i = tid; i < count; i += NT) put(i);
+        }
+    } else {
         if constexpr (OPT) {
-            if (pos >= (b + 1u) * opt.opt_cap) {
-                static_cast<TupT *>(opt.ov_out)[ovdelta[b] + i] = t;
-                return;
+            for (uint32_t i = tid; i < count; i += NT) {
+                const TupT     t   = stage[i];
+                const uint32_t b   = (uint32_t)t.key & mask;
+                const uint32_t pos = gdelta[b] + i;
+                if (pos >= (b + 1u) * opt.opt_cap) static_cast<TupT *>(opt.ov_out)[ovdelta[b] + i] = t;
+                else out[pos] = t;
             }
         }
-        out[pos] = t;
-    };
-    if constexpr (FULL) {
-#pragma unroll
-        for (int k = 0; k < U; ++k) put((uint32_t)(k * NT) + tid);
-    } else {
-        for (uint32_t i = tid; i < count; i += NT) put(i);
     }
-    __syncthreads();
+    __syncthreads();   // (E) stage and bin arrays free for the next tile
 }
 
 template <int NT, int U, int MINB, typename KeyT, bool OPT, bool CARRY = false>
@@ -416,6 +521,7 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
     uint32_t *gdelta  = loc + nbins;
     uint32_t *ovdelta = gdelta + nbins;   // OPT only (the launch reserves 4 bin arrays then)
     __shared__ uint32_t warp_sums[NT / 32 + 1];
+    __shared__ uint32_t s_over;
 
     // row ids are 32-bit: tile bases fit 32 bits as well
     const uint64_t n      = src.n;
@@ -425,12 +531,12 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
     const uint32_t per    = (nbins + NT - 1) / NT;
 
     for (uint32_t b = threadIdx.x; b < nbins; b += NT) cnt[b] = 0;
-    KeyT     keys[U];
+    uint64_t raw[U];
     uint64_t tile = blockIdx.x;
     if (tile < ntiles) {
         const uint64_t base  = tile * TILE;
         const uint32_t count = (uint32_t)min((uint64_t)TILE, n - base);
-        load_tile_keys<NT, U, KeyT, true>(src, base, count, vec_ok && count == TILE, keys);
+        load_tile_raw<NT, U>(src, base, count, vec_ok && count == TILE, raw);
         if constexpr (CARRY) prefetch_carry_tile<NT, U>(opt.carry_col, base, count);
     }
     __syncthreads();
@@ -445,13 +551,13 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
         const uint32_t ncount   = has_next ? (uint32_t)min((uint64_t)TILE, n - nbase) : 0u;
         const bool     nvec     = vec_ok && ncount == TILE;
         if (vec)
-            scatter_tile<NT, U, KeyT, true, OPT, CARRY>(src, keys, base, count, vec, nbase, ncount, nvec, has_next,
+            scatter_tile<NT, U, KeyT, true, OPT, CARRY>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
                                                         nbins, mask, per, stage, cnt, loc, gdelta, warp_sums, cursor,
-                                                        out, opt, ovdelta);
+                                                        out, opt, ovdelta, &s_over);
         else
-            scatter_tile<NT, U, KeyT, false, OPT, CARRY>(src, keys, base, count, vec, nbase, ncount, nvec, has_next,
+            scatter_tile<NT, U, KeyT, false, OPT, CARRY>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
                                                          nbins, mask, per, stage, cnt, loc, gdelta, warp_sums, cursor,
-                                                         out, opt, ovdelta);
+                                                         out, opt, ovdelta, &s_over);
     }
 }
 
