@@ -358,6 +358,70 @@ int   b200_stage_exchange_segments(const void *d_src_tup, int npay,
                                    int rewrite_rid, void *const *tup_dst,
                                    uint64_t *const *pay_dst);
 
+/* ---- multi-GPU plans behind the C ABI: no torch, no NCCL ---------------------
+ * The join of rhjoin.c:13-111 shards by radix bucket (rhjoin.c:42-57: one
+ * JoinJob per bucket pair, nothing shared between buckets).  One rank drives
+ * one GPU: a process per GPU (peers' memory through CUDA IPC: b200_multi_export
+ * / b200_multi_connect_ipc) or a host thread per GPU inside one process
+ * (b200_multi_connect_ptr, b200_join_sum_multi).  Ranks synchronise through
+ * epoch flags in each other's memory; a step enqueues device work only and may
+ * be captured in a CUDA graph ($B200_MULTI_GRAPH=1).
+ *   B200_PLAN_BROADCAST  small build side (config 2): every rank partitions its
+ *       build shard once into its region of a rank-major build buffer, its copy
+ *       engines push the region to every peer chunk by chunk, the probe shard
+ *       is partitioned locally and never moves, the join overlaps the tail of
+ *       the broadcast (it waits per partition for the chunks holding its runs).
+ *   B200_PLAN_EXCHANGE   radix-sharded all-to-all (config 4): both shards are
+ *       partitioned locally (the probe shard in chunks), the exchange kernel
+ *       stores every partition into its owner's receive buffer over NVLink (the
+ *       exchange of chunk c under the partition pass of chunk c + 1); owners are
+ *       contiguous partition ranges cut on the global histogram so that skewed
+ *       keys do not overload one GPU; every owner joins what it received.
+ * Query shape: join(build.key = probe.key) with SUM(build column) and / or
+ * SUM(probe column); keys and SUM values below 2^32 (they travel in 8-byte
+ * tuples).  Every rank must create its plan with the same totals / maxima. */
+#define B200_PLAN_BROADCAST 0
+#define B200_PLAN_EXCHANGE  1
+typedef struct b200_multi b200_multi;
+typedef struct {
+    int      plan, rank, world, device;
+    uint64_t n_build_total, n_probe_total;         /* rows over all ranks        */
+    uint64_t n_build_local, n_probe_local;         /* this rank's position shard */
+    uint64_t n_build_local_max, n_probe_local_max; /* largest shard of any rank  */
+    int      has_build_sum, has_probe_sum;
+    int      radix_bits;                           /* 0 = automatic              */
+    int      chunks;                               /* 0 = default (4 copy chunks / 8 probe chunks) */
+    uint64_t recv_rows_build, recv_rows_probe;     /* exchange: receive capacity per rank, 0 = mean + 1/8 */
+} b200_multi_config;
+b200_multi *b200_multi_create(const b200_multi_config *cfg);
+void  b200_multi_destroy(b200_multi *plan);
+int   b200_multi_export(b200_multi *plan, unsigned char *out_handle64);
+void *b200_multi_shared_ptr(b200_multi *plan);
+int   b200_multi_connect_ipc(b200_multi *plan, int peer, const unsigned char *handle64);
+int   b200_multi_connect_ptr(b200_multi *plan, int peer, void *peer_shared, int peer_device);
+int   b200_multi_radix_bits(b200_multi *plan);
+/* One step on the calling thread's stream, DEVICE pointers to this rank's
+ * shards.  phases: 0 = the whole step; otherwise a bit mask of the step's
+ * phases (broadcast: 1 partition + broadcast, 2 join + publish, 4 reduce;
+ * exchange: 1 histograms, 2 partition + exchange, 4 join + publish, 8 reduce)
+ * so that a test can drive several ranks on ONE GPU phase by phase — kernels
+ * that wait on one another must never share a GPU. */
+int   b200_multi_enqueue(b200_multi *plan, const uint64_t *d_build_keys, const uint64_t *d_build_sum,
+                         const uint64_t *d_probe_keys, const uint64_t *d_probe_sum, int phases);
+/* Synchronise; out_sums = {SUM(build column)?, SUM(probe column)?} over ALL
+ * ranks (the same on every rank).  Non-zero: a peer timed out, or the exchange
+ * receive buffers were too small for this input. */
+int   b200_multi_finish(b200_multi *plan, uint64_t *out_sums, uint64_t *out_matches);
+int   b200_multi_received(b200_multi *plan, uint64_t *out_rows_build_probe);
+/* One process, one host thread per GPU (devices 0 .. n_gpus-1), DEVICE-resident
+ * position shards [g]; `steps` > 0 additionally times that many steps and
+ * returns the slowest rank's milliseconds per step. */
+int   b200_join_sum_multi(int n_gpus, int plan_kind, const uint64_t *const *d_build_keys,
+                          const uint64_t *const *d_build_sum, const uint64_t *n_build,
+                          const uint64_t *const *d_probe_keys, const uint64_t *const *d_probe_sum,
+                          const uint64_t *n_probe, int steps, uint64_t *out_sums, uint64_t *out_matches,
+                          double *out_ms);
+
 /* Per-kernel device times of the calling thread's last RadixHashJoin /
  * b200_join_sum, measured with CUDA events on its stream when profiling is
  * enabled with b200_set_profiling(1).  Names: "hist_b", "hist_p", "scan",

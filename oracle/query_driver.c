@@ -22,7 +22,9 @@
  * by synthetic in-memory relations from include/b200_synth.h, or by relation
  * files read with fread.
  *
- * usage: driver [-t threads] [-r reps] REL... -- 'query' ['query' ...]
+ * usage: driver [-t threads] [-r reps] [-w warm] [-T seconds] REL... -- 'query' ['query' ...]
+ *   -T: time budget for the repetitions — stop once it is spent, but never before `warm` + 1 repetitions
+ *       (bench.py's reference arm: the whole run must end within minutes whatever --steps asks for)
  *   REL := file:<path>
  *        | synth:<rows>:<col>,<col>,...   col := perm<k>[@seed] | pay[@seed]
  *                                              | zipf<k>[@seed] | uni<mod>[@seed] | iota
@@ -135,10 +137,13 @@ static int load_relation(const char *spec, relation_map *rm, int rel_index) {
 }
 
 int main(int argc, char **argv) {
-    int threads = 4, reps = 1, a = 1;
+    int    threads = 4, reps = 1, warm = 0, a = 1;
+    double budget  = 0.0;
     while (a < argc && argv[a][0] == '-' && strcmp(argv[a], "--")) {
         if (!strcmp(argv[a], "-t") && a + 1 < argc) threads = atoi(argv[a + 1]);
         else if (!strcmp(argv[a], "-r") && a + 1 < argc) reps = atoi(argv[a + 1]);
+        else if (!strcmp(argv[a], "-w") && a + 1 < argc) warm = atoi(argv[a + 1]);
+        else if (!strcmp(argv[a], "-T") && a + 1 < argc) budget = atof(argv[a + 1]);
         else { fprintf(stderr, "unknown option %s\n", argv[a]); return 2; }
         a += 2;
     }
@@ -165,7 +170,9 @@ int main(int argc, char **argv) {
 #endif
 
     fprintf(stderr, "{\"threads\": %d, \"load_s\": %.3f, \"seconds\": [", threads, t_load);
+    const double t_first = now_s();
     for (int rep = 0; rep < reps; ++rep) {
+        if (budget > 0.0 && rep > warm && now_s() - t_first > budget) break;
         batch_listnode *batch = NULL;
         for (int q = 0; q < nquery; ++q) {
             char buff[250];

@@ -6,7 +6,7 @@
 set -u
 T=${1:-r2}
 mkdir -p gpurun_out
-(timeout 400 python -m pytest tests -m gpu -q -x > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest.log)
+(timeout 500 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest.log)
 tail -4 gpurun_out/${T}_pytest.log
 timeout 60 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 show() { python - "$1" <<'PY'

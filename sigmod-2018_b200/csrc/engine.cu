@@ -1216,19 +1216,36 @@ void stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, 
 
 // partition the local build shard straight into a caller-owned region (rank-major layout): tuples, and either
 // up to two payload columns (pay_out) or one 32-bit payload carried in the row-id slot (npay == 1, pay_out == NULL)
+size_t stage_scratch_bytes(int bits, int nseg) {
+    const size_t nparts = (size_t)1 << bits;
+    return (64 + 6 * (nparts + 1)) * sizeof(uint32_t) + 64 * sizeof(unsigned long long) +
+           ((size_t)nseg + 1) * nparts * sizeof(uint32_t) + 256;
+}
+
 void stage_scatter_build_local(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int bits,
                                const uint32_t *d_hist_local, void *d_tup_out, int npay, const uint64_t *const *pay_cols,
-                               uint64_t *const *pay_out) {
+                               uint64_t *const *pay_out, const StageScratch *scr, uint32_t *d_off_out) {
     B200_REQUIRE(npay >= 0 && npay <= 2, "bad payload count");
-    if (n == 0) return;
+    if (n == 0 && !d_off_out) return;
     Context       &c      = ctx();
     const uint32_t nparts = 1u << bits;
-    DevBufPtr ctrl = dev_alloc(5 * (size_t)(nparts + 1) * sizeof(uint32_t));
-    uint32_t *off_l = ctrl->as<uint32_t>(), *off_x = off_l + nparts + 1, *cur_l = off_x + nparts + 1,
+    DevBufPtr ctrl;
+    uint32_t *off_l;
+    if (scr) {
+        B200_REQUIRE(scr->bytes >= 5 * (size_t)(nparts + 1) * sizeof(uint32_t), "stage scratch too small");
+        off_l = static_cast<uint32_t *>(scr->ptr);
+    } else {
+        ctrl  = dev_alloc(5 * (size_t)(nparts + 1) * sizeof(uint32_t));
+        off_l = ctrl->as<uint32_t>();
+    }
+    if (d_off_out) off_l = d_off_out;   // the caller keeps the local offsets [nparts + 1] (exchange plan)
+    uint32_t *base5 = scr ? static_cast<uint32_t *>(scr->ptr) : ctrl->as<uint32_t>();
+    uint32_t *off_x = base5 + nparts + 1, *cur_l = off_x + nparts + 1,
              *cur_x = cur_l + nparts + 1, *items = cur_x + nparts + 1;
     partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_local, d_hist_local, nparts, 1u, 1u, off_l, off_x,
                                                           cur_l, cur_x, items, items, 0u);
     B200_LAUNCH_CHECK();
+    if (n == 0) return;
     PayArgs pay{};
     pay.rid_base = rid_base;
     const bool carry = npay == 1 && pay_out == nullptr;
@@ -1335,7 +1352,8 @@ void stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint3
 // part_vals arrays) starts at r * seg_rows and holds rank r's shard in partition order.
 JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p, const uint32_t *d_hist_p,
                           int bits, int nproj, const ProjDesc *proj, uint32_t opt_cap, const void *d_ov,
-                          const uint32_t *d_ovcnt, unsigned long long *d_result, int nseg, uint32_t seg_rows) {
+                          const uint32_t *d_ovcnt, unsigned long long *d_result, int nseg, uint32_t seg_rows,
+                          const StageScratch *scr, const JoinWait *wait) {
     Context   &c = ctx();
     Tuning    &t = tuning();
     JoinResult res;
@@ -1349,9 +1367,19 @@ JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const v
     a.radix_bits = (uint32_t)bits;
     a.slice      = t.slice;
     B200_REQUIRE(bits + (int)a.slots_log2 >= 17, "radix bits too small for the tag table");
-    DevBufPtr ctrl = dev_alloc((64 + 6 * (size_t)(nparts + 1)) * sizeof(uint32_t) + 64 * sizeof(unsigned long long));
-    B200_CUDA(cudaMemsetAsync(ctrl->ptr, 0, ctrl->bytes, c.stream));
-    unsigned long long *d_u64 = ctrl->as<unsigned long long>();
+    const size_t ctrl_bytes = (64 + 6 * (size_t)(nparts + 1)) * sizeof(uint32_t) + 64 * sizeof(unsigned long long);
+    DevBufPtr    ctrl;
+    void        *ctrl_ptr;
+    if (scr) {   // caller-owned control memory: nothing is allocated here (the step can be captured in a CUDA graph)
+        B200_REQUIRE(scr->bytes >= stage_scratch_bytes(bits, nseg), "stage scratch too small");
+        B200_REQUIRE(d_result != nullptr, "a stage with caller-owned scratch is asynchronous");
+        ctrl_ptr = scr->ptr;
+    } else {
+        ctrl     = dev_alloc(ctrl_bytes);
+        ctrl_ptr = ctrl->ptr;
+    }
+    B200_CUDA(cudaMemsetAsync(ctrl_ptr, 0, ctrl_bytes, c.stream));
+    unsigned long long *d_u64 = static_cast<unsigned long long *>(ctrl_ptr);
     uint32_t           *d_u32 = reinterpret_cast<uint32_t *>(d_u64 + 64);
     uint32_t *off_b = d_u32 + 64, *off_p = off_b + nparts + 1, *cur_b = off_p + nparts + 1,
              *cur_p = cur_b + nparts + 1, *items = cur_p + nparts + 1, *cnt_p = items + nparts + 1;
@@ -1362,15 +1390,28 @@ JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const v
     DevBufPtr seg;
     if (nseg > 0) {
         B200_REQUIRE(nseg <= kMaxPeers, "at most 8 build segments");
-        seg                = dev_alloc(((size_t)nseg + 1) * nparts * sizeof(uint32_t));
-        uint32_t *seg_off  = seg->as<uint32_t>(), *total = seg_off + (size_t)nseg * nparts;
+        uint32_t *seg_off;
+        if (scr) {
+            seg_off = reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(ctrl_ptr) + ((ctrl_bytes + 255) & ~(size_t)255));
+        } else {
+            seg     = dev_alloc(((size_t)nseg + 1) * nparts * sizeof(uint32_t));
+            seg_off = seg->as<uint32_t>();
+        }
+        uint32_t *total = seg_off + (size_t)nseg * nparts;
         segment_offsets_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_b, (uint32_t)nseg, nparts, seg_rows, seg_off,
                                                                 total);
         B200_LAUNCH_CHECK();
         a.nseg    = nseg;
         a.seg_off = seg_off;
         a.seg_cnt = d_hist_b;
+        a.seg_rows = seg_rows;
         d_hist_b  = total;   // the plan works on the global histogram (virtual concatenation of the runs)
+        if (wait) {
+            a.wait_flags = wait->flags;
+            a.wait_epoch = wait->epoch;
+            a.chunk_rows = wait->chunk_rows;
+            a.wait_error = wait->error;
+        }
     }
     {
         TimedScope ts("scan");

@@ -105,13 +105,28 @@ int        auto_radix_bits(uint64_t n_build, bool key64);
 void       stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint32_t opt_cap, uint32_t *d_cursor,
                                    void *d_tup_out, void *d_ov, uint32_t *d_ovcnt,
                                    const uint64_t *carry_col = nullptr);
+// caller-owned control memory for the stages of a step that must not allocate (CUDA-graph capture; multi.cu)
+struct StageScratch {
+    void  *ptr   = nullptr;
+    size_t bytes = 0;
+};
+size_t stage_scratch_bytes(int bits, int nseg);
+// the segmented join may start while the peers' broadcast is still in flight (kernels.cuh JoinArgs::wait_flags)
+struct JoinWait {
+    const uint32_t *flags, *epoch;
+    uint32_t        chunk_rows;
+    uint32_t       *error;
+};
 JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p,
                           const uint32_t *d_hist_p, int bits, int nproj, const ProjDesc *proj, uint32_t opt_cap,
                           const void *d_ov, const uint32_t *d_ovcnt, unsigned long long *d_result = nullptr,
-                          int nseg = 0, uint32_t seg_rows = 0);
+                          int nseg = 0, uint32_t seg_rows = 0, const StageScratch *scr = nullptr,
+                          const JoinWait *wait = nullptr);
+// d_off_out (optional): receives the local partition offsets [2^bits + 1]
 void       stage_scatter_build_local(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int bits,
                                      const uint32_t *d_hist_local, void *d_tup_out, int npay,
-                                     const uint64_t *const *pay_cols, uint64_t *const *pay_out);
+                                     const uint64_t *const *pay_cols, uint64_t *const *pay_out,
+                                     const StageScratch *scr = nullptr, uint32_t *d_off_out = nullptr);
 void       stage_build_cursors(const uint32_t *d_hist_all, int world, int rank, int bits, uint32_t *d_total,
                                uint32_t *d_my_start);
 void       stage_exchange_cursors(const uint32_t *d_hist_all, int world, int rank, int bits, uint32_t cap,

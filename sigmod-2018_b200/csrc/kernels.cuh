@@ -732,7 +732,7 @@ struct SegCopyArgs {
     uint64_t       *dst_tup[kMaxPeers];
     uint64_t       *dst_pay[2][kMaxPeers];
 };
-__global__ void __launch_bounds__(256) segment_broadcast_kernel(const SegCopyArgs s) {
+static __global__ void __launch_bounds__(256) segment_broadcast_kernel(const SegCopyArgs s) {
     const uint32_t p     = blockIdx.x;
     const uint32_t first = s.src_off[p];
     const uint32_t count = s.src_off[p + 1] - first;
@@ -806,6 +806,13 @@ struct JoinArgs {
     // describes the VIRTUAL concatenation of the runs (tag_join_kernel<SEG = true>)
     int             nseg;
     const uint32_t *seg_off, *seg_cnt;
+    // multi-GPU broadcast in flight (SEG only, wait_flags != nullptr): run r of a partition may be read once
+    // wait_flags[c * kMaxPeers + r] >= *wait_epoch, c = the chunk of region r (chunk_rows rows each, seg_rows rows
+    // per region) that holds the run's last tuple — the flags are written by rank r's copy engine behind each
+    // chunk of its broadcast, so the join of the first partitions overlaps the rest of the transfer
+    const uint32_t *wait_flags, *wait_epoch;
+    uint32_t        chunk_rows, seg_rows;
+    uint32_t       *wait_error;       // set to 1 when a flag did not arrive within the spin budget
     int             nproj;            // SUM
     int             need_brid;        // SUM: some build-side projection is gathered through the row id
     ProjDesc        proj[kMaxProj];
@@ -1190,6 +1197,23 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t saddr) {
     return v;
 }
 
+// flag written by a peer GPU (copy engine or remote store) into this GPU's memory
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *flag >= epoch; bounded (about 2 s) so that a lost peer cannot hang the GPU: returns false on time-out
+__device__ __forceinline__ bool spin_until_epoch(const uint32_t *flag, uint32_t epoch) {
+    if (ld_acquire_sys_u32(flag) >= epoch) return true;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u32(flag) < epoch) {
+        __nanosleep(200);
+        if (clock64() - t0 > 4000000000ll) return false;
+    }
+    return true;
+}
+
 // work item of the join kernels: (build chunk, probe slice)
 struct JoinItem {
     uint32_t valid, b_start, b_count, p_start, p_count, w, part;
@@ -1318,7 +1342,7 @@ tag_join_kernel(const JoinArgs a) {
     auto handle_inline = [&](uint32_t pos, uint32_t prid) {
         ++my_matches;
         if constexpr (MODE != MODE_COUNT) {
-            const uint32_t brid = tup_b[bphys(b_start + pos)].rid;
+            const uint32_t brid = SEG ? __ldcg(&tup_b[bphys(b_start + pos)].rid) : tup_b[bphys(b_start + pos)].rid;
             if constexpr (MODE == MODE_SUM) {
 #pragma unroll
                 for (int k = 0; k < NPA; ++k) {
@@ -1354,7 +1378,7 @@ tag_join_kernel(const JoinArgs a) {
         if constexpr (MODE == MODE_SUM) {
             const uint32_t bpos = bphys(b_start + (e.x & kIdxMask));
             uint32_t       brid = 0;
-            if (is_match && a.need_brid) brid = tup_b[bpos].rid;
+            if (is_match && a.need_brid) brid = SEG ? __ldcg(&tup_b[bpos].rid) : tup_b[bpos].rid;
 #pragma unroll
             for (int k = 0; k < NPA; ++k) {
                 my_sum[k] += pend[k];
@@ -1420,8 +1444,14 @@ tag_join_kernel(const JoinArgs a) {
                     }
                     if ((int)lane < a.nseg) {
                         const uint32_t vstart = a.off_b[it.part] + inc - cnt;
+                        const uint32_t phys   = a.seg_off[lane * a.nparts + it.part];
                         s_seg_vend[lane]      = a.off_b[it.part] + inc;
-                        s_seg_delta[lane]     = a.seg_off[lane * a.nparts + it.part] - vstart;
+                        s_seg_delta[lane]     = phys - vstart;
+                        if (a.wait_flags != nullptr && cnt != 0u) {
+                            const uint32_t chunk = (phys + cnt - 1u - lane * a.seg_rows) / a.chunk_rows;
+                            if (!spin_until_epoch(a.wait_flags + chunk * kMaxPeers + lane, *a.wait_epoch))
+                                *a.wait_error = 1u;
+                        }
                     }
                 }
             }
@@ -1473,7 +1503,11 @@ tag_join_kernel(const JoinArgs a) {
 #pragma unroll
             for (int u = 0; u < KB; ++u) {
                 const uint32_t i = i0 + (uint32_t)u * NT;
-                bk[u]            = i < b_count ? ld_stream_u32(&tup_b[bphys(b_start + i)].key) : 0u;
+                // (SEG: the tuples were written by peer GPUs while this kernel may already be running — read them
+                // at L2, the point of coherence, not through the non-coherent path)
+                bk[u] = i < b_count ? (SEG ? __ldcg(&tup_b[bphys(b_start + i)].key)
+                                           : ld_stream_u32(&tup_b[bphys(b_start + i)].key))
+                                    : 0u;
             }
 #pragma unroll
             for (int u = 0; u < KB; ++u) {
@@ -1686,7 +1720,7 @@ struct GatherArgs {
     uint32_t       *out[kMaxGather];
 };
 
-__global__ void __launch_bounds__(256) gather_columns_kernel(const GatherArgs g) {
+static __global__ void __launch_bounds__(256) gather_columns_kernel(const GatherArgs g) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < g.m; i += stride) {
         const uint32_t p = ld_stream_u32(g.pos + i);
@@ -1697,7 +1731,7 @@ __global__ void __launch_bounds__(256) gather_columns_kernel(const GatherArgs g)
 }
 
 // CartesianInterResults (inter_res.c:405-418): row index = i * n2 + j.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 cartesian_kernel(const uint32_t *__restrict__ in, uint32_t n1, uint32_t n2, int from_first,
                  uint32_t *__restrict__ out) {
     const uint64_t total  = (uint64_t)n1 * n2;
@@ -1719,7 +1753,7 @@ struct ChecksumArgs {
     unsigned long long *sums;
 };
 
-__global__ void __launch_bounds__(256) checksum_kernel(const ChecksumArgs c) {
+static __global__ void __launch_bounds__(256) checksum_kernel(const ChecksumArgs c) {
     unsigned long long acc[kMaxProj];
 #pragma unroll
     for (int k = 0; k < kMaxProj; ++k) acc[k] = 0;
@@ -1743,7 +1777,7 @@ __global__ void __launch_bounds__(256) checksum_kernel(const ChecksumArgs c) {
 }
 
 // Column maximum at registration (selects the 32-bit-key kernels).
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 column_max_kernel(const uint64_t *__restrict__ col, uint64_t n, unsigned long long *__restrict__ out) {
     unsigned long long m      = 0;
     const uint64_t     stride = (uint64_t)gridDim.x * blockDim.x;
@@ -1928,7 +1962,7 @@ struct ExchangeArgs {
     uint64_t       *dst_tup[kMaxPeers];
     uint64_t       *dst_pay[2][kMaxPeers];
 };
-__global__ void __launch_bounds__(256) segment_exchange_kernel(const ExchangeArgs x) {
+static __global__ void __launch_bounds__(256) segment_exchange_kernel(const ExchangeArgs x) {
     constexpr int  UN     = 4;
     const uint32_t nparts = 1u << x.radix_bits;
     const uint32_t base   = blockIdx.x * (256u * UN);
@@ -1957,14 +1991,14 @@ __global__ void __launch_bounds__(256) segment_exchange_kernel(const ExchangeArg
 }
 
 // cursors of the histogram-free probe-side scatter: partition p starts at p * opt_cap
-__global__ void init_opt_cursors_kernel(uint32_t *__restrict__ cursor, uint32_t nparts, uint32_t opt_cap) {
+static __global__ void init_opt_cursors_kernel(uint32_t *__restrict__ cursor, uint32_t nparts, uint32_t opt_cap) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < nparts) cursor[b] = b * opt_cap;
 }
 
 // Synthetic columns of BASELINE.json's configs, generated in HBM
 // (include/b200_synth.h is the single definition shared with the CPU side).
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 synth_column_kernel(uint64_t *__restrict__ out, uint64_t first, uint64_t n, int kind, uint64_t k, uint64_t seed) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
@@ -1972,11 +2006,11 @@ synth_column_kernel(uint64_t *__restrict__ out, uint64_t first, uint64_t n, int 
 }
 
 // Widening copies for the read-back entry points (tests only).
-__global__ void widen_u32_kernel(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
+static __global__ void widen_u32_kernel(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i];
 }
-__global__ void narrow_u64_kernel(const uint64_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ out) {
+static __global__ void narrow_u64_kernel(const uint64_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         out[i] = (uint32_t)in[i];

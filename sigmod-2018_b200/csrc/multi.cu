@@ -1,0 +1,702 @@
+// multi.cu — the join over the GPUs of one box, behind the C ABI (include/b200_join.h, "multi-GPU plans").
+//
+// The reference is one process with pthreads (scheduler.c); its join shards by bucket (rhjoin.c:42-57: one
+// JoinJob per bucket pair, nothing shared between buckets).  One rank drives one GPU — a process per GPU
+// (bench.py under torchrun: peers' memory through CUDA IPC) or a host thread per GPU inside one process
+// (host/b200_engine -g N, b200_join_sum_multi: cudaDeviceEnablePeerAccess).  No torch, no NCCL: ranks
+// synchronise through epoch flags in each other's memory (multi_kernels.cuh), data moves with copy engines or
+// with stores from the exchange kernel over NVLink, and the k + 1 result words are summed by every rank from
+// slots its peers wrote.  A step enqueues device work only (no allocation, no host round trip), so it can be
+// captured in a CUDA graph; b200_multi_finish is the one synchronisation.
+//
+// Plans:
+//   broadcast  small build side (config 2): every rank partitions its build shard ONCE into region `rank` of
+//              its build buffer (rank-major layout) and its copy engines push that region, chunk by chunk with
+//              a flag behind each chunk, into the same region of every peer; the probe shard is partitioned
+//              locally meanwhile and never moves; the join reads a partition as `world` runs and waits, per
+//              partition, only for the chunks that hold its runs — it overlaps the tail of the broadcast.
+//   exchange   radix-sharded all-to-all (config 4): both shards are partitioned locally (the probe shard in
+//              chunks), every partition is stored into the receive buffer of its owner by the exchange kernel
+//              (the exchange of chunk c runs under the partition pass of chunk c + 1), owners are contiguous
+//              partition ranges cut on the global histogram so that skew does not overload one GPU, and every
+//              owner joins what it received.
+#include "../../include/b200_join.h"
+#include "engine.cuh"
+#include "multi_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace b200 {
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Carver {   // carve one allocation into aligned pieces
+    unsigned char *base;
+    size_t         off = 0;
+    explicit Carver(void *p) : base(static_cast<unsigned char *>(p)) {}
+    template <typename T> T *take(size_t count) {
+        off      = align_up(off, 256);
+        T *p     = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+// run the stages of engine.cu on another stream of the calling thread's context
+struct StreamSwap {
+    Context     &c;
+    cudaStream_t saved;
+    StreamSwap(Context &ctx_, cudaStream_t s) : c(ctx_), saved(ctx_.stream) { c.stream = s; }
+    ~StreamSwap() { c.stream = saved; }
+};
+
+}  // namespace
+
+struct MultiPlan {
+    b200_multi_config cfg{};
+    int      rank = 0, world = 1, device = 0;
+    int      bits = 0, K = 1;
+    uint32_t P = 1, seg_rows = 0, chunk_rows = 0, opt_cap = 0, cap_b = 0, cap_p = 0;
+    int      nproj = 0;
+    // shared region (identical layout on every rank)
+    unsigned char *shared = nullptr;
+    size_t         shared_bytes = 0, off_hist_b = 0, off_hist_p = 0, off_build = 0, off_recv_p = 0;
+    unsigned char *peer[kMaxPeers] = {nullptr};
+    bool           peer_ipc[kMaxPeers] = {false};
+    // local device memory (one allocation)
+    unsigned char *local = nullptr;
+    uint32_t      *d_epoch = nullptr, *d_error = nullptr, *cur_p = nullptr, *ovcnt = nullptr;
+    unsigned long long *d_result = nullptr, *d_final = nullptr;
+    void          *tup_p = nullptr, *ov_p = nullptr, *stage_b = nullptr, *stage_p = nullptr;
+    uint32_t      *src_off_b = nullptr, *src_off_p = nullptr, *dst_start_b = nullptr, *dst_start_p = nullptr;
+    uint32_t      *own_total = nullptr, *total = nullptr, *cut = nullptr, *need = nullptr;
+    StageScratch   scr_a, scr_b;
+    unsigned long long *h_final = nullptr;   // pinned
+    cudaStream_t   copy_stream[kMaxPeers] = {nullptr}, xstream = nullptr;
+    cudaEvent_t    ev_build = nullptr, ev_copy[kMaxPeers] = {nullptr}, ev_chunk[kMaxChunks] = {nullptr}, ev_x = nullptr,
+                   ev_hist = nullptr;
+    // inputs of the step in flight (the overflow pass of finish() needs them)
+    const uint64_t *in_bk = nullptr, *in_bp = nullptr, *in_pk = nullptr, *in_pp = nullptr;
+    bool            pending = false;
+    // CUDA graph of the step (B200_MULTI_GRAPH=1): valid while the input pointers stay the same
+    cudaGraphExec_t graph = nullptr;
+    const uint64_t *g_in[4] = {nullptr, nullptr, nullptr, nullptr};
+    int             use_graph = 0;
+
+    SharedHeader *hdr(int r) const { return reinterpret_cast<SharedHeader *>(peer[r]); }
+    uint32_t     *hist_b(int r) const { return reinterpret_cast<uint32_t *>(peer[r] + off_hist_b); }
+    uint32_t     *hist_p(int r) const { return reinterpret_cast<uint32_t *>(peer[r] + off_hist_p); }
+    unsigned char *build(int r) const { return peer[r] + off_build; }
+    unsigned char *recv_p(int r) const { return peer[r] + off_recv_p; }
+    PeerPtrs peers() const {
+        PeerPtrs p{};
+        for (int r = 0; r < world; ++r) p.hdr[r] = hdr(r);
+        return p;
+    }
+};
+
+// broadcast: header | hist_b[world][P] | build[world][seg_rows]
+// exchange:  header | hist_b[world][P] | hist_p[world * K][P] | recv_b[cap_b] | recv_p[cap_p]   (build() = recv_b)
+static void layout_shared(MultiPlan &m) {
+    m.off_hist_b = align_up(sizeof(SharedHeader), 256);
+    if (m.cfg.plan == B200_PLAN_BROADCAST) {
+        m.off_hist_p   = m.off_hist_b;
+        m.off_build    = align_up(m.off_hist_b + (size_t)m.world * m.P * 4, 256);
+        m.off_recv_p   = m.off_build;
+        m.shared_bytes = align_up(m.off_build + ((size_t)m.world * m.seg_rows + 16) * 8, 256);
+    } else {
+        m.off_hist_p   = align_up(m.off_hist_b + (size_t)m.world * m.P * 4, 256);
+        m.off_build    = align_up(m.off_hist_p + (size_t)m.world * m.K * m.P * 4, 256);
+        m.off_recv_p   = align_up(m.off_build + ((size_t)m.cap_b + 16) * 8, 256);
+        m.shared_bytes = align_up(m.off_recv_p + ((size_t)m.cap_p + 16) * 8, 256);
+    }
+}
+
+static void layout_local(MultiPlan &m, void *base, size_t *bytes) {
+    Carver c(base);
+    const size_t P = m.P, np = m.cfg.n_probe_local, nb = m.cfg.n_build_local;
+    m.d_epoch  = c.take<uint32_t>(4);
+    m.d_error  = c.take<uint32_t>(4);
+    m.ovcnt    = c.take<uint32_t>(4);
+    m.d_result = c.take<unsigned long long>(8);
+    m.d_final  = c.take<unsigned long long>(8);
+    m.cur_p    = c.take<uint32_t>(P + 1);
+    const size_t sb = stage_scratch_bytes(m.bits, m.world);
+    m.scr_a = StageScratch{c.take<unsigned char>(sb), sb};
+    m.scr_b = StageScratch{c.take<unsigned char>(sb), sb};
+    if (m.cfg.plan == B200_PLAN_BROADCAST) {
+        m.tup_p = c.take<uint64_t>(std::max<size_t>(m.opt_cap ? (size_t)m.opt_cap * P : np, 1));
+        m.ov_p  = c.take<uint64_t>(std::max<size_t>(m.opt_cap ? np : 1, 1));
+    } else {
+        m.stage_b     = c.take<uint64_t>(std::max<size_t>(nb, 1));
+        m.stage_p     = c.take<uint64_t>(std::max<size_t>(np, 1));
+        m.src_off_b   = c.take<uint32_t>(P + 1);
+        m.src_off_p   = c.take<uint32_t>((size_t)m.K * (P + 1));
+        m.dst_start_b = c.take<uint32_t>(P);
+        m.dst_start_p = c.take<uint32_t>((size_t)m.K * P);
+        m.own_total   = c.take<uint32_t>(2 * P);
+        m.total       = c.take<uint32_t>(2 * P);
+        m.cut         = c.take<uint32_t>(kMaxPeers + 1);
+        m.need        = c.take<uint32_t>(4);
+    }
+    *bytes = align_up(c.off, 256);
+}
+
+static uint32_t chunk_first(const MultiPlan &m, uint64_t n, int c) { return (uint32_t)(n * (uint64_t)c / (uint64_t)m.K); }
+
+// ---------------------------------------------------------------------------
+// steps
+// ---------------------------------------------------------------------------
+static void enqueue_broadcast(MultiPlan &m, int phases) {
+    Context     &c    = ctx();
+    cudaStream_t main = c.stream;
+    const int    rank = m.rank, world = m.world;
+    const uint32_t P  = m.P;
+    const uint64_t nb = m.cfg.n_build_local, np = m.cfg.n_probe_local;
+    if (phases & 1) {
+        bump_epoch_kernel<<<1, 1, 0, main>>>(m.d_epoch);
+        B200_LAUNCH_CHECK();
+        B200_CUDA(cudaMemsetAsync(m.d_error, 0, 16, main));
+        B200_CUDA(cudaMemsetAsync(m.d_result, 0, 64, main));
+        // ---- build shard: histogram, ONE local partition pass into region `rank` of my build buffer ----
+        uint32_t      *my_hist   = m.hist_b(rank) + (size_t)rank * P;
+        unsigned char *my_region = m.build(rank) + (size_t)rank * m.seg_rows * 8;
+        stage_hist(m.in_bk, nb, m.bits, my_hist);
+        const uint64_t *pay_cols[1] = {m.in_bp};
+        stage_scatter_build_local(m.in_bk, nb, (uint32_t)((uint64_t)rank * m.seg_rows), m.bits, my_hist, my_region,
+                                  m.cfg.has_build_sum ? 1 : 0, pay_cols, nullptr, &m.scr_a);
+        B200_CUDA(cudaEventRecord(m.ev_build, main));
+        // ---- broadcast on the copy engines: per peer (every rank starts at a different one) the histogram, then the
+        //      region in K chunks, a 4-byte flag behind each; the join of the first partitions runs under the rest ----
+        for (int j = 1; j < world; ++j) {
+            const int    d = (rank + j) % world;
+            cudaStream_t s = m.copy_stream[j - 1];
+            B200_CUDA(cudaStreamWaitEvent(s, m.ev_build, 0));
+            B200_CUDA(cudaMemcpyAsync(m.hist_b(d) + (size_t)rank * P, my_hist, (size_t)P * 4, cudaMemcpyDeviceToDevice, s));
+            B200_CUDA(cudaMemcpyAsync(&m.hdr(d)->sig[SIG_HIST][rank], m.d_epoch, 4, cudaMemcpyDeviceToDevice, s));
+            for (int k = 0; k < m.K; ++k) {
+                const uint64_t first = (uint64_t)k * m.chunk_rows;
+                const uint64_t rows  = first < nb ? std::min<uint64_t>(m.chunk_rows, nb - first) : 0;
+                if (rows)
+                    B200_CUDA(cudaMemcpyAsync(m.build(d) + ((size_t)rank * m.seg_rows + first) * 8, my_region + first * 8,
+                                              rows * 8, cudaMemcpyDeviceToDevice, s));
+                B200_CUDA(cudaMemcpyAsync(&m.hdr(d)->sig[SIG_CHUNK0 + k][rank], m.d_epoch, 4, cudaMemcpyDeviceToDevice, s));
+            }
+            B200_CUDA(cudaEventRecord(m.ev_copy[j - 1], s));
+        }
+        // my own region needs no copy: raise my own flags
+        {
+            PeerPtrs self{};
+            self.hdr[0] = m.hdr(rank);
+            signal_peers_kernel<<<1, 32, 0, main>>>(self, 1, rank, SIG_HIST, m.d_epoch);
+            B200_LAUNCH_CHECK();
+            for (int k = 0; k < m.K; ++k) {
+                signal_peers_kernel<<<1, 32, 0, main>>>(self, 1, rank, SIG_CHUNK0 + k, m.d_epoch);
+                B200_LAUNCH_CHECK();
+            }
+        }
+        // ---- probe shard: partitioned locally (histogram-free regions + overflow), never moves ----
+        if (m.opt_cap) {
+            stage_scatter_probe_opt(m.in_pk, np, m.bits, m.opt_cap, m.cur_p, m.tup_p, m.ov_p, m.ovcnt,
+                                    m.cfg.has_probe_sum ? m.in_pp : nullptr);
+        } else {
+            // small shards: exact histogram + the payload-aware scatter
+            stage_hist(m.in_pk, np, m.bits, m.cur_p);
+            const uint64_t *pp[1] = {m.in_pp};
+            stage_scatter_build_local(m.in_pk, np, 0, m.bits, m.cur_p, m.tup_p, m.cfg.has_probe_sum ? 1 : 0, pp, nullptr,
+                                      &m.scr_b);
+            B200_CUDA(cudaMemsetAsync(m.ovcnt, 0, 4, main));
+        }
+    }
+    if (phases & 2) {
+        wait_peers_kernel<<<1, 32, 0, main>>>(m.hdr(rank)->sig[SIG_HIST], world, m.d_epoch, m.d_error);
+        B200_LAUNCH_CHECK();
+        ProjDesc pd[2];
+        int      k = 0;
+        if (m.cfg.has_build_sum) pd[k++] = ProjDesc{m.in_bp, nullptr, 0, B200_PROJ_IN_RID};
+        if (m.cfg.has_probe_sum) pd[k++] = ProjDesc{m.in_pp, nullptr, 1, B200_PROJ_IN_RID};
+        JoinWait w{&m.hdr(rank)->sig[SIG_CHUNK0][0], m.d_epoch, m.chunk_rows, m.d_error};
+        stage_join_sum(m.build(rank), m.hist_b(rank), m.tup_p, m.cur_p, m.bits, k, pd, m.opt_cap, m.ov_p, m.ovcnt,
+                       m.d_result, world, m.seg_rows, &m.scr_b, &w);
+        push_result_kernel<<<1, 32, 0, main>>>(m.peers(), world, rank, m.d_result, m.d_error, m.d_epoch);
+        B200_LAUNCH_CHECK();
+        // the next step must not overwrite my region (or histogram) under copies still in flight
+        for (int j = 1; j < world; ++j) B200_CUDA(cudaStreamWaitEvent(main, m.ev_copy[j - 1], 0));
+    }
+    if (phases & 4) {
+        wait_peers_kernel<<<1, 32, 0, main>>>(m.hdr(rank)->sig[SIG_RESULT], world, m.d_epoch, m.d_error);
+        B200_LAUNCH_CHECK();
+        reduce_result_kernel<<<1, 32, 0, main>>>(m.hdr(rank), world, m.d_final);
+        B200_LAUNCH_CHECK();
+        B200_CUDA(cudaMemcpyAsync(m.h_final, m.d_final, 64, cudaMemcpyDeviceToHost, main));
+    }
+}
+
+static void enqueue_exchange(MultiPlan &m, int phases) {
+    Context     &c    = ctx();
+    cudaStream_t main = c.stream;
+    const int    rank = m.rank, world = m.world, K = m.K;
+    const uint32_t P  = m.P;
+    const uint64_t nb = m.cfg.n_build_local, np = m.cfg.n_probe_local;
+    uint32_t *my_hb = m.hist_b(rank) + (size_t)rank * P;
+    uint32_t *my_hp = m.hist_p(rank) + (size_t)rank * K * P;
+    if (phases & 1) {
+        bump_epoch_kernel<<<1, 1, 0, main>>>(m.d_epoch);
+        B200_LAUNCH_CHECK();
+        B200_CUDA(cudaMemsetAsync(m.d_error, 0, 16, main));
+        B200_CUDA(cudaMemsetAsync(m.d_result, 0, 64, main));
+        // ---- histograms of both local shards (the probe shard per chunk), published to every rank ----
+        stage_hist(m.in_bk, nb, m.bits, my_hb);
+        for (int k = 0; k < K; ++k) {
+            const uint32_t a = chunk_first(m, np, k), b = chunk_first(m, np, k + 1);
+            stage_hist(m.in_pk + a, b - a, m.bits, my_hp + (size_t)k * P);
+        }
+        B200_CUDA(cudaEventRecord(m.ev_hist, main));
+        for (int j = 1; j < world; ++j) {
+            const int    d = (rank + j) % world;
+            cudaStream_t s = m.copy_stream[j - 1];
+            B200_CUDA(cudaStreamWaitEvent(s, m.ev_hist, 0));
+            B200_CUDA(cudaMemcpyAsync(m.hist_b(d) + (size_t)rank * P, my_hb, (size_t)P * 4, cudaMemcpyDeviceToDevice, s));
+            B200_CUDA(cudaMemcpyAsync(m.hist_p(d) + (size_t)rank * K * P, my_hp, (size_t)K * P * 4,
+                                      cudaMemcpyDeviceToDevice, s));
+            B200_CUDA(cudaMemcpyAsync(&m.hdr(d)->sig[SIG_HIST][rank], m.d_epoch, 4, cudaMemcpyDeviceToDevice, s));
+            B200_CUDA(cudaEventRecord(m.ev_copy[j - 1], s));
+        }
+        PeerPtrs self{};
+        self.hdr[0] = m.hdr(rank);
+        signal_peers_kernel<<<1, 32, 0, main>>>(self, 1, rank, SIG_HIST, m.d_epoch);
+        B200_LAUNCH_CHECK();
+    }
+    if (phases & 2) {
+        wait_peers_kernel<<<1, 32, 0, main>>>(m.hdr(rank)->sig[SIG_HIST], world, m.d_epoch, m.d_error);
+        B200_LAUNCH_CHECK();
+        // ---- ownership cuts on the global histogram, then where my segments go ----
+        uint32_t *total_b = m.total, *total_p = m.total + P;
+        balanced_cuts_kernel<1024><<<1, 1024, 0, main>>>(m.hist_b(rank), (uint32_t)world, m.hist_p(rank),
+                                                         (uint32_t)(world * K), P, (uint32_t)world, m.cut, total_b, total_p);
+        B200_LAUNCH_CHECK();
+        exchange_layout_kernel<1024><<<1, 1024, 0, main>>>(m.hist_b(rank), (uint32_t)world, (uint32_t)rank, 1u, P, m.cut,
+                                                           (uint32_t)world, (uint32_t)rank, m.cap_b, total_b,
+                                                           m.dst_start_b, m.own_total, m.need, m.d_error);
+        B200_LAUNCH_CHECK();
+        exchange_layout_kernel<1024><<<1, 1024, 0, main>>>(m.hist_p(rank), (uint32_t)(world * K), (uint32_t)(rank * K),
+                                                           (uint32_t)K, P, m.cut, (uint32_t)world, (uint32_t)rank, m.cap_p,
+                                                           total_p, m.dst_start_p, m.own_total + P, m.need + 2, m.d_error);
+        B200_LAUNCH_CHECK();
+        auto exchange = [&](const void *staged, uint64_t n, const uint32_t *src_off, const uint32_t *dst_start, uint32_t cap,
+                            bool build_side) {
+            if (n == 0) return;
+            ExchangeArgs2 x{};
+            x.src_tup   = static_cast<const uint64_t *>(staged);
+            x.src_off   = src_off;
+            x.dst_start = dst_start;
+            x.cut       = m.cut;
+            x.n         = (uint32_t)n;
+            x.nparts    = P;
+            x.world     = (uint32_t)world;
+            x.cap       = cap;
+            for (int d = 0; d < world; ++d)
+                x.dst_tup[d] = reinterpret_cast<uint64_t *>(build_side ? m.build(d) : m.recv_p(d));
+            StreamSwap sw(c, m.xstream);
+            TimedScope ts("exchange");
+            segment_exchange2_kernel<<<(unsigned)((n + 2047) / 2048), 256, 0, c.stream>>>(x);
+            B200_LAUNCH_CHECK();
+        };
+        // ---- build shard: partition locally, exchange ----
+        const uint64_t *bp[1] = {m.in_bp};
+        stage_scatter_build_local(m.in_bk, nb, 0, m.bits, my_hb, m.stage_b, m.cfg.has_build_sum ? 1 : 0, bp, nullptr, &m.scr_a,
+                                  m.src_off_b);
+        B200_CUDA(cudaEventRecord(m.ev_build, main));
+        B200_CUDA(cudaStreamWaitEvent(m.xstream, m.ev_build, 0));
+        exchange(m.stage_b, nb, m.src_off_b, m.dst_start_b, m.cap_b, true);
+        // ---- probe shard, chunk by chunk: the exchange of chunk k runs under the partition pass of chunk k + 1 ----
+        for (int k = 0; k < K; ++k) {
+            const uint32_t a = chunk_first(m, np, k), b = chunk_first(m, np, k + 1);
+            const uint64_t *pp[1] = {m.in_pp ? m.in_pp + a : nullptr};
+            uint64_t *staged = static_cast<uint64_t *>(m.stage_p) + a;
+            stage_scatter_build_local(m.in_pk + a, b - a, a, m.bits, my_hp + (size_t)k * P, staged,
+                                      m.cfg.has_probe_sum ? 1 : 0, pp, nullptr, &m.scr_a, m.src_off_p + (size_t)k * (P + 1));
+            B200_CUDA(cudaEventRecord(m.ev_chunk[k], main));
+            B200_CUDA(cudaStreamWaitEvent(m.xstream, m.ev_chunk[k], 0));
+            exchange(staged, b - a, m.src_off_p + (size_t)k * (P + 1), m.dst_start_p + (size_t)k * P, m.cap_p, false);
+        }
+        signal_peers_kernel<<<1, 32, 0, m.xstream>>>(m.peers(), world, rank, SIG_DATA, m.d_epoch);
+        B200_LAUNCH_CHECK();
+        B200_CUDA(cudaEventRecord(m.ev_x, m.xstream));
+        B200_CUDA(cudaStreamWaitEvent(main, m.ev_x, 0));
+        for (int j = 1; j < world; ++j) B200_CUDA(cudaStreamWaitEvent(main, m.ev_copy[j - 1], 0));
+    }
+    if (phases & 4) {
+        wait_peers_kernel<<<1, 32, 0, main>>>(m.hdr(rank)->sig[SIG_DATA], world, m.d_epoch, m.d_error);
+        B200_LAUNCH_CHECK();
+        ProjDesc pd[2];
+        int      k = 0;
+        if (m.cfg.has_build_sum) pd[k++] = ProjDesc{m.in_bp, nullptr, 0, B200_PROJ_IN_RID};
+        if (m.cfg.has_probe_sum) pd[k++] = ProjDesc{m.in_pp, nullptr, 1, B200_PROJ_IN_RID};
+        stage_join_sum(m.build(rank), m.own_total, m.recv_p(rank), m.own_total + P, m.bits, k, pd, 0, nullptr, nullptr,
+                       m.d_result, 0, 0, &m.scr_b, nullptr);
+        push_result_kernel<<<1, 32, 0, main>>>(m.peers(), world, rank, m.d_result, m.d_error, m.d_epoch);
+        B200_LAUNCH_CHECK();
+    }
+    if (phases & 8) {
+        wait_peers_kernel<<<1, 32, 0, main>>>(m.hdr(rank)->sig[SIG_RESULT], world, m.d_epoch, m.d_error);
+        B200_LAUNCH_CHECK();
+        reduce_result_kernel<<<1, 32, 0, main>>>(m.hdr(rank), world, m.d_final);
+        B200_LAUNCH_CHECK();
+        B200_CUDA(cudaMemcpyAsync(m.h_final, m.d_final, 64, cudaMemcpyDeviceToHost, main));
+    }
+}
+
+static void enqueue(MultiPlan &m, int phases) {
+    if (m.cfg.plan == B200_PLAN_BROADCAST) enqueue_broadcast(m, phases);
+    else enqueue_exchange(m, phases);
+}
+
+static int all_phases(const MultiPlan &m) { return m.cfg.plan == B200_PLAN_BROADCAST ? 7 : 15; }
+
+}  // namespace b200
+
+using namespace b200;
+
+namespace {
+int mfail(const char *msg) {
+    set_last_error(msg);
+    return 1;
+}
+}  // namespace
+
+extern "C" {
+
+b200_multi *b200_multi_create(const b200_multi_config *cfg) {
+    if (!cfg || cfg->world < 1 || cfg->world > kMaxPeers || cfg->rank < 0 || cfg->rank >= cfg->world) {
+        set_last_error("b200_multi_create: bad rank / world (1..8 ranks)");
+        return nullptr;
+    }
+    if (cfg->n_build_local > cfg->n_build_local_max || cfg->n_probe_local > cfg->n_probe_local_max ||
+        cfg->n_build_total > kMaxRows || cfg->n_probe_local_max > (1ull << 31)) {
+        set_last_error("b200_multi_create: inconsistent or too large row counts");
+        return nullptr;
+    }
+    set_thread_device(cfg->device);
+    ensure_init();
+    Context &c = ctx();
+    (void)c;
+    auto *m   = new MultiPlan();
+    m->cfg    = *cfg;
+    m->rank   = cfg->rank;
+    m->world  = cfg->world;
+    m->device = cfg->device;
+    m->nproj  = (cfg->has_build_sum ? 1 : 0) + (cfg->has_probe_sum ? 1 : 0);
+    m->bits   = cfg->radix_bits > 0 ? cfg->radix_bits : auto_radix_bits(cfg->n_build_total ? cfg->n_build_total : 1, false);
+    if (cfg->plan == B200_PLAN_EXCHANGE) {
+        int min_bits = 2;
+        while ((1 << min_bits) < 4 * cfg->world) ++min_bits;   // at least four partitions per rank
+        m->bits = std::max(m->bits, min_bits);
+    }
+    m->P = 1u << m->bits;
+    if (cfg->plan == B200_PLAN_BROADCAST) {
+        m->K          = cfg->chunks > 0 ? std::min(cfg->chunks, kMaxChunks) : 4;
+        m->seg_rows   = (uint32_t)std::max<uint64_t>(cfg->n_build_local_max, 1);
+        m->chunk_rows = (m->seg_rows + (uint32_t)m->K - 1) / (uint32_t)m->K;
+        m->opt_cap    = (cfg->n_probe_local_max >= (1u << 20) && cfg->n_probe_local_max <= (1u << 30))
+                            ? opt_region_cap(cfg->n_probe_local_max, m->bits) : 0;
+    } else {
+        m->K = cfg->chunks > 0 ? std::min(cfg->chunks, kMaxChunks) : (cfg->n_probe_local_max >= (1u << 24) ? 8 : 1);
+        const uint64_t nb_tot = cfg->n_build_total, np_tot = cfg->n_probe_total;
+        // receive capacity: the mean plus an eighth (cuts balance owners to within one partition's weight), never
+        // less than one chunk table's worth — or what the caller measured
+        uint64_t cb = cfg->recv_rows_build ? cfg->recv_rows_build : nb_tot / cfg->world + nb_tot / (8 * cfg->world) + 65536;
+        uint64_t cp = cfg->recv_rows_probe ? cfg->recv_rows_probe : np_tot / cfg->world + np_tot / (8 * cfg->world) + 65536;
+        cb = std::min<uint64_t>(cb, std::max<uint64_t>(nb_tot, 1));
+        cp = std::min<uint64_t>(cp, std::max<uint64_t>(np_tot, 1));
+        if (cb > kMaxRows || cp > kMaxRows) {
+            delete m;
+            set_last_error("b200_multi_create: receive buffers beyond 2^32-1 rows");
+            return nullptr;
+        }
+        m->cap_b = (uint32_t)cb;
+        m->cap_p = (uint32_t)cp;
+    }
+    layout_shared(*m);
+    B200_CUDA(cudaMalloc(&m->shared, m->shared_bytes));
+    B200_CUDA(cudaMemset(m->shared, 0, m->off_build));   // flags, result slots and histograms start at zero
+    size_t local_bytes = 0;
+    layout_local(*m, nullptr, &local_bytes);
+    B200_CUDA(cudaMalloc(&m->local, local_bytes));
+    layout_local(*m, m->local, &local_bytes);
+    B200_CUDA(cudaMemset(m->local, 0, 4096));
+    B200_CUDA(cudaMallocHost(&m->h_final, 64));
+    for (int j = 0; j < m->world; ++j) {
+        B200_CUDA(cudaStreamCreateWithFlags(&m->copy_stream[j], cudaStreamNonBlocking));
+        B200_CUDA(cudaEventCreateWithFlags(&m->ev_copy[j], cudaEventDisableTiming));
+    }
+    B200_CUDA(cudaStreamCreateWithFlags(&m->xstream, cudaStreamNonBlocking));
+    B200_CUDA(cudaEventCreateWithFlags(&m->ev_build, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&m->ev_hist, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&m->ev_x, cudaEventDisableTiming));
+    for (int k = 0; k < kMaxChunks; ++k) B200_CUDA(cudaEventCreateWithFlags(&m->ev_chunk[k], cudaEventDisableTiming));
+    m->peer[m->rank] = m->shared;
+    if (const char *g = getenv("B200_MULTI_GRAPH")) m->use_graph = atoi(g);
+    B200_CUDA(cudaDeviceSynchronize());
+    return reinterpret_cast<b200_multi *>(m);
+}
+
+void b200_multi_destroy(b200_multi *plan) {
+    auto *m = reinterpret_cast<MultiPlan *>(plan);
+    if (!m) return;
+    set_thread_device(m->device);
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    if (m->graph) cudaGraphExecDestroy(m->graph);
+    for (int r = 0; r < m->world; ++r)
+        if (r != m->rank && m->peer[r] && m->peer_ipc[r]) cudaIpcCloseMemHandle(m->peer[r]);
+    for (int j = 0; j < m->world; ++j) {
+        if (m->copy_stream[j]) cudaStreamDestroy(m->copy_stream[j]);
+        if (m->ev_copy[j]) cudaEventDestroy(m->ev_copy[j]);
+    }
+    if (m->xstream) cudaStreamDestroy(m->xstream);
+    if (m->ev_build) cudaEventDestroy(m->ev_build);
+    if (m->ev_hist) cudaEventDestroy(m->ev_hist);
+    if (m->ev_x) cudaEventDestroy(m->ev_x);
+    for (int k = 0; k < kMaxChunks; ++k)
+        if (m->ev_chunk[k]) cudaEventDestroy(m->ev_chunk[k]);
+    if (m->h_final) cudaFreeHost(m->h_final);
+    if (m->local) cudaFree(m->local);
+    if (m->shared) cudaFree(m->shared);
+    delete m;
+}
+
+int b200_multi_export(b200_multi *plan, unsigned char *out_handle64) {
+    auto *m = reinterpret_cast<MultiPlan *>(plan);
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, m->shared) != cudaSuccess) {
+        cudaGetLastError();
+        return mfail("cudaIpcGetMemHandle failed");
+    }
+    memcpy(out_handle64, &h, 64);
+    return 0;
+}
+
+void *b200_multi_shared_ptr(b200_multi *plan) { return reinterpret_cast<MultiPlan *>(plan)->shared; }
+
+int b200_multi_connect_ipc(b200_multi *plan, int peer, const unsigned char *handle64) {
+    auto *m = reinterpret_cast<MultiPlan *>(plan);
+    if (peer < 0 || peer >= m->world) return mfail("bad peer");
+    if (peer == m->rank) return 0;
+    set_thread_device(m->device);
+    (void)ctx();
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return mfail("cudaIpcOpenMemHandle failed (no peer access between the two GPUs?)");
+    }
+    m->peer[peer]     = static_cast<unsigned char *>(p);
+    m->peer_ipc[peer] = true;
+    return 0;
+}
+
+int b200_multi_connect_ptr(b200_multi *plan, int peer, void *peer_shared, int peer_device) {
+    auto *m = reinterpret_cast<MultiPlan *>(plan);
+    if (peer < 0 || peer >= m->world) return mfail("bad peer");
+    if (peer == m->rank) return 0;
+    set_thread_device(m->device);
+    (void)ctx();
+    if (peer_device != m->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+            cudaGetLastError();
+            return mfail("cudaDeviceEnablePeerAccess failed");
+        }
+        cudaGetLastError();
+    }
+    m->peer[peer] = static_cast<unsigned char *>(peer_shared);
+    return 0;
+}
+
+int b200_multi_radix_bits(b200_multi *plan) { return reinterpret_cast<MultiPlan *>(plan)->bits; }
+
+int b200_multi_enqueue(b200_multi *plan, const uint64_t *d_build_keys, const uint64_t *d_build_sum,
+                       const uint64_t *d_probe_keys, const uint64_t *d_probe_sum, int phases) {
+    auto *m = reinterpret_cast<MultiPlan *>(plan);
+    for (int r = 0; r < m->world; ++r)
+        if (!m->peer[r]) return mfail("b200_multi_enqueue: not every peer is connected");
+    if ((m->cfg.has_build_sum && !d_build_sum) || (m->cfg.has_probe_sum && !d_probe_sum)) return mfail("missing SUM column");
+    set_thread_device(m->device);
+    Context &c = ctx();
+    m->in_bk = d_build_keys;
+    m->in_bp = d_build_sum;
+    m->in_pk = d_probe_keys;
+    m->in_pp = d_probe_sum;
+    if (phases <= 0) phases = all_phases(*m);
+    if (m->use_graph && phases == all_phases(*m) && !profiling_enabled()) {
+        const uint64_t *in[4] = {d_build_keys, d_build_sum, d_probe_keys, d_probe_sum};
+        if (!m->graph || memcmp(in, m->g_in, sizeof(in)) != 0) {
+            if (m->graph) {
+                cudaGraphExecDestroy(m->graph);
+                m->graph = nullptr;
+            }
+            cudaGraph_t g = nullptr;
+            B200_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+            enqueue(*m, phases);
+            B200_CUDA(cudaStreamEndCapture(c.stream, &g));
+            B200_CUDA(cudaGraphInstantiate(&m->graph, g, 0));
+            cudaGraphDestroy(g);
+            memcpy(m->g_in, in, sizeof(in));
+        }
+        B200_CUDA(cudaGraphLaunch(m->graph, c.stream));
+    } else {
+        enqueue(*m, phases);
+    }
+    m->pending = true;
+    return 0;
+}
+
+int b200_multi_finish(b200_multi *plan, uint64_t *out_sums, uint64_t *out_matches) {
+    auto *m = reinterpret_cast<MultiPlan *>(plan);
+    set_thread_device(m->device);
+    Context &c = ctx();
+    B200_CUDA(cudaStreamSynchronize(c.stream));
+    m->pending = false;
+    const int k = m->nproj;
+    if (m->h_final[7] != 0) {
+        return mfail((m->h_final[7] & 1ull) || m->cfg.plan == B200_PLAN_BROADCAST
+                         ? "multi-GPU step failed: a peer's signal did not arrive (time-out)"
+                         : "multi-GPU step failed: exchange receive buffers too small for this input "
+                           "(raise recv_rows_build / recv_rows_probe)");
+    }
+    if (m->cfg.plan == B200_PLAN_BROADCAST && m->h_final[k + 1] != 0) {
+        // some rank's histogram-free probe scatter overflowed its regions (skewed keys): every rank sees the same
+        // total, redoes its join with the exact overflow pass, and the results are exchanged once more
+        ProjDesc pd[2];
+        int      n = 0;
+        if (m->cfg.has_build_sum) pd[n++] = ProjDesc{m->in_bp, nullptr, 0, B200_PROJ_IN_RID};
+        if (m->cfg.has_probe_sum) pd[n++] = ProjDesc{m->in_pp, nullptr, 1, B200_PROJ_IN_RID};
+        JoinResult j = stage_join_sum(m->build(m->rank), m->hist_b(m->rank), m->tup_p, m->cur_p, m->bits, n, pd, m->opt_cap,
+                                      m->ov_p, m->ovcnt, nullptr, m->world, m->seg_rows);
+        unsigned long long local[8] = {j.m, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < n; ++i) local[1 + i] = j.sums[i];
+        B200_CUDA(cudaMemcpyAsync(m->d_result, local, 64, cudaMemcpyHostToDevice, c.stream));
+        bump_epoch_kernel<<<1, 1, 0, c.stream>>>(m->d_epoch);
+        B200_LAUNCH_CHECK();
+        push_result_kernel<<<1, 32, 0, c.stream>>>(m->peers(), m->world, m->rank, m->d_result, m->d_error, m->d_epoch);
+        B200_LAUNCH_CHECK();
+        wait_peers_kernel<<<1, 32, 0, c.stream>>>(m->hdr(m->rank)->sig[SIG_RESULT], m->world, m->d_epoch, m->d_error);
+        B200_LAUNCH_CHECK();
+        reduce_result_kernel<<<1, 32, 0, c.stream>>>(m->hdr(m->rank), m->world, m->d_final);
+        B200_LAUNCH_CHECK();
+        B200_CUDA(cudaMemcpyAsync(m->h_final, m->d_final, 64, cudaMemcpyDeviceToHost, c.stream));
+        B200_CUDA(cudaStreamSynchronize(c.stream));
+        if (m->h_final[7] != 0) return mfail("multi-GPU step failed: a peer's signal did not arrive (time-out)");
+    }
+    if (out_matches) *out_matches = m->h_final[0];
+    for (int i = 0; i < k; ++i) out_sums[i] = m->h_final[1 + i];
+    return 0;
+}
+
+/* rows this rank received in the last exchange step: {build, probe} (after b200_multi_finish) */
+int b200_multi_received(b200_multi *plan, uint64_t *out2) {
+    auto *m = reinterpret_cast<MultiPlan *>(plan);
+    if (m->cfg.plan != B200_PLAN_EXCHANGE) return mfail("not an exchange plan");
+    set_thread_device(m->device);
+    uint32_t h[4];
+    B200_CUDA(cudaMemcpy(h, m->need, sizeof(h), cudaMemcpyDeviceToHost));
+    out2[0] = h[0];
+    out2[1] = h[2];
+    return 0;
+}
+
+/* One process, one host thread per GPU: the whole join from DEVICE-resident position shards.
+ * shard pointers: [g] = this GPU's shard of the column (NULL sum columns = no SUM on that side). */
+int b200_join_sum_multi(int n_gpus, int plan_kind, const uint64_t *const *d_build_keys, const uint64_t *const *d_build_sum,
+                        const uint64_t *n_build, const uint64_t *const *d_probe_keys, const uint64_t *const *d_probe_sum,
+                        const uint64_t *n_probe, int steps, uint64_t *out_sums, uint64_t *out_matches, double *out_ms) {
+    if (n_gpus < 1 || n_gpus > kMaxPeers) return mfail("1..8 GPUs");
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < n_gpus) return mfail("not enough visible GPUs");
+    uint64_t nb_tot = 0, np_tot = 0, nb_max = 0, np_max = 0;
+    for (int g = 0; g < n_gpus; ++g) {
+        nb_tot += n_build[g];
+        np_tot += n_probe[g];
+        nb_max = std::max(nb_max, n_build[g]);
+        np_max = std::max(np_max, n_probe[g]);
+    }
+    std::vector<b200_multi *> plans((size_t)n_gpus, nullptr);
+    std::vector<int>          rc((size_t)n_gpus, 0);
+    std::vector<std::string>  err((size_t)n_gpus);
+    auto on_all = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (int g = 0; g < n_gpus; ++g) th.emplace_back([&, g] { fn(g); });
+        for (auto &t : th) t.join();
+    };
+    on_all([&](int g) {
+        b200_multi_config cfg{};
+        cfg.plan = plan_kind;
+        cfg.rank = g;
+        cfg.world = n_gpus;
+        cfg.device = g;
+        cfg.n_build_total = nb_tot;
+        cfg.n_probe_total = np_tot;
+        cfg.n_build_local = n_build[g];
+        cfg.n_probe_local = n_probe[g];
+        cfg.n_build_local_max = nb_max;
+        cfg.n_probe_local_max = np_max;
+        cfg.has_build_sum = d_build_sum && d_build_sum[g];
+        cfg.has_probe_sum = d_probe_sum && d_probe_sum[g];
+        plans[(size_t)g] = b200_multi_create(&cfg);
+        if (!plans[(size_t)g]) { rc[(size_t)g] = 1; err[(size_t)g] = last_error_string(); }
+    });
+    for (int g = 0; g < n_gpus; ++g)
+        if (rc[(size_t)g]) {
+            for (auto *p : plans) b200_multi_destroy(p);
+            return mfail(err[(size_t)g].c_str());
+        }
+    on_all([&](int g) {
+        for (int r = 0; r < n_gpus; ++r)
+            if (b200_multi_connect_ptr(plans[(size_t)g], r, b200_multi_shared_ptr(plans[(size_t)r]), r)) {
+                rc[(size_t)g] = 1;
+                err[(size_t)g] = last_error_string();
+            }
+    });
+    std::vector<double> ms((size_t)n_gpus, 0.0);
+    if (!std::any_of(rc.begin(), rc.end(), [](int v) { return v != 0; })) {
+        on_all([&](int g) {
+            b200_multi *p = plans[(size_t)g];
+            uint64_t    sums[2] = {0, 0}, mm = 0;
+            auto step = [&]() {
+                int r = b200_multi_enqueue(p, d_build_keys[g], d_build_sum ? d_build_sum[g] : nullptr, d_probe_keys[g],
+                                           d_probe_sum ? d_probe_sum[g] : nullptr, 0);
+                if (!r) r = b200_multi_finish(p, sums, &mm);
+                if (r) { rc[(size_t)g] = 1; err[(size_t)g] = last_error_string(); }
+                return r;
+            };
+            if (step()) return;   // warm-up (and the answer, when steps == 0)
+            if (steps > 0) {
+                const auto t0 = std::chrono::steady_clock::now();
+                for (int s = 0; s < steps; ++s)
+                    if (step()) return;
+                ms[(size_t)g] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / steps;
+            }
+            if (g == 0) {   // every rank holds the same totals: {SUM(build column)?, SUM(probe column)?}
+                const int k = ((d_build_sum && d_build_sum[0]) ? 1 : 0) + ((d_probe_sum && d_probe_sum[0]) ? 1 : 0);
+                for (int i = 0; i < k; ++i) out_sums[i] = sums[i];
+                if (out_matches) *out_matches = mm;
+            }
+        });
+    }
+    on_all([&](int g) { b200_multi_destroy(plans[(size_t)g]); });
+    for (int g = 0; g < n_gpus; ++g)
+        if (rc[(size_t)g]) return mfail(err[(size_t)g].c_str());
+    if (out_ms) *out_ms = *std::max_element(ms.begin(), ms.end());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,268 @@
+// multi_kernels.cuh — the small kernels of the multi-GPU plans (multi.cu): synchronisation between GPUs through
+// flags in peer memory instead of NCCL collectives, the layout of the radix-sharded exchange, and the exchange
+// itself (the scatter's second half, fused with the all-to-all: stores straight into the owners' memory).
+//
+// The reference is a single process (no collective anywhere); what these kernels shard is its bucket
+// independence, rhjoin.c:42-57 — one JoinJob per bucket, no cross-bucket state.
+//
+// Flag protocol.  Every rank owns a SharedHeader at the start of its shared region.  sig[s][r] is written only by
+// rank r (a 4-byte copy-engine write behind the data it announces, or a st.release.sys from a kernel) and holds
+// the epoch (step number) of r's latest signal s; waiting = spinning until it reaches this rank's own epoch.
+// Epochs only grow, so nothing is ever reset, and they live in device memory (not in kernel arguments), so a
+// captured CUDA graph of a step stays valid for the next step.
+#pragma once
+
+#include "kernels.cuh"
+
+namespace b200 {
+
+constexpr int kNSig      = 16;
+constexpr int kMaxChunks = 8;
+enum MultiSig {
+    SIG_HIST   = 0,   // my histograms are in your hist_all
+    SIG_RESULT = 1,   // my {matches, sums, flags} are in your result[]
+    SIG_DATA   = 2,   // exchange plan: every row I owe you has landed
+    SIG_CHUNK0 = 8,   // broadcast plan: chunk c of my build region has landed (SIG_CHUNK0 + c)
+};
+
+struct SharedHeader {
+    uint32_t           sig[kNSig][kMaxPeers];
+    unsigned long long result[kMaxPeers][8];
+};
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void bump_epoch_kernel(uint32_t *epoch) { *epoch += 1u; }
+
+// one lane per peer: wait for signal row `row` (kMaxPeers flags) of every rank
+__global__ void wait_peers_kernel(const uint32_t *row, int world, const uint32_t *epoch, uint32_t *error) {
+    const int r = threadIdx.x;
+    if (r < world && !spin_until_epoch(row + r, *epoch)) *error = 1u;
+}
+
+struct PeerPtrs {
+    SharedHeader *hdr[kMaxPeers];
+};
+
+// announce `sig` to every rank (stream-ordered behind this rank's stores into their memory)
+__global__ void signal_peers_kernel(PeerPtrs peers, int world, int rank, int sig, const uint32_t *epoch) {
+    const int d = threadIdx.x;
+    if (d < world) {
+        __threadfence_system();
+        st_release_sys_u32(&peers.hdr[d]->sig[sig][rank], *epoch);
+    }
+}
+
+// {matches, sums..., flags} of this rank into slot `rank` of every rank's header, then SIG_RESULT
+__global__ void push_result_kernel(PeerPtrs peers, int world, int rank, const unsigned long long *local,
+                                   const uint32_t *extra_flag, const uint32_t *epoch) {
+    const int d = threadIdx.x;
+    if (d < world) {
+        volatile unsigned long long *dst = peers.hdr[d]->result[rank];
+        for (int k = 0; k < 8; ++k) dst[k] = local[k] + (k == 7 && extra_flag ? (unsigned long long)*extra_flag : 0ull);
+        __threadfence_system();
+        st_release_sys_u32(&peers.hdr[d]->sig[SIG_RESULT][rank], *epoch);
+    }
+}
+
+// sum of all ranks' result slots (u64 sums wrap mod 2^64 exactly as inter_res.c:332-333's accumulation does)
+__global__ void reduce_result_kernel(const SharedHeader *hdr, int world, unsigned long long *final8) {
+    const int k = threadIdx.x;
+    if (k < 8) {
+        unsigned long long s = 0;
+        for (int r = 0; r < world; ++r) s += reinterpret_cast<const volatile unsigned long long *>(hdr->result[r])[k];
+        final8[k] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Radix-sharded exchange (SURVEY §8e "all-to-all"; config 4).
+//
+// Ownership: rank g owns the contiguous partition range [cut[g], cut[g+1]).  The cuts are placed on the GLOBAL
+// histogram (build + probe rows per partition, all ranks, all chunks) so that every owner receives about the same
+// number of rows: with Zipf(1.0) probe keys the partition of the hottest key alone holds 1/k of all probe rows
+// (3.7 % for k = 27), and equal-width ranges would hand its owner 1.3x the mean; cut placement keeps max/mean
+// within a partition's weight of 1.
+// hist_b[Vb][P], hist_p[Vp][P]: all-gathered histograms per virtual rank (a virtual rank is one (rank, chunk)
+// pair: the probe shard is partitioned and exchanged chunk by chunk so that the exchange of chunk c overlaps the
+// partition pass of chunk c + 1).  One CTA.
+//   cut[world + 1], total_b[P], total_p[P]
+// ---------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT)
+balanced_cuts_kernel(const uint32_t *__restrict__ hist_b, uint32_t vb, const uint32_t *__restrict__ hist_p, uint32_t vp,
+                     uint32_t nparts, uint32_t world, uint32_t *__restrict__ cut, uint32_t *__restrict__ total_b,
+                     uint32_t *__restrict__ total_p) {
+    __shared__ unsigned long long wsum[NT / 32 + 1];
+    const uint32_t per   = (nparts + NT - 1) / NT;
+    const uint32_t first = threadIdx.x * per;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    unsigned long long s = 0;
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t p = first + k;
+        if (p < nparts) {
+            uint32_t tb = 0, tp = 0;
+            for (uint32_t v = 0; v < vb; ++v) tb += hist_b[(size_t)v * nparts + p];
+            for (uint32_t v = 0; v < vp; ++v) tp += hist_p[(size_t)v * nparts + p];
+            total_b[p] = tb;
+            total_p[p] = tp;
+            s += (unsigned long long)tb + tp;
+        }
+    }
+    unsigned long long incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int w = 0; w < NT / 32; ++w) {
+            const unsigned long long t = wsum[w];
+            wsum[w] = run;
+            run += t;
+        }
+        wsum[NT / 32] = run;
+        cut[0]        = 0;
+        cut[world]    = nparts;
+    }
+    __syncthreads();
+    const unsigned long long grand = wsum[NT / 32];
+    unsigned long long       run   = wsum[wid] + incl - s;   // weight of all partitions before `first`
+    // cut[g] (0 < g < world) = first partition whose preceding weight reaches g * grand / world
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t p = first + k;
+        if (p < nparts) {
+            const unsigned long long w = (unsigned long long)total_b[p] + total_p[p];
+            for (uint32_t g = 1; g < world; ++g) {
+                const unsigned long long target = (grand * g + world - 1) / world;
+                // p is the cut when the prefix crosses the target inside (run, run + w]; an empty tail is handled below
+                if (run < target && run + w >= target) cut[g] = p + 1u;
+            }
+            run += w;
+        }
+    }
+    if (threadIdx.x == 0 && grand == 0) {
+        for (uint32_t g = 1; g < world; ++g) cut[g] = (uint32_t)(((unsigned long long)nparts * g) / world);
+    }
+}
+
+__device__ __forceinline__ uint32_t owner_of(uint32_t p, const uint32_t *cut, uint32_t world) {
+    uint32_t g = 0;
+    while (g + 1 < world && p >= cut[g + 1]) ++g;
+    return g;
+}
+
+// Layout of one side of the exchange for this rank's virtual ranks [v0, v0 + nv) out of `vtot`:
+//   dst_start[c][p]  where the segment of partition p of my virtual rank v0 + c starts in owner(p)'s receive
+//                    buffer (partition-major, virtual-rank-minor: an owned partition is contiguous)
+//   own_total[p]     global size of p if this rank owns it, else 0 (the histogram the local join runs on; all
+//                    zero when the rows this rank receives exceed `cap`: the join then reads nothing, the
+//                    exchange drops what does not fit and need[1] = 1 fails the step)
+//   need[0]          rows this rank receives
+// One CTA.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+exchange_layout_kernel(const uint32_t *__restrict__ hist, uint32_t vtot, uint32_t v0, uint32_t nv, uint32_t nparts,
+                       const uint32_t *__restrict__ cut, uint32_t world, uint32_t rank, uint32_t cap,
+                       const uint32_t *__restrict__ total, uint32_t *__restrict__ dst_start,
+                       uint32_t *__restrict__ own_total, uint32_t *__restrict__ need, uint32_t *__restrict__ error) {
+    __shared__ uint32_t warp_sums[NT / 32 + 1];
+    __shared__ uint32_t owner_base[kMaxPeers + 1];
+    const uint32_t per   = (nparts + NT - 1) / NT;
+    const uint32_t first = threadIdx.x * per;
+    uint32_t       s     = 0;
+    for (uint32_t k = 0; k < per; ++k)
+        if (first + k < nparts) s += total[first + k];
+    const uint32_t start = block_exclusive_scan<NT>(s, warp_sums);
+    const uint32_t grand = warp_sums[NT / 32];
+    uint32_t       run   = start;
+    // owner_base[g] = rows of all partitions before cut[g]: where owner g's receive buffer starts in the global order
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t p = first + k;
+        if (p < nparts) {
+            for (uint32_t g = 0; g < world; ++g)
+                if (cut[g] == p) owner_base[g] = run;
+            run += total[p];
+        }
+    }
+    if (threadIdx.x == 0)
+        for (uint32_t g = 0; g <= world; ++g)
+            if (cut[g] >= nparts) owner_base[g] = grand;   // empty tail ranges, and the end sentinel
+    __syncthreads();
+    const uint32_t mine = owner_base[rank + 1] - owner_base[rank];
+    const bool     over = mine > cap;
+    run = start;
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t p = first + k;
+        if (p < nparts) {
+            const uint32_t o = owner_of(p, cut, world);
+            uint32_t before = 0;
+            for (uint32_t v = 0; v < v0; ++v) before += hist[(size_t)v * nparts + p];
+            for (uint32_t c = 0; c < nv; ++c) {
+                dst_start[(size_t)c * nparts + p] = run - owner_base[o] + before;
+                before += hist[(size_t)(v0 + c) * nparts + p];
+            }
+            own_total[p] = (o == rank && !over) ? total[p] : 0u;
+            run += total[p];
+        }
+    }
+    if (threadIdx.x == 0) {
+        need[0] = mine;
+        need[1] = over ? 1u : 0u;
+        if (over) *error = 2u;
+    }
+    (void)vtot;
+}
+
+// The exchange of one staged chunk: element e of partition p (src_off[p] <= e < src_off[p + 1]) goes to owner(p)'s
+// receive buffer at dst_start[p] + (e - src_off[p]).  Flat decomposition (a CTA takes 2048 consecutive staged
+// tuples whatever partition they belong to: a skewed partition is copied by as many CTAs as it has kilo-tuples);
+// consecutive lanes copy consecutive tuples, so a warp's stores are 256 contiguous bytes in the peer's memory
+// (full NVLink packets) except where a partition ends.
+struct ExchangeArgs2 {
+    const uint64_t *src_tup;
+    const uint32_t *src_off;     // [nparts + 1]
+    const uint32_t *dst_start;   // [nparts]
+    const uint32_t *cut;         // [world + 1]
+    uint32_t        n, nparts, world, cap;
+    uint64_t       *dst_tup[kMaxPeers];
+};
+__global__ void __launch_bounds__(256) segment_exchange2_kernel(const ExchangeArgs2 x) {
+    constexpr int  UN   = 8;
+    const uint32_t base = blockIdx.x * (256u * UN);
+    uint32_t       e    = base + threadIdx.x;
+    uint32_t       lo = 0, hi = x.nparts;   // invariant: src_off[lo] <= e < src_off[hi]
+    if (e < x.n) {
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(x.src_off + mid) <= e) lo = mid; else hi = mid;
+        }
+    }
+    uint32_t p = lo;
+    uint32_t cuts[kMaxPeers];   // cut[1 .. world - 1] in registers: owner(p) = number of cuts <= p
+#pragma unroll
+    for (int g = 0; g < kMaxPeers; ++g) cuts[g] = (uint32_t)(g + 1) < x.world ? __ldg(x.cut + g + 1) : 0xFFFFFFFFu;
+    uint64_t t[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+        const uint32_t eu = e + (uint32_t)u * 256u;
+        t[u]              = eu < x.n ? ld_stream_u64(x.src_tup + eu) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u, e += 256u) {
+        if (e >= x.n) break;
+        while (__ldg(x.src_off + p + 1) <= e) ++p;   // empty partitions are skipped as well
+        uint32_t d = 0;
+#pragma unroll
+        for (int g = 0; g < kMaxPeers; ++g) d += p >= cuts[g] ? 1u : 0u;
+        const uint32_t pos = __ldg(x.dst_start + p) + (e - __ldg(x.src_off + p));
+        if (pos < x.cap) x.dst_tup[d][pos] = t[u];   // too small a receive buffer is flagged by the layout kernel
+    }
+}
+
+}  // namespace b200

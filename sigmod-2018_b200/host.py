@@ -24,7 +24,7 @@ __all__ = [
     "scan_filter", "radix_partition", "hash_join_pairs", "gather_sum", "join_sum",
     "join_sum_device", "synth_column_device", "DeviceColumn", "kernel_launches", "last_kernel_ms",
     "SYNTH_PERM", "SYNTH_PAYLOAD", "SYNTH_ZIPF", "SYNTH_UNIFORM", "SYNTH_IOTA",
-    "SEED_R", "SEED_S",
+    "SEED_R", "SEED_S", "CMultiConfig", "PLAN_BROADCAST", "PLAN_EXCHANGE",
 ]
 
 _HERE = Path(__file__).resolve().parent
@@ -89,6 +89,19 @@ class CBatchListnode(C.Structure):
 CBatchListnode._fields_ = [("num_of_relations", C.c_int), ("relations", C.POINTER(C.c_int)),
                            ("predicate_list", C.c_void_p), ("views", C.POINTER(CQueryStringArray)),
                            ("next", C.POINTER(CBatchListnode))]
+
+
+class CMultiConfig(C.Structure):
+    """b200_multi_config (include/b200_join.h)"""
+    _fields_ = [("plan", C.c_int), ("rank", C.c_int), ("world", C.c_int), ("device", C.c_int),
+                ("n_build_total", C.c_uint64), ("n_probe_total", C.c_uint64),
+                ("n_build_local", C.c_uint64), ("n_probe_local", C.c_uint64),
+                ("n_build_local_max", C.c_uint64), ("n_probe_local_max", C.c_uint64),
+                ("has_build_sum", C.c_int), ("has_probe_sum", C.c_int), ("radix_bits", C.c_int), ("chunks", C.c_int),
+                ("recv_rows_build", C.c_uint64), ("recv_rows_probe", C.c_uint64)]
+
+
+PLAN_BROADCAST, PLAN_EXCHANGE = 0, 1
 
 
 # --------------------------------------------------------------------------
@@ -209,6 +222,18 @@ def _declare(L: C.CDLL) -> None:
         "b200_stage_join_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                           P(C.c_void_p), P(C.c_int), P(C.c_void_p), C.c_uint32, C.c_void_p,
                                           C.c_void_p, u64p, u64p]),
+        "b200_multi_create": (C.c_void_p, [P(CMultiConfig)]),
+        "b200_multi_destroy": (None, [C.c_void_p]),
+        "b200_multi_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+        "b200_multi_shared_ptr": (C.c_void_p, [C.c_void_p]),
+        "b200_multi_connect_ipc": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
+        "b200_multi_connect_ptr": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+        "b200_multi_radix_bits": (C.c_int, [C.c_void_p]),
+        "b200_multi_enqueue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+        "b200_multi_finish": (C.c_int, [C.c_void_p, u64p, u64p]),
+        "b200_multi_received": (C.c_int, [C.c_void_p, u64p]),
+        "b200_join_sum_multi": (C.c_int, [C.c_int, C.c_int, P(C.c_void_p), P(C.c_void_p), u64p, P(C.c_void_p),
+                                          P(C.c_void_p), u64p, C.c_int, u64p, u64p, P(C.c_double)]),
         "b200_set_profiling": (C.c_int, [C.c_int]),
         "b200_last_kernel_ms": (C.c_double, [C.c_char_p]),
         "b200_kernel_launches": (C.c_uint64, [C.c_int]),

@@ -558,3 +558,86 @@ class ShardedExchangeJoin:
         for p in self._imported:
             self.L.b200_ipc_close(p)
         self._imported = []
+
+
+class MultiJoin:
+    """Thin binding over the C-ABI multi-GPU plans (csrc/multi.cu: b200_multi_*): no torch in the step, no NCCL.
+
+    One instance per rank.  `dist` (any torch.distributed backend, may be None for world = 1) is used ONCE, at
+    construction, to swap the CUDA-IPC handles of the ranks' shared regions and to agree on the row totals; a step
+    is `enqueue` (device work only: partition, copy-engine broadcast or NVLink exchange, join, result exchange
+    through flags in peer memory) + `finish` (the one host synchronisation).  Keys and SUM values must be below
+    2^32 (8-byte tuples); wider columns take the general classes above.
+    """
+
+    def __init__(self, b200, dist, rank, world, device_index, plan, n_build_local, n_probe_local, has_build_sum=True,
+                 has_probe_sum=True, radix_bits=0, chunks=0, recv_rows_build=0, recv_rows_probe=0, peers_in_process=None):
+        import ctypes as C
+        self.b, self.L, self.C, self.rank, self.world = b200, b200.lib(), C, rank, world
+        counts = [(n_build_local, n_probe_local)]
+        if world > 1 and peers_in_process is None:
+            counts = [None] * world
+            dist.all_gather_object(counts, (n_build_local, n_probe_local))
+        elif peers_in_process is not None:
+            counts = peers_in_process["counts"]
+        cfg = b200.CMultiConfig(plan=plan, rank=rank, world=world, device=device_index,
+                                n_build_total=sum(c[0] for c in counts), n_probe_total=sum(c[1] for c in counts),
+                                n_build_local=n_build_local, n_probe_local=n_probe_local,
+                                n_build_local_max=max(c[0] for c in counts), n_probe_local_max=max(c[1] for c in counts),
+                                has_build_sum=int(has_build_sum), has_probe_sum=int(has_probe_sum),
+                                radix_bits=radix_bits, chunks=chunks, recv_rows_build=recv_rows_build,
+                                recv_rows_probe=recv_rows_probe)
+        self.nproj = int(has_build_sum) + int(has_probe_sum)
+        self.plan = self.L.b200_multi_create(C.byref(cfg))
+        if not self.plan:
+            raise RuntimeError("b200_multi_create: " + (self.L.b200_last_error() or b"").decode())
+        if world > 1 and peers_in_process is None:
+            buf = C.create_string_buffer(64)
+            _ck(self.L, self.L.b200_multi_export(self.plan, buf))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(buf.raw))
+            for r in range(world):
+                if r != rank:
+                    _ck(self.L, self.L.b200_multi_connect_ipc(self.plan, r, handles[r]))
+
+    def connect_in_process(self, others, devices):
+        """Several ranks inside ONE process (tests: ranks emulated on one GPU; b200_join_sum_multi does the same
+        with one thread per GPU): peers are plain pointers."""
+        for r, o in enumerate(others):
+            if r != self.rank:
+                _ck(self.L, self.L.b200_multi_connect_ptr(self.plan, r, self.L.b200_multi_shared_ptr(o.plan), devices[r]))
+
+    @property
+    def bits(self):
+        return int(self.L.b200_multi_radix_bits(self.plan))
+
+    def enqueue(self, build_keys_ptr, build_sum_ptr, probe_keys_ptr, probe_sum_ptr, phases=0):
+        _ck(self.L, self.L.b200_multi_enqueue(self.plan, build_keys_ptr, build_sum_ptr, probe_keys_ptr, probe_sum_ptr,
+                                              phases))
+
+    def finish(self):
+        C = self.C
+        sums = (C.c_uint64 * 2)()
+        m = C.c_uint64(0)
+        _ck(self.L, self.L.b200_multi_finish(self.plan, sums, C.byref(m)))
+        return [int(x) for x in sums[: self.nproj]], int(m.value)
+
+    def step(self, build_keys_ptr, build_sum_ptr, probe_keys_ptr, probe_sum_ptr):
+        self.enqueue(build_keys_ptr, build_sum_ptr, probe_keys_ptr, probe_sum_ptr)
+        return self.finish()
+
+    def received(self):
+        out = (self.C.c_uint64 * 2)()
+        _ck(self.L, self.L.b200_multi_received(self.plan, out))
+        return int(out[0]), int(out[1])
+
+    def close(self):
+        if self.plan:
+            self.L.b200_multi_destroy(self.plan)
+            self.plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -84,6 +84,28 @@ def main():
             assert m == wm and got == want, ("broadcast", carry, rank_major, carry_probe, got, m, want, wm)
         plan.close()
         cases += 1
+    # ---- the C-ABI plans (csrc/multi.cu): no NCCL in the step, flags in peer memory over CUDA IPC ----
+    for plan_kind, nr, ns, zipf in [(b200.PLAN_BROADCAST, (1 << 18) - 5, (1 << 22) + 9, False),
+                                    (b200.PLAN_BROADCAST, 1 << 16, 1 << 21, True),      # overflow pass + 2nd result round
+                                    (b200.PLAN_EXCHANGE, (1 << 17) - 9, (1 << 21) + 77, True),
+                                    (b200.PLAN_EXCHANGE, 1 << 16, 3 * world + 1, False)]:
+        k = int(np.ceil(np.log2(nr + 1)))
+        kr = orc.synth_column(1 << k, 0, k, b200.SEED_R)[:nr]
+        ks = orc.synth_column(ns, 2, k, 41) if zipf else orc.synth_column(ns, 0, k + 2, b200.SEED_S)
+        pr, ps = orc.synth_column(nr, 1, 0, 3), orc.synth_column(ns, 1, 0, 13)
+        want, wm = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
+        d_kr, d_ks, d_pr, d_ps = shard(kr, nr), shard(ks, ns), shard(pr, nr), shard(ps, ns)
+        for graph in (0, 1):
+            os.environ["B200_MULTI_GRAPH"] = str(graph)
+            plan = sh.MultiJoin(b200, dist, rank, world, local, plan_kind, d_kr.numel(), d_ks.numel(),
+                                recv_rows_build=nr, recv_rows_probe=ns)
+            for _ in range(3):
+                got, m = plan.step(d_kr.data_ptr(), d_pr.data_ptr(), d_ks.data_ptr(), d_ps.data_ptr())
+                assert m == wm and got == want, ("multi", plan_kind, graph, nr, ns, zipf, got, m, want, wm)
+            torch.cuda.synchronize()
+            dist.barrier()
+            plan.close()
+        cases += 1
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
