@@ -128,11 +128,11 @@ int b200_copy_to_host(void *host_dst, const void *device_src, uint64_t bytes) {
 void *b200_get_stream(void) { return ctx().stream; }
 
 int b200_set_stream(void *cuda_stream) {
-    // the context's own stream stays alive (buffers allocated on it are freed in its order); a NULL argument
-    // returns to it
+    // the context's own stream stays alive (buffers allocated on it are freed in its order).  NULL is a stream
+    // too: the legacy default stream (what torch.cuda.current_stream() is unless the caller changed it)
     Context &c = ctx();
-    if (c.stream == c.own_stream && cuda_stream) cudaStreamSynchronize(c.own_stream);   // adopted streams are the caller's to order
-    c.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c.own_stream;
+    if (c.stream == c.own_stream) cudaStreamSynchronize(c.own_stream);   // adopted streams are the caller's to order
+    c.stream = static_cast<cudaStream_t>(cuda_stream);
     return 0;
 }
 

@@ -20,7 +20,7 @@ import numpy as np
 
 __all__ = [
     "LIB_PATH", "load_library", "lib", "declared_symbols",
-    "RelationMapArray", "parse_query", "execute_query", "execute_batch", "QueryResult",
+    "RelationMapArray", "DeviceRelationMap", "parse_query", "execute_query", "execute_batch", "QueryResult",
     "scan_filter", "radix_partition", "hash_join_pairs", "gather_sum", "join_sum",
     "join_sum_device", "synth_column_device", "DeviceColumn", "kernel_launches", "last_kernel_ms",
     "SYNTH_PERM", "SYNTH_PAYLOAD", "SYNTH_ZIPF", "SYNTH_UNIFORM", "SYNTH_IOTA",
@@ -302,6 +302,41 @@ class RelationMapArray:
             self.unregister()
         except Exception:
             pass
+
+
+class DeviceRelationMap:
+    """`relation_map rel_map[n]` over columns that are already resident in HBM (bench.py: data generated on the
+    device).  relations[r] = [(device_ptr, rows, max_value), ...].  The library keys device copies by the column
+    pointer the caller's relation_map holds (b200_register_device_column); here that key is the device address
+    itself, so nothing is uploaded."""
+
+    def __init__(self, relations):
+        n = len(relations)
+        self.array = (CRelationMap * n)()
+        self._keep = []
+        L = lib()
+        for r, cols in enumerate(relations):
+            rows = cols[0][1] if cols else 0
+            ptrs = (u64p * len(cols))(*[C.cast(C.c_void_p(p), u64p) for p, _, _ in cols])
+            stats = (CColumnStats * len(cols))()
+            for j, (p, nrows, mx) in enumerate(cols):
+                stats[j].l, stats[j].u, stats[j].f, stats[j].d = 0, int(mx), float(nrows), float(nrows)
+                _check(L.b200_register_device_column(p, p, nrows, int(mx)))
+            self._keep += [ptrs, stats]
+            self.array[r].num_tuples = rows
+            self.array[r].num_columns = len(cols)
+            self.array[r].columns = ptrs
+            self.array[r].col_stats = stats
+
+    def __len__(self):
+        return len(self.array)
+
+    def register(self):
+        pass
+
+    def unregister(self):
+        if _lib is not None:
+            _lib.b200_unregister_relations(self.array, len(self))
 
 
 # --------------------------------------------------------------------------
