@@ -79,7 +79,7 @@ struct MultiPlan {
     uint32_t      *own_total = nullptr, *total = nullptr, *cut = nullptr, *need = nullptr;
     StageScratch   scr_a, scr_b;
     unsigned long long *h_final = nullptr;   // pinned
-    cudaStream_t   copy_stream[kMaxPeers] = {nullptr}, xstream = nullptr;
+    cudaStream_t   copy_stream[kMaxPeers] = {nullptr}, xstream = nullptr, gstream = nullptr;
     cudaEvent_t    ev_build = nullptr, ev_copy[kMaxPeers] = {nullptr}, ev_chunk[kMaxChunks] = {nullptr}, ev_x = nullptr,
                    ev_hist = nullptr;
     // inputs of the step in flight (the overflow pass of finish() needs them)
@@ -438,6 +438,7 @@ b200_multi *b200_multi_create(const b200_multi_config *cfg) {
         B200_CUDA(cudaEventCreateWithFlags(&m->ev_copy[j], cudaEventDisableTiming));
     }
     B200_CUDA(cudaStreamCreateWithFlags(&m->xstream, cudaStreamNonBlocking));
+    B200_CUDA(cudaStreamCreateWithFlags(&m->gstream, cudaStreamNonBlocking));
     B200_CUDA(cudaEventCreateWithFlags(&m->ev_build, cudaEventDisableTiming));
     B200_CUDA(cudaEventCreateWithFlags(&m->ev_hist, cudaEventDisableTiming));
     B200_CUDA(cudaEventCreateWithFlags(&m->ev_x, cudaEventDisableTiming));
@@ -462,6 +463,7 @@ void b200_multi_destroy(b200_multi *plan) {
         if (m->ev_copy[j]) cudaEventDestroy(m->ev_copy[j]);
     }
     if (m->xstream) cudaStreamDestroy(m->xstream);
+    if (m->gstream) cudaStreamDestroy(m->gstream);
     if (m->ev_build) cudaEventDestroy(m->ev_build);
     if (m->ev_hist) cudaEventDestroy(m->ev_hist);
     if (m->ev_x) cudaEventDestroy(m->ev_x);
@@ -544,10 +546,15 @@ int b200_multi_enqueue(b200_multi *plan, const uint64_t *d_build_keys, const uin
                 cudaGraphExecDestroy(m->graph);
                 m->graph = nullptr;
             }
+            // captured on a stream of the plan's own: the caller's may be the legacy default stream, which cannot be
+            // captured; the copy / exchange streams fork from it and join it again through the step's events
             cudaGraph_t g = nullptr;
-            B200_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
-            enqueue(*m, phases);
-            B200_CUDA(cudaStreamEndCapture(c.stream, &g));
+            {
+                StreamSwap sw(c, m->gstream);
+                B200_CUDA(cudaStreamBeginCapture(m->gstream, cudaStreamCaptureModeThreadLocal));
+                enqueue(*m, phases);
+                B200_CUDA(cudaStreamEndCapture(m->gstream, &g));
+            }
             B200_CUDA(cudaGraphInstantiate(&m->graph, g, 0));
             cudaGraphDestroy(g);
             memcpy(m->g_in, in, sizeof(in));
