@@ -183,6 +183,11 @@ static void execute_query(query_t *q) {
     batch_listnode node = {q->nrel, q->rel, NULL, &views, NULL};
     uint64_t       sums[MAX_VIEWS], rows = 0;
     b200_calculate_sums(inter, g_map, &node, sums, &rows);
+    if (b200_last_result_null()) {                     /* a filter fused into a join let nothing through */
+        null_line(q);
+        FreeInterResults(inter);
+        return;
+    }
     char *p = q->line;
     for (int i = 0; i < q->nview; ++i) p += sprintf(p, "%s%lu", i ? " " : "", (unsigned long)sums[i]);
     FreeInterResults(inter);

@@ -162,6 +162,21 @@ int  b200_calculate_sums(inter_res *inter, relation_map *map,
  * of the read-back calls below has materialised it. */
 int  b200_set_lazy_join(int on);
 
+/* Filter fusion (default on; B200_FUSE_FILTERS=0 or b200_set_fuse_filters(0)
+ * turns it off; returns the previous setting): Filter on a base relation of at
+ * least 2^18 rows that is in no intermediate yet returns a deferred result,
+ * InsertSingleRowIdsToInterResult parks its predicate (up to 4 predicates on 3
+ * columns per binding), GetRelation hands the join a key vector that carries
+ * them, and the partition kernels evaluate them in their load stage: no scan
+ * per predicate, no row-id list, no host round trip, no compaction gather
+ * (query.c:337-399 unchanged).  An operator that looks at the binding before
+ * a join does scans the parked predicates the eager way.  A fused filter that
+ * lets nothing through still yields the reference's NULL line:
+ * CalculateQueryResults prints it; after b200_calculate_sums ask
+ * b200_last_result_null(). */
+int  b200_set_fuse_filters(int on);
+int  b200_last_result_null(void);
+
 /* Read-back for tests: copy a result (row ids, or pairs as r[],s[]) and one
  * intermediate column to host as uint64. */
 int  b200_result_kind(const result *res);               /* 1 row ids, 2 pairs */

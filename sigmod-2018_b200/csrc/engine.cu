@@ -396,12 +396,36 @@ template <> struct PartCfg<uint32_t, 3> { static constexpr int NT = 256, U = 48,
 template <> struct PartCfg<uint64_t, 3> { static constexpr int NT = 256, U = 24, MINB = 2; };
 
 template <typename KeyT>
-static void launch_hist(const KeySrc &src, int bits, uint32_t *ghist, int ctas_per_sm = 4) {
+static void launch_hist(const KeySrc &src, int bits, uint32_t *ghist, int ctas_per_sm = 4, const PredSet *ps = nullptr) {
     constexpr int U    = PartCfg<KeyT, 0>::U;
     const size_t  smem = (size_t)(1u << bits) * sizeof(uint32_t);
-    auto          k    = radix_hist_kernel<kPartNT, U, KeyT>;
+    if (ps && ps->npred) {
+        B200_REQUIRE(src.ids == nullptr, "fused predicates apply to base relations");
+        auto k = radix_hist_kernel<kPartNT, U, KeyT, true>;
+        allow_smem(k, smem);
+        k<<<grid_for(src.n, kPartNT * U, ctas_per_sm), kPartNT, smem, launch_stream()>>>(src, (uint32_t)bits, ghist, *ps);
+    } else {
+        auto k = radix_hist_kernel<kPartNT, U, KeyT>;
+        allow_smem(k, smem);
+        k<<<grid_for(src.n, kPartNT * U, ctas_per_sm), kPartNT, smem, launch_stream()>>>(src, (uint32_t)bits, ghist,
+                                                                                        PredSet{});
+    }
+    B200_LAUNCH_CHECK();
+}
+
+// scatter with the relation's filter predicates folded into its load stage (plain and histogram-free instance)
+template <typename KeyT, bool OPT>
+static void launch_scatter_pred(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
+    using TupT         = typename TupOf<KeyT>::type;
+    constexpr int NT   = PartCfg<KeyT, 1>::NT;
+    constexpr int U    = PartCfg<KeyT, 1>::U;
+    constexpr int MINB = PartCfg<KeyT, 1>::MINB;
+    B200_REQUIRE(src.ids == nullptr && opt.pred.npred > 0, "fused predicates apply to base relations");
+    const size_t smem = (size_t)NT * U * sizeof(TupT) + (OPT ? 4 : 3) * (size_t)(1u << bits) * sizeof(uint32_t);
+    auto         k    = radix_scatter_kernel<NT, U, MINB, KeyT, OPT, false, true>;
     allow_smem(k, smem);
-    k<<<grid_for(src.n, kPartNT * U, ctas_per_sm), kPartNT, smem, launch_stream()>>>(src, (uint32_t)bits, ghist);
+    k<<<grid_for(src.n, NT * U, MINB), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor, static_cast<TupT *>(out),
+                                                                 opt);
     B200_LAUNCH_CHECK();
 }
 
@@ -421,7 +445,7 @@ static void launch_scatter_c(const KeySrc &src, int bits, uint32_t *cursor, void
 
 template <typename KeyT>
 static void launch_scatter(const KeySrc &src, int bits, uint32_t *cursor, void *out) {
-    const OptArgs none{0, nullptr, nullptr, nullptr};
+    const OptArgs none{0, nullptr, nullptr, nullptr, PredSet{}};
     switch (tuning().scatter_cfg) {
         case 0: launch_scatter_c<KeyT, 0, false>(src, bits, cursor, out, none); break;
         case 2: launch_scatter_c<KeyT, 2, false>(src, bits, cursor, out, none); break;
@@ -439,7 +463,7 @@ static void launch_scatter_carry_tuned(const KeySrc &src, int bits, uint32_t *cu
     const size_t  smem = (size_t)NT * U * sizeof(Tup32) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
     auto          k    = radix_scatter_kernel<NT, U, MINB, uint32_t, false, true>;
     allow_smem(k, smem);
-    const OptArgs carry{0, nullptr, nullptr, carry_col};
+    const OptArgs carry{0, nullptr, nullptr, carry_col, PredSet{}};
     k<<<grid_for(src.n, NT * U, MINB), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor,
                                                                  static_cast<Tup32 *>(out), carry);
     B200_LAUNCH_CHECK();
@@ -711,7 +735,10 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     const KeyVec &P       = swapped ? R : S;
     // A build side that fits one shared-memory table is joined without a
     // partition pass (DIRECT), by the chained-table kernel on 64-bit keys.
-    const bool direct = t.radix_bits <= 0 && B.src.n <= t.cap64;
+    const bool pred_b = B.preds.npred > 0, pred_p = P.preds.npred > 0;
+    // (a relation with fused predicates is a large base relation — operators.cu fuses from 2^18 rows up — so it is
+    // never the build side of an unpartitioned join)
+    const bool direct = t.radix_bits <= 0 && B.src.n <= t.cap64 && !pred_b;
     // 32-bit keys (8-byte partition tuples, tag-table kernel) when every key fits
     const bool key64 = direct || t.force_key64 || B.max_val > 0xFFFFFFFFull || P.max_val > 0xFFFFFFFFull;
     const uint32_t cap = key64 ? t.cap64 : t.cap32;
@@ -745,6 +772,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     a.total        = d_u64;
     a.out_cursor   = d_u64 + 1;
     a.sums         = d_u64 + 8;
+    unsigned long long *d_valid_p = d_u64 + 2;   // DIRECT: probe rows that passed their fused predicates
 
     DevBufPtr tup_b, tup_p, ov_tup;
     bool      opt     = false;
@@ -755,6 +783,10 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     if (direct) {
         a.src_b = B.src;
         a.src_p = P.src;
+        if (pred_p) {
+            a.pred_p  = P.preds;
+            a.valid_p = d_valid_p;
+        }
         // slices big enough to amortise rebuilding the table, small enough to
         // spread over the SMs
         uint64_t slice = std::max<uint64_t>({4096, 4ull * std::min<uint64_t>(B.src.n, cap),
@@ -780,7 +812,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         // SUM travel with the build tuples into partition order (32-bit-key path)
         PayArgs pay{};
         int     npay = 0;
-        if (mode == JoinOut::Sum && !key64 && t.early_mat) {
+        if (mode == JoinOut::Sum && !key64 && t.early_mat && !pred_b) {
             const int side_b  = swapped ? 1 : 0;   // proj[].side is relative to (R, S)
             int       n_build = 0, first = -1;
             for (int k = 0; k < nproj; ++k)
@@ -813,7 +845,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         // instead of the join gathering it at random (8 B per MATCH at ~38 G gathers/s), which pays
         // when matches are not rare: expected matches per probe row = build rows / key domain for a unique
         // build side (stats.c estimates join cardinalities the same way from the column ranges).
-        if (mode == JoinOut::Sum && opt && t.carry32 && t.carry_probe && P.src.ids == nullptr) {
+        if (mode == JoinOut::Sum && opt && t.carry32 && t.carry_probe && P.src.ids == nullptr && !pred_p) {
             const int side_p  = swapped ? 0 : 1;
             int       n_probe = 0, first = -1;
             for (int k = 0; k < nproj; ++k)
@@ -831,7 +863,11 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         }
         auto scatter_build = [&](uint32_t *cursor) {
             TimedScope ts("scatter_b");
-            if (npay > 0)
+            if (pred_b) {
+                const OptArgs o{0, nullptr, nullptr, nullptr, B.preds};
+                if (key64) launch_scatter_pred<uint64_t, false>(B.src, bits, cursor, tup_b->ptr, o);
+                else launch_scatter_pred<uint32_t, false>(B.src, bits, cursor, tup_b->ptr, o);
+            } else if (npay > 0)
                 launch_scatter_pay<uint32_t>(B.src, bits, cursor, tup_b->ptr, pay, npay);
             else if (key64)
                 launch_scatter<uint64_t>(B.src, bits, cursor, tup_b->ptr);
@@ -841,9 +877,9 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         {
             TimedScope ts("hist_b");
             if (key64)
-                launch_hist<uint64_t>(B.src, bits, hist_b);
+                launch_hist<uint64_t>(B.src, bits, hist_b, 4, &B.preds);
             else
-                launch_hist<uint32_t>(B.src, bits, hist_b);
+                launch_hist<uint32_t>(B.src, bits, hist_b, 4, &B.preds);
         }
         if (opt) {
             // build side: exact (its histogram is cheap); hist_p is still all zero here
@@ -855,12 +891,15 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             B200_LAUNCH_CHECK();
             ov_tup = dev_alloc((size_t)P.src.n * tsz);
             {
-                TimedScope ts(carry_p >= 0 ? "scatter_pc" : "scatter_p");   // pc: with the carried SUM column
-                if (carry_p >= 0)
+                TimedScope ts(carry_p >= 0 ? "scatter_pc" : pred_p ? "filter_fused" : "scatter_p");   // pc: carried SUM column
+                if (pred_p)
+                    launch_scatter_pred<uint32_t, true>(P.src, bits, cur_p, tup_p->ptr,
+                                                        OptArgs{opt_cap, d_ovcnt, ov_tup->ptr, nullptr, P.preds});
+                else if (carry_p >= 0)
                     launch_scatter_opt_carry(P.src, bits, cur_p, tup_p->ptr,
-                                             OptArgs{opt_cap, d_ovcnt, ov_tup->ptr, proj[carry_p].col});
+                                             OptArgs{opt_cap, d_ovcnt, ov_tup->ptr, proj[carry_p].col, PredSet{}});
                 else
-                    launch_scatter_opt(P.src, bits, cur_p, tup_p->ptr, OptArgs{opt_cap, d_ovcnt, ov_tup->ptr, nullptr});
+                    launch_scatter_opt(P.src, bits, cur_p, tup_p->ptr, OptArgs{opt_cap, d_ovcnt, ov_tup->ptr, nullptr, PredSet{}});
             }
             {
                 TimedScope ts("scan");
@@ -872,9 +911,9 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             {
                 TimedScope ts("hist_p");
                 if (key64)
-                    launch_hist<uint64_t>(P.src, bits, hist_p);
+                    launch_hist<uint64_t>(P.src, bits, hist_p, 4, &P.preds);
                 else
-                    launch_hist<uint32_t>(P.src, bits, hist_p);
+                    launch_hist<uint32_t>(P.src, bits, hist_p, 4, &P.preds);
             }
             {
                 TimedScope ts("scan");
@@ -884,8 +923,12 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             }
             scatter_build(cur_b);
             {
-                TimedScope ts("scatter_p");
-                if (key64)
+                TimedScope ts(pred_p ? "filter_fused" : "scatter_p");
+                if (pred_p) {
+                    const OptArgs o{0, nullptr, nullptr, nullptr, P.preds};
+                    if (key64) launch_scatter_pred<uint64_t, false>(P.src, bits, cur_p, tup_p->ptr, o);
+                    else launch_scatter_pred<uint32_t, false>(P.src, bits, cur_p, tup_p->ptr, o);
+                } else if (key64)
                     launch_scatter<uint64_t>(P.src, bits, cur_p, tup_p->ptr);
                 else
                     launch_scatter<uint32_t>(P.src, bits, cur_p, tup_p->ptr);
@@ -920,10 +963,23 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             B200_CUDA(cudaMemcpyAsync(c.h_scratch, d_u64, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                       c.stream));
             B200_CUDA(cudaMemcpyAsync(c.h_scratch + 16, d_ovcnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+            if (!direct && (pred_b || pred_p)) {   // tuples that reached the partition buffers = rows that passed
+                B200_CUDA(cudaMemcpyAsync(c.h_scratch + 17, off_b + nparts, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+                B200_CUDA(cudaMemcpyAsync(c.h_scratch + 18, off_p + nparts, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+            }
             B200_CUDA(cudaStreamSynchronize(c.stream));
         };
         read_back();
         const uint32_t n_over = opt ? *reinterpret_cast<uint32_t *>(c.h_scratch + 16) : 0u;
+        uint64_t valid_b = UINT64_MAX, valid_p = UINT64_MAX;
+        if (direct) {
+            if (pred_p) valid_p = c.h_scratch[2];
+        } else {
+            if (pred_b) valid_b = *reinterpret_cast<uint32_t *>(c.h_scratch + 17);
+            if (pred_p) valid_p = (uint64_t)*reinterpret_cast<uint32_t *>(c.h_scratch + 18) + n_over;
+        }
+        res.valid_r = swapped ? valid_p : valid_b;
+        res.valid_s = swapped ? valid_b : valid_p;
         if (n_over) {
             // second pass over the overflow only: exact histogram, scatter, join against the same build partitions
             // (matches and sums keep accumulating in the same device counters)
@@ -952,6 +1008,8 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             B200_CUDA(cudaMemcpyAsync(c.h_scratch, items + nparts, sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                       c.stream));
             B200_CUDA(cudaMemcpyAsync(c.h_scratch + 1, d_ovcnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+            B200_CUDA(cudaMemcpyAsync(c.h_scratch + 17, off_b + nparts, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+            B200_CUDA(cudaMemcpyAsync(c.h_scratch + 18, off_p + nparts, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
             B200_CUDA(cudaStreamSynchronize(c.stream));
             n_items = *reinterpret_cast<uint32_t *>(c.h_scratch);
         };
@@ -963,16 +1021,25 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             const size_t tsz = sizeof(Tup32);
             B200_CUDA(cudaMemsetAsync(hist_p, 0, (size_t)nparts * sizeof(uint32_t), c.stream));
             B200_CUDA(cudaMemsetAsync(d_ovcnt, 0, sizeof(uint32_t), c.stream));
-            launch_hist<uint32_t>(P.src, bits, hist_p);
+            launch_hist<uint32_t>(P.src, bits, hist_p, 4, &P.preds);
             partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, hist_p, nparts, cap, a.slice, off_b, off_p,
                                                                   cur_b, cur_p, items, cnt_p, 0u);
             B200_LAUNCH_CHECK();
             tup_p = dev_alloc((size_t)P.src.n * tsz);
-            launch_scatter<uint32_t>(P.src, bits, cur_p, tup_p->ptr);
+            if (pred_p)
+                launch_scatter_pred<uint32_t, false>(P.src, bits, cur_p, tup_p->ptr,
+                                                     OptArgs{0, nullptr, nullptr, nullptr, P.preds});
+            else
+                launch_scatter<uint32_t>(P.src, bits, cur_p, tup_p->ptr);
             a.tup_p = tup_p->ptr;
             opt     = false;
             read_items();
         }
+        uint64_t valid_b = UINT64_MAX, valid_p = UINT64_MAX;
+        if (pred_b) valid_b = *reinterpret_cast<uint32_t *>(c.h_scratch + 17);
+        if (pred_p) valid_p = *reinterpret_cast<uint32_t *>(c.h_scratch + 18);   // (an overflowing pass was redone exactly)
+        res.valid_r = swapped ? valid_p : valid_b;
+        res.valid_s = swapped ? valid_b : valid_p;
     }
     DevBufPtr item_count = dev_alloc((n_items + 1) * sizeof(unsigned long long));
     a.item_count         = item_count->as<unsigned long long>();
@@ -981,6 +1048,11 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         launch_join(a, key64, direct, MODE_COUNT);
     }
     res.m = read_counter(a.total);
+    if (direct && pred_p) {
+        const uint64_t v = read_counter(d_valid_p);
+        (swapped ? res.valid_r : res.valid_s) = v;
+        a.valid_p = nullptr;   // the write pass loads the same rows again: count them once
+    }
     B200_REQUIRE(res.m <= kMaxRows, "join output exceeds 2^32-1 pairs (32-bit device positions)");
     DevBufPtr out_b = dev_alloc(res.m * sizeof(uint32_t));
     DevBufPtr out_p = dev_alloc(res.m * sizeof(uint32_t));
@@ -1003,9 +1075,7 @@ constexpr int kScanNT = 256;
 constexpr int kScanU  = 8;
 
 IdList run_filter(const KeySrc &src, char cmp, int value) {
-    Context &c = ctx();
-    IdList   out;
-    int      code;
+    int code;
     switch (cmp) {
         case '<': code = 0; break;
         case '>': code = 1; break;
@@ -1015,11 +1085,17 @@ IdList run_filter(const KeySrc &src, char cmp, int value) {
             fprintf(stderr, "Wrong comperator in filter function\n");
             exit(2);
     }
+    // `uint64_t ⋄ int`: the int is converted to uint64_t (sign-extended)
+    return run_filter_u64(src, code, (uint64_t)(int64_t)value);
+}
+
+IdList run_filter_u64(const KeySrc &src, int code, uint64_t constant) {
+    Context &c = ctx();
+    IdList   out;
     out.ids = dev_alloc((size_t)src.n * sizeof(uint32_t));
     if (src.n == 0) return out;
+    TimedScope ts("filter");
     B200_CUDA(cudaMemsetAsync(c.d_scratch, 0, sizeof(unsigned long long), c.stream));
-    // `uint64_t ⋄ int`: the int is converted to uint64_t (sign-extended)
-    const uint64_t constant = (uint64_t)(int64_t)value;
     scan_filter_kernel<kScanNT, kScanU>
         <<<grid_for(src.n, kScanNT * kScanU, 8), kScanNT, 0, c.stream>>>(src, code, constant,
                                                                          out.ids->as<uint32_t>(), c.d_scratch);
@@ -1339,9 +1415,9 @@ void stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint3
     KeySrc src{d_keys, nullptr, (uint32_t)n};
     TimedScope ts(carry_col ? "scatter_pc" : "scatter_p");
     if (carry_col)
-        launch_scatter_opt_carry(src, bits, d_cursor, d_tup_out, OptArgs{opt_cap, d_ovcnt, d_ov, carry_col});
+        launch_scatter_opt_carry(src, bits, d_cursor, d_tup_out, OptArgs{opt_cap, d_ovcnt, d_ov, carry_col, PredSet{}});
     else
-        launch_scatter_opt(src, bits, d_cursor, d_tup_out, OptArgs{opt_cap, d_ovcnt, d_ov, nullptr});
+        launch_scatter_opt(src, bits, d_cursor, d_tup_out, OptArgs{opt_cap, d_ovcnt, d_ov, nullptr, PredSet{}});
 }
 
 // d_hist_p: probe-side histogram (opt_cap == 0) or the cursor array stage_scatter_probe_opt left behind

@@ -32,6 +32,9 @@ struct KeyVec {
     KeySrc    src{nullptr, nullptr, 0};
     DevBufPtr ids_owner;
     uint64_t  max_val = UINT64_MAX;
+    // filter predicates of this (base) relation evaluated inside the partition kernels' load stage instead of by a
+    // scan + row-id list: rows that fail do not take part; row ids stay base row ids (ids == nullptr)
+    PredSet   preds;
 };
 
 struct Tuning {
@@ -54,6 +57,9 @@ Tuning &tuning();
 enum class JoinOut { Pairs, Sum };
 
 struct JoinResult {
+    // rows of R / S that passed their fused predicates (UINT64_MAX: that side had none).  Zero means the filter
+    // was empty: the reference prints NULL for the whole query then (query.c:360-369)
+    uint64_t  valid_r = UINT64_MAX, valid_s = UINT64_MAX;
     uint64_t  m = 0;              // number of matching pairs
     DevBufPtr r_ids, s_ids;       // Pairs: 32-bit row ids, m each
     uint64_t  sums[kMaxProj] = {0};
@@ -76,6 +82,7 @@ struct IdList {
     uint64_t  n = 0;
 };
 IdList run_filter(const KeySrc &src, char cmp, int value);
+IdList run_filter_u64(const KeySrc &src, int cmp_code, uint64_t constant);   // cmp_code: 0 '<', 1 '>', 2 '='
 IdList run_inter_equal(const uint64_t *col_a, const uint32_t *ta, const uint64_t *col_b,
                        const uint32_t *tb, uint64_t n);
 

@@ -58,6 +58,29 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
     return v;
 }
 
+// ---- predicates folded into the load stage (types.cuh PredSet; filter.c:115-170's comparisons) ----
+__device__ __forceinline__ bool pred_holds(int cmp, uint64_t v, uint64_t k) {
+    return cmp == 0 ? v < k : cmp == 1 ? v > k : v == k;
+}
+__device__ __forceinline__ bool preds_hold(const PredSet &ps, const uint64_t (&v)[kMaxPredCols]) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < kMaxPred; ++i) {
+        if (i < ps.npred) {
+            const int      c  = ps.p[i].col;
+            const uint64_t vv = c == 0 ? v[0] : c == 1 ? v[1] : v[2];
+            ok                = ok && pred_holds(ps.p[i].cmp, vv, ps.p[i].k);
+        }
+    }
+    return ok;
+}
+__device__ __forceinline__ bool preds_hold_row(const PredSet &ps, uint64_t row) {
+    uint64_t v[kMaxPredCols];
+#pragma unroll
+    for (int c = 0; c < kMaxPredCols; ++c) v[c] = c < ps.ncols ? ld_stream_u64(ps.col[c] + row) : 0ull;
+    return preds_hold(ps, v);
+}
+
 // Exclusive block scan of one value per thread.  warp_sums needs NT/32+1
 // slots; slot NT/32 receives the block total.  Ends with a barrier so the
 // scratch can be reused immediately.
@@ -155,9 +178,10 @@ __device__ __forceinline__ void load_tile_keys(const KeySrc &src, uint64_t base,
 // K3: histogram of key & mask (preprocess.c:189-192 with N_LSB = radix bits).
 // Shared-memory bins per CTA, one global atomicAdd per non-empty bin at exit.
 // ---------------------------------------------------------------------------
-template <int NT, int U, typename KeyT>
+// PRED: rows that fail the predicates are not counted (they will not be scattered either).
+template <int NT, int U, typename KeyT, bool PRED = false>
 __global__ void __launch_bounds__(NT)
-radix_hist_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ ghist) {
+radix_hist_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ ghist, const PredSet ps) {
     extern __shared__ uint32_t sh_hist[];
     constexpr uint32_t TILE  = NT * U;
     const uint32_t     nbins = 1u << radix_bits;
@@ -175,8 +199,10 @@ radix_hist_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ ghist)
         load_tile_keys<NT, U, KeyT>(src, base, count, vec, keys);
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-            if (tile_local_index<NT, U>(j, vec) < count)
-                atomicAdd(&sh_hist[(uint32_t)keys[j] & mask], 1u);
+            const uint32_t li = tile_local_index<NT, U>(j, vec);
+            bool           on = li < count;
+            if constexpr (PRED) on = on && preds_hold_row(ps, base + li);
+            if (on) atomicAdd(&sh_hist[(uint32_t)keys[j] & mask], 1u);
         }
     }
     __syncthreads();
@@ -283,6 +309,7 @@ struct OptArgs {
     uint32_t       *ov_cursor;
     void           *ov_out;
     const uint64_t *carry_col;   // CARRY instances only
+    PredSet         pred;        // PRED instances only
 };
 // CARRY: the row-id slot of a tuple carries (uint32)carry_col[row] instead of the row id (a SUM column whose
 // values fit 32 bits travels inside the tuple: the probe side of the multi-GPU exchange plan).  The column is
@@ -337,7 +364,10 @@ __device__ __forceinline__ KeyT narrow_key(uint64_t v) {
     else return (KeyT)v;
 }
 
-template <int NT, int U, typename KeyT, bool FULL, bool OPT, bool CARRY = false>
+// PRED (never FULL): rows that fail opt.pred are skipped — a filtered base relation feeds the join without a row-id
+// list, a host round trip or a compaction gather.  The predicate columns of a tile are pulled into L2
+// one tile ahead like a carried column and read with 128-bit loads at the top of the tile.
+template <int NT, int U, typename KeyT, bool FULL, bool OPT, bool CARRY = false, bool PRED = false>
 __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[U], uint64_t base, uint32_t count,
                                              bool vec, uint64_t nbase, uint32_t ncount, bool nvec, bool has_next,
                                              uint32_t nbins, uint32_t mask, uint32_t per,
@@ -353,6 +383,41 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     KeyT           keys[U];
 #pragma unroll
     for (int j = 0; j < U; ++j) keys[j] = narrow_key<KeyT>(raw[j]);
+    static_assert(!(PRED && FULL), "the predicated instance takes the general path");
+    static_assert(U <= 64, "one validity bit per key");
+    [[maybe_unused]] uint64_t valid = 0;   // PRED: bit j = row of register j passes every predicate
+    if constexpr (PRED) {
+        const PredSet &ps = opt.pred;
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < U; j += 2) {
+                const uint32_t li = ((uint32_t)((j >> 1) * NT) + tid) * 2u;
+                uint64_t       v0[kMaxPredCols], v1[kMaxPredCols];
+#pragma unroll
+                for (int cc = 0; cc < kMaxPredCols; ++cc) {
+                    v0[cc] = v1[cc] = 0;
+                    if (cc < ps.ncols) {
+                        const ulonglong2 t = ld_stream_u64x2(ps.col[cc] + base + li);
+                        v0[cc]             = t.x;
+                        v1[cc]             = t.y;
+                    }
+                }
+                valid |= (uint64_t)(preds_hold(ps, v0) ? 1u : 0u) << j;
+                valid |= (uint64_t)(preds_hold(ps, v1) ? 1u : 0u) << (j + 1);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const uint32_t li = (uint32_t)(j * NT) + tid;
+                if (li < count && preds_hold_row(ps, base + li)) valid |= 1ull << j;
+            }
+        }
+    }
+    auto row_on = [&](int j, uint32_t li) -> bool {
+        if constexpr (FULL) return true;
+        else if constexpr (PRED) return ((valid >> j) & 1ull) != 0ull;
+        else return li < count;
+    };
     uint32_t rank2[(U + 1) / 2];   // two 16-bit ranks per register
 #pragma unroll
     for (int j = 0; j < (U + 1) / 2; ++j) rank2[j] = 0;
@@ -361,7 +426,7 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     for (int j = 0; j < U; ++j) {
         const uint32_t li = FULL ? ((uint32_t)((j >> 1) * NT) + tid) * 2u + (uint32_t)(j & 1)
                                  : tile_local_index<NT, U>(j, vec);
-        if (FULL || li < count) {
+        if (row_on(j, li)) {
             const uint32_t r = atomicAdd(&cnt[(uint32_t)keys[j] & mask], 1u);
             rank2[j >> 1] |= r << (16 * (j & 1));
         }
@@ -383,7 +448,7 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     if (lane == 31) warp_sums[wid] = incl;
     if (OPT && tid == 0) *s_over = 0u;
     __syncthreads();   // (B) warp totals visible (every warp scans them redundantly: no second barrier)
-    uint32_t wbase = 0;
+    uint32_t wbase = 0, staged = 0;
     {
         const uint32_t w = lane < (uint32_t)NW ? warp_sums[lane] : 0u;
         uint32_t       wi = w;
@@ -393,6 +458,7 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
             if (lane >= (uint32_t)d) wi += t;
         }
         wbase = __shfl_sync(kFullMask, wi - w, (int)wid);
+        staged = __shfl_sync(kFullMask, wi, NW - 1);   // tuples of this tile (< count when rows were filtered out)
     }
     // global position of stage slot i of partition b is gdelta[b] + i; a run that leaves its OPT region goes to
     // the overflow array at ovdelta[b] + i
@@ -438,7 +504,7 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     for (int j = 0; j < U; ++j) {
         const uint32_t li = FULL ? ((uint32_t)((j >> 1) * NT) + tid) * 2u + (uint32_t)(j & 1)
                                  : tile_local_index<NT, U>(j, vec);
-        if (FULL || li < count) {
+        if (row_on(j, li)) {
             TupT t;
             t.key = keys[j];
             if constexpr (CARRY) {
@@ -477,6 +543,9 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     if (has_next) {
         load_tile_raw<NT, U>(src, nbase, ncount, nvec, raw);
         if constexpr (CARRY) prefetch_carry_tile<NT, U>(opt.carry_col, nbase, ncount);
+        if constexpr (PRED) {
+            for (int cc = 0; cc < opt.pred.ncols; ++cc) prefetch_carry_tile<NT, U>(opt.pred.col[cc], nbase, ncount);
+        }
     }
     // ---- (5) copy-out: a warp stores consecutive addresses inside each run ----
     bool over = false;
@@ -490,11 +559,11 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
 #pragma unroll
             for (int k = 0; k < U; ++k) put((uint32_t)(k * NT) + tid);
         } else {
-            for (uint32_t i = tid; i < count; i += NT) put(i);
+            for (uint32_t i = tid; i < staged; i += NT) put(i);
         }
     } else {
         if constexpr (OPT) {
-            for (uint32_t i = tid; i < count; i += NT) {
+            for (uint32_t i = tid; i < staged; i += NT) {
                 const TupT     t   = stage[i];
                 const uint32_t b   = (uint32_t)t.key & mask;
                 const uint32_t pos = gdelta[b] + i;
@@ -506,7 +575,7 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     __syncthreads();   // (E) stage and bin arrays free for the next tile
 }
 
-template <int NT, int U, int MINB, typename KeyT, bool OPT, bool CARRY = false>
+template <int NT, int U, int MINB, typename KeyT, bool OPT, bool CARRY = false, bool PRED = false>
 __global__ void __launch_bounds__(NT, MINB)
 radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cursor,
                      typename TupOf<KeyT>::type *__restrict__ out, const OptArgs opt) {
@@ -526,8 +595,11 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
     // row ids are 32-bit: tile bases fit 32 bits as well
     const uint64_t n      = src.n;
     const uint64_t ntiles = (n + TILE - 1) / TILE;
-    const bool     vec_ok = src.ids == nullptr && ((reinterpret_cast<uintptr_t>(src.col) & 15) == 0) &&
-                        (!CARRY || (reinterpret_cast<uintptr_t>(opt.carry_col) & 15) == 0);
+    bool           vec_ok = src.ids == nullptr && ((reinterpret_cast<uintptr_t>(src.col) & 15) == 0) &&
+                  (!CARRY || (reinterpret_cast<uintptr_t>(opt.carry_col) & 15) == 0);
+    if constexpr (PRED) {
+        for (int cc = 0; cc < opt.pred.ncols; ++cc) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(opt.pred.col[cc]) & 15) == 0;
+    }
     const uint32_t per    = (nbins + NT - 1) / NT;
 
     for (uint32_t b = threadIdx.x; b < nbins; b += NT) cnt[b] = 0;
@@ -538,6 +610,9 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
         const uint32_t count = (uint32_t)min((uint64_t)TILE, n - base);
         load_tile_raw<NT, U>(src, base, count, vec_ok && count == TILE, raw);
         if constexpr (CARRY) prefetch_carry_tile<NT, U>(opt.carry_col, base, count);
+        if constexpr (PRED) {
+            for (int cc = 0; cc < opt.pred.ncols; ++cc) prefetch_carry_tile<NT, U>(opt.pred.col[cc], base, count);
+        }
     }
     __syncthreads();
 
@@ -550,14 +625,19 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
         const uint64_t nbase    = ntile * TILE;
         const uint32_t ncount   = has_next ? (uint32_t)min((uint64_t)TILE, n - nbase) : 0u;
         const bool     nvec     = vec_ok && ncount == TILE;
-        if (vec)
+        if constexpr (PRED) {
+            scatter_tile<NT, U, KeyT, false, OPT, CARRY, true>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
+                                                               nbins, mask, per, stage, cnt, loc, gdelta, warp_sums,
+                                                               cursor, out, opt, ovdelta, &s_over);
+        } else if (vec) {
             scatter_tile<NT, U, KeyT, true, OPT, CARRY>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
                                                         nbins, mask, per, stage, cnt, loc, gdelta, warp_sums, cursor,
                                                         out, opt, ovdelta, &s_over);
-        else
+        } else {
             scatter_tile<NT, U, KeyT, false, OPT, CARRY>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
                                                          nbins, mask, per, stage, cnt, loc, gdelta, warp_sums, cursor,
                                                          out, opt, ovdelta, &s_over);
+        }
     }
 }
 
@@ -813,6 +893,10 @@ struct JoinArgs {
     const uint32_t *wait_flags, *wait_epoch;
     uint32_t        chunk_rows, seg_rows;
     uint32_t       *wait_error;       // set to 1 when a flag did not arrive within the spin budget
+    // DIRECT only: predicates folded into the probe-side load (a filtered base relation probing a small build side);
+    // valid_p counts the probe rows that passed (an empty filter makes the whole query NULL, query.c:360-369)
+    PredSet             pred_p;
+    unsigned long long *valid_p;
     int             nproj;            // SUM
     int             need_brid;        // SUM: some build-side projection is gathered through the row id
     ProjDesc        proj[kMaxProj];
@@ -903,6 +987,7 @@ hash_join_kernel(const JoinArgs a) {
     const TupT *tup_p = static_cast<const TupT *>(a.tup_p);
 
     unsigned long long my_matches = 0;
+    uint32_t           my_valid   = 0;   // DIRECT with predicates: probe rows that passed
     unsigned long long my_sum[NPA];
     unsigned long long pend[NPA];   // values loaded by the previous drain
 #pragma unroll
@@ -1064,6 +1149,10 @@ hash_join_kernel(const JoinArgs a) {
                     t.rid = p_start + li;
                     t.key = (KeyT)(a.src_p.ids ? __ldg(a.src_p.col + ld_stream_u32(a.src_p.ids + t.rid))
                                                : ld_stream_u64(a.src_p.col + t.rid));
+                    if (a.pred_p.npred) {
+                        if (preds_hold_row(a.pred_p, t.rid)) ++my_valid;
+                        else t.rid = 0xFFFFFFFFu;   // filtered out (never a row id: at most 2^32 - 1 rows)
+                    }
                 } else if constexpr (sizeof(KeyT) == 8) {
                     const ulonglong2 v = ld_stream_u64x2(reinterpret_cast<const uint64_t *>(tup_p + p_start + li));
                     t.key = v.x;
@@ -1108,7 +1197,8 @@ hash_join_kernel(const JoinArgs a) {
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 uint32_t nh = 0;
-                if (full_round || off + (uint32_t)(j * NT) + tid < p_count) nh = probe_one(cur[j].key, cur[j].rid);
+                if ((full_round || off + (uint32_t)(j * NT) + tid < p_count) && (!DIRECT || cur[j].rid != 0xFFFFFFFFu))
+                    nh = probe_one(cur[j].key, cur[j].rid);
                 if constexpr (MODE == MODE_COUNT) {
                     item_matches += nh;
                 } else {
@@ -1150,6 +1240,12 @@ hash_join_kernel(const JoinArgs a) {
         __syncthreads();   // table and s_item are reused by the next item
     }
 
+    if constexpr (DIRECT) {
+        if (a.pred_p.npred && a.valid_p) {   // (every mode loads each probe row exactly once per build chunk)
+            const unsigned long long wv = warp_sum_u64(my_valid);
+            if (lane == 0 && wv) atomicAdd(a.valid_p, wv);
+        }
+    }
     if constexpr (MODE == MODE_SUM) {
         // K9: warp-shuffle reduction, one atomicAdd(u64) per warp and projection
         const unsigned long long wm = warp_sum_u64(my_matches);

@@ -19,12 +19,18 @@ struct B200Relation : relation {
     KeyVec kv;
 };
 
-enum ResultKind { kRowIds = 1, kPairs = 2, kDeferredJoin = 3 };
+enum ResultKind { kRowIds = 1, kPairs = 2, kDeferredJoin = 3, kDeferredFilter = 4 };
 struct B200Result : result {
     int       kind = 0;
     DevBufPtr a, b;   // row ids / (R ids, S ids)
     uint64_t  n = 0;
     KeyVec    kr, ks;   // kDeferredJoin: the two inputs of a join that has not run yet
+    bool      fused_r = false, fused_s = false;   // join inputs whose filter predicates ran inside the join's load stage
+    bool      null_query = false;                 // ... and one of those filters turned out empty
+    // kDeferredFilter: one predicate on a base column that has not been scanned (see PendingFilter)
+    const uint64_t *f_col = nullptr;
+    int             f_cmp = 0;
+    uint64_t        f_k   = 0;
 };
 
 // Lazy last join ("fold the last join into the SUM"; query.c:408-461 runs the joins one after
@@ -42,12 +48,45 @@ struct PendingJoin {
     int    active_side = -1;   // -1: both bindings are new to the node; 0 / 1: rel1 / rel2 was already in it
 };
 
+// Filter fusion (query.c:337-399 runs every filter of a binding before its first join, each one a full
+// scan, filter.c:92-190).  A filter on a LARGE base relation that is in no intermediate node yet is not scanned:
+// Filter returns a deferred result, InsertSingleRowIdsToInterResult parks its predicate on a node that holds nothing
+// but that binding (which reads as active from then on), further filters on the binding join the parked set, and
+// GetRelation hands the join a key vector that carries the predicates: the partition kernels evaluate them in
+// their load stage — no row-id list, no host round trip, no compaction gather — and the join reports base row
+// ids for the binding, exactly what the eager path's row-id list would have translated its positions into.
+// Any other operator that looks at the node first scans the parked predicates the eager way (resolve_filter).  An
+// empty filter still makes the whole query NULL (query.c:360-369): the kernels count the rows that passed.
+struct PendingFilter {
+    bool    active  = false;
+    int     binding = -1;
+    uint64_t rows   = 0;      // rows of the base relation
+    uint64_t max_val[kMaxPredCols] = {0, 0, 0};
+    PredSet preds;
+};
+
 struct B200InterData : inter_data {
     std::vector<DevBufPtr> bufs;
     PendingJoin            pending;
+    PendingFilter          pfilter;
+    bool                   null_query = false;   // a fused filter was empty: the query's answer is NULL
 };
 
-uint64_t *const kParked = reinterpret_cast<uint64_t *>(8);   // table[] entry of a binding whose join is parked
+uint64_t *const kParked  = reinterpret_cast<uint64_t *>(8);    // table[] entry of a binding whose join is parked
+uint64_t *const kParkedF = reinterpret_cast<uint64_t *>(16);   // ... whose filter predicates are parked
+constexpr uint64_t kFuseMinRows = 1ull << 18;                  // smaller relations are filtered the eager way
+
+thread_local bool t_null_result = false;   // see b200_last_result_null
+std::atomic<int> g_fuse_filters{-1};   // -1: B200_FUSE_FILTERS from the environment (default on)
+bool fuse_filters_enabled() {
+    int v = g_fuse_filters.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = getenv("B200_FUSE_FILTERS");
+        v             = e ? (atoi(e) != 0) : 1;
+        g_fuse_filters.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
 
 std::atomic<int> g_lazy_join{-1};   // -1: B200_LAZY_JOIN from the environment (default on)
 bool lazy_join_enabled() {
@@ -160,16 +199,75 @@ void resolve(inter_res *node) {
     if (pj.active_side != 1) d->table[pj.rel2] = nullptr;
     if (pj.active_side < 0) d->num_tuples = 0;
     JoinResult j = run_join(pj.kr, pj.ks, JoinOut::Pairs, 0, nullptr);
+    if (j.valid_r == 0 || j.valid_s == 0) d->null_query = true;   // a fused filter was empty
     insert_pairs(node, pj.rel1, pj.rel2, pj.active_side, j.m, j.r_ids, j.s_ids);
 }
 void resolve_all(inter_res *head) {
     for (; head; head = head->next) resolve(head);
 }
 
+// scan the parked predicates of `node` the eager way (filter.c:92-190 once per predicate, filter.c:11-89 in between)
+void resolve_filter(inter_res *node) {
+    B200InterData *d = idata(node);
+    if (!d->pfilter.active) return;
+    PendingFilter pf = d->pfilter;
+    d->pfilter       = PendingFilter{};
+    const int b      = pf.binding;
+    d->table[b]      = nullptr;
+    d->num_tuples    = 0;
+    DevBufPtr ids;
+    uint64_t  n = pf.rows;
+    for (int i = 0; i < pf.preds.npred && n > 0; ++i) {
+        KeySrc src{pf.preds.col[pf.preds.p[i].col], ids ? ids->as<uint32_t>() : nullptr, (uint32_t)n};
+        IdList l = run_filter_u64(src, pf.preds.p[i].cmp, pf.preds.p[i].k);
+        if (ids && l.n) {   // positions in the previous list -> base row ids
+            std::vector<DevBufPtr> out = run_gather(l.ids->as<uint32_t>(), l.n, {ids->as<uint32_t>()});
+            ids                        = out[0];
+        } else {
+            ids = l.ids;
+        }
+        n = l.n;
+    }
+    if (n == 0) {
+        d->null_query = true;
+        ids           = dev_alloc(16);
+    }
+    d->num_tuples = n;
+    set_column(d, b, ids);
+}
+void resolve_filters(inter_res *head) {
+    for (; head; head = head->next) resolve_filter(head);
+}
+// the parked filter of `binding` was consumed by a join: its node is an empty node again
+void clear_parked_filter(inter_res *head, int binding) {
+    for (; head; head = head->next) {
+        B200InterData *d = idata(head);
+        if (d->pfilter.active && d->pfilter.binding == binding) {
+            d->pfilter        = PendingFilter{};
+            d->table[binding] = nullptr;
+            d->num_tuples     = 0;
+        }
+    }
+}
+bool any_null_query(inter_res *head) {
+    for (; head; head = head->next)
+        if (idata(head)->null_query) return true;
+    return false;
+}
+
 // a deferred join result that is looked at directly (tests) turns into its pairs
 void materialise(B200Result *r) {
+    if (r && r->kind == kDeferredFilter) {   // looked at directly (tests): scan now
+        IdList l        = run_filter_u64(KeySrc{r->f_col, nullptr, (uint32_t)r->n}, r->f_cmp, r->f_k);
+        r->kind         = kRowIds;
+        r->a            = l.ids;
+        r->n            = l.n;
+        r->current_load = l.n;
+        return;
+    }
     if (!r || r->kind != kDeferredJoin) return;
     JoinResult j    = run_join(r->kr, r->ks, JoinOut::Pairs, 0, nullptr);
+    if (j.valid_r == 0 || j.valid_s == 0) r->null_query = true;
     r->kind         = kPairs;
     r->n            = j.m;
     r->current_load = j.m;
@@ -205,6 +303,37 @@ result *Filter(inter_res *head, filter_pred *filter_p, relation_map *map, int *q
     const int  rel  = filter_p->relation;
     DevColumn  col  = binding_column(map, query_relations, rel, filter_p->column);
     inter_res *node = find_node(head, rel);
+    int        code;
+    switch (filter_p->comperator) {
+        case '<': code = 0; break;
+        case '>': code = 1; break;
+        case '=': code = 2; break;
+        default:
+            fprintf(stderr, "Wrong comperator in filter function\n");   // filter.c:184-186
+            exit(2);
+    }
+    if (fuse_filters_enabled()) {
+        bool defer = false;
+        if (node && idata(node)->pfilter.active) {
+            // another filter on a binding whose predicates are parked: it joins them while there is room
+            const PredSet &ps = idata(node)->pfilter.preds;
+            bool known = false;
+            for (int c = 0; c < ps.ncols; ++c) known = known || ps.col[c] == col.d;
+            defer = ps.npred < kMaxPred && (known || ps.ncols < kMaxPredCols);
+            if (!defer) resolve_filter(node);
+        } else if (!node && col.n >= kFuseMinRows) {
+            defer = true;
+        }
+        if (defer) {
+            B200Result *r = new_result(kDeferredFilter, 0, nullptr, nullptr);
+            r->f_col      = col.d;
+            r->f_cmp      = code;
+            r->f_k        = (uint64_t)(int64_t)filter_p->value;   // `uint64_t (cmp) int`: sign-extended (filter.c:118)
+            r->n          = col.n;
+            r->kr.max_val = col.max_val;
+            return r;
+        }
+    }
     KeySrc     src;
     src.col = col.d;
     if (node) {   // filter.c:124-133: scan through the row ids, emit positions
@@ -226,8 +355,44 @@ result *Filter(inter_res *head, filter_pred *filter_p, relation_map *map, int *q
 // appended in that case.
 int InsertSingleRowIdsToInterResult(inter_res **head, int relation_num, result *res) {
     B200Result *r = static_cast<B200Result *>(res);
-    B200_REQUIRE(r && r->kind == kRowIds, "InsertSingleRowIdsToInterResult needs a row-id result");
+    B200_REQUIRE(r && (r->kind == kRowIds || r->kind == kDeferredFilter),
+                 "InsertSingleRowIdsToInterResult needs a row-id result");
     resolve_all(*head);
+    if (r->kind == kDeferredFilter) {
+        // park the predicate: on the node that already holds this binding's parked set, else on the first empty
+        // node (filter.c:19-40 installs a fresh binding there), else on a new node
+        inter_res *node = *head, *last = nullptr, *target = nullptr;
+        for (; node; last = node, node = node->next) {
+            B200InterData *d = idata(node);
+            if (d->pfilter.active && d->pfilter.binding == relation_num) { target = node; break; }
+        }
+        if (!target)
+            for (node = *head; node; node = node->next)
+                if (node->data->num_tuples == 0 && !idata(node)->pending.active) { target = node; break; }
+        if (!target) {
+            last->next = new_node(last->num_of_relations);
+            target     = last->next;
+        }
+        B200InterData *d  = idata(target);
+        PendingFilter &pf = d->pfilter;
+        if (!pf.active) {
+            pf                     = PendingFilter{};
+            pf.active              = true;
+            pf.binding             = relation_num;
+            pf.rows                = r->n;
+            d->table[relation_num] = kParkedF;
+            d->num_tuples          = 1;   // "not an empty node"; the real count exists once the predicates ran
+        }
+        int c = 0;
+        while (c < pf.preds.ncols && pf.preds.col[c] != r->f_col) ++c;
+        B200_REQUIRE(c < kMaxPredCols && pf.preds.npred < kMaxPred, "parked filter set is full");
+        if (c == pf.preds.ncols) pf.preds.col[pf.preds.ncols++] = r->f_col;
+        pf.preds.p[pf.preds.npred].col = c;
+        pf.preds.p[pf.preds.npred].cmp = r->f_cmp;
+        pf.preds.p[pf.preds.npred].k   = r->f_k;
+        ++pf.preds.npred;
+        return 1;
+    }
     inter_res *node = *head, *last = nullptr;
     for (; node; last = node, node = node->next) {
         if (node->data->num_tuples == 0) {   // filter.c:19-40: first instance of the node
@@ -255,6 +420,14 @@ relation *GetRelation(int given_rel, int column, inter_res *inter, relation_map 
     rel->tuples     = nullptr;
     rel->kv.src.col = col.d;
     rel->kv.max_val = col.max_val;
+    if (node && idata(node)->pfilter.active) {
+        // the binding's filters are parked: the join evaluates them in its load stage and reports base row ids
+        rel->kv.src.ids = nullptr;
+        rel->kv.src.n   = (uint32_t)col.n;
+        rel->kv.preds   = idata(node)->pfilter.preds;
+        rel->num_tuples = col.n;
+        return rel;
+    }
     if (node) {
         B200InterData *d   = idata(node);
         rel->kv.src.ids    = column_ids(d, given_rel);
@@ -280,11 +453,18 @@ result *RadixHashJoin(relation *relR, relation *relS, scheduler *sched) {
         B200Result *d = new_result(kDeferredJoin, 0, nullptr, nullptr);
         d->kr         = r->kv;
         d->ks         = s->kv;
+        d->fused_r    = r->kv.preds.npred > 0;
+        d->fused_s    = s->kv.preds.npred > 0;
         return d;
     }
     JoinResult    j = run_join(r->kv, s->kv, JoinOut::Pairs, 0, nullptr);
+    // a fused filter that let nothing through is the reference's empty Filter: the whole query is NULL (query.c:360-369)
+    if (j.valid_r == 0 || j.valid_s == 0) return nullptr;
     // an empty join is a non-NULL result with zero pairs (rhjoin.c:356-359)
-    return new_result(kPairs, j.m, j.r_ids, j.s_ids);
+    B200Result *res = new_result(kPairs, j.m, j.r_ids, j.s_ids);
+    res->fused_r    = r->kv.preds.npred > 0;
+    res->fused_s    = s->kv.preds.npred > 0;
+    return res;
 }
 
 // inter_res.c:34-152
@@ -292,6 +472,10 @@ int InsertJoinToInterResults(inter_res *head, int rel1, int rel2, result *res) {
     B200Result *r = static_cast<B200Result *>(res);
     B200_REQUIRE(r && (r->kind == kPairs || r->kind == kDeferredJoin), "InsertJoinToInterResults needs a join result");
     resolve_all(head);
+    // a side whose parked filter ran (or will run) inside the join comes back as base row ids: its node is empty again
+    if (r->fused_r) clear_parked_filter(head, rel1);
+    if (r->fused_s) clear_parked_filter(head, rel2);
+    if (r->null_query) idata(head)->null_query = true;
     inter_res *node = head, *last = nullptr;
     for (; node; last = node, node = node->next) {
         B200InterData *d    = idata(node);
@@ -333,6 +517,7 @@ int AreActiveInInter(inter_res *inter, int rel1, int rel2) {
 int JoinInterNode(inter_res **inter, relation_map *rel_map, int rel1, int col1, int rel2, int col2,
                   int *relations) {
     resolve_all(*inter);
+    resolve_filters(*inter);
     inter_res *node = *inter;
     for (; node; node = node->next)
         if (node->data->table[rel1] != nullptr && node->data->table[rel2] != nullptr) break;
@@ -350,7 +535,7 @@ int JoinInterNode(inter_res **inter, relation_map *rel_map, int rel1, int col1, 
 // inter_res.c:265-318: a later node that shares an active binding with an
 // earlier one is folded into it through that binding's positions.
 void MergeInterNodes(inter_res **inter) {
-    resolve_all(*inter);
+    resolve_all(*inter);   // (a node that only parks a filter shares no materialised binding with any other: it is skipped)
     for (inter_res *head = *inter; head; head = head->next) {
         bool merged = true;
         while (merged) {
@@ -387,6 +572,7 @@ void CartesianInterResults(inter_res **inter) {
     inter_res *cur = *inter;
     if (cur->next == nullptr) return;
     resolve_all(cur);
+    resolve_filters(cur);
     CartesianInterResults(&cur->next);
     inter_res     *nxt = cur->next;
     B200InterData *a = idata(cur), *b = idata(nxt);
@@ -415,7 +601,9 @@ int b200_calculate_sums(inter_res *inter, relation_map *map, batch_listnode *que
     const int                      nv = query->views->num_of_elements;
     std::vector<const uint64_t *>  cols((size_t)nv);
     std::vector<const uint32_t *>  ids((size_t)nv);
+    resolve_filters(inter);   // a filter still parked here was never consumed by a join: scan it now
     B200InterData                 *d = idata(inter);
+    t_null_result                    = false;
     if (d->pending.active) {
         // the last join is still parked on the node: run it fused with the SUMs.  A projection on a binding that
         // was in the node before the join reads through that binding's row ids at the position the join reports
@@ -452,6 +640,7 @@ int b200_calculate_sums(inter_res *inter, relation_map *map, batch_listnode *que
             JoinResult j = run_join(pj.kr, pj.ks, JoinOut::Sum, nv, pd);
             for (int i = 0; i < nv; ++i) sums[i] = j.sums[i];
             if (num_rows) *num_rows = j.m;
+            t_null_result = any_null_query(inter) || j.valid_r == 0 || j.valid_s == 0;
             return 0;
         }
         resolve(inter);
@@ -469,7 +658,18 @@ int b200_calculate_sums(inter_res *inter, relation_map *map, batch_listnode *que
     }
     run_checksum(d->num_tuples, nv, cols.data(), ids.data(), sums);
     if (num_rows) *num_rows = d->num_tuples;
+    t_null_result = any_null_query(inter);
     return 0;
+}
+
+// 1 when the calling thread's last b200_calculate_sums found that a filter fused into a join had let nothing
+// through: the reference prints NULL for every projection then (its Filter returns NULL, query.c:360-369)
+int b200_last_result_null(void) { return t_null_result ? 1 : 0; }
+
+int b200_set_fuse_filters(int on) {
+    const int before = fuse_filters_enabled() ? 1 : 0;
+    g_fuse_filters.store(on ? 1 : 0, std::memory_order_relaxed);
+    return before;
 }
 
 // inter_res.c:320-339
@@ -477,6 +677,10 @@ void CalculateQueryResults(inter_res *inter, relation_map *map, batch_listnode *
     const int             nv = query->views->num_of_elements;
     std::vector<uint64_t> sums((size_t)nv);
     b200_calculate_sums(inter, map, query, sums.data(), nullptr);
+    if (t_null_result) {
+        PrintNullResults(query);
+        return;
+    }
     for (int i = 0; i < nv; ++i) {
         printf("%lu", (unsigned long)sums[(size_t)i]);
         if (i != nv - 1) printf(" ");
@@ -499,6 +703,7 @@ result *SelfJoin(int given_rel, int column1, int column2, inter_res **inter, rel
     DevColumn  c1   = binding_column(map, query_relations, given_rel, column1);
     DevColumn  c2   = binding_column(map, query_relations, given_rel, column2);
     resolve_all(*inter);
+    resolve_filters(*inter);
     inter_res *node = find_node(*inter, given_rel);
     IdList     l;
     if (node) {
@@ -544,6 +749,7 @@ static int ids_to_host(const uint32_t *d, uint64_t n, uint64_t *out) {
 }
 
 int b200_result_rowids_to_host(const result *res, uint64_t *out) {
+    materialise(static_cast<B200Result *>(const_cast<result *>(res)));   // a deferred filter is scanned now
     const B200Result *r = static_cast<const B200Result *>(res);
     if (!r || r->kind != kRowIds) return 1;
     return ids_to_host(r->a->as<uint32_t>(), r->n, out);
@@ -559,6 +765,7 @@ int b200_result_pairs_to_host(const result *res, uint64_t *out_r, uint64_t *out_
 
 int b200_inter_column_to_host(const inter_res *node, int binding, uint64_t *out) {
     resolve(const_cast<inter_res *>(node));
+    resolve_filter(const_cast<inter_res *>(node));
     const B200InterData *d = idata(node);
     if (!d->table[binding]) return 1;
     return ids_to_host(column_ids(d, binding), d->num_tuples, out);

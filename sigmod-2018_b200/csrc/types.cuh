@@ -18,6 +18,21 @@ struct KeySrc {
     uint32_t        n;
 };
 
+// Filter predicates folded into the load stage of the partition kernels (query.c:337-399 runs the
+// filters of a binding before its first join, filter.c:92-190 scans once per predicate): row r of a base relation
+// takes part in the join iff every predicate col[p.col][r] (cmp) p.k holds — cmp 0 '<', 1 '>', 2 '=' on uint64,
+// the constant being the reference's 32-bit int converted by the usual C rules (filter.c:118).
+constexpr int kMaxPred     = 4;
+constexpr int kMaxPredCols = 3;
+struct PredSet {
+    int             npred = 0, ncols = 0;
+    const uint64_t *col[kMaxPredCols] = {nullptr, nullptr, nullptr};
+    struct {
+        int      col, cmp;
+        uint64_t k;
+    } p[kMaxPred] = {};
+};
+
 struct alignas(8) Tup32 {
     uint32_t key;
     uint32_t rid;

@@ -178,6 +178,8 @@ def _declare(L: C.CDLL) -> None:
         "b200_synchronize": (C.c_int, []),
         "b200_calculate_sums": (C.c_int, [P(CInterRes), P(CRelationMap), P(CBatchListnode), u64p, u64p]),
         "b200_set_lazy_join": (C.c_int, [C.c_int]),
+        "b200_set_fuse_filters": (C.c_int, [C.c_int]),
+        "b200_last_result_null": (C.c_int, []),
         "b200_result_kind": (C.c_int, [P(CResult)]),
         "b200_result_rowids_to_host": (C.c_int, [P(CResult), u64p]),
         "b200_result_pairs_to_host": (C.c_int, [P(CResult), u64p, u64p]),
@@ -445,6 +447,8 @@ def execute_query(text: str, rel_map: RelationMapArray) -> QueryResult:
         sums = (C.c_uint64 * len(q.views))()
         rows = C.c_uint64(0)
         _check(L.b200_calculate_sums(inter, rel_map.array, C.byref(node), sums, C.byref(rows)))
+        if L.b200_last_result_null():      # a filter fused into a join let nothing through (query.c:360-369)
+            return QueryResult(None, len(q.views))
         return QueryResult([int(s) for s in sums], int(rows.value))
     finally:
         L.FreeInterResults(inter)
