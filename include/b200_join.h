@@ -116,6 +116,14 @@ int  b200_is_cuda(void);
  * preparation phase).  Device copies are keyed by the host column pointer.
  * Columns that were never registered are uploaded on first use. */
 int  b200_register_relations(const relation_map *map, int count);
+/* relation_map.c:53-83 on the GPU: fill map[r].col_stats[j] = {l = min, u = max,
+ * f = rows, d = distinct values} from the device copies (columns not yet
+ * registered are uploaded first).  d is the reference's count: a marker array
+ * of min(u - l + 1, 50 000 000) entries indexed by v - l, or by
+ * (v - l) % 5 000 000 once the range reaches the cap.  These are the inputs of
+ * stats.c / best_tree.c's join ordering; a host without the reference's
+ * relation_map.o (host/b200_engine.c) gets them from here. */
+int  b200_compute_column_stats(relation_map *map, int count);
 /* Make an already device-resident column known under a host-side key pointer
  * (bench.py: data generated in HBM).  `max_value` may be UINT64_MAX when
  * unknown; it only selects the 32-bit-key kernels when < 2^32. */
@@ -162,8 +170,12 @@ int  b200_calculate_sums(inter_res *inter, relation_map *map,
  * of the read-back calls below has materialised it. */
 int  b200_set_lazy_join(int on);
 
-/* Filter fusion (default on; B200_FUSE_FILTERS=0 or b200_set_fuse_filters(0)
- * turns it off; returns the previous setting): Filter on a base relation of at
+/* Filter fusion (B200_FUSE_FILTERS / b200_set_fuse_filters: 0 off, 1 where it
+ * pays = default, 2 wherever possible; returns the previous setting).  Mode 1
+ * estimates the surviving rows from the column statistics the way stats.c does
+ * and fuses when at least 2^18 rows and 1/64 of the relation survive; a more
+ * selective filter is scanned the eager way when the binding is first used,
+ * which leaves the join a small relation.  Filter on a base relation of at
  * least 2^18 rows that is in no intermediate yet returns a deferred result,
  * InsertSingleRowIdsToInterResult parks its predicate (up to 4 predicates on 3
  * columns per binding), GetRelation hands the join a key vector that carries

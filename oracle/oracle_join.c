@@ -253,3 +253,28 @@ ORC_EXPORT void orc_synth_column(uint64_t *out, uint64_t first, uint64_t n, int 
                                  uint64_t seed) {
     for (uint64_t i = 0; i < n; ++i) out[i] = b200_synth_value(kind, first + i, k, seed);
 }
+
+/* relation_map.c:53-83 — the column statistics the reference's loader keeps: l = smallest value, u = largest,
+ * d = "distinct values" as the reference counts them: a marker array of min(u - l + 1, 50 000 000) entries, entry
+ * v - l when that size is below 50 000 000, else entry (v - l) % 5 000 000 (sic, relation_map.c:71), then the
+ * number of marked entries (relation_map.c:75-79).  n >= 1 (the reference reads row 0 unconditionally). */
+ORC_EXPORT void orc_column_stats(const uint64_t *col, uint64_t n, uint64_t *out_l, uint64_t *out_u, uint64_t *out_d) {
+    uint64_t l = col[0], u = col[0];
+    for (uint64_t k = 1; k < n; ++k) {
+        if (col[k] > u) u = col[k];
+        if (col[k] < l) l = col[k];
+    }
+    uint64_t size = u - l + 1;
+    if (size > 50000000ull) size = 50000000ull;
+    unsigned short *seen = calloc(size, sizeof(unsigned short));
+    for (uint64_t k = 0; k < n; ++k) {
+        if (size < 50000000ull) seen[col[k] - l] = 1;
+        else seen[(col[k] - l) % 5000000ull] = 1;
+    }
+    uint64_t d = 0;
+    for (uint64_t k = 0; k < size; ++k) d += seen[k] == 1;
+    free(seen);
+    *out_l = l;
+    *out_u = u;
+    *out_d = d;
+}

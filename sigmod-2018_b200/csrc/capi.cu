@@ -75,6 +75,28 @@ int b200_register_relations(const relation_map *map, int count) {
     return 0;
 }
 
+// relation_map.c:53-83 on the GPU: fills map[r].col_stats[j] = {l, u, f, d} from the device copies (uploading the
+// columns first when they are not registered yet)
+int b200_compute_column_stats(relation_map *map, int count) {
+    for (int r = 0; r < count; ++r) {
+        if (!map[r].col_stats) continue;
+        for (uint64_t j = 0; j < map[r].num_columns; ++j) {
+            DevColumn     c  = lookup_column(map[r].columns[j], map[r].num_tuples);
+            column_stats &st = map[r].col_stats[j];
+            st.f             = (double)map[r].num_tuples;
+            if (c.n && c.distinct == 0) {   // registered without statistics: compute them now
+                uint64_t mx = 0;
+                device_column_stats(c.d, c.n, &c.min_val, &mx, &c.distinct);
+                c.max_val = mx;
+            }
+            st.l = c.min_val;
+            st.u = c.n ? c.max_val : 0;
+            st.d = (double)c.distinct;
+        }
+    }
+    return 0;
+}
+
 int b200_register_device_column(const uint64_t *host_key, const uint64_t *device_ptr, uint64_t n,
                                 uint64_t max_value) {
     register_device_column(host_key, device_ptr, n, max_value);

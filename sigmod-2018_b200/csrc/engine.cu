@@ -231,9 +231,14 @@ uint64_t read_counter(const unsigned long long *d_ptr) {
     return c.h_scratch[0];
 }
 
+// SMs the streaming kernels of the calling thread leave free (multi-GPU broadcast plan: the probe-side scatter is a
+// persistent grid that would otherwise own every SM, and the concurrent broadcast kernel must stay resident)
+static thread_local int t_reserved_sms = 0;
+void set_reserved_sms(int n) { t_reserved_sms = n < 0 ? 0 : n; }
+
 int grid_for(uint64_t work_items, int per_block, int max_blocks_per_sm) {
     uint64_t blocks = (work_items + per_block - 1) / per_block;
-    uint64_t cap    = (uint64_t)sm_count() * max_blocks_per_sm;
+    uint64_t cap    = (uint64_t)std::max(1, sm_count() - t_reserved_sms) * max_blocks_per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
@@ -259,6 +264,34 @@ static uint64_t device_column_max(const uint64_t *d, uint64_t n) {
     return read_counter(c.d_scratch + 8);
 }
 
+void device_column_stats(const uint64_t *d_col, uint64_t n, uint64_t *out_min, uint64_t *out_max, uint64_t *out_distinct) {
+    Context &c = ctx();
+    *out_min = *out_max = *out_distinct = 0;
+    if (n == 0) return;
+    unsigned long long init[3] = {~0ull, 0ull, 0ull};
+    B200_CUDA(cudaMemcpyAsync(c.d_scratch + 40, init, sizeof(init), cudaMemcpyHostToDevice, c.stream));
+    column_minmax_kernel<<<grid_for(n, 256 * 8, 8), 256, 0, c.stream>>>(d_col, n, c.d_scratch + 40, c.d_scratch + 41);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cudaMemcpyAsync(c.h_scratch + 40, c.d_scratch + 40, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                              c.stream));
+    B200_CUDA(cudaStreamSynchronize(c.stream));
+    const uint64_t lo = c.h_scratch[40], hi = c.h_scratch[41];
+    // relation_map.c:64-83: min(u - l + 1, 50 000 000) entries; below the cap entry v - l, else (v - l) % 5 000 000
+    uint64_t size = hi - lo + 1;
+    if (size > 50000000ull || size == 0) size = 50000000ull;
+    const uint64_t modulus = size < 50000000ull ? 0ull : 5000000ull;
+    const uint64_t nwords  = (size + 31) / 32;
+    DevBufPtr      bits    = dev_alloc(nwords * sizeof(uint32_t));
+    B200_CUDA(cudaMemsetAsync(bits->ptr, 0, nwords * sizeof(uint32_t), c.stream));
+    column_mark_kernel<<<grid_for(n, 256 * 8, 8), 256, 0, c.stream>>>(d_col, n, lo, modulus, bits->as<uint32_t>());
+    B200_LAUNCH_CHECK();
+    bitmap_count_kernel<<<grid_for(nwords, 256 * 8, 8), 256, 0, c.stream>>>(bits->as<uint32_t>(), nwords, c.d_scratch + 42);
+    B200_LAUNCH_CHECK();
+    *out_min      = lo;
+    *out_max      = hi;
+    *out_distinct = read_counter(c.d_scratch + 42);
+}
+
 static ColumnEntry upload_entry(const uint64_t *host_col, uint64_t n) {
     B200_REQUIRE(n <= kMaxRows, "relation has more than 2^32-1 rows (32-bit device row ids)");
     Context    &c = ctx();
@@ -270,6 +303,10 @@ static ColumnEntry upload_entry(const uint64_t *host_col, uint64_t n) {
     e.col.d       = e.owned;
     e.col.n       = n;
     e.col.max_val = device_column_max(e.owned, n);   // also synchronises the copy
+    if (n) {
+        uint64_t mx = 0;
+        device_column_stats(e.owned, n, &e.col.min_val, &mx, &e.col.distinct);
+    }
     return e;
 }
 
@@ -290,7 +327,11 @@ void register_host_column(const uint64_t *host_col, uint64_t n, bool replace) {
                 const uint64_t mx = device_column_max(dst, n);
                 lk.lock();
                 auto again = g_columns.find(host_col);
-                if (again != g_columns.end() && again->second.owned == dst) again->second.col.max_val = mx;
+                if (again != g_columns.end() && again->second.owned == dst) {
+                    again->second.col.max_val  = mx;
+                    again->second.col.min_val  = 0;   // unknown until asked for again
+                    again->second.col.distinct = 0;
+                }
                 return;
             }
             if (it->second.owned) cudaFree(it->second.owned);

@@ -16,7 +16,13 @@ struct DevColumn {
     const uint64_t *d       = nullptr;
     uint64_t        n       = 0;
     uint64_t        max_val = UINT64_MAX;
+    // relation_map.c:53-83's other statistics, computed on the GPU when the column is uploaded (0 / 0: unknown,
+    // e.g. a caller-registered device column): smallest value and number of distinct values (the reference's count)
+    uint64_t        min_val  = 0;
+    uint64_t        distinct = 0;
 };
+// min, max and the reference's distinct count of a DEVICE column (relation_map.c:53-83), on the calling thread's stream
+void device_column_stats(const uint64_t *d_col, uint64_t n, uint64_t *out_min, uint64_t *out_max, uint64_t *out_distinct);
 
 // Device copy of a host column (relation_map.columns[j]); uploads on a miss.
 DevColumn lookup_column(const uint64_t *host_col, uint64_t n);
@@ -151,5 +157,6 @@ const std::string &last_error_string();
 // small helpers
 uint64_t read_counter(const unsigned long long *d_ptr);   // D2H + sync on ctx stream
 int      grid_for(uint64_t work_items, int per_block, int max_blocks_per_sm);
+void     set_reserved_sms(int n);   // SMs grid_for leaves free on the calling thread (0 = none)
 
 }  // namespace b200

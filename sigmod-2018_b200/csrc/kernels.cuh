@@ -1872,6 +1872,50 @@ static __global__ void __launch_bounds__(256) checksum_kernel(const ChecksumArgs
     }
 }
 
+// Column statistics at registration (relation_map.c:53-83: min, max and the number of distinct values, the inputs of
+// stats.c's selectivity formulas).  min / max: one pass.  distinct: the reference marks a `unsigned short` array of
+// min(u - l + 1, 50 000 000) entries — entry v - l when the range is below 50 000 000, else entry (v - l) % 5 000 000
+// (sic: five million, relation_map.c:71) — and counts the marked entries; here the array is a bitmap in L2
+// (at most 6.25 MB), marked with atomicOr and counted with popc.
+static __global__ void __launch_bounds__(256)
+column_minmax_kernel(const uint64_t *__restrict__ col, uint64_t n, unsigned long long *__restrict__ out_min,
+                     unsigned long long *__restrict__ out_max) {
+    unsigned long long lo = ~0ull, hi = 0;
+    const uint64_t     stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long v = ld_stream_u64(col + i);
+        lo                         = v < lo ? v : lo;
+        hi                         = v > hi ? v : hi;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(kFullMask, lo, d), b = __shfl_xor_sync(kFullMask, hi, d);
+        lo                         = a < lo ? a : lo;
+        hi                         = b > hi ? b : hi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out_min, lo);
+        atomicMax(out_max, hi);
+    }
+}
+static __global__ void __launch_bounds__(256)
+column_mark_kernel(const uint64_t *__restrict__ col, uint64_t n, uint64_t lo, uint64_t modulus, uint32_t *__restrict__ bits) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t e = ld_stream_u64(col + i) - lo;
+        if (modulus) e %= modulus;
+        atomicOr(&bits[e >> 5], 1u << (e & 31));
+    }
+}
+static __global__ void __launch_bounds__(256)
+bitmap_count_kernel(const uint32_t *__restrict__ bits, uint64_t nwords, unsigned long long *__restrict__ out) {
+    unsigned long long c      = 0;
+    const uint64_t     stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) c += __popc(bits[i]);
+    c = warp_sum_u64(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 // Column maximum at registration (selects the 32-bit-key kernels).
 static __global__ void __launch_bounds__(256)
 column_max_kernel(const uint64_t *__restrict__ col, uint64_t n, unsigned long long *__restrict__ out) {

@@ -72,7 +72,8 @@ struct MultiPlan {
     bool           peer_ipc[kMaxPeers] = {false};
     // local device memory (one allocation)
     unsigned char *local = nullptr;
-    uint32_t      *d_epoch = nullptr, *d_error = nullptr, *cur_p = nullptr, *ovcnt = nullptr;
+    uint32_t      *d_epoch = nullptr, *d_error = nullptr, *cur_p = nullptr, *ovcnt = nullptr, *bc_work = nullptr;
+    int            bcast_ce = 0, reserve_sms = 0;   // broadcast on the copy engines instead of the SM kernel; SMs it keeps
     unsigned long long *d_result = nullptr, *d_final = nullptr;
     void          *tup_p = nullptr, *ov_p = nullptr, *stage_b = nullptr, *stage_p = nullptr;
     uint32_t      *src_off_b = nullptr, *src_off_p = nullptr, *dst_start_b = nullptr, *dst_start_p = nullptr;
@@ -125,6 +126,7 @@ static void layout_local(MultiPlan &m, void *base, size_t *bytes) {
     m.d_epoch  = c.take<uint32_t>(4);
     m.d_error  = c.take<uint32_t>(4);
     m.ovcnt    = c.take<uint32_t>(4);
+    m.bc_work  = c.take<uint32_t>(1 + kMaxChunks + 7);
     m.d_result = c.take<unsigned long long>(8);
     m.d_final  = c.take<unsigned long long>(8);
     m.cur_p    = c.take<uint32_t>(P + 1);
@@ -173,26 +175,56 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
         stage_scatter_build_local(m.in_bk, nb, (uint32_t)((uint64_t)rank * m.seg_rows), m.bits, my_hist, my_region,
                                   m.cfg.has_build_sum ? 1 : 0, pay_cols, nullptr, &m.scr_a);
         B200_CUDA(cudaEventRecord(m.ev_build, main));
-        // ---- broadcast on the copy engines: per peer (every rank starts at a different one) the histogram, then the
-        //      region in K chunks, a 4-byte flag behind each; the join of the first partitions runs under the rest ----
-        for (int j = 1; j < world; ++j) {
-            const int    d = (rank + j) % world;
-            cudaStream_t s = m.copy_stream[j - 1];
-            B200_CUDA(cudaStreamWaitEvent(s, m.ev_build, 0));
-            B200_CUDA(cudaMemcpyAsync(m.hist_b(d) + (size_t)rank * P, my_hist, (size_t)P * 4, cudaMemcpyDeviceToDevice, s));
-            B200_CUDA(cudaMemcpyAsync(&m.hdr(d)->sig[SIG_HIST][rank], m.d_epoch, 4, cudaMemcpyDeviceToDevice, s));
-            for (int k = 0; k < m.K; ++k) {
-                const uint64_t first = (uint64_t)k * m.chunk_rows;
-                const uint64_t rows  = first < nb ? std::min<uint64_t>(m.chunk_rows, nb - first) : 0;
-                if (rows)
-                    B200_CUDA(cudaMemcpyAsync(m.build(d) + ((size_t)rank * m.seg_rows + first) * 8, my_region + first * 8,
-                                              rows * 8, cudaMemcpyDeviceToDevice, s));
-                B200_CUDA(cudaMemcpyAsync(&m.hdr(d)->sig[SIG_CHUNK0 + k][rank], m.d_epoch, 4, cudaMemcpyDeviceToDevice, s));
+        if (!m.bcast_ce) {
+            // ---- broadcast by a small persistent kernel (multi_kernels.cuh): stores over NVLink, a flag per chunk raised
+            //      by the kernel itself; it runs on the SMs the probe-side scatter below leaves free ----
+            B200_CUDA(cudaStreamWaitEvent(m.xstream, m.ev_build, 0));
+            B200_CUDA(cudaMemsetAsync(m.bc_work, 0, (1 + kMaxChunks) * sizeof(uint32_t), m.xstream));
+            BroadcastArgs b{};
+            b.src        = reinterpret_cast<const uint64_t *>(my_region);
+            b.hist       = my_hist;
+            b.nb         = (uint32_t)nb;
+            b.nparts     = P;
+            b.chunk_rows = m.chunk_rows;
+            b.nchunks    = (uint32_t)m.K;
+            b.slice_rows = 4096;
+            b.rank       = rank;
+            b.world      = world;
+            for (int d = 0; d < world; ++d) {
+                b.dst_region[d] = reinterpret_cast<uint64_t *>(m.build(d) + (size_t)rank * m.seg_rows * 8);
+                b.dst_hist[d]   = m.hist_b(d) + (size_t)rank * P;
+                b.hdr[d]        = m.hdr(d);
             }
-            B200_CUDA(cudaEventRecord(m.ev_copy[j - 1], s));
-        }
-        // my own region needs no copy: raise my own flags
-        {
+            b.work  = m.bc_work;
+            b.done  = m.bc_work + 1;
+            b.epoch = m.d_epoch;
+            {
+                StreamSwap sw(c, m.xstream);
+                TimedScope ts("broadcast");
+                broadcast_region_kernel<<<std::max(1, m.reserve_sms) * 4, 256, 0, c.stream>>>(b);
+                B200_LAUNCH_CHECK();
+            }
+            B200_CUDA(cudaEventRecord(m.ev_x, m.xstream));
+        } else {
+            // ---- broadcast on the copy engines: per peer (every rank starts at a different one) the histogram, then the
+            //      region in K chunks, a 4-byte flag behind each (about 5 us per operation, serialised) ----
+            for (int j = 1; j < world; ++j) {
+                const int    d = (rank + j) % world;
+                cudaStream_t s = m.copy_stream[j - 1];
+                B200_CUDA(cudaStreamWaitEvent(s, m.ev_build, 0));
+                B200_CUDA(cudaMemcpyAsync(m.hist_b(d) + (size_t)rank * P, my_hist, (size_t)P * 4, cudaMemcpyDeviceToDevice, s));
+                B200_CUDA(cudaMemcpyAsync(&m.hdr(d)->sig[SIG_HIST][rank], m.d_epoch, 4, cudaMemcpyDeviceToDevice, s));
+                for (int k = 0; k < m.K; ++k) {
+                    const uint64_t first = (uint64_t)k * m.chunk_rows;
+                    const uint64_t rows  = first < nb ? std::min<uint64_t>(m.chunk_rows, nb - first) : 0;
+                    if (rows)
+                        B200_CUDA(cudaMemcpyAsync(m.build(d) + ((size_t)rank * m.seg_rows + first) * 8,
+                                                  my_region + first * 8, rows * 8, cudaMemcpyDeviceToDevice, s));
+                    B200_CUDA(cudaMemcpyAsync(&m.hdr(d)->sig[SIG_CHUNK0 + k][rank], m.d_epoch, 4, cudaMemcpyDeviceToDevice, s));
+                }
+                B200_CUDA(cudaEventRecord(m.ev_copy[j - 1], s));
+            }
+            // my own region needs no copy: raise my own flags
             PeerPtrs self{};
             self.hdr[0] = m.hdr(rank);
             signal_peers_kernel<<<1, 32, 0, main>>>(self, 1, rank, SIG_HIST, m.d_epoch);
@@ -203,6 +235,7 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
             }
         }
         // ---- probe shard: partitioned locally (histogram-free regions + overflow), never moves ----
+        set_reserved_sms(m.bcast_ce ? 0 : m.reserve_sms);
         if (m.opt_cap) {
             stage_scatter_probe_opt(m.in_pk, np, m.bits, m.opt_cap, m.cur_p, m.tup_p, m.ov_p, m.ovcnt,
                                     m.cfg.has_probe_sum ? m.in_pp : nullptr);
@@ -214,6 +247,7 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
                                       &m.scr_b);
             B200_CUDA(cudaMemsetAsync(m.ovcnt, 0, 4, main));
         }
+        set_reserved_sms(0);
     }
     if (phases & 2) {
         wait_peers_kernel<<<1, 32, 0, main>>>(m.hdr(rank)->sig[SIG_HIST], world, m.d_epoch, m.d_error);
@@ -227,8 +261,10 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
                        m.d_result, world, m.seg_rows, &m.scr_b, &w);
         push_result_kernel<<<1, 32, 0, main>>>(m.peers(), world, rank, m.d_result, m.d_error, m.d_epoch);
         B200_LAUNCH_CHECK();
-        // the next step must not overwrite my region (or histogram) under copies still in flight
-        for (int j = 1; j < world; ++j) B200_CUDA(cudaStreamWaitEvent(main, m.ev_copy[j - 1], 0));
+        // the next step must not overwrite my region (or histogram) under a broadcast still in flight
+        if (!m.bcast_ce) B200_CUDA(cudaStreamWaitEvent(main, m.ev_x, 0));
+        else
+            for (int j = 1; j < world; ++j) B200_CUDA(cudaStreamWaitEvent(main, m.ev_copy[j - 1], 0));
     }
     if (phases & 4) {
         wait_peers_kernel<<<1, 32, 0, main>>>(m.hdr(rank)->sig[SIG_RESULT], world, m.d_epoch, m.d_error);
@@ -402,9 +438,13 @@ b200_multi *b200_multi_create(const b200_multi_config *cfg) {
     }
     m->P = 1u << m->bits;
     if (cfg->plan == B200_PLAN_BROADCAST) {
-        m->K          = cfg->chunks > 0 ? std::min(cfg->chunks, kMaxChunks) : 4;
-        m->seg_rows   = (uint32_t)std::max<uint64_t>(cfg->n_build_local_max, 1);
-        m->chunk_rows = (m->seg_rows + (uint32_t)m->K - 1) / (uint32_t)m->K;
+        m->K          = cfg->chunks > 0 ? std::min(cfg->chunks, kMaxChunks) : kMaxChunks;
+        m->seg_rows   = (uint32_t)((std::max<uint64_t>(cfg->n_build_local_max, 2) + 1) & ~1ull);   // even: 16-byte moves
+        m->chunk_rows = (((m->seg_rows + (uint32_t)m->K - 1) / (uint32_t)m->K) + 1u) & ~1u;
+        if (const char *e = getenv("B200_BCAST_CE")) m->bcast_ce = atoi(e);
+        m->reserve_sms = 16;
+        if (const char *e = getenv("B200_BCAST_SMS")) m->reserve_sms = std::max(1, std::min(atoi(e), 64));
+        if (m->world == 1) m->reserve_sms = 1;
         m->opt_cap    = (cfg->n_probe_local_max >= (1u << 20) && cfg->n_probe_local_max <= (1u << 30))
                             ? opt_region_cap(cfg->n_probe_local_max, m->bits) : 0;
     } else {

@@ -78,6 +78,98 @@ __global__ void reduce_result_kernel(const SharedHeader *hdr, int world, unsigne
 }
 
 // ---------------------------------------------------------------------------
+// Broadcast of this rank's partitioned build shard (its region of the rank-major build buffer) to every peer with
+// stores over NVLink, fused with its own signalling: the region is cut into chunks (partition ranges, since the
+// region is in partition order) and slices; a persistent grid pulls slices in chunk order, loads a slice ONCE and
+// stores it into the same place of every peer's buffer, and the CTA that completes the last slice of a chunk
+// raises that chunk's flag on every peer — so the peers' joins start on the first partitions while the rest is
+// still in flight, and no copy-engine operation (about 5 us each, serialised: 70 of them cost more than the data at
+// 8 GPUs) is spent on flags.  CTA 0 first publishes the histogram (SIG_HIST).  The grid is small (it runs on SMs
+// the concurrent probe-side scatter leaves free, see multi.cu) and never waits on anything remote.
+// ---------------------------------------------------------------------------
+struct BroadcastArgs {
+    const uint64_t *src;    // my region: nb tuples in partition order
+    const uint32_t *hist;   // my histogram [nparts]
+    uint32_t        nb, nparts, chunk_rows, nchunks, slice_rows;
+    int             rank, world;
+    uint64_t       *dst_region[kMaxPeers];   // region `rank` inside peer d's build buffer
+    uint32_t       *dst_hist[kMaxPeers];     // hist_all[rank] inside peer d's shared region
+    SharedHeader   *hdr[kMaxPeers];
+    uint32_t       *work;   // slice counter, zero at launch
+    uint32_t       *done;   // [kMaxChunks] slices completed per chunk, zero at launch
+    const uint32_t *epoch;
+};
+static __global__ void __launch_bounds__(256) broadcast_region_kernel(const BroadcastArgs b) {
+    __shared__ uint32_t s_item;
+    const uint32_t tid   = threadIdx.x;
+    const uint32_t epoch = *b.epoch;
+    auto chunk_rows_of = [&](uint32_t c) -> uint32_t {
+        const uint64_t first = (uint64_t)c * b.chunk_rows;
+        return first < b.nb ? (uint32_t)min((uint64_t)b.chunk_rows, (uint64_t)b.nb - first) : 0u;
+    };
+    auto slices_of = [&](uint32_t c) -> uint32_t { return (chunk_rows_of(c) + b.slice_rows - 1) / b.slice_rows; };
+    if (blockIdx.x == 0) {
+        // the histogram first (the peers need every rank's before they can lay out their joins)
+        for (int j = 0; j < b.world; ++j) {
+            const int d = (b.rank + j) % b.world;
+            if (d != b.rank)
+                for (uint32_t i = tid; i < b.nparts; i += 256) b.dst_hist[d][i] = b.hist[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)tid < b.world) {
+            st_release_sys_u32(&b.hdr[tid]->sig[SIG_HIST][b.rank], epoch);
+            for (uint32_t c = 0; c < b.nchunks; ++c)   // chunks beyond my shard hold nothing: raise their flags now
+                if (chunk_rows_of(c) == 0) st_release_sys_u32(&b.hdr[tid]->sig[SIG_CHUNK0 + c][b.rank], epoch);
+        }
+    }
+    uint32_t total = 0;
+    for (uint32_t c = 0; c < b.nchunks; ++c) total += slices_of(c);
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(b.work, 1u);
+        __syncthreads();
+        uint32_t item = s_item;
+        if (item >= total) break;
+        uint32_t c = 0;
+        while (item >= slices_of(c)) item -= slices_of(c++);
+        const uint32_t first = c * b.chunk_rows + item * b.slice_rows;
+        const uint32_t rows  = min(b.slice_rows, c * b.chunk_rows + chunk_rows_of(c) - first);
+        // 16-byte moves (two tuples), four per thread in flight; the odd last tuple of the shard goes alone
+        const uint32_t pairs = rows >> 1;
+        for (uint32_t i0 = tid; i0 < pairs; i0 += 256 * 4) {
+            ulonglong2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = i0 + (uint32_t)u * 256;
+                if (i < pairs) v[u] = ld_stream_u64x2(b.src + first + 2 * (size_t)i);
+            }
+            for (int j = 1; j < b.world; ++j) {
+                const int d = (b.rank + j) % b.world;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = i0 + (uint32_t)u * 256;
+                    if (i < pairs) *reinterpret_cast<ulonglong2 *>(b.dst_region[d] + first + 2 * (size_t)i) = v[u];
+                }
+            }
+        }
+        if ((rows & 1u) && tid == 0) {
+            const uint64_t v = b.src[first + rows - 1];
+            for (int j = 1; j < b.world; ++j) b.dst_region[(b.rank + j) % b.world][first + rows - 1] = v;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t finished = atomicAdd(&b.done[c], 1u) + 1u;
+            if (finished == slices_of(c)) {
+                __threadfence_system();
+                for (int d = 0; d < b.world; ++d) st_release_sys_u32(&b.hdr[d]->sig[SIG_CHUNK0 + c][b.rank], epoch);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Radix-sharded exchange (SURVEY §8e "all-to-all"; config 4).
 //
 // Ownership: rank g owns the contiguous partition range [cut[g], cut[g+1]).  The cuts are placed on the GLOBAL
@@ -140,8 +232,8 @@ balanced_cuts_kernel(const uint32_t *__restrict__ hist_b, uint32_t vb, const uin
             const unsigned long long w = (unsigned long long)total_b[p] + total_p[p];
             for (uint32_t g = 1; g < world; ++g) {
                 const unsigned long long target = (grand * g + world - 1) / world;
-                // p is the cut when the prefix crosses the target inside (run, run + w]; an empty tail is handled below
-                if (run < target && run + w >= target) cut[g] = p + 1u;
+                // the prefix crosses the target inside partition p: cut at whichever of its two ends is nearer
+                if (run < target && run + w >= target) cut[g] = (run + w - target <= target - run) ? p + 1u : p;
             }
             run += w;
         }

@@ -7,6 +7,7 @@
 #include "../../include/b200_join.h"
 #include "engine.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <vector>
@@ -31,6 +32,7 @@ struct B200Result : result {
     const uint64_t *f_col = nullptr;
     int             f_cmp = 0;
     uint64_t        f_k   = 0;
+    double          f_sel = 1.0;   // estimated selectivity of this predicate
 };
 
 // Lazy last join ("fold the last join into the SUM"; query.c:408-461 runs the joins one after
@@ -58,11 +60,11 @@ struct PendingJoin {
 // Any other operator that looks at the node first scans the parked predicates the eager way (resolve_filter).  An
 // empty filter still makes the whole query NULL (query.c:360-369): the kernels count the rows that passed.
 struct PendingFilter {
-    bool    active  = false;
-    int     binding = -1;
-    uint64_t rows   = 0;      // rows of the base relation
-    uint64_t max_val[kMaxPredCols] = {0, 0, 0};
-    PredSet preds;
+    bool     active  = false;
+    int      binding = -1;
+    uint64_t rows    = 0;      // rows of the base relation
+    double   est_sel = 1.0;    // estimated fraction of rows that pass (stats.c's formulas on the column statistics)
+    PredSet  preds;
 };
 
 struct B200InterData : inter_data {
@@ -77,15 +79,38 @@ uint64_t *const kParkedF = reinterpret_cast<uint64_t *>(16);   // ... whose filt
 constexpr uint64_t kFuseMinRows = 1ull << 18;                  // smaller relations are filtered the eager way
 
 thread_local bool t_null_result = false;   // see b200_last_result_null
-std::atomic<int> g_fuse_filters{-1};   // -1: B200_FUSE_FILTERS from the environment (default on)
-bool fuse_filters_enabled() {
+// 0 = off, 1 = where it pays (default), 2 = wherever possible (tests); -1: B200_FUSE_FILTERS from the environment
+std::atomic<int> g_fuse_filters{-1};
+int fuse_filters_mode() {
     int v = g_fuse_filters.load(std::memory_order_relaxed);
     if (v < 0) {
         const char *e = getenv("B200_FUSE_FILTERS");
-        v             = e ? (atoi(e) != 0) : 1;
+        v             = e ? std::max(0, std::min(atoi(e), 2)) : 1;
         g_fuse_filters.store(v, std::memory_order_relaxed);
     }
-    return v != 0;
+    return v;
+}
+bool fuse_filters_enabled() { return fuse_filters_mode() != 0; }
+
+// stats.c:88-259's selectivity estimates from min / max / distinct (uniform values): the fraction of rows that pass
+double estimate_selectivity(const DevColumn &c, int cmp, uint64_t k) {
+    const double lo = (double)c.min_val, hi = (double)c.max_val, kk = (double)k;
+    if (c.max_val == UINT64_MAX || hi < lo) return 0.5;
+    const double range = hi - lo + 1.0;
+    double       sel;
+    if (cmp == 2) sel = (kk < lo || kk > hi) ? 0.0 : 1.0 / (c.distinct ? (double)c.distinct : range);
+    else if (cmp == 0) sel = (kk - lo) / range;          // v < k
+    else sel = (hi - kk) / range;                        // v > k
+    return std::min(1.0, std::max(0.0, sel));
+}
+
+// Fusing pays when enough rows survive: the fused kernels stream the key column and every predicate column over ALL
+// rows of the relation and keep it out of the small-build-side plans, while the eager scans cost one pass per
+// predicate but leave the join a relation of the filtered size.
+bool worth_fusing(const PendingFilter &pf) {
+    if (fuse_filters_mode() == 2) return true;
+    const double est = pf.est_sel * (double)pf.rows;
+    return est >= (double)kFuseMinRows && est * 64.0 >= (double)pf.rows;
 }
 
 std::atomic<int> g_lazy_join{-1};   // -1: B200_LAZY_JOIN from the environment (default on)
@@ -329,6 +354,7 @@ result *Filter(inter_res *head, filter_pred *filter_p, relation_map *map, int *q
             r->f_col      = col.d;
             r->f_cmp      = code;
             r->f_k        = (uint64_t)(int64_t)filter_p->value;   // `uint64_t (cmp) int`: sign-extended (filter.c:118)
+            r->f_sel      = estimate_selectivity(col, code, r->f_k);
             r->n          = col.n;
             r->kr.max_val = col.max_val;
             return r;
@@ -391,6 +417,7 @@ int InsertSingleRowIdsToInterResult(inter_res **head, int relation_num, result *
         pf.preds.p[pf.preds.npred].cmp = r->f_cmp;
         pf.preds.p[pf.preds.npred].k   = r->f_k;
         ++pf.preds.npred;
+        pf.est_sel *= r->f_sel;
         return 1;
     }
     inter_res *node = *head, *last = nullptr;
@@ -420,6 +447,7 @@ relation *GetRelation(int given_rel, int column, inter_res *inter, relation_map 
     rel->tuples     = nullptr;
     rel->kv.src.col = col.d;
     rel->kv.max_val = col.max_val;
+    if (node && idata(node)->pfilter.active && !worth_fusing(idata(node)->pfilter)) resolve_filter(node);
     if (node && idata(node)->pfilter.active) {
         // the binding's filters are parked: the join evaluates them in its load stage and reports base row ids
         rel->kv.src.ids = nullptr;
@@ -666,9 +694,9 @@ int b200_calculate_sums(inter_res *inter, relation_map *map, batch_listnode *que
 // through: the reference prints NULL for every projection then (its Filter returns NULL, query.c:360-369)
 int b200_last_result_null(void) { return t_null_result ? 1 : 0; }
 
-int b200_set_fuse_filters(int on) {
-    const int before = fuse_filters_enabled() ? 1 : 0;
-    g_fuse_filters.store(on ? 1 : 0, std::memory_order_relaxed);
+int b200_set_fuse_filters(int mode) {
+    const int before = fuse_filters_mode();
+    g_fuse_filters.store(std::max(0, std::min(mode, 2)), std::memory_order_relaxed);
     return before;
 }
 

@@ -165,6 +165,7 @@ def _declare(L: C.CDLL) -> None:
         "b200_last_error": (C.c_char_p, []),
         "b200_is_cuda": (C.c_int, []),
         "b200_register_relations": (C.c_int, [P(CRelationMap), C.c_int]),
+        "b200_compute_column_stats": (C.c_int, [P(CRelationMap), C.c_int]),
         "b200_register_device_column": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
         "b200_upload_column": (C.c_int, [C.c_void_p, C.c_uint64]),
         "b200_unregister_all": (None, []),
@@ -294,6 +295,13 @@ class RelationMapArray:
 
     def register(self):
         _check(lib().b200_register_relations(self.array, len(self)))
+
+    def device_stats(self):
+        """relation_map.c:53-83 computed on the GPU: per relation and column (l, u, f, d)."""
+        _check(lib().b200_compute_column_stats(self.array, len(self)))
+        return [[(int(self.array[r].col_stats[j].l), int(self.array[r].col_stats[j].u),
+                  float(self.array[r].col_stats[j].f), float(self.array[r].col_stats[j].d))
+                 for j in range(len(cols))] for r, cols in enumerate(self.columns)]
 
     def unregister(self):
         if _lib is not None:

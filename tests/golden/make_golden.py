@@ -55,6 +55,13 @@ QUERY_CASES = [  # sizes, ncols, domain, seed, query
 ]
 
 
+STATS_CASES = [  # rows, [(domain, offset) per column], seed
+    (5000, [(64, 0), (1 << 20, 7), (1, 123)], 31),
+    (200000, [(1 << 40, 0), (60_000_000, 1000), (49_999_999, 5)], 32),
+    (1, [(10, 3)], 33),
+]
+
+
 def query_relations(sizes, ncols, domain, seed):
     return [[col(n, domain, seed * 1000 + r * 10 + c) for c in range(ncols)] for r, n in enumerate(sizes)]
 
@@ -80,6 +87,17 @@ def main():
         line = refbind.run_driver("ref_driver", rels, [q])[0]
         out["queries"].append({"sizes": sizes, "ncols": ncols, "domain": domain, "seed": seed, "query": q,
                                "line": line})
+    # column statistics of the reference's loader (relation_map.c:53-83) on relation files written from the generator:
+    # small ranges (direct marker array), a range beyond 50 000 000 (the modulo branch) and a constant column
+    import tempfile
+    out["stats"] = []
+    for n, domains, seed in STATS_CASES:
+        cols = [col(n, d, seed * 100 + j) + np.uint64(off) for j, (d, off) in enumerate(domains)]
+        with tempfile.TemporaryDirectory() as tmp:
+            path = Path(tmp) / "rel"
+            refbind.write_relation_file(path, cols)
+            st = refbind.init_relation_map([path])[0]
+        out["stats"].append({"n": n, "domains": domains, "seed": seed, "stats": st})
     (HERE / "reference_vectors.json").write_text(json.dumps(out, indent=1))
     print("wrote", HERE / "reference_vectors.json")
 

@@ -56,6 +56,8 @@ def lib():
         L.orc_join_sum.restype = C.c_uint64
         L.orc_join_sum.argtypes = [u64p, C.c_uint64, u64p, C.c_uint64, C.c_int, C.c_int, C.POINTER(u64p),
                                    C.POINTER(C.c_int), u64p]
+        L.orc_column_stats.restype = None
+        L.orc_column_stats.argtypes = [u64p, C.c_uint64, u64p, u64p, u64p]
         L.orc_synth_column.restype = None
         L.orc_synth_column.argtypes = [u64p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64]
         _lib = L
@@ -250,3 +252,11 @@ def execute_query(text, relations, n_lsb=4):
         nodes[:2] = [new]
     nd = nodes[0]
     return " ".join(str(checksum(col(b, c), nd[b])) for b, c in views)
+
+
+def column_stats(col):
+    """(l, u, d) of relation_map.c:53-83 (oracle_join.c orc_column_stats)."""
+    col = _u64(col)
+    l, u, d = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    lib().orc_column_stats(_p(col), len(col), C.byref(l), C.byref(u), C.byref(d))
+    return int(l.value), int(u.value), int(d.value)

@@ -198,3 +198,35 @@ def run_driver(binary: str, relations, queries, threads: int = 4, timeout: int =
     if out.returncode != 0:
         raise RuntimeError(f"{binary} exited {out.returncode}: {out.stderr[-2000:]}")
     return out.stdout.splitlines()
+
+
+class RelationListNode(C.Structure):
+    pass
+
+
+RelationListNode._fields_ = [("filename", C.c_char_p), ("fd", C.c_int), ("next", C.POINTER(RelationListNode))]
+
+
+class ColumnStats(C.Structure):
+    _fields_ = [("l", C.c_uint64), ("u", C.c_uint64), ("f", C.c_double), ("d", C.c_double)]
+
+
+class RelationMap(C.Structure):
+    _fields_ = [("num_tuples", C.c_uint64), ("num_columns", C.c_uint64), ("columns", C.POINTER(C.POINTER(C.c_uint64))),
+                ("col_stats", C.POINTER(ColumnStats))]
+
+
+def init_relation_map(paths):
+    """The reference's loader (relation_map.c:13-88) on relation files: per relation and column (l, u, f, d)."""
+    L = lib()
+    L.InitRelationMap.argtypes = [C.POINTER(RelationListNode), C.POINTER(RelationMap)]
+    nodes = [RelationListNode(str(p).encode(), -1, None) for p in paths]
+    for a, b in zip(nodes, nodes[1:]):
+        a.next = C.pointer(b)
+    maps = (RelationMap * len(paths))()
+    L.InitRelationMap(C.byref(nodes[0]), maps)
+    out = []
+    for m in maps:
+        out.append([(int(m.col_stats[j].l), int(m.col_stats[j].u), float(m.col_stats[j].f), float(m.col_stats[j].d))
+                    for j in range(m.num_columns)])
+    return out

@@ -41,7 +41,7 @@ def test_fused_filters_match_the_oracle(gpu, orc, rels, q):
     rm = gpu.RelationMapArray(rels)
     rm.register()
     try:
-        for fuse in (1, 0):
+        for fuse in (2, 1, 0):        # wherever possible / where the estimate says it pays / never
             for lazy in (1, 0):
                 L.b200_set_fuse_filters(fuse)
                 before = L.b200_set_lazy_join(lazy)
@@ -54,23 +54,26 @@ def test_fused_filters_match_the_oracle(gpu, orc, rels, q):
         rm.unregister()
 
 
-def test_fused_filter_launches_no_scan(gpu, orc, rels):
-    """With fusion the three predicates cost no filter scan, no compaction and no host round trip of their own:
-    fewer kernels than the eager path, same line."""
+def test_fusion_is_chosen_by_estimated_selectivity(gpu, orc, rels):
+    """Mode 1 (default): a filter that keeps a quarter of a large relation is fused — no scan, no row-id list, no
+    host round trip of its own, so fewer kernels than the eager path; one that keeps 0.2 % is scanned the eager way
+    (the join then takes the tiny unpartitioned plan) and launches exactly what mode 0 launches."""
     L = gpu.lib()
-    q = "0 1|0.0=1.0&1.1>100&1.1<130&1.2=7|0.2 1.1"
     rm = gpu.RelationMapArray(rels)
     rm.register()
+
+    def launches(q, mode):
+        L.b200_set_fuse_filters(mode)
+        gpu.execute_query(q, rm)
+        gpu.kernel_launches(reset=True)
+        line = gpu.execute_query(q, rm).line()
+        assert line == orc.execute_query(q, rels), (q, mode)
+        return gpu.kernel_launches()
+
     try:
-        counts = {}
-        for fuse in (1, 0):
-            L.b200_set_fuse_filters(fuse)
-            gpu.execute_query(q, rm)
-            gpu.kernel_launches(reset=True)
-            line = gpu.execute_query(q, rm).line()
-            counts[fuse] = gpu.kernel_launches()
-            assert line == orc.execute_query(q, rels)
-        assert counts[1] < counts[0], counts
+        wide, narrow = "0 1|0.0=1.0&1.1<500&1.1>0|0.2 1.1", "0 1|0.0=1.0&1.1>100&1.1<130&1.2=7|0.2 1.1"
+        assert launches(wide, 1) == launches(wide, 2) < launches(wide, 0)
+        assert launches(narrow, 1) == launches(narrow, 0)
     finally:
         L.b200_set_fuse_filters(1)
         rm.unregister()

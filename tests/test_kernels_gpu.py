@@ -529,3 +529,25 @@ def test_exchange_overflow_is_flagged_not_written(gpu, orc):
     for r in recv:
         tail = _from_dev(gpu, r.ptr + 8 * cap, guard, np.uint64)
         assert np.all(tail == np.uint64(0xABCDABCDABCDABCD))
+
+
+# ---- column statistics at registration (relation_map.c:53-83) ----
+def test_column_stats_match_the_reference_loader(gpu, orc):
+    """min / max / the reference's distinct count on the GPU against the golden vectors of the reference's own
+    InitRelationMap (direct marker array, the modulo branch beyond a range of 50 000 000, a constant column) and
+    against the oracle restatement on the shipped small relations."""
+    from golden_cases import GOLDEN, col, load_small
+    for case in GOLDEN["stats"]:
+        cols = [col(case["n"], d, case["seed"] * 100 + j) + np.uint64(off) for j, (d, off) in enumerate(case["domains"])]
+        rm = gpu.RelationMapArray([cols])
+        assert rm.device_stats()[0] == [tuple(x) for x in case["stats"]], case
+        rm.unregister()
+    small = load_small()
+    if small is not None:
+        rm = gpu.RelationMapArray(small)
+        got = rm.device_stats()
+        for r, rel in enumerate(small):
+            for j, c in enumerate(rel):
+                l, u, d = orc.column_stats(c)
+                assert got[r][j] == (l, u, float(len(c)), float(d)), (r, j)
+        rm.unregister()

@@ -67,3 +67,14 @@ def test_synth_generator_properties(orc):
     assert int(z.max()) < (1 << 16)
     _, counts = np.unique(z, return_counts=True)
     assert counts.max() > 0.04 * len(z)       # hottest key carries ~1/(k+1) of the mass
+
+
+def test_column_stats_golden(orc):
+    """relation_map.c:53-83 (min, max, the reference's distinct count incl. its modulo branch) restated in the oracle."""
+    from golden_cases import GOLDEN, col
+    assert GOLDEN["stats"]
+    for case in GOLDEN["stats"]:
+        for j, ((d, off), want) in enumerate(zip(case["domains"], case["stats"])):
+            c = col(case["n"], d, case["seed"] * 100 + j) + np.uint64(off)
+            l, u, dd = orc.column_stats(c)
+            assert (l, u, float(case["n"]), float(dd)) == tuple(want), (case, j)
