@@ -403,7 +403,10 @@ int   b200_stage_exchange_segments(const void *d_src_tup, int npay,
  *       stores every partition into its owner's receive buffer over NVLink (the
  *       exchange of chunk c under the partition pass of chunk c + 1); owners are
  *       contiguous partition ranges cut on the global histogram so that skewed
- *       keys do not overload one GPU; every owner joins what it received.
+ *       keys do not overload one GPU; every owner joins what it received.  Hot
+ *       keys (a sample of the probe keys decides) are not exchanged at all: every
+ *       rank learns the count and SUM of the build rows carrying them, and probe
+ *       rows with a hot key are joined where they are, during the histogram pass.
  * Query shape: join(build.key = probe.key) with SUM(build column) and / or
  * SUM(probe column); keys and SUM values below 2^32 (they travel in 8-byte
  * tuples).  Every rank must create its plan with the same totals / maxima. */
@@ -419,6 +422,7 @@ typedef struct {
     int      radix_bits;                           /* 0 = automatic              */
     int      chunks;                               /* 0 = default (4 copy chunks / 8 probe chunks) */
     uint64_t recv_rows_build, recv_rows_probe;     /* exchange: receive capacity per rank, 0 = mean + 1/8 */
+    int      hot_keys;                             /* exchange: 0 = hot keys are joined where they are (default), -1 = off */
 } b200_multi_config;
 b200_multi *b200_multi_create(const b200_multi_config *cfg);
 void  b200_multi_destroy(b200_multi *plan);
@@ -430,7 +434,9 @@ int   b200_multi_radix_bits(b200_multi *plan);
 /* One step on the calling thread's stream, DEVICE pointers to this rank's
  * shards.  phases: 0 = the whole step; otherwise a bit mask of the step's
  * phases (broadcast: 1 partition + broadcast, 2 join + publish, 4 reduce;
- * exchange: 1 histograms, 2 partition + exchange, 4 join + publish, 8 reduce)
+ * exchange: 1 build histogram + hot-key candidates, 2 hot-key table + build-side
+ * aggregates, 4 probe histograms, 8 partition + exchange, 16 join + publish,
+ * 32 reduce)
  * so that a test can drive several ranks on ONE GPU phase by phase — kernels
  * that wait on one another must never share a GPU. */
 int   b200_multi_enqueue(b200_multi *plan, const uint64_t *d_build_keys, const uint64_t *d_build_sum,

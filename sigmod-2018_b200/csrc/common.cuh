@@ -16,6 +16,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <vector>
 
 namespace b200 {
 
@@ -54,6 +55,17 @@ struct Context {
     unsigned long long *h_scratch = nullptr;   // 64 x u64, pinned
     unsigned long long *d_scratch = nullptr;   // 64 x u64, device
     std::map<std::string, KernelTimer> timers;
+    // large transient buffers (partition buffers, row-id lists of big relations) are kept here when they are
+    // released and handed out again to the next request of a similar size on the same stream: the stream-ordered
+    // pool splits its big free blocks for small requests, so a query that needs two 1.6 GB buffers per join paid a
+    // fresh physical allocation (milliseconds) every time
+    struct BigBlock {
+        void        *ptr;
+        size_t       bytes;
+        cudaStream_t stream;
+    };
+    std::vector<BigBlock> big_cache;
+    size_t                big_cached = 0;
     ~Context();
 };
 
@@ -83,7 +95,8 @@ inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed);
 // Stream-ordered device buffer (cudaMallocAsync on the owning thread's stream).
 struct DevBuf {
     void        *ptr   = nullptr;
-    size_t       bytes = 0;
+    size_t       bytes = 0;      // what was asked for
+    size_t       capacity = 0;   // what the block holds (a recycled big block may be larger)
     cudaStream_t stream = nullptr;
     DevBuf(size_t nbytes, cudaStream_t s);
     ~DevBuf();

@@ -215,12 +215,43 @@ TimedScope::~TimedScope() {
     if (t) cudaEventRecord(t->stop, ctx().stream);
 }
 
-DevBuf::DevBuf(size_t nbytes, cudaStream_t s) : bytes(nbytes), stream(s) {
+constexpr size_t kBigBuf       = 64ull << 20;    // blocks from this size up are recycled through the context
+constexpr size_t kBigCacheMax  = 24ull << 30;    // ... up to this many bytes per context
+
+DevBuf::DevBuf(size_t nbytes, cudaStream_t s) : bytes(nbytes), capacity(nbytes ? nbytes : 16), stream(s) {
+    if (nbytes >= kBigBuf) {
+        Context &c    = ctx();
+        int      best = -1;
+        for (size_t i = 0; i < c.big_cache.size(); ++i) {
+            const auto &b = c.big_cache[i];
+            if (b.stream == s && b.bytes >= nbytes && b.bytes <= 2 * nbytes &&
+                (best < 0 || b.bytes < c.big_cache[(size_t)best].bytes))
+                best = (int)i;
+        }
+        if (best >= 0) {
+            ptr      = c.big_cache[(size_t)best].ptr;
+            capacity = c.big_cache[(size_t)best].bytes;
+            c.big_cached -= capacity;
+            c.big_cache.erase(c.big_cache.begin() + best);
+            return;
+        }
+    }
     // never hand out NULL: a 0-row table must still read as "active"
-    B200_CUDA(cudaMallocAsync(&ptr, nbytes ? nbytes : 16, s));
+    B200_CUDA(cudaMallocAsync(&ptr, capacity, s));
 }
 DevBuf::~DevBuf() {
-    if (ptr) cudaFreeAsync(ptr, stream);
+    if (!ptr) return;
+    if (capacity >= kBigBuf) {
+        // stream order makes the hand-over safe: whoever takes the block enqueues its work on the same stream, behind
+        // whatever still uses it
+        Context &c = ctx();
+        if (c.device == thread_device() && c.big_cached + capacity <= kBigCacheMax) {
+            c.big_cache.push_back(Context::BigBlock{ptr, capacity, stream});
+            c.big_cached += capacity;
+            return;
+        }
+    }
+    cudaFreeAsync(ptr, stream);
 }
 
 uint64_t read_counter(const unsigned long long *d_ptr) {
@@ -454,6 +485,19 @@ static void launch_hist(const KeySrc &src, int bits, uint32_t *ghist, int ctas_p
     B200_LAUNCH_CHECK();
 }
 
+// the tuned scatter carrying a 32-bit payload, skipping the rows opt.pred rules out (hot keys of the exchange plan)
+static void launch_scatter_pred_carry(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
+    constexpr int NT   = PartCfg<uint32_t, 1>::NT;
+    constexpr int U    = PartCfg<uint32_t, 1>::U;
+    constexpr int MINB = PartCfg<uint32_t, 1>::MINB;
+    const size_t  smem = (size_t)NT * U * sizeof(Tup32) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
+    auto          k    = radix_scatter_kernel<NT, U, MINB, uint32_t, false, true, true>;
+    allow_smem(k, smem);
+    k<<<grid_for(src.n, NT * U, MINB), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor, static_cast<Tup32 *>(out),
+                                                                 opt);
+    B200_LAUNCH_CHECK();
+}
+
 // scatter with the relation's filter predicates folded into its load stage (plain and histogram-free instance)
 template <typename KeyT, bool OPT>
 static void launch_scatter_pred(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
@@ -461,7 +505,7 @@ static void launch_scatter_pred(const KeySrc &src, int bits, uint32_t *cursor, v
     constexpr int NT   = PartCfg<KeyT, 1>::NT;
     constexpr int U    = PartCfg<KeyT, 1>::U;
     constexpr int MINB = PartCfg<KeyT, 1>::MINB;
-    B200_REQUIRE(src.ids == nullptr && opt.pred.npred > 0, "fused predicates apply to base relations");
+    B200_REQUIRE(src.ids == nullptr && (opt.pred.npred > 0 || opt.pred.hot_keys), "fused predicates apply to base relations");
     const size_t smem = (size_t)NT * U * sizeof(TupT) + (OPT ? 4 : 3) * (size_t)(1u << bits) * sizeof(uint32_t);
     auto         k    = radix_scatter_kernel<NT, U, MINB, KeyT, OPT, false, true>;
     allow_smem(k, smem);
@@ -1341,7 +1385,8 @@ size_t stage_scratch_bytes(int bits, int nseg) {
 
 void stage_scatter_build_local(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int bits,
                                const uint32_t *d_hist_local, void *d_tup_out, int npay, const uint64_t *const *pay_cols,
-                               uint64_t *const *pay_out, const StageScratch *scr, uint32_t *d_off_out) {
+                               uint64_t *const *pay_out, const StageScratch *scr, uint32_t *d_off_out,
+                               const PredSet *skip) {
     B200_REQUIRE(npay >= 0 && npay <= 2, "bad payload count");
     if (n == 0 && !d_off_out) return;
     Context       &c      = ctx();
@@ -1376,6 +1421,14 @@ void stage_scatter_build_local(const uint64_t *d_keys, uint64_t n, uint32_t rid_
     }
     KeySrc src{d_keys, nullptr, (uint32_t)n};
     TimedScope ts("scatter_b");
+    if (skip && skip->hot_keys) {
+        // rows the caller's histogram did not count (hot keys, joined on the spot) are skipped here as well
+        B200_REQUIRE(carry || npay == 0, "the skipping scatter carries at most one 32-bit payload");
+        const OptArgs o{0, nullptr, nullptr, carry ? pay_cols[0] : nullptr, *skip};
+        if (carry) launch_scatter_pred_carry(src, bits, cur_l, d_tup_out, o);
+        else launch_scatter_pred<uint32_t, false>(src, bits, cur_l, d_tup_out, o);
+        return;
+    }
     // large shards with a carried payload (the probe side of the exchange plan) take the tuned scatter instance
     if (carry && n >= (1u << 18))
         launch_scatter_carry_tuned(src, bits, cur_l, d_tup_out, pay_cols[0]);

@@ -139,7 +139,8 @@ JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const v
 void       stage_scatter_build_local(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int bits,
                                      const uint32_t *d_hist_local, void *d_tup_out, int npay,
                                      const uint64_t *const *pay_cols, uint64_t *const *pay_out,
-                                     const StageScratch *scr = nullptr, uint32_t *d_off_out = nullptr);
+                                     const StageScratch *scr = nullptr, uint32_t *d_off_out = nullptr,
+                                     const PredSet *skip = nullptr);
 void       stage_build_cursors(const uint32_t *d_hist_all, int world, int rank, int bits, uint32_t *d_total,
                                uint32_t *d_my_start);
 void       stage_exchange_cursors(const uint32_t *d_hist_all, int world, int rank, int bits, uint32_t cap,

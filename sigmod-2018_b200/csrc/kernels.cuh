@@ -320,6 +320,15 @@ template <int NT, int U>
 __device__ __forceinline__ void prefetch_carry_tile(const uint64_t *col, uint64_t base, uint32_t count) {
     for (uint32_t e = threadIdx.x * 16u; e < count; e += NT * 16u) prefetch_l2(col + base + e);
 }
+// direct-mapped table of hot keys (multi-GPU exchange plan, multi_kernels.cuh): rows carrying one are skipped here
+constexpr uint32_t kHotSlots = 8192;
+constexpr uint32_t kHotEmpty = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t hot_slot(uint32_t key) { return (key * 0x9E3779B1u) >> (32 - 13); }
+static_assert(kHotSlots == (1u << 13), "hot_slot produces 13 bits");
+__device__ __forceinline__ bool key_is_hot(const PredSet &ps, bool hot_on, uint32_t key) {
+    return hot_on && key != kHotEmpty && __ldg(ps.hot_keys + hot_slot(key)) == key;
+}
+
 // Raw tile loads of the scatter: 64-bit values exactly as the column holds them (two per 128-bit load on the vector
 // path).  They stay raw in registers across the copy-out of the previous tile and are narrowed to KeyT only at the
 // top of their own tile: ncu (profiles/r1_g_probe_carry_summary.txt, source page) showed 11 % of all warp samples
@@ -387,7 +396,8 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     static_assert(U <= 64, "one validity bit per key");
     [[maybe_unused]] uint64_t valid = 0;   // PRED: bit j = row of register j passes every predicate
     if constexpr (PRED) {
-        const PredSet &ps = opt.pred;
+        const PredSet &ps     = opt.pred;
+        const bool     hot_on = ps.hot_keys != nullptr && __ldg(ps.hot_n) != 0u;
         if (vec) {
 #pragma unroll
             for (int j = 0; j < U; j += 2) {
@@ -402,14 +412,15 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
                         v1[cc]             = t.y;
                     }
                 }
-                valid |= (uint64_t)(preds_hold(ps, v0) ? 1u : 0u) << j;
-                valid |= (uint64_t)(preds_hold(ps, v1) ? 1u : 0u) << (j + 1);
+                valid |= (uint64_t)(preds_hold(ps, v0) && !key_is_hot(ps, hot_on, (uint32_t)keys[j]) ? 1u : 0u) << j;
+                valid |= (uint64_t)(preds_hold(ps, v1) && !key_is_hot(ps, hot_on, (uint32_t)keys[j + 1]) ? 1u : 0u) << (j + 1);
             }
         } else {
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 const uint32_t li = (uint32_t)(j * NT) + tid;
-                if (li < count && preds_hold_row(ps, base + li)) valid |= 1ull << j;
+                if (li < count && preds_hold_row(ps, base + li) && !key_is_hot(ps, hot_on, (uint32_t)keys[j]))
+                    valid |= 1ull << j;
             }
         }
     }

@@ -78,6 +78,11 @@ struct MultiPlan {
     void          *tup_p = nullptr, *ov_p = nullptr, *stage_b = nullptr, *stage_p = nullptr;
     uint32_t      *src_off_b = nullptr, *src_off_p = nullptr, *dst_start_b = nullptr, *dst_start_p = nullptr;
     uint32_t      *own_total = nullptr, *total = nullptr, *cut = nullptr, *need = nullptr;
+    // hot keys (exchange plan): sampling table, the agreed table, build-side aggregates, the hot rows' result
+    int            hot = 0;
+    uint32_t      *hs_keys = nullptr, *hs_cnt = nullptr, *hot_keys = nullptr, *hot_n = nullptr;
+    unsigned long long *hot_agg = nullptr, *hot_acc = nullptr;
+    size_t         off_cand = 0, off_agg = 0;
     StageScratch   scr_a, scr_b;
     unsigned long long *h_final = nullptr;   // pinned
     cudaStream_t   copy_stream[kMaxPeers] = {nullptr}, xstream = nullptr, gstream = nullptr;
@@ -96,6 +101,8 @@ struct MultiPlan {
     uint32_t     *hist_p(int r) const { return reinterpret_cast<uint32_t *>(peer[r] + off_hist_p); }
     unsigned char *build(int r) const { return peer[r] + off_build; }
     unsigned char *recv_p(int r) const { return peer[r] + off_recv_p; }
+    uint32_t      *cand(int r) const { return reinterpret_cast<uint32_t *>(peer[r] + off_cand); }   // [world][1 + kHotMaxCand]
+    unsigned long long *agg(int r) const { return reinterpret_cast<unsigned long long *>(peer[r] + off_agg); }
     PeerPtrs peers() const {
         PeerPtrs p{};
         for (int r = 0; r < world; ++r) p.hdr[r] = hdr(r);
@@ -104,7 +111,8 @@ struct MultiPlan {
 };
 
 // broadcast: header | hist_b[world][P] | build[world][seg_rows]
-// exchange:  header | hist_b[world][P] | hist_p[world * K][P] | recv_b[cap_b] | recv_p[cap_p]   (build() = recv_b)
+// exchange:  header | hist_b[world][P] | hist_p[world * K][P] | cand[world][1 + 2048] | agg[world][8192][2] |
+//            recv_b[cap_b] | recv_p[cap_p]   (build() = recv_b)
 static void layout_shared(MultiPlan &m) {
     m.off_hist_b = align_up(sizeof(SharedHeader), 256);
     if (m.cfg.plan == B200_PLAN_BROADCAST) {
@@ -114,7 +122,9 @@ static void layout_shared(MultiPlan &m) {
         m.shared_bytes = align_up(m.off_build + ((size_t)m.world * m.seg_rows + 16) * 8, 256);
     } else {
         m.off_hist_p   = align_up(m.off_hist_b + (size_t)m.world * m.P * 4, 256);
-        m.off_build    = align_up(m.off_hist_p + (size_t)m.world * m.K * m.P * 4, 256);
+        m.off_cand     = align_up(m.off_hist_p + (size_t)m.world * m.K * m.P * 4, 256);
+        m.off_agg      = align_up(m.off_cand + (size_t)m.world * (1 + kHotMaxCand) * 4, 256);
+        m.off_build    = align_up(m.off_agg + (size_t)m.world * kHotSlots * 16, 256);
         m.off_recv_p   = align_up(m.off_build + ((size_t)m.cap_b + 16) * 8, 256);
         m.shared_bytes = align_up(m.off_recv_p + ((size_t)m.cap_p + 16) * 8, 256);
     }
@@ -147,6 +157,12 @@ static void layout_local(MultiPlan &m, void *base, size_t *bytes) {
         m.total       = c.take<uint32_t>(2 * P);
         m.cut         = c.take<uint32_t>(kMaxPeers + 1);
         m.need        = c.take<uint32_t>(4);
+        m.hs_keys     = c.take<uint32_t>(kHotSample);
+        m.hs_cnt      = c.take<uint32_t>(kHotSample);
+        m.hot_keys    = c.take<uint32_t>(kHotSlots);
+        m.hot_n       = c.take<uint32_t>(4);
+        m.hot_agg     = c.take<unsigned long long>(2 * kHotSlots);
+        m.hot_acc     = c.take<unsigned long long>(4);
     }
     *bytes = align_up(c.off, 256);
 }
@@ -275,6 +291,29 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
     }
 }
 
+static void push_block(MultiPlan &m, cudaStream_t stream, const void *src, size_t bytes, size_t shared_offset, int sig) {
+    PushArgs a{};
+    a.src   = static_cast<const uint32_t *>(src);
+    a.words = (uint32_t)(bytes / 4);
+    a.rank  = m.rank;
+    a.world = m.world;
+    a.sig   = sig;
+    a.epoch = m.d_epoch;
+    for (int d = 0; d < m.world; ++d) {
+        a.dst[d] = reinterpret_cast<uint32_t *>(m.peer[d] + shared_offset);
+        a.hdr[d] = m.hdr(d);
+    }
+    push_to_peers_kernel<<<m.world, 256, 0, stream>>>(a);
+    B200_LAUNCH_CHECK();
+}
+
+static void wait_signal(MultiPlan &m, cudaStream_t stream, int sig) {
+    wait_peers_kernel<<<1, 32, 0, stream>>>(m.hdr(m.rank)->sig[sig], m.world, m.d_epoch, m.d_error);
+    B200_LAUNCH_CHECK();
+}
+
+// exchange plan, phases (bits): 1 build histogram + hot-key candidates, 2 hot table + build-side aggregates,
+// 4 probe histograms (hot rows joined on the spot), 8 cuts + partition + exchange, 16 join + publish, 32 reduce
 static void enqueue_exchange(MultiPlan &m, int phases) {
     Context     &c    = ctx();
     cudaStream_t main = c.stream;
@@ -283,36 +322,80 @@ static void enqueue_exchange(MultiPlan &m, int phases) {
     const uint64_t nb = m.cfg.n_build_local, np = m.cfg.n_probe_local;
     uint32_t *my_hb = m.hist_b(rank) + (size_t)rank * P;
     uint32_t *my_hp = m.hist_p(rank) + (size_t)rank * K * P;
+    const size_t cand_words = 1 + kHotMaxCand;
     if (phases & 1) {
         bump_epoch_kernel<<<1, 1, 0, main>>>(m.d_epoch);
         B200_LAUNCH_CHECK();
         B200_CUDA(cudaMemsetAsync(m.d_error, 0, 16, main));
         B200_CUDA(cudaMemsetAsync(m.d_result, 0, 64, main));
-        // ---- histograms of both local shards (the probe shard per chunk), published to every rank ----
+        B200_CUDA(cudaMemsetAsync(m.hot_acc, 0, 32, main));
+        B200_CUDA(cudaMemsetAsync(m.hot_n, 0, 16, main));
         stage_hist(m.in_bk, nb, m.bits, my_hb);
+        push_block(m, main, my_hb, (size_t)P * 4, m.off_hist_b + (size_t)rank * P * 4, SIG_HIST);
+        if (m.hot) {
+            // ---- candidates: keys that at least 1 / 16384 of a sample of my probe rows carry ----
+            uint32_t *my_cand = m.cand(rank) + (size_t)rank * cand_words;
+            B200_CUDA(cudaMemsetAsync(m.hs_keys, 0xFF, kHotSample * 4, main));
+            B200_CUDA(cudaMemsetAsync(m.hs_cnt, 0, kHotSample * 4, main));
+            B200_CUDA(cudaMemsetAsync(my_cand, 0, 4, main));
+            const uint64_t nsample = std::min<uint64_t>(np, 1u << 20);
+            if (nsample) {
+                hot_sample_kernel<<<grid_for(nsample, 256, 8), 256, 0, main>>>(m.in_pk, np, nsample, m.hs_keys, m.hs_cnt);
+                B200_LAUNCH_CHECK();
+                const uint32_t threshold = (uint32_t)std::max<uint64_t>(8, nsample >> 14);
+                hot_select_kernel<<<kHotSample / 256, 256, 0, main>>>(m.hs_keys, m.hs_cnt, threshold, my_cand);
+                B200_LAUNCH_CHECK();
+            }
+            push_block(m, main, my_cand, cand_words * 4, m.off_cand + (size_t)rank * cand_words * 4, SIG_HOT);
+        }
+    }
+    if ((phases & 2) && m.hot) {
+        wait_signal(m, main, SIG_HOT);
+        hot_table_kernel<<<1, 1024, 0, main>>>(m.cand(rank), world, m.hot_keys, m.hot_n);
+        B200_LAUNCH_CHECK();
+        // ---- how many of my build rows carry each hot key, and the sum of their SUM column ----
+        unsigned long long *my_agg = m.agg(rank) + (size_t)rank * 2 * kHotSlots;
+        B200_CUDA(cudaMemsetAsync(my_agg, 0, (size_t)kHotSlots * 16, main));
+        if (nb) {
+            hot_build_kernel<<<grid_for(nb, 256 * 4, 8), 256, 0, main>>>(m.in_bk, m.cfg.has_build_sum ? m.in_bp : nullptr, nb,
+                                                                        m.hot_keys, m.hot_n, my_agg);
+            B200_LAUNCH_CHECK();
+        }
+        push_block(m, main, my_agg, (size_t)kHotSlots * 16, m.off_agg + (size_t)rank * kHotSlots * 16, SIG_AGG);
+    }
+    if (phases & 4) {
+        if (m.hot) {
+            wait_signal(m, main, SIG_AGG);
+            hot_reduce_kernel<<<2 * kHotSlots / 256, 256, 0, main>>>(m.agg(rank), world, m.hot_agg);
+            B200_LAUNCH_CHECK();
+        }
+        // ---- histograms of the probe shard per chunk; rows with a hot key are joined here and not counted ----
         for (int k = 0; k < K; ++k) {
             const uint32_t a = chunk_first(m, np, k), b = chunk_first(m, np, k + 1);
-            stage_hist(m.in_pk + a, b - a, m.bits, my_hp + (size_t)k * P);
+            uint32_t      *h = my_hp + (size_t)k * P;
+            if (!m.hot) {
+                stage_hist(m.in_pk + a, b - a, m.bits, h);
+                continue;
+            }
+            B200_CUDA(cudaMemsetAsync(h, 0, (size_t)P * 4, main));
+            if (b > a) {
+                constexpr int NT   = 512;
+                const size_t  smem = ((size_t)P + kHotSlots) * 4;
+                auto          kern = hot_hist_kernel<NT>;
+                if (smem > 48 * 1024)
+                    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                TimedScope ts("hist");
+                kern<<<grid_for(b - a, NT * 16, 4), NT, smem, main>>>(m.in_pk + a, m.cfg.has_probe_sum ? m.in_pp + a : nullptr,
+                                                                      b - a, (uint32_t)m.bits, m.hot_keys, m.hot_n, m.hot_agg,
+                                                                      h, m.hot_acc);
+                B200_LAUNCH_CHECK();
+            }
         }
-        B200_CUDA(cudaEventRecord(m.ev_hist, main));
-        for (int j = 1; j < world; ++j) {
-            const int    d = (rank + j) % world;
-            cudaStream_t s = m.copy_stream[j - 1];
-            B200_CUDA(cudaStreamWaitEvent(s, m.ev_hist, 0));
-            B200_CUDA(cudaMemcpyAsync(m.hist_b(d) + (size_t)rank * P, my_hb, (size_t)P * 4, cudaMemcpyDeviceToDevice, s));
-            B200_CUDA(cudaMemcpyAsync(m.hist_p(d) + (size_t)rank * K * P, my_hp, (size_t)K * P * 4,
-                                      cudaMemcpyDeviceToDevice, s));
-            B200_CUDA(cudaMemcpyAsync(&m.hdr(d)->sig[SIG_HIST][rank], m.d_epoch, 4, cudaMemcpyDeviceToDevice, s));
-            B200_CUDA(cudaEventRecord(m.ev_copy[j - 1], s));
-        }
-        PeerPtrs self{};
-        self.hdr[0] = m.hdr(rank);
-        signal_peers_kernel<<<1, 32, 0, main>>>(self, 1, rank, SIG_HIST, m.d_epoch);
-        B200_LAUNCH_CHECK();
+        push_block(m, main, my_hp, (size_t)K * P * 4, m.off_hist_p + (size_t)rank * K * P * 4, SIG_HIST2);
     }
-    if (phases & 2) {
-        wait_peers_kernel<<<1, 32, 0, main>>>(m.hdr(rank)->sig[SIG_HIST], world, m.d_epoch, m.d_error);
-        B200_LAUNCH_CHECK();
+    if (phases & 8) {
+        wait_signal(m, main, SIG_HIST);
+        wait_signal(m, main, SIG_HIST2);
         // ---- ownership cuts on the global histogram, then where my segments go ----
         uint32_t *total_b = m.total, *total_p = m.total + P;
         balanced_cuts_kernel<1024><<<1, 1024, 0, main>>>(m.hist_b(rank), (uint32_t)world, m.hist_p(rank),
@@ -334,7 +417,7 @@ static void enqueue_exchange(MultiPlan &m, int phases) {
             x.src_off   = src_off;
             x.dst_start = dst_start;
             x.cut       = m.cut;
-            x.n         = (uint32_t)n;
+            x.n         = (uint32_t)n;   // upper bound: the kernel reads the staged count from src_off[nparts]
             x.nparts    = P;
             x.world     = (uint32_t)world;
             x.cap       = cap;
@@ -353,12 +436,18 @@ static void enqueue_exchange(MultiPlan &m, int phases) {
         B200_CUDA(cudaStreamWaitEvent(m.xstream, m.ev_build, 0));
         exchange(m.stage_b, nb, m.src_off_b, m.dst_start_b, m.cap_b, true);
         // ---- probe shard, chunk by chunk: the exchange of chunk k runs under the partition pass of chunk k + 1 ----
+        PredSet skip{};
+        if (m.hot) {
+            skip.hot_keys = m.hot_keys;
+            skip.hot_n    = m.hot_n;
+        }
         for (int k = 0; k < K; ++k) {
             const uint32_t a = chunk_first(m, np, k), b = chunk_first(m, np, k + 1);
             const uint64_t *pp[1] = {m.in_pp ? m.in_pp + a : nullptr};
             uint64_t *staged = static_cast<uint64_t *>(m.stage_p) + a;
             stage_scatter_build_local(m.in_pk + a, b - a, a, m.bits, my_hp + (size_t)k * P, staged,
-                                      m.cfg.has_probe_sum ? 1 : 0, pp, nullptr, &m.scr_a, m.src_off_p + (size_t)k * (P + 1));
+                                      m.cfg.has_probe_sum ? 1 : 0, pp, nullptr, &m.scr_a, m.src_off_p + (size_t)k * (P + 1),
+                                      m.hot ? &skip : nullptr);
             B200_CUDA(cudaEventRecord(m.ev_chunk[k], main));
             B200_CUDA(cudaStreamWaitEvent(m.xstream, m.ev_chunk[k], 0));
             exchange(staged, b - a, m.src_off_p + (size_t)k * (P + 1), m.dst_start_p + (size_t)k * P, m.cap_p, false);
@@ -367,23 +456,24 @@ static void enqueue_exchange(MultiPlan &m, int phases) {
         B200_LAUNCH_CHECK();
         B200_CUDA(cudaEventRecord(m.ev_x, m.xstream));
         B200_CUDA(cudaStreamWaitEvent(main, m.ev_x, 0));
-        for (int j = 1; j < world; ++j) B200_CUDA(cudaStreamWaitEvent(main, m.ev_copy[j - 1], 0));
     }
-    if (phases & 4) {
-        wait_peers_kernel<<<1, 32, 0, main>>>(m.hdr(rank)->sig[SIG_DATA], world, m.d_epoch, m.d_error);
-        B200_LAUNCH_CHECK();
+    if (phases & 16) {
+        wait_signal(m, main, SIG_DATA);
         ProjDesc pd[2];
         int      k = 0;
         if (m.cfg.has_build_sum) pd[k++] = ProjDesc{m.in_bp, nullptr, 0, B200_PROJ_IN_RID};
         if (m.cfg.has_probe_sum) pd[k++] = ProjDesc{m.in_pp, nullptr, 1, B200_PROJ_IN_RID};
         stage_join_sum(m.build(rank), m.own_total, m.recv_p(rank), m.own_total + P, m.bits, k, pd, 0, nullptr, nullptr,
                        m.d_result, 0, 0, &m.scr_b, nullptr);
+        if (m.hot) {
+            add_hot_result_kernel<<<1, 32, 0, main>>>(m.d_result, m.hot_acc, m.cfg.has_build_sum, m.cfg.has_probe_sum);
+            B200_LAUNCH_CHECK();
+        }
         push_result_kernel<<<1, 32, 0, main>>>(m.peers(), world, rank, m.d_result, m.d_error, m.d_epoch);
         B200_LAUNCH_CHECK();
     }
-    if (phases & 8) {
-        wait_peers_kernel<<<1, 32, 0, main>>>(m.hdr(rank)->sig[SIG_RESULT], world, m.d_epoch, m.d_error);
-        B200_LAUNCH_CHECK();
+    if (phases & 32) {
+        wait_signal(m, main, SIG_RESULT);
         reduce_result_kernel<<<1, 32, 0, main>>>(m.hdr(rank), world, m.d_final);
         B200_LAUNCH_CHECK();
         B200_CUDA(cudaMemcpyAsync(m.h_final, m.d_final, 64, cudaMemcpyDeviceToHost, main));
@@ -395,7 +485,7 @@ static void enqueue(MultiPlan &m, int phases) {
     else enqueue_exchange(m, phases);
 }
 
-static int all_phases(const MultiPlan &m) { return m.cfg.plan == B200_PLAN_BROADCAST ? 7 : 15; }
+static int all_phases(const MultiPlan &m) { return m.cfg.plan == B200_PLAN_BROADCAST ? 7 : 63; }
 
 }  // namespace b200
 
@@ -442,6 +532,8 @@ b200_multi *b200_multi_create(const b200_multi_config *cfg) {
         m->seg_rows   = (uint32_t)((std::max<uint64_t>(cfg->n_build_local_max, 2) + 1) & ~1ull);   // even: 16-byte moves
         m->chunk_rows = (((m->seg_rows + (uint32_t)m->K - 1) / (uint32_t)m->K) + 1u) & ~1u;
         if (const char *e = getenv("B200_BCAST_CE")) m->bcast_ce = atoi(e);
+        if (const char *e = getenv("B200_BCAST_CHUNKS")) m->K = std::max(1, std::min(atoi(e), kMaxChunks));
+        m->chunk_rows = (((m->seg_rows + (uint32_t)m->K - 1) / (uint32_t)m->K) + 1u) & ~1u;
         m->reserve_sms = 16;
         if (const char *e = getenv("B200_BCAST_SMS")) m->reserve_sms = std::max(1, std::min(atoi(e), 64));
         if (m->world == 1) m->reserve_sms = 1;
@@ -463,6 +555,8 @@ b200_multi *b200_multi_create(const b200_multi_config *cfg) {
         }
         m->cap_b = (uint32_t)cb;
         m->cap_p = (uint32_t)cp;
+        m->hot   = cfg->hot_keys >= 0 ? 1 : 0;
+        if (const char *e = getenv("B200_HOT_KEYS")) m->hot = atoi(e) != 0;
     }
     layout_shared(*m);
     B200_CUDA(cudaMalloc(&m->shared, m->shared_bytes));

@@ -19,9 +19,12 @@ namespace b200 {
 constexpr int kNSig      = 16;
 constexpr int kMaxChunks = 8;
 enum MultiSig {
-    SIG_HIST   = 0,   // my histograms are in your hist_all
+    SIG_HIST   = 0,   // my (build-side) histogram is in your hist_all
     SIG_RESULT = 1,   // my {matches, sums, flags} are in your result[]
     SIG_DATA   = 2,   // exchange plan: every row I owe you has landed
+    SIG_HIST2  = 3,   // exchange plan: my probe-side histograms (per chunk) are in your hist_all
+    SIG_HOT    = 4,   // exchange plan: my hot-key candidates are in your cand[]
+    SIG_AGG    = 5,   // exchange plan: my build-side aggregates of the hot keys are in your agg[]
     SIG_CHUNK0 = 8,   // broadcast plan: chunk c of my build region has landed (SIG_CHUNK0 + c)
 };
 
@@ -166,6 +169,181 @@ static __global__ void __launch_bounds__(256) broadcast_region_kernel(const Broa
                 for (int d = 0; d < b.world; ++d) st_release_sys_u32(&b.hdr[d]->sig[SIG_CHUNK0 + c][b.rank], epoch);
             }
         }
+    }
+}
+
+// a block of this rank's memory into the same place of every peer's shared region, then `sig` (small blocks:
+// histograms, candidate lists, aggregates — a few KB to 128 KB; one CTA per peer)
+struct PushArgs {
+    const uint32_t *src;
+    uint32_t        words;
+    uint32_t       *dst[kMaxPeers];
+    SharedHeader   *hdr[kMaxPeers];
+    int             rank, world, sig;
+    const uint32_t *epoch;
+};
+static __global__ void __launch_bounds__(256) push_to_peers_kernel(const PushArgs a) {
+    const int d = blockIdx.x;
+    if (d >= a.world) return;
+    if (d != a.rank)
+        for (uint32_t i = threadIdx.x; i < a.words; i += 256) a.dst[d][i] = a.src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys_u32(&a.hdr[d]->sig[a.sig][a.rank], *a.epoch);
+}
+
+// ---------------------------------------------------------------------------
+// Hot keys (config 4: Zipf probe keys).  A key that a large share of the probe rows carries would send all of them
+// to one owner and hammer one histogram bin and one hash-table slot on the way.  Instead the ranks agree on a
+// small set of hot keys, every rank learns how many build rows carry each of them and the sum of their SUM column
+// (replicating the hot build keys), and a probe row with a hot key is joined where it is, while the histogram pass
+// streams by: matches += cnt[key], SUM(build) += sum[key], SUM(probe) += cnt[key] * value.  Such rows are neither
+// partitioned nor exchanged nor probed.
+//   hot_sample_kernel    counts a sample of the local probe keys in an open-addressing table
+//   hot_select_kernel    keys seen at least `threshold` times -> this rank's candidate list {n, keys...}
+//   hot_table_kernel     every rank, from the SAME gathered candidate lists in the same order: a direct-mapped
+//                        table of kHotSlots keys (a candidate whose slot is taken is simply not hot)
+//   hot_build_kernel     local build rows with a hot key: agg[slot] += {1, value}
+//   hot_reduce_kernel    sum of all ranks' aggregates
+//   hot_hist_kernel      the probe-side histogram pass: hot rows are accumulated, the others counted
+// ---------------------------------------------------------------------------
+// (kHotSlots = 8192 direct-mapped slots, hot_slot(), kHotEmpty: kernels.cuh — the scatter skips hot rows too)
+constexpr uint32_t kHotMaxCand = 2048;       // candidates per rank
+constexpr uint32_t kHotSample  = 1u << 16;   // slots of the sampling table
+
+static __global__ void __launch_bounds__(256)
+hot_sample_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint64_t nsample, uint32_t *__restrict__ t_keys,
+                  uint32_t *__restrict__ t_cnt) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nsample; s += stride) {
+        const uint32_t key = (uint32_t)ld_stream_u64(keys + (s * n) / nsample);
+        if (key == kHotEmpty) continue;
+        uint32_t slot = (key * 0x85EBCA6Bu) >> 16;
+        for (int probe = 0; probe < 16; ++probe, slot = (slot + 1) & (kHotSample - 1)) {
+            const uint32_t old = atomicCAS(&t_keys[slot], kHotEmpty, key);
+            if (old == kHotEmpty || old == key) {
+                atomicAdd(&t_cnt[slot], 1u);
+                break;
+            }
+        }
+    }
+}
+static __global__ void __launch_bounds__(256)
+hot_select_kernel(const uint32_t *__restrict__ t_keys, const uint32_t *__restrict__ t_cnt, uint32_t threshold,
+                  uint32_t *__restrict__ cand /* [1 + kHotMaxCand] */) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < kHotSample && t_keys[slot] != kHotEmpty && t_cnt[slot] >= threshold) {
+        const uint32_t at = atomicAdd(&cand[0], 1u);
+        if (at < kHotMaxCand) cand[1 + at] = t_keys[slot];
+    }
+}
+static __global__ void __launch_bounds__(1024)
+hot_table_kernel(const uint32_t *__restrict__ cand_all /* [world][1 + kHotMaxCand] */, int world,
+                 uint32_t *__restrict__ hot_keys /* [kHotSlots] */, uint32_t *__restrict__ hot_n) {
+    __shared__ uint32_t s_tab[kHotSlots];
+    for (uint32_t i = threadIdx.x; i < kHotSlots; i += 1024) s_tab[i] = kHotEmpty;
+    __syncthreads();
+    if (threadIdx.x == 0) {   // sequential on purpose: every rank must end up with the same table
+        uint32_t n = 0;
+        for (int r = 0; r < world; ++r) {
+            const uint32_t *c   = cand_all + (size_t)r * (1 + kHotMaxCand);
+            const uint32_t  cnt = min(c[0], kHotMaxCand);
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const uint32_t key = c[1 + i], slot = hot_slot(key);
+                if (s_tab[slot] == kHotEmpty) {
+                    s_tab[slot] = key;
+                    ++n;
+                }
+            }
+        }
+        *hot_n = n;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kHotSlots; i += 1024) hot_keys[i] = s_tab[i];
+}
+static __global__ void __launch_bounds__(256)
+hot_build_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals, uint64_t n,
+                 const uint32_t *__restrict__ hot_keys, const uint32_t *__restrict__ hot_n,
+                 unsigned long long *__restrict__ agg /* [kHotSlots][2] */) {
+    if (*hot_n == 0) return;
+    __shared__ uint32_t s_tab[kHotSlots];
+    for (uint32_t i = threadIdx.x; i < kHotSlots; i += 256) s_tab[i] = hot_keys[i];
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t key = (uint32_t)ld_stream_u64(keys + i), slot = hot_slot(key);
+        if (s_tab[slot] == key && key != kHotEmpty) {
+            atomicAdd(&agg[2 * slot], 1ull);
+            if (vals) atomicAdd(&agg[2 * slot + 1], (unsigned long long)ld_stream_u64(vals + i));
+        }
+    }
+}
+static __global__ void __launch_bounds__(256)
+hot_reduce_kernel(const unsigned long long *__restrict__ agg_all /* [world][kHotSlots][2] */, int world,
+                  unsigned long long *__restrict__ hot_agg /* [kHotSlots][2] */) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * kHotSlots) {
+        unsigned long long s = 0;
+        for (int r = 0; r < world; ++r) s += agg_all[(size_t)r * 2 * kHotSlots + i];
+        hot_agg[i] = s;
+    }
+}
+// probe-side histogram of key & mask over rows [0, n) with the hot rows taken out and joined on the spot:
+// acc[0] += cnt, acc[1] += build sum, acc[2] += cnt * probe value
+template <int NT>
+__global__ void __launch_bounds__(NT)
+hot_hist_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals, uint64_t n, uint32_t radix_bits,
+                const uint32_t *__restrict__ hot_keys, const uint32_t *__restrict__ hot_n,
+                const unsigned long long *__restrict__ hot_agg, uint32_t *__restrict__ ghist,
+                unsigned long long *__restrict__ acc) {
+    extern __shared__ uint32_t sh_dyn[];
+    uint32_t      *sh_hist = sh_dyn;
+    const uint32_t nbins   = 1u << radix_bits, mask = nbins - 1u;
+    uint32_t      *s_tab   = sh_dyn + nbins;
+    const bool     hot     = *hot_n != 0;
+    for (uint32_t b = threadIdx.x; b < nbins; b += NT) sh_hist[b] = 0;
+    if (hot)
+        for (uint32_t i = threadIdx.x; i < kHotSlots; i += NT) s_tab[i] = hot_keys[i];
+    __syncthreads();
+    unsigned long long m = 0, sb = 0, sp = 0;
+    const uint64_t     stride = (uint64_t)gridDim.x * NT;
+    for (uint64_t i = (uint64_t)blockIdx.x * NT + threadIdx.x; i < n; i += stride) {
+        const uint32_t key = (uint32_t)ld_stream_u64(keys + i);
+        bool           is_hot = false;
+        if (hot) {
+            const uint32_t slot = hot_slot(key);
+            if (s_tab[slot] == key && key != kHotEmpty) {
+                is_hot                       = true;
+                const unsigned long long cnt = hot_agg[2 * slot];
+                m += cnt;
+                sb += hot_agg[2 * slot + 1];
+                if (vals) sp += cnt * (unsigned long long)ld_stream_u64(vals + i);
+            }
+        }
+        if (!is_hot) atomicAdd(&sh_hist[key & mask], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbins; b += NT) {
+        const uint32_t c = sh_hist[b];
+        if (c) atomicAdd(&ghist[b], c);
+    }
+    m  = warp_sum_u64(m);
+    sb = warp_sum_u64(sb);
+    sp = warp_sum_u64(sp);
+    if ((threadIdx.x & 31) == 0 && m) {
+        atomicAdd(acc + 0, m);
+        atomicAdd(acc + 1, sb);
+        atomicAdd(acc + 2, sp);
+    }
+}
+// {matches, SUM(build), SUM(probe)} of the hot rows into the join's result slots
+static __global__ void add_hot_result_kernel(unsigned long long *result, const unsigned long long *acc, int has_build_sum,
+                                             int has_probe_sum) {
+    if (threadIdx.x == 0) {
+        result[0] += acc[0];
+        int k = 1;
+        if (has_build_sum) result[k++] += acc[1];
+        if (has_probe_sum) result[k] += acc[2];
     }
 }
 
@@ -324,10 +502,11 @@ struct ExchangeArgs2 {
     uint32_t        n, nparts, world, cap;
     uint64_t       *dst_tup[kMaxPeers];
 };
-__global__ void __launch_bounds__(256) segment_exchange2_kernel(const ExchangeArgs2 x) {
+__global__ void __launch_bounds__(256) segment_exchange2_kernel(ExchangeArgs2 x) {
     constexpr int  UN   = 8;
     const uint32_t base = blockIdx.x * (256u * UN);
     uint32_t       e    = base + threadIdx.x;
+    x.n                 = min(x.n, __ldg(x.src_off + x.nparts));   // staged tuples (rows taken out as hot are not staged)
     uint32_t       lo = 0, hi = x.nparts;   // invariant: src_off[lo] <= e < src_off[hi]
     if (e < x.n) {
         while (hi - lo > 1) {

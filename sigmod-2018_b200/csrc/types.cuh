@@ -31,6 +31,9 @@ struct PredSet {
         int      col, cmp;
         uint64_t k;
     } p[kMaxPred] = {};
+    // multi-GPU exchange plan: rows whose key sits in this direct-mapped table of hot keys (multi_kernels.cuh) were
+    // joined during the histogram pass and are skipped; *hot_n == 0 disables the check
+    const uint32_t *hot_keys = nullptr, *hot_n = nullptr;
 };
 
 struct alignas(8) Tup32 {

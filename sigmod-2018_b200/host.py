@@ -98,7 +98,7 @@ class CMultiConfig(C.Structure):
                 ("n_build_local", C.c_uint64), ("n_probe_local", C.c_uint64),
                 ("n_build_local_max", C.c_uint64), ("n_probe_local_max", C.c_uint64),
                 ("has_build_sum", C.c_int), ("has_probe_sum", C.c_int), ("radix_bits", C.c_int), ("chunks", C.c_int),
-                ("recv_rows_build", C.c_uint64), ("recv_rows_probe", C.c_uint64)]
+                ("recv_rows_build", C.c_uint64), ("recv_rows_probe", C.c_uint64), ("hot_keys", C.c_int)]
 
 
 PLAN_BROADCAST, PLAN_EXCHANGE = 0, 1

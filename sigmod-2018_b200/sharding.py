@@ -571,7 +571,8 @@ class MultiJoin:
     """
 
     def __init__(self, b200, dist, rank, world, device_index, plan, n_build_local, n_probe_local, has_build_sum=True,
-                 has_probe_sum=True, radix_bits=0, chunks=0, recv_rows_build=0, recv_rows_probe=0, peers_in_process=None):
+                 has_probe_sum=True, radix_bits=0, chunks=0, recv_rows_build=0, recv_rows_probe=0, peers_in_process=None,
+                 hot_keys=True):
         import ctypes as C
         self.b, self.L, self.C, self.rank, self.world = b200, b200.lib(), C, rank, world
         counts = [(n_build_local, n_probe_local)]
@@ -586,7 +587,7 @@ class MultiJoin:
                                 n_build_local_max=max(c[0] for c in counts), n_probe_local_max=max(c[1] for c in counts),
                                 has_build_sum=int(has_build_sum), has_probe_sum=int(has_probe_sum),
                                 radix_bits=radix_bits, chunks=chunks, recv_rows_build=recv_rows_build,
-                                recv_rows_probe=recv_rows_probe)
+                                recv_rows_probe=recv_rows_probe, hot_keys=0 if hot_keys else -1)
         self.nproj = int(has_build_sum) + int(has_probe_sum)
         self.plan = self.L.b200_multi_create(C.byref(cfg))
         if not self.plan:

@@ -34,7 +34,7 @@ def _run(gpu, orc, plan, world, kr, ks, pr, ps, has_b=True, has_p=True, reps=2, 
                                       peers_in_process={"counts": counts}, **kw))
         for p in plans:
             p.connect_in_process(plans, [0] * world)
-        phases = (1, 2, 4) if plan == gpu.PLAN_BROADCAST else (1, 2, 4, 8)
+        phases = (1, 2, 4) if plan == gpu.PLAN_BROADCAST else (1, 2, 4, 8, 16, 32)
         for _ in range(reps):          # buffers, flags and epochs are reused across steps
             for ph in phases:
                 for r in range(world):
@@ -82,16 +82,30 @@ def test_broadcast_plan_projection_subsets(gpu, orc, has_b, has_p):
     _run(gpu, orc, gpu.PLAN_BROADCAST, 2, kr, ks, pr, ps, has_b, has_p, reps=1)
 
 
+@pytest.mark.parametrize("hot", [True, False])
 @pytest.mark.parametrize("world,kr_bits,ns,zipf,chunks,bits", [(1, 16, 1 << 20, True, 0, 0), (2, 17, (1 << 21) + 5, True, 4, 0),
                                                               (3, 16, (1 << 20) + 77, False, 2, 0), (4, 15, 9, True, 0, 0),
                                                               (2, 17, 1 << 20, False, 8, 8), (8, 16, 1 << 21, True, 2, 0)])
-def test_exchange_plan_emulated_ranks(gpu, orc, world, kr_bits, ns, zipf, chunks, bits):
+def test_exchange_plan_emulated_ranks(gpu, orc, world, kr_bits, ns, zipf, chunks, bits, hot):
+    """hot: keys a large share of a sample of the probe rows carries are joined where they are, during the histogram
+    pass (Zipf inputs have them, the uniform ones do not); off: everything is exchanged."""
     nr = (1 << kr_bits) - 9
     kr = orc.synth_column(1 << kr_bits, 0, kr_bits, gpu.SEED_R)[:nr]
     ks = orc.synth_column(ns, 2, kr_bits, 41) if zipf else orc.synth_column(ns, 0, kr_bits + 2, gpu.SEED_S)
     pr, ps = orc.synth_column(nr, 1, 0, 3), orc.synth_column(ns, 1, 0, 13)
     _run(gpu, orc, gpu.PLAN_EXCHANGE, world, kr, ks, pr, ps, chunks=chunks, radix_bits=bits,
-         recv_rows_build=nr, recv_rows_probe=ns)
+         recv_rows_build=nr, recv_rows_probe=ns, hot_keys=hot)
+
+
+def test_exchange_plan_hot_keys_with_duplicate_build_keys(gpu, orc):
+    """A hot key that several build rows carry: every probe row with it matches all of them (count and SUM of the
+    build rows are replicated, the probe value is multiplied by the count)."""
+    ns = 1 << 21
+    kr = orc.synth_column(1 << 16, 3, 1 << 14, 5)                 # 2^16 build rows over 2^14 keys: ~4 rows per key
+    ks = orc.synth_column(ns, 2, 14, 41)                          # Zipf over the same 2^14 keys (perm14)
+    pr, ps = orc.synth_column(len(kr), 1, 0, 3), orc.synth_column(ns, 1, 0, 13)
+    for has_b, has_p in ((True, True), (False, True), (True, False)):
+        _run(gpu, orc, gpu.PLAN_EXCHANGE, 2, kr, ks, pr, ps, has_b, has_p, reps=1, recv_rows_build=len(kr), recv_rows_probe=ns)
 
 
 def test_exchange_plan_balances_owners_under_zipf(gpu, orc):
