@@ -262,14 +262,9 @@ uint64_t read_counter(const unsigned long long *d_ptr) {
     return c.h_scratch[0];
 }
 
-// SMs the streaming kernels of the calling thread leave free (multi-GPU broadcast plan: the probe-side scatter is a
-// persistent grid that would otherwise own every SM, and the concurrent broadcast kernel must stay resident)
-static thread_local int t_reserved_sms = 0;
-void set_reserved_sms(int n) { t_reserved_sms = n < 0 ? 0 : n; }
-
 int grid_for(uint64_t work_items, int per_block, int max_blocks_per_sm) {
     uint64_t blocks = (work_items + per_block - 1) / per_block;
-    uint64_t cap    = (uint64_t)std::max(1, sm_count() - t_reserved_sms) * max_blocks_per_sm;
+    uint64_t cap    = (uint64_t)sm_count() * max_blocks_per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
@@ -554,7 +549,7 @@ static void launch_scatter_carry_tuned(const KeySrc &src, int bits, uint32_t *cu
     B200_LAUNCH_CHECK();
 }
 
-// histogram-free probe-side scatter (32-bit keys): fixed regions of opt.opt_cap tuples + overflow
+// histogram-free probe-side scatter: fixed regions of opt.opt_cap tuples + overflow
 static void launch_scatter_opt(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
     switch (tuning().scatter_cfg) {
         case 0: launch_scatter_c<uint32_t, 0, true>(src, bits, cursor, out, opt); break;
@@ -563,26 +558,30 @@ static void launch_scatter_opt(const KeySrc &src, int bits, uint32_t *cursor, vo
         default: launch_scatter_c<uint32_t, 1, true>(src, bits, cursor, out, opt); break;
     }
 }
+static void launch_scatter_opt64(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
+    launch_scatter_c<uint64_t, 1, true>(src, bits, cursor, out, opt);
+}
 
 // ... the same with a 32-bit probe-side SUM column carried in the row-id slot of the probe tuples
-template <int CFG>
-static void launch_scatter_opt_carry_c(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
-    constexpr int NT   = PartCfg<uint32_t, CFG>::NT;
-    constexpr int U    = PartCfg<uint32_t, CFG>::U;
-    constexpr int MINB = PartCfg<uint32_t, CFG>::MINB;
-    const size_t  smem = (size_t)NT * U * sizeof(Tup32) + 4 * (size_t)(1u << bits) * sizeof(uint32_t);
-    auto          k    = radix_scatter_kernel<NT, U, MINB, uint32_t, true, true>;
+template <typename KeyT, int CFG, bool OPT>
+static void launch_scatter_carry_c(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
+    using TupT         = typename TupOf<KeyT>::type;
+    constexpr int NT   = PartCfg<KeyT, CFG>::NT;
+    constexpr int U    = PartCfg<KeyT, CFG>::U;
+    constexpr int MINB = PartCfg<KeyT, CFG>::MINB;
+    const size_t  smem = (size_t)NT * U * sizeof(TupT) + (OPT ? 4 : 3) * (size_t)(1u << bits) * sizeof(uint32_t);
+    auto          k    = radix_scatter_kernel<NT, U, MINB, KeyT, OPT, true>;
     allow_smem(k, smem);
     k<<<grid_for(src.n, NT * U, MINB), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor,
-                                                                 static_cast<Tup32 *>(out), opt);
+                                                                 static_cast<TupT *>(out), opt);
     B200_LAUNCH_CHECK();
 }
 static void launch_scatter_opt_carry(const KeySrc &src, int bits, uint32_t *cursor, void *out, const OptArgs &opt) {
     switch (tuning().scatter_cfg) {
-        case 0: launch_scatter_opt_carry_c<0>(src, bits, cursor, out, opt); break;
-        case 2: launch_scatter_opt_carry_c<2>(src, bits, cursor, out, opt); break;
-        case 3: launch_scatter_opt_carry_c<3>(src, bits, cursor, out, opt); break;
-        default: launch_scatter_opt_carry_c<1>(src, bits, cursor, out, opt); break;
+        case 0: launch_scatter_carry_c<uint32_t, 0, true>(src, bits, cursor, out, opt); break;
+        case 2: launch_scatter_carry_c<uint32_t, 2, true>(src, bits, cursor, out, opt); break;
+        case 3: launch_scatter_carry_c<uint32_t, 3, true>(src, bits, cursor, out, opt); break;
+        default: launch_scatter_carry_c<uint32_t, 1, true>(src, bits, cursor, out, opt); break;
     }
 }
 
@@ -613,13 +612,15 @@ static void launch_scatter_tuples(const uint64_t *tuples, uint32_t n, int bits, 
 }
 
 // build-side scatter whose tuples carry a 32-bit payload in the row-id slot
+template <typename KeyT>
 static void launch_scatter_carry(const KeySrc &src, int bits, uint32_t *cursor, void *out, const PayArgs &pay) {
+    using TupT         = typename TupOf<KeyT>::type;
     constexpr int NT   = 1024;
     constexpr int U    = 8;
-    const size_t  smem = (size_t)NT * U * sizeof(Tup32) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
-    auto          k    = radix_scatter_pay_kernel<NT, U, uint32_t, 0, false, true>;
+    const size_t  smem = (size_t)NT * U * sizeof(TupT) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
+    auto          k    = radix_scatter_pay_kernel<NT, U, KeyT, 0, false, true>;
     allow_smem(k, smem);
-    k<<<grid_for(src.n, NT * U, 1), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor, static_cast<Tup32 *>(out),
+    k<<<grid_for(src.n, NT * U, 1), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor, static_cast<TupT *>(out),
                                                                 pay);
     B200_LAUNCH_CHECK();
 }
@@ -627,7 +628,12 @@ static void launch_scatter_carry(const KeySrc &src, int bits, uint32_t *cursor, 
 template <typename KeyT>
 static void launch_scatter_pay(const KeySrc &src, int bits, uint32_t *cursor, void *out, const PayArgs &pay, int npay) {
     if (pay.carry32) {
-        launch_scatter_carry(src, bits, cursor, out, pay);
+        launch_scatter_carry<KeyT>(src, bits, cursor, out, pay);
+        return;
+    }
+    if constexpr (sizeof(KeyT) == 8) {
+        B200_REQUIRE(npay == 0, "64-bit keys carry their one build-side SUM column in the tuple");
+        launch_scatter_pay_n<KeyT, 0>(src, bits, cursor, out, pay);
         return;
     }
     if (npay == 0)
@@ -731,13 +737,31 @@ static void launch_join32(const JoinArgs &a, int mode, size_t smem) {
         launch_join32_cfg<512, 2>(a, mode, smem);
 }
 
+// 64-bit keys, partitioned: the tag table with verified candidates (tag_join_kernel<K64>), 768 threads per CTA so
+// that slots (128 KB) + links (68 KB) + the 16-byte queue entries of 24 warps fit one SM's shared memory
+constexpr int kJoin64NT = 768;
+constexpr int kJoin64G  = 2;
+static size_t tag_join64_smem(uint32_t cap, uint32_t slots_log2) {
+    return ((size_t)4 << slots_log2) + (size_t)4 * cap + (size_t)16 * kTagQueue * (kJoin64NT / 32);
+}
+static void launch_join_tag64(const JoinArgs &a, int mode) {
+    const size_t smem = tag_join64_smem(a.cap, a.slots_log2);
+    if (mode == MODE_COUNT)
+        launch_persistent_join_nt(tag_join_kernel<kJoin64NT, 1, kJoin64G, MODE_COUNT, 0, false, true>, a, smem, kJoin64NT);
+    else if (mode == MODE_WRITE)
+        launch_persistent_join_nt(tag_join_kernel<kJoin64NT, 1, kJoin64G, MODE_WRITE, 0, false, true>, a, smem, kJoin64NT);
+    else if (a.nproj <= 2)
+        launch_persistent_join_nt(tag_join_kernel<kJoin64NT, 1, kJoin64G, MODE_SUM, 2, false, true>, a, smem, kJoin64NT);
+    else
+        launch_persistent_join_nt(tag_join_kernel<kJoin64NT, 1, kJoin64G, MODE_SUM, kMaxProj, false, true>, a, smem, kJoin64NT);
+}
+
 static void launch_join(const JoinArgs &a, bool key64, bool direct, int mode) {
-    if (key64) {
+    if (key64 && !direct) {
+        launch_join_tag64(a, mode);
+    } else if (key64) {
         const size_t smem = TableView<uint64_t>::bytes(a.cap, a.slots_log2);
-        if (direct)
-            launch_join64<true>(a, mode, smem);
-        else
-            launch_join64<false>(a, mode, smem);
+        launch_join64<true>(a, mode, smem);
     } else {
         B200_REQUIRE(!direct, "32-bit keys are joined partitioned");
         launch_join32(a, mode, tag_join_smem(a.cap, a.slots_log2));
@@ -789,9 +813,11 @@ PartitionOut run_partition(const KeyVec &kv, int bits) {
 // uniform split, mean + 5 sigma; a larger one is split into build chunks — fits one shared-memory table.  Fewer
 // partitions mean longer runs per scatter tile.  The tag table (32-bit keys) needs radix_bits + slots_log2 >= 17.
 int auto_radix_bits(uint64_t n_build, bool key64) {
+    // (both key widths use the tag table, cap32 build tuples per table; only 32-bit keys need radix_bits +
+    // slots_log2 >= 17 so that slot and tag identify the key)
     const Tuning  &t          = tuning();
-    const uint32_t cap        = key64 ? t.cap64 : t.cap32;
-    const uint32_t slots_log2 = key64 ? TableView<uint64_t>::slots_log2_for(cap) : tag_slots_log2_for(cap);
+    const uint32_t cap        = t.cap32;
+    const uint32_t slots_log2 = tag_slots_log2_for(cap);
     const int      min_bits   = key64 ? 1 : std::max(2, 17 - (int)slots_log2);
     if (t.radix_bits > 0) return std::max(min_bits, std::min(t.radix_bits, t.max_bits));
     auto fits = [&](int b) {
@@ -826,9 +852,10 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     const bool direct = t.radix_bits <= 0 && B.src.n <= t.cap64 && !pred_b;
     // 32-bit keys (8-byte partition tuples, tag-table kernel) when every key fits
     const bool key64 = direct || t.force_key64 || B.max_val > 0xFFFFFFFFull || P.max_val > 0xFFFFFFFFull;
-    const uint32_t cap = key64 ? t.cap64 : t.cap32;
-    B200_REQUIRE(cap >= 32 && cap <= (key64 ? 65534u : 32766u), "table capacity out of range");
-    const uint32_t slots_log2 = key64 ? TableView<uint64_t>::slots_log2_for(cap) : tag_slots_log2_for(cap);
+    // unpartitioned joins run the chained table (16-bit links, keys in shared memory), partitioned ones the tag table
+    const uint32_t cap = direct ? t.cap64 : t.cap32;
+    B200_REQUIRE(cap >= 32 && cap <= (direct ? 65534u : 32766u), "table capacity out of range");
+    const uint32_t slots_log2 = direct ? TableView<uint64_t>::slots_log2_for(cap) : tag_slots_log2_for(cap);
     const int bits = direct ? 0 : auto_radix_bits(B.src.n, key64);
 
     JoinArgs a;
@@ -889,7 +916,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         const size_t tsz = key64 ? sizeof(Tup64) : sizeof(Tup32);
         // Histogram-free probe side (fused SUM, 32-bit keys): every partition owns a region a few percent
         // above the uniform expectation; what does not fit overflows and is partitioned exactly afterwards.
-        opt = !key64 && t.opt_partition && P.src.n >= (1u << 20) && P.src.n <= (1u << 30);
+        opt = t.opt_partition && P.src.n >= (1u << 20) && P.src.n <= (1u << 30);
         if (opt) opt_cap = opt_region_cap(P.src.n, bits);
         tup_b = dev_alloc((size_t)B.src.n * tsz);
         tup_p = dev_alloc(opt ? (size_t)opt_cap * nparts * tsz : (size_t)P.src.n * tsz);
@@ -897,7 +924,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         // SUM travel with the build tuples into partition order (32-bit-key path)
         PayArgs pay{};
         int     npay = 0;
-        if (mode == JoinOut::Sum && !key64 && t.early_mat && !pred_b) {
+        if (mode == JoinOut::Sum && t.early_mat && !pred_b) {
             const int side_b  = swapped ? 1 : 0;   // proj[].side is relative to (R, S)
             int       n_build = 0, first = -1;
             for (int k = 0; k < nproj; ++k)
@@ -913,7 +940,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
                 pay.col[0]   = proj[first].col;
                 pay.ids[0]   = proj[first].ids;
                 npay         = 1;   // selects the payload-aware scatter
-            } else {
+            } else if (!key64) {   // (16-byte tuples leave no room to stage payload columns beside them)
                 for (int k = 0; k < nproj && npay < 2; ++k) {
                     if (proj[k].side != side_b) continue;
                     part_vals[k]  = dev_alloc((size_t)B.src.n * sizeof(uint64_t));
@@ -952,7 +979,9 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
                 const OptArgs o{0, nullptr, nullptr, nullptr, B.preds};
                 if (key64) launch_scatter_pred<uint64_t, false>(B.src, bits, cursor, tup_b->ptr, o);
                 else launch_scatter_pred<uint32_t, false>(B.src, bits, cursor, tup_b->ptr, o);
-            } else if (npay > 0)
+            } else if (npay > 0 && key64)
+                launch_scatter_pay<uint64_t>(B.src, bits, cursor, tup_b->ptr, pay, npay);
+            else if (npay > 0)
                 launch_scatter_pay<uint32_t>(B.src, bits, cursor, tup_b->ptr, pay, npay);
             else if (key64)
                 launch_scatter<uint64_t>(B.src, bits, cursor, tup_b->ptr);
@@ -977,14 +1006,14 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             ov_tup = dev_alloc((size_t)P.src.n * tsz);
             {
                 TimedScope ts(carry_p >= 0 ? "scatter_pc" : pred_p ? "filter_fused" : "scatter_p");   // pc: carried SUM column
-                if (pred_p)
-                    launch_scatter_pred<uint32_t, true>(P.src, bits, cur_p, tup_p->ptr,
-                                                        OptArgs{opt_cap, d_ovcnt, ov_tup->ptr, nullptr, P.preds});
-                else if (carry_p >= 0)
-                    launch_scatter_opt_carry(P.src, bits, cur_p, tup_p->ptr,
-                                             OptArgs{opt_cap, d_ovcnt, ov_tup->ptr, proj[carry_p].col, PredSet{}});
-                else
-                    launch_scatter_opt(P.src, bits, cur_p, tup_p->ptr, OptArgs{opt_cap, d_ovcnt, ov_tup->ptr, nullptr, PredSet{}});
+                const OptArgs oa{opt_cap, d_ovcnt, ov_tup->ptr, carry_p >= 0 ? proj[carry_p].col : nullptr,
+                                 pred_p ? P.preds : PredSet{}};
+                if (pred_p && key64) launch_scatter_pred<uint64_t, true>(P.src, bits, cur_p, tup_p->ptr, oa);
+                else if (pred_p) launch_scatter_pred<uint32_t, true>(P.src, bits, cur_p, tup_p->ptr, oa);
+                else if (carry_p >= 0 && key64) launch_scatter_carry_c<uint64_t, 1, true>(P.src, bits, cur_p, tup_p->ptr, oa);
+                else if (carry_p >= 0) launch_scatter_opt_carry(P.src, bits, cur_p, tup_p->ptr, oa);
+                else if (key64) launch_scatter_opt64(P.src, bits, cur_p, tup_p->ptr, oa);
+                else launch_scatter_opt(P.src, bits, cur_p, tup_p->ptr, oa);
             }
             {
                 TimedScope ts("scan");
@@ -1065,7 +1094,28 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         }
         res.valid_r = swapped ? valid_p : valid_b;
         res.valid_s = swapped ? valid_b : valid_p;
-        if (n_over) {
+        if (n_over && key64) {
+            // 64-bit keys: the probe side is partitioned again, exactly, and joined from scratch
+            TimedScope ts("overflow");
+            B200_CUDA(cudaMemsetAsync(d_u64, 0, 16 * sizeof(unsigned long long), c.stream));
+            B200_CUDA(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), c.stream));
+            B200_CUDA(cudaMemsetAsync(hist_p, 0, (size_t)nparts * sizeof(uint32_t), c.stream));
+            launch_hist<uint64_t>(P.src, bits, hist_p, 4, &P.preds);
+            partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, hist_p, nparts, cap, a.slice, off_b, off_p,
+                                                                  cur_b, cur_p, items, cnt_p, 0u);
+            B200_LAUNCH_CHECK();
+            tup_p = dev_alloc((size_t)P.src.n * sizeof(Tup64));
+            const OptArgs oa{0, nullptr, nullptr, carry_p >= 0 ? proj[carry_p].col : nullptr, pred_p ? P.preds : PredSet{}};
+            if (pred_p) launch_scatter_pred<uint64_t, false>(P.src, bits, cur_p, tup_p->ptr, oa);
+            else if (carry_p >= 0) launch_scatter_carry_c<uint64_t, 1, false>(P.src, bits, cur_p, tup_p->ptr, oa);
+            else launch_scatter<uint64_t>(P.src, bits, cur_p, tup_p->ptr);
+            a.tup_p = tup_p->ptr;
+            launch_join(a, key64, direct, MODE_SUM);
+            read_back();
+            if (pred_p) valid_p = *reinterpret_cast<uint32_t *>(c.h_scratch + 18);
+            res.valid_r = swapped ? valid_p : valid_b;
+            res.valid_s = swapped ? valid_b : valid_p;
+        } else if (n_over) {
             // second pass over the overflow only: exact histogram, scatter, join against the same build partitions
             // (matches and sums keep accumulating in the same device counters)
             TimedScope ts("overflow");
@@ -1103,19 +1153,20 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             // the histogram-free scatter overflowed its regions (skewed keys): the pair-materialising path
             // simply partitions the probe side again, exactly
             TimedScope ts("overflow");
-            const size_t tsz = sizeof(Tup32);
+            const size_t tsz = key64 ? sizeof(Tup64) : sizeof(Tup32);
             B200_CUDA(cudaMemsetAsync(hist_p, 0, (size_t)nparts * sizeof(uint32_t), c.stream));
             B200_CUDA(cudaMemsetAsync(d_ovcnt, 0, sizeof(uint32_t), c.stream));
-            launch_hist<uint32_t>(P.src, bits, hist_p, 4, &P.preds);
+            if (key64) launch_hist<uint64_t>(P.src, bits, hist_p, 4, &P.preds);
+            else launch_hist<uint32_t>(P.src, bits, hist_p, 4, &P.preds);
             partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(hist_b, hist_p, nparts, cap, a.slice, off_b, off_p,
                                                                   cur_b, cur_p, items, cnt_p, 0u);
             B200_LAUNCH_CHECK();
             tup_p = dev_alloc((size_t)P.src.n * tsz);
-            if (pred_p)
-                launch_scatter_pred<uint32_t, false>(P.src, bits, cur_p, tup_p->ptr,
-                                                     OptArgs{0, nullptr, nullptr, nullptr, P.preds});
-            else
-                launch_scatter<uint32_t>(P.src, bits, cur_p, tup_p->ptr);
+            const OptArgs oa{0, nullptr, nullptr, nullptr, P.preds};
+            if (pred_p && key64) launch_scatter_pred<uint64_t, false>(P.src, bits, cur_p, tup_p->ptr, oa);
+            else if (pred_p) launch_scatter_pred<uint32_t, false>(P.src, bits, cur_p, tup_p->ptr, oa);
+            else if (key64) launch_scatter<uint64_t>(P.src, bits, cur_p, tup_p->ptr);
+            else launch_scatter<uint32_t>(P.src, bits, cur_p, tup_p->ptr);
             a.tup_p = tup_p->ptr;
             opt     = false;
             read_items();
@@ -1523,7 +1574,7 @@ void stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint3
 JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const void *d_tup_p, const uint32_t *d_hist_p,
                           int bits, int nproj, const ProjDesc *proj, uint32_t opt_cap, const void *d_ov,
                           const uint32_t *d_ovcnt, unsigned long long *d_result, int nseg, uint32_t seg_rows,
-                          const StageScratch *scr, const JoinWait *wait) {
+                          const StageScratch *scr, const JoinWait *wait, uint32_t seg_head) {
     Context   &c = ctx();
     Tuning    &t = tuning();
     JoinResult res;
@@ -1569,7 +1620,7 @@ JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const v
         }
         uint32_t *total = seg_off + (size_t)nseg * nparts;
         segment_offsets_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_b, (uint32_t)nseg, nparts, seg_rows, seg_off,
-                                                                total);
+                                                                total, seg_head);
         B200_LAUNCH_CHECK();
         a.nseg    = nseg;
         a.seg_off = seg_off;

@@ -134,7 +134,7 @@ JoinResult stage_join_sum(const void *d_tup_b, const uint32_t *d_hist_b, const v
                           const uint32_t *d_hist_p, int bits, int nproj, const ProjDesc *proj, uint32_t opt_cap,
                           const void *d_ov, const uint32_t *d_ovcnt, unsigned long long *d_result = nullptr,
                           int nseg = 0, uint32_t seg_rows = 0, const StageScratch *scr = nullptr,
-                          const JoinWait *wait = nullptr);
+                          const JoinWait *wait = nullptr, uint32_t seg_head = 0);
 // d_off_out (optional): receives the local partition offsets [2^bits + 1]
 void       stage_scatter_build_local(const uint64_t *d_keys, uint64_t n, uint32_t rid_base, int bits,
                                      const uint32_t *d_hist_local, void *d_tup_out, int npay,
@@ -158,6 +158,5 @@ const std::string &last_error_string();
 // small helpers
 uint64_t read_counter(const unsigned long long *d_ptr);   // D2H + sync on ctx stream
 int      grid_for(uint64_t work_items, int per_block, int max_blocks_per_sm);
-void     set_reserved_sms(int n);   // SMs grid_for leaves free on the calling thread (0 = none)
 
 }  // namespace b200

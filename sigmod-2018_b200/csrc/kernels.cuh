@@ -34,6 +34,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 namespace b200 {
 
@@ -392,7 +393,6 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     KeyT           keys[U];
 #pragma unroll
     for (int j = 0; j < U; ++j) keys[j] = narrow_key<KeyT>(raw[j]);
-    static_assert(!(PRED && FULL), "the predicated instance takes the general path");
     static_assert(U <= 64, "one validity bit per key");
     [[maybe_unused]] uint64_t valid = 0;   // PRED: bit j = row of register j passes every predicate
     if constexpr (PRED) {
@@ -425,8 +425,8 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
         }
     }
     auto row_on = [&](int j, uint32_t li) -> bool {
-        if constexpr (FULL) return true;
-        else if constexpr (PRED) return ((valid >> j) & 1ull) != 0ull;
+        if constexpr (PRED) return ((valid >> j) & 1ull) != 0ull;
+        else if constexpr (FULL) return true;
         else return li < count;
     };
     uint32_t rank2[(U + 1) / 2];   // two 16-bit ranks per register
@@ -515,17 +515,19 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     for (int j = 0; j < U; ++j) {
         const uint32_t li = FULL ? ((uint32_t)((j >> 1) * NT) + tid) * 2u + (uint32_t)(j & 1)
                                  : tile_local_index<NT, U>(j, vec);
+        if constexpr (CARRY && FULL) {
+            // registers j, j+1 hold two consecutive rows: one 128-bit load for both (skipped when neither row is on)
+            if ((j & 1) == 0 && (!PRED || ((valid >> j) & 3ull) != 0ull)) {
+                const ulonglong2 v = ld_stream_u64x2(opt.carry_col + base + li);
+                carry_lo           = narrow_key<uint32_t>(v.x);
+                carry_hi           = narrow_key<uint32_t>(v.y);
+            }
+        }
         if (row_on(j, li)) {
             TupT t;
             t.key = keys[j];
             if constexpr (CARRY) {
                 if constexpr (FULL) {
-                    // registers j, j+1 hold two consecutive rows: one 128-bit load for both
-                    if ((j & 1) == 0) {
-                        const ulonglong2 v = ld_stream_u64x2(opt.carry_col + base + li);
-                        carry_lo           = narrow_key<uint32_t>(v.x);
-                        carry_hi           = narrow_key<uint32_t>(v.y);
-                    }
                     t.rid = (j & 1) ? carry_hi : carry_lo;
                 } else {
                     t.rid = (uint32_t)ld_stream_u64(opt.carry_col + base + li);
@@ -566,7 +568,7 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
             const TupT t = stage[i];
             out[gdelta[(uint32_t)t.key & mask] + i] = t;
         };
-        if constexpr (FULL) {
+        if constexpr (FULL && !PRED) {
 #pragma unroll
             for (int k = 0; k < U; ++k) put((uint32_t)(k * NT) + tid);
         } else {
@@ -637,9 +639,14 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
         const uint32_t ncount   = has_next ? (uint32_t)min((uint64_t)TILE, n - nbase) : 0u;
         const bool     nvec     = vec_ok && ncount == TILE;
         if constexpr (PRED) {
-            scatter_tile<NT, U, KeyT, false, OPT, CARRY, true>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
-                                                               nbins, mask, per, stage, cnt, loc, gdelta, warp_sums,
-                                                               cursor, out, opt, ovdelta, &s_over);
+            if (vec)
+                scatter_tile<NT, U, KeyT, true, OPT, CARRY, true>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
+                                                                  nbins, mask, per, stage, cnt, loc, gdelta, warp_sums,
+                                                                  cursor, out, opt, ovdelta, &s_over);
+            else
+                scatter_tile<NT, U, KeyT, false, OPT, CARRY, true>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
+                                                                   nbins, mask, per, stage, cnt, loc, gdelta, warp_sums,
+                                                                   cursor, out, opt, ovdelta, &s_over);
         } else if (vec) {
             scatter_tile<NT, U, KeyT, true, OPT, CARRY>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
                                                         nbins, mask, per, stage, cnt, loc, gdelta, warp_sums, cursor,
@@ -1398,14 +1405,23 @@ __device__ __forceinline__ uint64_t ld_gather_u64(const uint64_t *p) {
     return v;
 }
 
-template <int NT, int MINB, int G, int MODE, int NP, bool SEG = false>
+// K64: genuinely 64-bit keys (16-byte tuples).  The table is the same one-word-per-slot tag table, but slot and tag
+// come from a hash of the key bits above the radix, so a tag match is only a candidate: the queue entry carries
+// the probe key and the drain compares it with the build tuple's key — which it reads anyway, in the same 16-byte
+// load as the row id / carried value.  The probe stays one shared-memory load; rhjoin.c:154-216 compares full keys
+// on every chain step.
+template <int NT, int MINB, int G, int MODE, int NP, bool SEG = false, bool K64 = false>
 __global__ void __launch_bounds__(NT, MINB)
 tag_join_kernel(const JoinArgs a) {
-    constexpr int NW  = NT / 32;
-    constexpr int NPA = NP > 0 ? NP : 1;
-    constexpr int QN  = kTagQueue;
+    using KeyT = typename std::conditional<K64, uint64_t, uint32_t>::type;
+    using TupT = typename TupOf<KeyT>::type;
+    static_assert(!(K64 && SEG), "the segmented (multi-GPU) build side carries 32-bit keys");
+    constexpr int      NW  = NT / 32;
+    constexpr int      NPA = NP > 0 ? NP : 1;
+    constexpr int      QN  = kTagQueue;
+    constexpr uint32_t QE  = K64 ? 16u : 8u;   // bytes per queue entry: {word, probe row id[, probe key]}
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: slots [4 << L bytes] | tagnext [4 * cap bytes] | queues [NW * QN * 8 bytes]
+    // layout: slots [4 << L bytes] | tagnext [4 * cap bytes] | queues [NW * QN * QE bytes]
     const uint32_t L       = a.slots_log2;
     const uint32_t smask   = (1u << L) - 1u;
     const uint32_t s_slots = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -1424,7 +1440,7 @@ tag_join_kernel(const JoinArgs a) {
     const uint32_t lane = tid & 31u;
     const uint32_t wid  = tid >> 5;
     const uint32_t lt   = (1u << lane) - 1u;
-    const uint32_t my_q = s_queue + wid * (uint32_t)(QN * 8);
+    const uint32_t my_q = s_queue + wid * (uint32_t)QN * QE;
     // virtual build position (off_b space) -> physical index in tup_b / part_vals
     auto bphys = [&](uint32_t v) -> uint32_t {
         if constexpr (SEG) {
@@ -1435,8 +1451,30 @@ tag_join_kernel(const JoinArgs a) {
             return v;
         }
     };
-    const Tup32 *tup_b = static_cast<const Tup32 *>(a.tup_b);
-    const Tup32 *tup_p = static_cast<const Tup32 *>(a.tup_p);
+    const TupT *tup_b = static_cast<const TupT *>(a.tup_b);
+    const TupT *tup_p = static_cast<const TupT *>(a.tup_p);
+    // slot and tag of a key: exact (a bijection on the bits above the radix) for 32-bit keys, a hash for 64-bit keys
+    auto slot_tag = [&](KeyT key, uint32_t &slot, uint32_t &tag) {
+        if constexpr (K64) {
+            const uint64_t x = (uint64_t)key >> a.radix_bits;
+            const uint32_t h = ((uint32_t)x ^ (uint32_t)(x >> 32)) * 0x9E3779B1u;
+            slot             = (h ^ (h >> 15)) & smask;
+            tag              = h >> 17;   // 15 bits: never the all-ones tag of an empty slot
+        } else {
+            slot_and_tag((uint32_t)key >> a.radix_bits, L, smask, slot, tag);
+        }
+    };
+    // build tuple at physical position p: row id (or carried value) and, for 64-bit keys, the key to verify against
+    auto build_rid = [&](uint32_t p, KeyT &bkey) -> uint32_t {
+        if constexpr (K64) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(tup_b + p);
+            bkey               = v.x;
+            return (uint32_t)v.y;
+        } else {
+            bkey = 0;
+            return SEG ? __ldcg(&tup_b[p].rid) : tup_b[p].rid;
+        }
+    };
 
     unsigned long long my_matches = 0;
     unsigned long long my_sum[NPA], pend[NPA];
@@ -1446,10 +1484,14 @@ tag_join_kernel(const JoinArgs a) {
     uint32_t queued  = 0;   // warp-uniform number of entries in this warp's queue
 
     // one match (build tuple at position pos of the chunk, probe row prid), handled in place
-    auto handle_inline = [&](uint32_t pos, uint32_t prid) {
+    auto handle_inline = [&](uint32_t pos, uint32_t prid, KeyT pkey) {
+        KeyT           bkey;
+        const uint32_t brid = (K64 || MODE != MODE_COUNT) ? build_rid(bphys(b_start + pos), bkey) : 0u;
+        if constexpr (K64) {
+            if (bkey != pkey) return;   // the tag matched, the key does not
+        }
         ++my_matches;
         if constexpr (MODE != MODE_COUNT) {
-            const uint32_t brid = SEG ? __ldcg(&tup_b[bphys(b_start + pos)].rid) : tup_b[bphys(b_start + pos)].rid;
             if constexpr (MODE == MODE_SUM) {
 #pragma unroll
                 for (int k = 0; k < NPA; ++k) {
@@ -1478,14 +1520,29 @@ tag_join_kernel(const JoinArgs a) {
     auto drain = [&](uint32_t take) {
         queued -= take;
         const bool  mine = lane < take;
-        const uint2 e    = lds_v2(my_q + (queued + (mine ? lane : 0u)) * 8u);
+        const uint32_t qa = my_q + (queued + (mine ? lane : 0u)) * QE;
+        const uint2 e    = lds_v2(qa);
+        [[maybe_unused]] KeyT ekey = 0;
+        if constexpr (K64) {
+            const uint2 kk = lds_v2(qa + 8u);
+            ekey           = (uint64_t)kk.x | ((uint64_t)kk.y << 32);
+        }
         const uint32_t t = (e.x >> 16) & 0x7FFFu;
         // ---- match entries ----
-        const bool is_match = mine && (e.x & kQMatch) != 0u;
+        bool is_match = mine && (e.x & kQMatch) != 0u;
+        [[maybe_unused]] uint32_t brid64 = 0;
+        if constexpr (K64) {
+            if (is_match) {   // verify the candidate: one 16-byte load gives the key and the row id / carried value
+                KeyT bkey;
+                brid64   = build_rid(bphys(b_start + (e.x & kIdxMask)), bkey);
+                is_match = bkey == ekey;
+            }
+        }
         if constexpr (MODE == MODE_SUM) {
             const uint32_t bpos = bphys(b_start + (e.x & kIdxMask));
             uint32_t       brid = 0;
-            if (is_match && a.need_brid) brid = SEG ? __ldcg(&tup_b[bpos].rid) : tup_b[bpos].rid;
+            if constexpr (K64) brid = brid64;
+            else if (is_match && a.need_brid) brid = SEG ? __ldcg(&tup_b[bpos].rid) : tup_b[bpos].rid;
 #pragma unroll
             for (int k = 0; k < NPA; ++k) {
                 my_sum[k] += pend[k];
@@ -1510,7 +1567,7 @@ tag_join_kernel(const JoinArgs a) {
             pos = __shfl_sync(kFullMask, pos, 0);
             if (is_match) {
                 const uint32_t o  = pos + __popc(bal & lt);
-                a.out_b[s_base + o] = tup_b[bphys(b_start + (e.x & kIdxMask))].rid;
+                a.out_b[s_base + o] = K64 ? brid64 : tup_b[bphys(b_start + (e.x & kIdxMask))].rid;
                 a.out_p[s_base + o] = e.y;
             }
         } else {
@@ -1526,8 +1583,12 @@ tag_join_kernel(const JoinArgs a) {
             const uint32_t bal = __ballot_sync(kFullMask, hit);
             if (hit) {
                 const uint32_t slot = queued + __popc(bal & lt);
-                if (slot < (uint32_t)QN) sts_v2(my_q + slot * 8u, kQMatch | (t << 16) | (w & kIdxMask), e.y);
-                else handle_inline(w & kIdxMask, e.y);
+                if (slot < (uint32_t)QN) {
+                    sts_v2(my_q + slot * QE, kQMatch | (t << 16) | (w & kIdxMask), e.y);
+                    if constexpr (K64) sts_v2(my_q + slot * QE + 8u, (uint32_t)ekey, (uint32_t)((uint64_t)ekey >> 32));
+                } else {
+                    handle_inline(w & kIdxMask, e.y, ekey);
+                }
             }
             queued  = min(queued + (uint32_t)__popc(bal), (uint32_t)QN);
             walking = walking && (w & kNextBit) != 0u;
@@ -1585,17 +1646,24 @@ tag_join_kernel(const JoinArgs a) {
 
         // (a padding lane of the last round is recognised by its index, never by a row-id sentinel: the row-id slot
         // may carry an arbitrary 32-bit SUM value)
-        auto load_probe = [&](uint32_t li, uint32_t &key, uint32_t &rid) {
+        auto load_probe = [&](uint32_t li, KeyT &key, uint32_t &rid) {
             key = 0;
             rid = 0;
             if (li < p_count) {
-                const uint64_t v = ld_stream_u64(reinterpret_cast<const uint64_t *>(tup_p + p_start + li));
-                key              = (uint32_t)v;
-                rid              = (uint32_t)(v >> 32);
+                if constexpr (K64) {
+                    const ulonglong2 v = ld_stream_u64x2(reinterpret_cast<const uint64_t *>(tup_p + p_start + li));
+                    key                = v.x;
+                    rid                = (uint32_t)v.y;
+                } else {
+                    const uint64_t v = ld_stream_u64(reinterpret_cast<const uint64_t *>(tup_p + p_start + li));
+                    key              = (uint32_t)v;
+                    rid              = (uint32_t)(v >> 32);
+                }
             }
         };
         // first group in flight while the table is built
-        uint32_t ckey[G], crid[G], nkey[G], nrid[G];
+        KeyT     ckey[G], nkey[G];
+        uint32_t crid[G], nrid[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) load_probe((uint32_t)(j * NT) + tid, ckey[j], crid[j]);
 
@@ -1606,22 +1674,26 @@ tag_join_kernel(const JoinArgs a) {
         // one exposed global-memory latency per eight inserts instead of one per insert
         constexpr int KB = 8;
         for (uint32_t i0 = tid; i0 < b_count; i0 += NT * KB) {
-            uint32_t bk[KB];
+            KeyT bk[KB];
 #pragma unroll
             for (int u = 0; u < KB; ++u) {
                 const uint32_t i = i0 + (uint32_t)u * NT;
                 // (SEG: the tuples were written by peer GPUs while this kernel may already be running — read them
                 // at L2, the point of coherence, not through the non-coherent path)
-                bk[u] = i < b_count ? (SEG ? __ldcg(&tup_b[bphys(b_start + i)].key)
-                                           : ld_stream_u32(&tup_b[bphys(b_start + i)].key))
-                                    : 0u;
+                if constexpr (K64) {
+                    bk[u] = i < b_count ? ld_stream_u64(&tup_b[b_start + i].key) : 0ull;
+                } else {
+                    bk[u] = i < b_count ? (SEG ? __ldcg(&tup_b[bphys(b_start + i)].key)
+                                               : ld_stream_u32(&tup_b[bphys(b_start + i)].key))
+                                        : 0u;
+                }
             }
 #pragma unroll
             for (int u = 0; u < KB; ++u) {
                 const uint32_t i = i0 + (uint32_t)u * NT;
                 if (i < b_count) {
                     uint32_t h, t;
-                    slot_and_tag(bk[u] >> a.radix_bits, L, smask, h, t);
+                    slot_tag(bk[u], h, t);
                     uint32_t old = slots[h], assumed;
                     do {
                         assumed           = old;
@@ -1637,12 +1709,12 @@ tag_join_kernel(const JoinArgs a) {
         // ---- probe (K7) ---------------------------------------------------
         // groups of G probes, ping-pong between two register sets: while one group is probed the next one's
         // tuples are in flight
-        auto probe_group = [&](const uint32_t (&key)[G], const uint32_t (&rid)[G], uint32_t first) {
+        auto probe_group = [&](const KeyT (&key)[G], const uint32_t (&rid)[G], uint32_t first) {
             uint32_t w[G], t[G];
 #pragma unroll
             for (int j = 0; j < G; ++j) {
                 uint32_t h;
-                slot_and_tag(key[j] >> a.radix_bits, L, smask, h, t[j]);
+                slot_tag(key[j], h, t[j]);
                 w[j] = lds_u32(s_slots + h * 4u);
             }
 #pragma unroll
@@ -1653,9 +1725,11 @@ tag_join_kernel(const JoinArgs a) {
                 const uint32_t act  = __ballot_sync(kFullMask, need);
                 if (act) {
                     // queued <= 31 here and a probe adds <= 32 entries: no overflow (QN = 64)
-                    if (need)
-                        sts_v2(my_q + (queued + __popc(act & lt)) * 8u,
-                               (is_m ? kQMatch : 0u) | (t[j] << 16) | (w[j] & 0xFFFFu), rid[j]);
+                    if (need) {
+                        const uint32_t qs = my_q + (queued + __popc(act & lt)) * QE;
+                        sts_v2(qs, (is_m ? kQMatch : 0u) | (t[j] << 16) | (w[j] & 0xFFFFu), rid[j]);
+                        if constexpr (K64) sts_v2(qs + 8u, (uint32_t)key[j], (uint32_t)((uint64_t)key[j] >> 32));
+                    }
                     queued += __popc(act);
                     __syncwarp();
                     while (queued >= 32u) drain(32u);
@@ -1982,7 +2056,7 @@ build_cursors_kernel(const uint32_t *__restrict__ hist_all, uint32_t world, uint
 template <int NT>
 __global__ void __launch_bounds__(NT)
 segment_offsets_kernel(const uint32_t *__restrict__ hist_all, uint32_t world, uint32_t nparts, uint32_t seg_rows,
-                       uint32_t *__restrict__ seg_off, uint32_t *__restrict__ total) {
+                       uint32_t *__restrict__ seg_off, uint32_t *__restrict__ total, uint32_t seg_head) {
     __shared__ uint32_t warp_sums[NT / 32 + 1];
     const uint32_t per   = (nparts + NT - 1) / NT;
     const uint32_t first = threadIdx.x * per;
@@ -1994,7 +2068,7 @@ segment_offsets_kernel(const uint32_t *__restrict__ hist_all, uint32_t world, ui
         for (uint32_t k = 0; k < per; ++k) {
             const uint32_t b = first + k;
             if (b < nparts) {
-                seg_off[r * nparts + b] = r * seg_rows + run;
+                seg_off[r * nparts + b] = r * seg_rows + seg_head + run;   // (seg_head: tuple slots a region keeps for its header)
                 run += hist_all[r * nparts + b];
             }
         }

@@ -63,7 +63,7 @@ struct MultiPlan {
     b200_multi_config cfg{};
     int      rank = 0, world = 1, device = 0;
     int      bits = 0, K = 1;
-    uint32_t P = 1, seg_rows = 0, chunk_rows = 0, opt_cap = 0, cap_b = 0, cap_p = 0;
+    uint32_t P = 1, seg_rows = 0, seg_head = 0, chunk_rows = 0, opt_cap = 0, cap_b = 0, cap_p = 0;   // seg_rows: region stride
     int      nproj = 0;
     // shared region (identical layout on every rank)
     unsigned char *shared = nullptr;
@@ -72,8 +72,7 @@ struct MultiPlan {
     bool           peer_ipc[kMaxPeers] = {false};
     // local device memory (one allocation)
     unsigned char *local = nullptr;
-    uint32_t      *d_epoch = nullptr, *d_error = nullptr, *cur_p = nullptr, *ovcnt = nullptr, *bc_work = nullptr;
-    int            bcast_ce = 0, reserve_sms = 0;   // broadcast on the copy engines instead of the SM kernel; SMs it keeps
+    uint32_t      *d_epoch = nullptr, *d_error = nullptr, *cur_p = nullptr, *ovcnt = nullptr;
     unsigned long long *d_result = nullptr, *d_final = nullptr;
     void          *tup_p = nullptr, *ov_p = nullptr, *stage_b = nullptr, *stage_p = nullptr;
     uint32_t      *src_off_b = nullptr, *src_off_p = nullptr, *dst_start_b = nullptr, *dst_start_p = nullptr;
@@ -136,7 +135,6 @@ static void layout_local(MultiPlan &m, void *base, size_t *bytes) {
     m.d_epoch  = c.take<uint32_t>(4);
     m.d_error  = c.take<uint32_t>(4);
     m.ovcnt    = c.take<uint32_t>(4);
-    m.bc_work  = c.take<uint32_t>(1 + kMaxChunks + 7);
     m.d_result = c.take<unsigned long long>(8);
     m.d_final  = c.take<unsigned long long>(8);
     m.cur_p    = c.take<uint32_t>(P + 1);
@@ -172,86 +170,34 @@ static uint32_t chunk_first(const MultiPlan &m, uint64_t n, int c) { return (uin
 // ---------------------------------------------------------------------------
 // steps
 // ---------------------------------------------------------------------------
+static void wait_signal_row(MultiPlan &m, cudaStream_t stream, int sig) {
+    wait_peers_kernel<<<1, 32, 0, stream>>>(m.hdr(m.rank)->sig[sig], m.world, m.d_epoch, m.d_error);
+    B200_LAUNCH_CHECK();
+}
+
 static void enqueue_broadcast(MultiPlan &m, int phases) {
     Context     &c    = ctx();
     cudaStream_t main = c.stream;
     const int    rank = m.rank, world = m.world;
     const uint32_t P  = m.P;
     const uint64_t nb = m.cfg.n_build_local, np = m.cfg.n_probe_local;
+    const size_t   region_bytes = (size_t)m.seg_rows * 8;
     if (phases & 1) {
         bump_epoch_kernel<<<1, 1, 0, main>>>(m.d_epoch);
         B200_LAUNCH_CHECK();
         B200_CUDA(cudaMemsetAsync(m.d_error, 0, 16, main));
         B200_CUDA(cudaMemsetAsync(m.d_result, 0, 64, main));
-        // ---- build shard: histogram, ONE local partition pass into region `rank` of my build buffer ----
-        uint32_t      *my_hist   = m.hist_b(rank) + (size_t)rank * P;
-        unsigned char *my_region = m.build(rank) + (size_t)rank * m.seg_rows * 8;
+        // ---- build shard: histogram into the head of my region, ONE local partition pass into the rest of it ----
+        unsigned char *my_region = m.build(rank) + (size_t)rank * region_bytes;
+        uint32_t      *my_hist   = reinterpret_cast<uint32_t *>(my_region);
+        unsigned char *my_tuples = my_region + (size_t)m.seg_head * 8;
         stage_hist(m.in_bk, nb, m.bits, my_hist);
         const uint64_t *pay_cols[1] = {m.in_bp};
-        stage_scatter_build_local(m.in_bk, nb, (uint32_t)((uint64_t)rank * m.seg_rows), m.bits, my_hist, my_region,
-                                  m.cfg.has_build_sum ? 1 : 0, pay_cols, nullptr, &m.scr_a);
+        stage_scatter_build_local(m.in_bk, nb, 0, m.bits, my_hist, my_tuples, m.cfg.has_build_sum ? 1 : 0, pay_cols, nullptr,
+                                  &m.scr_a);
         B200_CUDA(cudaEventRecord(m.ev_build, main));
-        if (!m.bcast_ce) {
-            // ---- broadcast by a small persistent kernel (multi_kernels.cuh): stores over NVLink, a flag per chunk raised
-            //      by the kernel itself; it runs on the SMs the probe-side scatter below leaves free ----
-            B200_CUDA(cudaStreamWaitEvent(m.xstream, m.ev_build, 0));
-            B200_CUDA(cudaMemsetAsync(m.bc_work, 0, (1 + kMaxChunks) * sizeof(uint32_t), m.xstream));
-            BroadcastArgs b{};
-            b.src        = reinterpret_cast<const uint64_t *>(my_region);
-            b.hist       = my_hist;
-            b.nb         = (uint32_t)nb;
-            b.nparts     = P;
-            b.chunk_rows = m.chunk_rows;
-            b.nchunks    = (uint32_t)m.K;
-            b.slice_rows = 4096;
-            b.rank       = rank;
-            b.world      = world;
-            for (int d = 0; d < world; ++d) {
-                b.dst_region[d] = reinterpret_cast<uint64_t *>(m.build(d) + (size_t)rank * m.seg_rows * 8);
-                b.dst_hist[d]   = m.hist_b(d) + (size_t)rank * P;
-                b.hdr[d]        = m.hdr(d);
-            }
-            b.work  = m.bc_work;
-            b.done  = m.bc_work + 1;
-            b.epoch = m.d_epoch;
-            {
-                StreamSwap sw(c, m.xstream);
-                TimedScope ts("broadcast");
-                broadcast_region_kernel<<<std::max(1, m.reserve_sms) * 4, 256, 0, c.stream>>>(b);
-                B200_LAUNCH_CHECK();
-            }
-            B200_CUDA(cudaEventRecord(m.ev_x, m.xstream));
-        } else {
-            // ---- broadcast on the copy engines: per peer (every rank starts at a different one) the histogram, then the
-            //      region in K chunks, a 4-byte flag behind each (about 5 us per operation, serialised) ----
-            for (int j = 1; j < world; ++j) {
-                const int    d = (rank + j) % world;
-                cudaStream_t s = m.copy_stream[j - 1];
-                B200_CUDA(cudaStreamWaitEvent(s, m.ev_build, 0));
-                B200_CUDA(cudaMemcpyAsync(m.hist_b(d) + (size_t)rank * P, my_hist, (size_t)P * 4, cudaMemcpyDeviceToDevice, s));
-                B200_CUDA(cudaMemcpyAsync(&m.hdr(d)->sig[SIG_HIST][rank], m.d_epoch, 4, cudaMemcpyDeviceToDevice, s));
-                for (int k = 0; k < m.K; ++k) {
-                    const uint64_t first = (uint64_t)k * m.chunk_rows;
-                    const uint64_t rows  = first < nb ? std::min<uint64_t>(m.chunk_rows, nb - first) : 0;
-                    if (rows)
-                        B200_CUDA(cudaMemcpyAsync(m.build(d) + ((size_t)rank * m.seg_rows + first) * 8,
-                                                  my_region + first * 8, rows * 8, cudaMemcpyDeviceToDevice, s));
-                    B200_CUDA(cudaMemcpyAsync(&m.hdr(d)->sig[SIG_CHUNK0 + k][rank], m.d_epoch, 4, cudaMemcpyDeviceToDevice, s));
-                }
-                B200_CUDA(cudaEventRecord(m.ev_copy[j - 1], s));
-            }
-            // my own region needs no copy: raise my own flags
-            PeerPtrs self{};
-            self.hdr[0] = m.hdr(rank);
-            signal_peers_kernel<<<1, 32, 0, main>>>(self, 1, rank, SIG_HIST, m.d_epoch);
-            B200_LAUNCH_CHECK();
-            for (int k = 0; k < m.K; ++k) {
-                signal_peers_kernel<<<1, 32, 0, main>>>(self, 1, rank, SIG_CHUNK0 + k, m.d_epoch);
-                B200_LAUNCH_CHECK();
-            }
-        }
-        // ---- probe shard: partitioned locally (histogram-free regions + overflow), never moves ----
-        set_reserved_sms(m.bcast_ce ? 0 : m.reserve_sms);
+        // ---- probe shard: partitioned locally (histogram-free regions + overflow), never moves.  Enqueued before the
+        //      copies so that the host's enqueue time of those does not delay it ----
         if (m.opt_cap) {
             stage_scatter_probe_opt(m.in_pk, np, m.bits, m.opt_cap, m.cur_p, m.tup_p, m.ov_p, m.ovcnt,
                                     m.cfg.has_probe_sum ? m.in_pp : nullptr);
@@ -263,10 +209,35 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
                                       &m.scr_b);
             B200_CUDA(cudaMemsetAsync(m.ovcnt, 0, 4, main));
         }
-        set_reserved_sms(0);
+        // ---- broadcast on the copy engines: my region (histogram + tuples) into the same place of every peer's build
+        //      buffer, every rank starting at a different peer, in K chunks with a 4-byte flag behind each ----
+        const uint64_t used = m.seg_head + nb;   // tuple slots of my region that hold something
+        for (int j = 1; j < world; ++j) {
+            const int    d = (rank + j) % world;
+            cudaStream_t s = m.copy_stream[j - 1];
+            B200_CUDA(cudaStreamWaitEvent(s, m.ev_build, 0));
+            for (int k = 0; k < m.K; ++k) {
+                const uint64_t first = (uint64_t)k * m.chunk_rows;
+                const uint64_t rows  = first < used ? std::min<uint64_t>(m.chunk_rows, used - first) : 0;
+                if (rows)
+                    B200_CUDA(cudaMemcpyAsync(m.build(d) + (size_t)rank * region_bytes + first * 8, my_region + first * 8,
+                                              rows * 8, cudaMemcpyDeviceToDevice, s));
+                B200_CUDA(cudaMemcpyAsync(&m.hdr(d)->sig[SIG_CHUNK0 + k][rank], m.d_epoch, 4, cudaMemcpyDeviceToDevice, s));
+            }
+            B200_CUDA(cudaEventRecord(m.ev_copy[j - 1], s));
+        }
+        // my own region needs no copy: raise my own flags
+        PeerPtrs self{};
+        self.hdr[0] = m.hdr(rank);
+        for (int k = 0; k < m.K; ++k) {
+            signal_peers_kernel<<<1, 32, 0, main>>>(self, 1, rank, SIG_CHUNK0 + k, m.d_epoch);
+            B200_LAUNCH_CHECK();
+        }
     }
     if (phases & 2) {
-        wait_peers_kernel<<<1, 32, 0, main>>>(m.hdr(rank)->sig[SIG_HIST], world, m.d_epoch, m.d_error);
+        // the histograms travel at the head of the regions: chunk 0 of every rank, then one contiguous copy of them
+        wait_signal_row(m, main, SIG_CHUNK0);
+        collect_hist_kernel<<<world, 256, 0, main>>>(m.build(rank), region_bytes, P, m.hist_b(rank));
         B200_LAUNCH_CHECK();
         ProjDesc pd[2];
         int      k = 0;
@@ -274,17 +245,14 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
         if (m.cfg.has_probe_sum) pd[k++] = ProjDesc{m.in_pp, nullptr, 1, B200_PROJ_IN_RID};
         JoinWait w{&m.hdr(rank)->sig[SIG_CHUNK0][0], m.d_epoch, m.chunk_rows, m.d_error};
         stage_join_sum(m.build(rank), m.hist_b(rank), m.tup_p, m.cur_p, m.bits, k, pd, m.opt_cap, m.ov_p, m.ovcnt,
-                       m.d_result, world, m.seg_rows, &m.scr_b, &w);
+                       m.d_result, world, m.seg_rows, &m.scr_b, m.K > 1 ? &w : nullptr, m.seg_head);
         push_result_kernel<<<1, 32, 0, main>>>(m.peers(), world, rank, m.d_result, m.d_error, m.d_epoch);
         B200_LAUNCH_CHECK();
-        // the next step must not overwrite my region (or histogram) under a broadcast still in flight
-        if (!m.bcast_ce) B200_CUDA(cudaStreamWaitEvent(main, m.ev_x, 0));
-        else
-            for (int j = 1; j < world; ++j) B200_CUDA(cudaStreamWaitEvent(main, m.ev_copy[j - 1], 0));
+        // the next step must not overwrite my region under copies still in flight
+        for (int j = 1; j < world; ++j) B200_CUDA(cudaStreamWaitEvent(main, m.ev_copy[j - 1], 0));
     }
     if (phases & 4) {
-        wait_peers_kernel<<<1, 32, 0, main>>>(m.hdr(rank)->sig[SIG_RESULT], world, m.d_epoch, m.d_error);
-        B200_LAUNCH_CHECK();
+        wait_signal_row(m, main, SIG_RESULT);
         reduce_result_kernel<<<1, 32, 0, main>>>(m.hdr(rank), world, m.d_final);
         B200_LAUNCH_CHECK();
         B200_CUDA(cudaMemcpyAsync(m.h_final, m.d_final, 64, cudaMemcpyDeviceToHost, main));
@@ -385,7 +353,7 @@ static void enqueue_exchange(MultiPlan &m, int phases) {
                 if (smem > 48 * 1024)
                     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 TimedScope ts("hist");
-                kern<<<grid_for(b - a, NT * 16, 4), NT, smem, main>>>(m.in_pk + a, m.cfg.has_probe_sum ? m.in_pp + a : nullptr,
+                kern<<<grid_for(b - a, NT * 8, 2), NT, smem, main>>>(m.in_pk + a, m.cfg.has_probe_sum ? m.in_pp + a : nullptr,
                                                                       b - a, (uint32_t)m.bits, m.hot_keys, m.hot_n, m.hot_agg,
                                                                       h, m.hot_acc);
                 B200_LAUNCH_CHECK();
@@ -528,15 +496,16 @@ b200_multi *b200_multi_create(const b200_multi_config *cfg) {
     }
     m->P = 1u << m->bits;
     if (cfg->plan == B200_PLAN_BROADCAST) {
-        m->K          = cfg->chunks > 0 ? std::min(cfg->chunks, kMaxChunks) : kMaxChunks;
-        m->seg_rows   = (uint32_t)((std::max<uint64_t>(cfg->n_build_local_max, 2) + 1) & ~1ull);   // even: 16-byte moves
-        m->chunk_rows = (((m->seg_rows + (uint32_t)m->K - 1) / (uint32_t)m->K) + 1u) & ~1u;
-        if (const char *e = getenv("B200_BCAST_CE")) m->bcast_ce = atoi(e);
+        // a region = [histogram: P u32 = P / 2 tuple slots][this rank's tuples]; seg_rows is the region stride in tuples
+        m->seg_head   = m->P / 2;
+        m->seg_rows   = m->seg_head + (uint32_t)((std::max<uint64_t>(cfg->n_build_local_max, 2) + 1) & ~1ull);
+        // the copy engines move it.  Measured on 2 and 8 B200 (profiles/r2_broadcast_variants.txt): stores from an SM
+        // kernel slow the concurrent probe scatter by a third even on reserved SMs, and every copy-engine operation
+        // costs about 5 us whatever its size, serialised across streams — 70 operations (4 chunks + flags + histogram
+        // per peer) cost more than the data at 8 GPUs.  So: one region copy and one flag per peer.
+        m->K = cfg->chunks > 0 ? std::min(cfg->chunks, kMaxChunks) : 1;
         if (const char *e = getenv("B200_BCAST_CHUNKS")) m->K = std::max(1, std::min(atoi(e), kMaxChunks));
         m->chunk_rows = (((m->seg_rows + (uint32_t)m->K - 1) / (uint32_t)m->K) + 1u) & ~1u;
-        m->reserve_sms = 16;
-        if (const char *e = getenv("B200_BCAST_SMS")) m->reserve_sms = std::max(1, std::min(atoi(e), 64));
-        if (m->world == 1) m->reserve_sms = 1;
         m->opt_cap    = (cfg->n_probe_local_max >= (1u << 20) && cfg->n_probe_local_max <= (1u << 30))
                             ? opt_region_cap(cfg->n_probe_local_max, m->bits) : 0;
     } else {
@@ -722,7 +691,7 @@ int b200_multi_finish(b200_multi *plan, uint64_t *out_sums, uint64_t *out_matche
         if (m->cfg.has_build_sum) pd[n++] = ProjDesc{m->in_bp, nullptr, 0, B200_PROJ_IN_RID};
         if (m->cfg.has_probe_sum) pd[n++] = ProjDesc{m->in_pp, nullptr, 1, B200_PROJ_IN_RID};
         JoinResult j = stage_join_sum(m->build(m->rank), m->hist_b(m->rank), m->tup_p, m->cur_p, m->bits, n, pd, m->opt_cap,
-                                      m->ov_p, m->ovcnt, nullptr, m->world, m->seg_rows);
+                                      m->ov_p, m->ovcnt, nullptr, m->world, m->seg_rows, nullptr, nullptr, m->seg_head);
         unsigned long long local[8] = {j.m, 0, 0, 0, 0, 0, 0, 0};
         for (int i = 0; i < n; ++i) local[1 + i] = j.sums[i];
         B200_CUDA(cudaMemcpyAsync(m->d_result, local, 64, cudaMemcpyHostToDevice, c.stream));

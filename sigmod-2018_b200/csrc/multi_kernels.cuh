@@ -80,96 +80,12 @@ __global__ void reduce_result_kernel(const SharedHeader *hdr, int world, unsigne
     }
 }
 
-// ---------------------------------------------------------------------------
-// Broadcast of this rank's partitioned build shard (its region of the rank-major build buffer) to every peer with
-// stores over NVLink, fused with its own signalling: the region is cut into chunks (partition ranges, since the
-// region is in partition order) and slices; a persistent grid pulls slices in chunk order, loads a slice ONCE and
-// stores it into the same place of every peer's buffer, and the CTA that completes the last slice of a chunk
-// raises that chunk's flag on every peer — so the peers' joins start on the first partitions while the rest is
-// still in flight, and no copy-engine operation (about 5 us each, serialised: 70 of them cost more than the data at
-// 8 GPUs) is spent on flags.  CTA 0 first publishes the histogram (SIG_HIST).  The grid is small (it runs on SMs
-// the concurrent probe-side scatter leaves free, see multi.cu) and never waits on anything remote.
-// ---------------------------------------------------------------------------
-struct BroadcastArgs {
-    const uint64_t *src;    // my region: nb tuples in partition order
-    const uint32_t *hist;   // my histogram [nparts]
-    uint32_t        nb, nparts, chunk_rows, nchunks, slice_rows;
-    int             rank, world;
-    uint64_t       *dst_region[kMaxPeers];   // region `rank` inside peer d's build buffer
-    uint32_t       *dst_hist[kMaxPeers];     // hist_all[rank] inside peer d's shared region
-    SharedHeader   *hdr[kMaxPeers];
-    uint32_t       *work;   // slice counter, zero at launch
-    uint32_t       *done;   // [kMaxChunks] slices completed per chunk, zero at launch
-    const uint32_t *epoch;
-};
-static __global__ void __launch_bounds__(256) broadcast_region_kernel(const BroadcastArgs b) {
-    __shared__ uint32_t s_item;
-    const uint32_t tid   = threadIdx.x;
-    const uint32_t epoch = *b.epoch;
-    auto chunk_rows_of = [&](uint32_t c) -> uint32_t {
-        const uint64_t first = (uint64_t)c * b.chunk_rows;
-        return first < b.nb ? (uint32_t)min((uint64_t)b.chunk_rows, (uint64_t)b.nb - first) : 0u;
-    };
-    auto slices_of = [&](uint32_t c) -> uint32_t { return (chunk_rows_of(c) + b.slice_rows - 1) / b.slice_rows; };
-    if (blockIdx.x == 0) {
-        // the histogram first (the peers need every rank's before they can lay out their joins)
-        for (int j = 0; j < b.world; ++j) {
-            const int d = (b.rank + j) % b.world;
-            if (d != b.rank)
-                for (uint32_t i = tid; i < b.nparts; i += 256) b.dst_hist[d][i] = b.hist[i];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if ((int)tid < b.world) {
-            st_release_sys_u32(&b.hdr[tid]->sig[SIG_HIST][b.rank], epoch);
-            for (uint32_t c = 0; c < b.nchunks; ++c)   // chunks beyond my shard hold nothing: raise their flags now
-                if (chunk_rows_of(c) == 0) st_release_sys_u32(&b.hdr[tid]->sig[SIG_CHUNK0 + c][b.rank], epoch);
-        }
-    }
-    uint32_t total = 0;
-    for (uint32_t c = 0; c < b.nchunks; ++c) total += slices_of(c);
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_item = atomicAdd(b.work, 1u);
-        __syncthreads();
-        uint32_t item = s_item;
-        if (item >= total) break;
-        uint32_t c = 0;
-        while (item >= slices_of(c)) item -= slices_of(c++);
-        const uint32_t first = c * b.chunk_rows + item * b.slice_rows;
-        const uint32_t rows  = min(b.slice_rows, c * b.chunk_rows + chunk_rows_of(c) - first);
-        // 16-byte moves (two tuples), four per thread in flight; the odd last tuple of the shard goes alone
-        const uint32_t pairs = rows >> 1;
-        for (uint32_t i0 = tid; i0 < pairs; i0 += 256 * 4) {
-            ulonglong2 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t i = i0 + (uint32_t)u * 256;
-                if (i < pairs) v[u] = ld_stream_u64x2(b.src + first + 2 * (size_t)i);
-            }
-            for (int j = 1; j < b.world; ++j) {
-                const int d = (b.rank + j) % b.world;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t i = i0 + (uint32_t)u * 256;
-                    if (i < pairs) *reinterpret_cast<ulonglong2 *>(b.dst_region[d] + first + 2 * (size_t)i) = v[u];
-                }
-            }
-        }
-        if ((rows & 1u) && tid == 0) {
-            const uint64_t v = b.src[first + rows - 1];
-            for (int j = 1; j < b.world; ++j) b.dst_region[(b.rank + j) % b.world][first + rows - 1] = v;
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t finished = atomicAdd(&b.done[c], 1u) + 1u;
-            if (finished == slices_of(c)) {
-                __threadfence_system();
-                for (int d = 0; d < b.world; ++d) st_release_sys_u32(&b.hdr[d]->sig[SIG_CHUNK0 + c][b.rank], epoch);
-            }
-        }
-    }
+// hist_all[r][i] = the histogram at the head of region r of the build buffer (broadcast plan: a region travels with its
+// histogram in front of its tuples, so that one copy per peer moves both)
+static __global__ void __launch_bounds__(256)
+collect_hist_kernel(const unsigned char *__restrict__ build, size_t region_bytes, uint32_t nparts, uint32_t *__restrict__ hist_all) {
+    const uint32_t *h = reinterpret_cast<const uint32_t *>(build + (size_t)blockIdx.x * region_bytes);
+    for (uint32_t i = threadIdx.x; i < nparts; i += 256) hist_all[(size_t)blockIdx.x * nparts + i] = __ldcg(h + i);
 }
 
 // a block of this rank's memory into the same place of every peer's shared region, then `sig` (small blocks:
@@ -297,6 +213,7 @@ hot_hist_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ 
                 const unsigned long long *__restrict__ hot_agg, uint32_t *__restrict__ ghist,
                 unsigned long long *__restrict__ acc) {
     extern __shared__ uint32_t sh_dyn[];
+    constexpr int  U       = 8;                       // rows per thread and tile: all loads of a tile in flight together
     uint32_t      *sh_hist = sh_dyn;
     const uint32_t nbins   = 1u << radix_bits, mask = nbins - 1u;
     uint32_t      *s_tab   = sh_dyn + nbins;
@@ -306,21 +223,52 @@ hot_hist_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ 
         for (uint32_t i = threadIdx.x; i < kHotSlots; i += NT) s_tab[i] = hot_keys[i];
     __syncthreads();
     unsigned long long m = 0, sb = 0, sp = 0;
-    const uint64_t     stride = (uint64_t)gridDim.x * NT;
-    for (uint64_t i = (uint64_t)blockIdx.x * NT + threadIdx.x; i < n; i += stride) {
-        const uint32_t key = (uint32_t)ld_stream_u64(keys + i);
-        bool           is_hot = false;
-        if (hot) {
-            const uint32_t slot = hot_slot(key);
-            if (s_tab[slot] == key && key != kHotEmpty) {
-                is_hot                       = true;
-                const unsigned long long cnt = hot_agg[2 * slot];
-                m += cnt;
-                sb += hot_agg[2 * slot + 1];
-                if (vals) sp += cnt * (unsigned long long)ld_stream_u64(vals + i);
+    const bool     vec    = ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(vals)) & 15) == 0;
+    const uint64_t ntiles = (n + (uint64_t)NT * U - 1) / ((uint64_t)NT * U);
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t base = tile * NT * U;
+        uint64_t       k[U], v[U];
+        const bool     full = vec && base + (uint64_t)NT * U <= n;
+        if (full) {   // thread t holds rows base + ((j / 2) * NT + t) * 2 + (j & 1): 128-bit loads
+#pragma unroll
+            for (int j = 0; j < U; j += 2) {
+                const uint64_t   r  = base + ((uint64_t)(j >> 1) * NT + threadIdx.x) * 2u;
+                const ulonglong2 kk = ld_stream_u64x2(keys + r);
+                k[j]                = kk.x;
+                k[j + 1]            = kk.y;
+                if (vals) {
+                    const ulonglong2 vv = ld_stream_u64x2(vals + r);
+                    v[j]                = vv.x;
+                    v[j + 1]            = vv.y;
+                } else {
+                    v[j] = v[j + 1] = 0;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const uint64_t r = base + (uint64_t)j * NT + threadIdx.x;
+                k[j]             = r < n ? ld_stream_u64(keys + r) : 0ull;
+                v[j]             = (r < n && vals) ? ld_stream_u64(vals + r) : 0ull;
             }
         }
-        if (!is_hot) atomicAdd(&sh_hist[key & mask], 1u);
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (!full && base + (uint64_t)j * NT + threadIdx.x >= n) continue;
+            const uint32_t key    = (uint32_t)k[j];
+            bool           is_hot = false;
+            if (hot) {
+                const uint32_t slot = hot_slot(key);
+                if (s_tab[slot] == key && key != kHotEmpty) {
+                    is_hot                       = true;
+                    const unsigned long long cnt = hot_agg[2 * slot];
+                    m += cnt;
+                    sb += hot_agg[2 * slot + 1];
+                    sp += cnt * (unsigned long long)v[j];
+                }
+            }
+            if (!is_hot) atomicAdd(&sh_hist[key & mask], 1u);
+        }
     }
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < nbins; b += NT) {

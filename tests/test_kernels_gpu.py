@@ -551,3 +551,54 @@ def test_column_stats_match_the_reference_loader(gpu, orc):
                 l, u, d = orc.column_stats(c)
                 assert got[r][j] == (l, u, float(len(c)), float(d)), (r, j)
         rm.unregister()
+
+
+# ---- genuinely 64-bit keys: 16-byte tuples, histogram-free probe side, carried SUM values, verified tag table ----
+@pytest.mark.parametrize("kr_bits,ks_bits,zipf", [(16, 21, False), (18, 21, False), (16, 21, True), (12, 16, False)])
+def test_join_sum_64bit_keys(gpu, orc, kr_bits, ks_bits, zipf):
+    """Keys beyond 2^32 (the low bits carry the radix, the high bits differ too): fused join -> SUM with registered
+    32-bit SUM columns (carried in the tuples), with wide ones (gathered) and through the pair-materialising path.
+    Zipf probe keys overflow the histogram-free regions: the probe side is then partitioned again, exactly."""
+    nr, ns = 1 << kr_bits, 1 << ks_bits
+    wide_key = lambda k: k | ((k * np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFF00000000000))
+    kr = wide_key(orc.synth_column(nr, 0, kr_bits, gpu.SEED_R))
+    ks = wide_key(orc.synth_column(ns, 2, kr_bits, 21) if zipf else orc.synth_column(ns, 0, ks_bits, gpu.SEED_S))
+    assert int(kr.max()) > (1 << 44)
+    pr, ps = orc.synth_column(nr, 1, 0, 7), orc.synth_column(ns, 1, 0, 8)
+    want, wm = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
+    cols = [gpu.DeviceColumn(len(a)) for a in (kr, ks, pr, ps)]
+    try:
+        for c, a in zip(cols, (kr, ks, pr, ps)):
+            gpu.lib().b200_copy_to_device(c.ptr, a.ctypes.data, 8 * len(a))
+        max_key = int(max(kr.max(), ks.max()))
+        for register in (False, True):
+            if register:
+                gpu.lib().b200_register_device_column(cols[2].ptr, cols[2].ptr, nr, int(pr.max()))
+                gpu.lib().b200_register_device_column(cols[3].ptr, cols[3].ptr, ns, int(ps.max()))
+            got, m = gpu.join_sum_device(cols[0].ptr, nr, cols[1].ptr, ns, [cols[2].ptr, cols[3].ptr], [0, 1], max_key)
+            assert m == wm and got == want, register
+            got, m = gpu.join_sum_device(cols[1].ptr, ns, cols[0].ptr, nr, [cols[3].ptr, cols[2].ptr, cols[3].ptr],
+                                         [0, 1, 0], max_key)
+            assert m == wm and got == [want[1], want[0], want[1]], register
+    finally:
+        gpu.lib().b200_unregister_all()
+        for c in cols:
+            c.free()
+    if wm <= 3_000_000:
+        r, s_, m = gpu.hash_join_pairs(kr, ks)
+        assert m == wm and orc.checksum(pr, r) == want[0] and orc.checksum(ps, s_) == want[1]
+        assert np.array_equal(kr[r.astype(np.int64)], ks[s_.astype(np.int64)])
+
+
+def test_join_64bit_keys_that_share_their_low_32_bits(gpu, orc):
+    """Keys that differ only above bit 32 land in the same partition, often the same slot with the same tag: the
+    drain's key comparison is what keeps them apart."""
+    n = 1 << 17
+    low = orc.synth_column(n, 3, 1 << 12, 3)
+    kr = low | (orc.synth_column(n, 3, 8, 4) << np.uint64(40))
+    ks = low[::-1].copy() | (orc.synth_column(n, 3, 8, 5) << np.uint64(40))
+    o_r, o_s = orc.radix_hash_join(kr, ks, 4)
+    r, s_, m = gpu.hash_join_pairs(kr, ks)
+    assert m == len(o_r) and np.array_equal(sorted_pairs(r, s_), sorted_pairs(o_r, o_s))
+    p = orc.synth_column(n, 1, 0, 9)
+    assert gpu.join_sum(kr, ks, [p, p], [0, 1]) == orc.join_sum(kr, ks, [p, p], [0, 1], 4)

@@ -118,7 +118,8 @@ def test_exchange_plan_balances_owners_under_zipf(gpu, orc):
     _, recv = _run(gpu, orc, gpu.PLAN_EXCHANGE, world, kr, ks, pr, ps, reps=1, recv_rows_build=len(kr), recv_rows_probe=ns,
                    radix_bits=10)       # 1024 partitions (a 2^16-row build side alone would get 16: too coarse to cut)
     rows = [b + p for b, p in recv]
-    assert sum(p for _, p in recv) == ns and sum(b for b, _ in recv) == len(kr)
+    # (probe rows with a hot key are joined where they are and never exchanged: fewer than ns arrive)
+    assert sum(p for _, p in recv) < ns and sum(b for b, _ in recv) == len(kr)
     assert max(rows) <= 1.10 * (sum(rows) / world), rows
 
 
