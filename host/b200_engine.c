@@ -17,7 +17,12 @@
  *   - join order: textual order with one rule, "start from a filtered binding if there is one"; the
  *     reference's JoinEnum DP (best_tree.c:105-223) only changes cost, never results.
  *
- * usage: b200_engine [-w workers]      (default 4; B200_WORKERS overrides)
+ * usage: b200_engine [-w workers] [-g gpus]      (defaults 4 and 1; B200_WORKERS / B200_GPUS override)
+ *
+ * -g N (N = 2..8): every relation is additionally position-sharded over N GPUs when it is loaded, and a query that is
+ * one equi-join of two relations with at most one SUM per side and no filter (BASELINE config 2's shape) runs through
+ * the library's multi-GPU plan (b200_join_sum_multi: one host thread per GPU, no NCCL); every other query runs on
+ * GPU 0 as before.
  */
 #define _GNU_SOURCE
 #include <fcntl.h>
@@ -55,6 +60,81 @@ static int g_timing = 0;   /* B200_TIMING=1: phase times on stderr */
 
 static relation_map *g_map   = NULL;
 static int           g_nrel  = 0;
+static int           g_gpus  = 1;
+/* -g N: g_shard[r][j][g] = DEVICE pointer of rows [first(g), first(g + 1)) of column j of relation r on GPU g */
+static uint64_t   ****g_shard = NULL;
+
+static uint64_t shard_first(uint64_t n, int g) { return g >= g_gpus ? n : (n / (uint64_t)g_gpus) * (uint64_t)g; }
+
+static int shard_relations(void) {
+    g_shard = calloc((size_t)g_nrel, sizeof *g_shard);
+    for (int r = 0; r < g_nrel; ++r) {
+        g_shard[r] = calloc(g_map[r].num_columns, sizeof **g_shard);
+        for (uint64_t j = 0; j < g_map[r].num_columns; ++j) g_shard[r][j] = calloc((size_t)g_gpus, sizeof(uint64_t *));
+    }
+    for (int g = 0; g < g_gpus; ++g) {
+        if (b200_set_thread_device(g)) return 1;
+        for (int r = 0; r < g_nrel; ++r) {
+            const uint64_t a = shard_first(g_map[r].num_tuples, g), b = shard_first(g_map[r].num_tuples, g + 1);
+            for (uint64_t j = 0; j < g_map[r].num_columns; ++j) {
+                uint64_t *d = b200_device_malloc((b - a) * 8);
+                if (!d || b200_copy_to_device(d, g_map[r].columns[j] + a, (b - a) * 8)) return 1;
+                g_shard[r][j][g] = d;
+            }
+        }
+    }
+    return b200_set_thread_device(-1);
+}
+
+/* config 2's shape: one join of two different relations, no filter, at most one SUM per side, 32-bit keys and values */
+static int try_multi_gpu(query_t *q) {
+    if (g_gpus < 2 || q->nrel != 2 || q->njoin != 1 || q->nfilter != 0 || q->rel[0] == q->rel[1]) return 0;
+    join_pred *j = &q->joins[0];
+    if (j->relation1 == j->relation2) return 0;
+    int kcol[2], vcol[2] = {-1, -1};
+    kcol[j->relation1] = j->column1;
+    kcol[j->relation2] = j->column2;
+    for (int i = 0; i < q->nview; ++i) {
+        if (vcol[q->view_b[i]] >= 0) return 0;                       /* two SUMs on one side: single-GPU path */
+        vcol[q->view_b[i]] = q->view_c[i];
+    }
+    for (int b = 0; b < 2; ++b) {
+        relation_map *rm = &g_map[q->rel[b]];
+        if (rm->col_stats[kcol[b]].u >= 0xFFFFFFFFull) return 0;
+        if (vcol[b] >= 0 && rm->col_stats[vcol[b]].u > 0xFFFFFFFFull) return 0;
+        if (rm->num_tuples < (uint64_t)g_gpus) return 0;
+    }
+    const int bb = g_map[q->rel[0]].num_tuples <= g_map[q->rel[1]].num_tuples ? 0 : 1, pb = 1 - bb;   /* build = smaller */
+    const uint64_t *bk[8], *bs[8], *pk[8], *ps[8];
+    uint64_t        nb[8], np[8];
+    for (int g = 0; g < g_gpus; ++g) {
+        const int rb = q->rel[bb], rp = q->rel[pb];
+        bk[g] = g_shard[rb][kcol[bb]][g];
+        pk[g] = g_shard[rp][kcol[pb]][g];
+        bs[g] = vcol[bb] >= 0 ? g_shard[rb][vcol[bb]][g] : NULL;
+        ps[g] = vcol[pb] >= 0 ? g_shard[rp][vcol[pb]][g] : NULL;
+        nb[g] = shard_first(g_map[rb].num_tuples, g + 1) - shard_first(g_map[rb].num_tuples, g);
+        np[g] = shard_first(g_map[rp].num_tuples, g + 1) - shard_first(g_map[rp].num_tuples, g);
+    }
+    uint64_t sums[2] = {0, 0}, matches = 0;
+    double   ms      = 0.0;
+    const int steps  = g_timing ? 20 : 0;
+    if (b200_join_sum_multi(g_gpus, B200_PLAN_BROADCAST, bk, bs, nb, pk, ps, np, steps, sums, &matches, &ms)) {
+        fprintf(stderr, "b200_engine: multi-GPU plan failed (%s): single-GPU path\n", b200_last_error());
+        return 0;
+    }
+    if (g_timing)
+        fprintf(stderr, "b200_engine: multi-GPU join on %d GPUs, %lu matches, %.4f ms per step (%d steps)\n", g_gpus,
+                (unsigned long)matches, ms, steps);
+    /* sums come back as {SUM(build column)?, SUM(probe column)?}; print them in the query's view order */
+    uint64_t by_binding[2] = {0, 0};
+    int      k = 0;
+    if (vcol[bb] >= 0) by_binding[bb] = sums[k++];
+    if (vcol[pb] >= 0) by_binding[pb] = sums[k];
+    char *p = q->line;
+    for (int i = 0; i < q->nview; ++i) p += sprintf(p, "%s%lu", i ? " " : "", (unsigned long)by_binding[q->view_b[i]]);
+    return 1;
+}
 
 /* ---- relation loading (relation_map.c:13-88) ------------------------------------------------------ */
 static int load_relation(const char *path, relation_map *rm) {
@@ -126,6 +206,7 @@ static void null_line(query_t *q) {
 
 /* ---- ExecuteQuery (query.c:325-467) over the operator API ------------------------------------------- */
 static void execute_query(query_t *q) {
+    if (try_multi_gpu(q)) return;
     inter_res *inter = NULL;
     InitInterResults(&inter, q->nrel);
     for (int i = 0; i < q->nfilter; ++i) {
@@ -259,9 +340,15 @@ static void run_batch(query_t *queries, int n) {
 int main(int argc, char **argv) {
     int workers = 4;
     if (getenv("B200_WORKERS")) workers = atoi(getenv("B200_WORKERS"));
-    if (argc == 3 && !strcmp(argv[1], "-w")) workers = atoi(argv[2]);
+    if (getenv("B200_GPUS")) g_gpus = atoi(getenv("B200_GPUS"));
+    for (int a = 1; a + 1 < argc; a += 2) {
+        if (!strcmp(argv[a], "-w")) workers = atoi(argv[a + 1]);
+        else if (!strcmp(argv[a], "-g")) g_gpus = atoi(argv[a + 1]);
+    }
     if (workers < 1) workers = 1;
     if (workers > 64) workers = 64;
+    if (g_gpus < 1) g_gpus = 1;
+    if (g_gpus > 8) g_gpus = 8;
 
     char buff[1024];
     int  cap = 16;
@@ -277,6 +364,10 @@ int main(int argc, char **argv) {
     double t1 = now_s();
     b200_register_relations(g_map, g_nrel);     /* the untimed preparation phase: columns go to HBM once */
     b200_compute_column_stats(g_map, g_nrel);   /* relation_map.c:53-83's min / max / distinct, computed on the GPU */
+    if (g_gpus > 1) {
+        if (shard_relations()) { fprintf(stderr, "b200_engine: cannot shard over %d GPUs: %s\n", g_gpus, b200_last_error()); return 1; }
+        workers = 1;                            /* the multi-GPU plan runs one query at a time over all GPUs */
+    }
     if (g_timing) fprintf(stderr, "b200_engine: CUDA start-up %.3f s, upload of %d relations %.3f s\n", t1 - t0, g_nrel, now_s() - t1);
 
     if (workers > 1) pool_start(workers);

@@ -107,6 +107,10 @@ void FreeRelation(relation *rel);
  * the reference's unmodified handler.o still works. */
 int  b200_init(int device);
 void b200_shutdown(void);
+/* The calling thread works on `device` from now on (b200_device_malloc, copies,
+ * operators): one host thread per GPU is how a single process drives several
+ * (host/b200_engine -g N).  -1 returns to the process default. */
+int  b200_set_thread_device(int device);
 const char *b200_last_error(void);
 /* 1 when the library was built from the CUDA sources (always, for this
  * library; the CPU oracle exports the same symbol returning 0). */

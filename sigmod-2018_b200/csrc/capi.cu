@@ -59,6 +59,19 @@ int b200_init(int device) {
     return 0;
 }
 
+// the calling thread works on `device` from now on (its own context: stream, scratch); -1 = the process default
+int b200_set_thread_device(int device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) {
+        cudaGetLastError();
+        return fail("no such CUDA device");
+    }
+    ensure_init();
+    set_thread_device(device);
+    (void)ctx();
+    return 0;
+}
+
 void b200_shutdown(void) {
     cudaDeviceSynchronize();
     unregister_all_columns();

@@ -162,6 +162,7 @@ def _declare(L: C.CDLL) -> None:
         # Part 2 — the shim
         "b200_init": (C.c_int, [C.c_int]),
         "b200_shutdown": (None, []),
+        "b200_set_thread_device": (C.c_int, [C.c_int]),
         "b200_last_error": (C.c_char_p, []),
         "b200_is_cuda": (C.c_int, []),
         "b200_register_relations": (C.c_int, [P(CRelationMap), C.c_int]),
