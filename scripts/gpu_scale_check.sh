@@ -17,7 +17,7 @@ except Exception as e:
 PY
 }
 port=29600
-for N in 8 4 2; do
+for N in 8 4; do
   for g in 1 0; do
     port=$((port + 1))
     B200_MULTI_GRAPH=$g timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \

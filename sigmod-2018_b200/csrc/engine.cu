@@ -979,7 +979,11 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
                 const OptArgs o{0, nullptr, nullptr, nullptr, B.preds};
                 if (key64) launch_scatter_pred<uint64_t, false>(B.src, bits, cursor, tup_b->ptr, o);
                 else launch_scatter_pred<uint32_t, false>(B.src, bits, cursor, tup_b->ptr, o);
-            } else if (npay > 0 && key64)
+            } else if (pay.carry32 && !key64 && B.src.ids == nullptr && pay.ids[0] == nullptr && B.src.n >= (1u << 18) &&
+                       (reinterpret_cast<uintptr_t>(pay.col[0]) & 15) == 0)
+                // a large base relation with its one SUM column carried: the tuned instance (16 K-tuple tiles)
+                launch_scatter_carry_tuned(B.src, bits, cursor, tup_b->ptr, pay.col[0]);
+            else if (npay > 0 && key64)
                 launch_scatter_pay<uint64_t>(B.src, bits, cursor, tup_b->ptr, pay, npay);
             else if (npay > 0)
                 launch_scatter_pay<uint32_t>(B.src, bits, cursor, tup_b->ptr, pay, npay);
