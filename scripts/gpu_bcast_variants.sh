@@ -1,6 +1,6 @@
 #!/bin/bash
-# Broadcast-plan variants of the config-2 bench on N GPUs: SM broadcast kernel with R reserved SMs, copy engines with
-# K chunks.   gpurun --gpus N -- 'bash scripts/gpu_bcast_variants.sh N tag'
+# Broadcast-plan variants of the config-2 bench on N GPUs: copy engines pushing (K chunks), or a fetch kernel pulling
+# the peers' regions on R reserved SMs.   gpurun --gpus N -- 'bash scripts/gpu_bcast_variants.sh N tag'
 set -u
 N=${1:-2}; T=${2:-r2v}
 mkdir -p gpurun_out
@@ -19,11 +19,10 @@ except Exception as e:
     print(sys.argv[1], "unreadable:", e)
 PY
 }
-one sm16 B200_BCAST_SMS=16
-one sm8 B200_BCAST_SMS=8
-one sm4 B200_BCAST_SMS=4
-one sm2 B200_BCAST_SMS=2
-one sm8g B200_BCAST_SMS=8 B200_MULTI_GRAPH=1
-one ce1 B200_BCAST_CE=1 B200_BCAST_CHUNKS=1
-one ce2 B200_BCAST_CE=1 B200_BCAST_CHUNKS=2
-one ce1g B200_BCAST_CE=1 B200_BCAST_CHUNKS=1 B200_MULTI_GRAPH=1
+one ce1 B200_BCAST_CHUNKS=1
+one ce1g B200_BCAST_CHUNKS=1 B200_MULTI_GRAPH=1
+one pull12 B200_BCAST=pull B200_BCAST_SMS=12
+one pull12g B200_BCAST=pull B200_BCAST_SMS=12 B200_MULTI_GRAPH=1
+one pull6g B200_BCAST=pull B200_BCAST_SMS=6 B200_MULTI_GRAPH=1
+one pull20g B200_BCAST=pull B200_BCAST_SMS=20 B200_MULTI_GRAPH=1
+one pull12k2g B200_BCAST=pull B200_BCAST_SMS=12 B200_BCAST_CHUNKS=2 B200_MULTI_GRAPH=1

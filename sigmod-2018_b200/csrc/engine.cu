@@ -262,9 +262,14 @@ uint64_t read_counter(const unsigned long long *d_ptr) {
     return c.h_scratch[0];
 }
 
+// SMs the streaming kernels of the calling thread leave free (multi-GPU broadcast plan, pull variant: the probe-side
+// scatter is a persistent grid that would otherwise own every SM, and the fetch kernel beside it must stay resident)
+static thread_local int t_reserved_sms = 0;
+void set_reserved_sms(int n) { t_reserved_sms = n < 0 ? 0 : n; }
+
 int grid_for(uint64_t work_items, int per_block, int max_blocks_per_sm) {
     uint64_t blocks = (work_items + per_block - 1) / per_block;
-    uint64_t cap    = (uint64_t)sm_count() * max_blocks_per_sm;
+    uint64_t cap    = (uint64_t)std::max(1, sm_count() - t_reserved_sms) * max_blocks_per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;

@@ -158,5 +158,6 @@ const std::string &last_error_string();
 // small helpers
 uint64_t read_counter(const unsigned long long *d_ptr);   // D2H + sync on ctx stream
 int      grid_for(uint64_t work_items, int per_block, int max_blocks_per_sm);
+void     set_reserved_sms(int n);   // SMs grid_for leaves free on the calling thread (0 = none)
 
 }  // namespace b200

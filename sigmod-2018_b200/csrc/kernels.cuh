@@ -508,27 +508,33 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
             cnt[b] = 0;
         }
     }
+    // the carried column of the tile (its lines were pulled into L2 one tile ahead): every load is issued here, ahead
+    // of the barrier, so that ONE L2 latency is exposed per tile — ncu showed 17 % of the warp samples waiting on these
+    // loads when each was issued right where its value was staged (profiles/r2_summary.txt)
+    [[maybe_unused]] uint64_t craw[(CARRY && FULL) ? U : 1];
+    if constexpr (CARRY && FULL) {
+#pragma unroll
+        for (int j = 0; j < U; j += 2) {
+            // registers j, j+1 hold two consecutive rows: one 128-bit load for both (skipped when neither row is on)
+            if (!PRED || ((valid >> j) & 3ull) != 0ull) {
+                const ulonglong2 v = ld_stream_u64x2(opt.carry_col + base + ((uint32_t)((j >> 1) * NT) + tid) * 2u);
+                craw[j]            = v.x;
+                craw[j + 1]        = v.y;
+            }
+        }
+    }
     __syncthreads();   // (C) local offsets visible
     // ---- (3) tuples into shared memory in partition order ----
-    [[maybe_unused]] uint32_t carry_lo = 0, carry_hi = 0;
 #pragma unroll
     for (int j = 0; j < U; ++j) {
         const uint32_t li = FULL ? ((uint32_t)((j >> 1) * NT) + tid) * 2u + (uint32_t)(j & 1)
                                  : tile_local_index<NT, U>(j, vec);
-        if constexpr (CARRY && FULL) {
-            // registers j, j+1 hold two consecutive rows: one 128-bit load for both (skipped when neither row is on)
-            if ((j & 1) == 0 && (!PRED || ((valid >> j) & 3ull) != 0ull)) {
-                const ulonglong2 v = ld_stream_u64x2(opt.carry_col + base + li);
-                carry_lo           = narrow_key<uint32_t>(v.x);
-                carry_hi           = narrow_key<uint32_t>(v.y);
-            }
-        }
         if (row_on(j, li)) {
             TupT t;
             t.key = keys[j];
             if constexpr (CARRY) {
                 if constexpr (FULL) {
-                    t.rid = (j & 1) ? carry_hi : carry_lo;
+                    t.rid = narrow_key<uint32_t>(craw[j]);
                 } else {
                     t.rid = (uint32_t)ld_stream_u64(opt.carry_col + base + li);
                 }

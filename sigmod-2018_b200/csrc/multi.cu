@@ -72,7 +72,8 @@ struct MultiPlan {
     bool           peer_ipc[kMaxPeers] = {false};
     // local device memory (one allocation)
     unsigned char *local = nullptr;
-    uint32_t      *d_epoch = nullptr, *d_error = nullptr, *cur_p = nullptr, *ovcnt = nullptr;
+    uint32_t      *d_epoch = nullptr, *d_error = nullptr, *cur_p = nullptr, *ovcnt = nullptr, *pull_work = nullptr;
+    int            pull = 0, pull_sms = 12;   // broadcast plan: fetch the peers' regions with a kernel instead of pushing
     unsigned long long *d_result = nullptr, *d_final = nullptr;
     void          *tup_p = nullptr, *ov_p = nullptr, *stage_b = nullptr, *stage_p = nullptr;
     uint32_t      *src_off_b = nullptr, *src_off_p = nullptr, *dst_start_b = nullptr, *dst_start_p = nullptr;
@@ -135,6 +136,7 @@ static void layout_local(MultiPlan &m, void *base, size_t *bytes) {
     m.d_epoch  = c.take<uint32_t>(4);
     m.d_error  = c.take<uint32_t>(4);
     m.ovcnt    = c.take<uint32_t>(4);
+    m.pull_work = c.take<uint32_t>(1 + kMaxChunks * kMaxPeers);
     m.d_result = c.take<unsigned long long>(8);
     m.d_final  = c.take<unsigned long long>(8);
     m.cur_p    = c.take<uint32_t>(P + 1);
@@ -196,6 +198,43 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
         stage_scatter_build_local(m.in_bk, nb, 0, m.bits, my_hist, my_tuples, m.cfg.has_build_sum ? 1 : 0, pay_cols, nullptr,
                                   &m.scr_a);
         B200_CUDA(cudaEventRecord(m.ev_build, main));
+        if (m.pull) {
+            // ---- pull variant: announce my region, then fetch the peers' regions with a small persistent kernel that
+            //      runs beside the probe-side scatter (on SMs that scatter leaves free) and raises the chunk flags ----
+            signal_peers_kernel<<<1, 32, 0, main>>>(m.peers(), world, rank, SIG_READY, m.d_epoch);
+            B200_LAUNCH_CHECK();
+            B200_CUDA(cudaEventRecord(m.ev_build, main));
+            B200_CUDA(cudaStreamWaitEvent(m.xstream, m.ev_build, 0));
+            B200_CUDA(cudaMemsetAsync(m.pull_work, 0, (1 + kMaxChunks * kMaxPeers) * sizeof(uint32_t), m.xstream));
+            PullArgs a{};
+            for (int d = 0; d < world; ++d) a.src_build[d] = m.build(d);
+            a.dst_build   = m.build(rank);
+            a.hdr         = m.hdr(rank);
+            a.region_rows = m.seg_rows;
+            a.chunk_rows  = m.chunk_rows;
+            a.nchunks     = (uint32_t)m.K;
+            a.slice_rows  = 32768;
+            a.rank        = rank;
+            a.world       = world;
+            a.work        = m.pull_work;
+            a.done        = m.pull_work + 1;
+            a.epoch       = m.d_epoch;
+            a.error       = m.d_error;
+            if (world > 1) {
+                StreamSwap sw(c, m.xstream);
+                TimedScope ts("broadcast");
+                static bool smem_set = false;
+                if (!smem_set) {
+                    B200_CUDA(cudaFuncSetAttribute(pull_regions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)kPullSmem));
+                    smem_set = true;
+                }
+                pull_regions_kernel<<<m.pull_sms, kPullNT, kPullSmem, c.stream>>>(a);
+                B200_LAUNCH_CHECK();
+            }
+            B200_CUDA(cudaEventRecord(m.ev_x, m.xstream));
+            set_reserved_sms(world > 1 ? m.pull_sms : 0);
+        }
         // ---- probe shard: partitioned locally (histogram-free regions + overflow), never moves.  Enqueued before the
         //      copies so that the host's enqueue time of those does not delay it ----
         if (m.opt_cap) {
@@ -209,10 +248,11 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
                                       &m.scr_b);
             B200_CUDA(cudaMemsetAsync(m.ovcnt, 0, 4, main));
         }
+        set_reserved_sms(0);
         // ---- broadcast on the copy engines: my region (histogram + tuples) into the same place of every peer's build
         //      buffer, every rank starting at a different peer, in K chunks with a 4-byte flag behind each ----
         const uint64_t used = m.seg_head + nb;   // tuple slots of my region that hold something
-        for (int j = 1; j < world; ++j) {
+        for (int j = 1; j < world && !m.pull; ++j) {
             const int    d = (rank + j) % world;
             cudaStream_t s = m.copy_stream[j - 1];
             B200_CUDA(cudaStreamWaitEvent(s, m.ev_build, 0));
@@ -226,13 +266,9 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
             }
             B200_CUDA(cudaEventRecord(m.ev_copy[j - 1], s));
         }
-        // my own region needs no copy: raise my own flags
-        PeerPtrs self{};
-        self.hdr[0] = m.hdr(rank);
-        for (int k = 0; k < m.K; ++k) {
-            signal_peers_kernel<<<1, 32, 0, main>>>(self, 1, rank, SIG_CHUNK0 + k, m.d_epoch);
-            B200_LAUNCH_CHECK();
-        }
+        // my own region needs no transfer: raise my own flags
+        signal_self_chunks_kernel<<<1, 32, 0, main>>>(m.hdr(rank), rank, m.K, m.d_epoch);
+        B200_LAUNCH_CHECK();
     }
     if (phases & 2) {
         // the histograms travel at the head of the regions: chunk 0 of every rank, then one contiguous copy of them
@@ -248,8 +284,10 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
                        m.d_result, world, m.seg_rows, &m.scr_b, m.K > 1 ? &w : nullptr, m.seg_head);
         push_result_kernel<<<1, 32, 0, main>>>(m.peers(), world, rank, m.d_result, m.d_error, m.d_epoch);
         B200_LAUNCH_CHECK();
-        // the next step must not overwrite my region under copies still in flight
-        for (int j = 1; j < world; ++j) B200_CUDA(cudaStreamWaitEvent(main, m.ev_copy[j - 1], 0));
+        // the next step must not overwrite my build buffer under transfers still in flight
+        if (m.pull) B200_CUDA(cudaStreamWaitEvent(main, m.ev_x, 0));
+        else
+            for (int j = 1; j < world; ++j) B200_CUDA(cudaStreamWaitEvent(main, m.ev_copy[j - 1], 0));
     }
     if (phases & 4) {
         wait_signal_row(m, main, SIG_RESULT);
@@ -503,7 +541,9 @@ b200_multi *b200_multi_create(const b200_multi_config *cfg) {
         // kernel slow the concurrent probe scatter by a third even on reserved SMs, and every copy-engine operation
         // costs about 5 us whatever its size, serialised across streams — 70 operations (4 chunks + flags + histogram
         // per peer) cost more than the data at 8 GPUs.  So: one region copy and one flag per peer.
-        m->K = cfg->chunks > 0 ? std::min(cfg->chunks, kMaxChunks) : 1;
+        if (const char *e = getenv("B200_BCAST")) m->pull = !strcmp(e, "pull");
+        if (const char *e = getenv("B200_BCAST_SMS")) m->pull_sms = std::max(1, std::min(atoi(e), 64));
+        m->K = cfg->chunks > 0 ? std::min(cfg->chunks, kMaxChunks) : (m->pull ? kMaxChunks : 1);
         if (const char *e = getenv("B200_BCAST_CHUNKS")) m->K = std::max(1, std::min(atoi(e), kMaxChunks));
         m->chunk_rows = (((m->seg_rows + (uint32_t)m->K - 1) / (uint32_t)m->K) + 1u) & ~1u;
         m->opt_cap    = (cfg->n_probe_local_max >= (1u << 20) && cfg->n_probe_local_max <= (1u << 30))

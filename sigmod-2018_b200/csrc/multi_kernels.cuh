@@ -25,6 +25,7 @@ enum MultiSig {
     SIG_HIST2  = 3,   // exchange plan: my probe-side histograms (per chunk) are in your hist_all
     SIG_HOT    = 4,   // exchange plan: my hot-key candidates are in your cand[]
     SIG_AGG    = 5,   // exchange plan: my build-side aggregates of the hot keys are in your agg[]
+    SIG_READY  = 6,   // broadcast plan, pull variant: my region of my build buffer is complete — fetch it
     SIG_CHUNK0 = 8,   // broadcast plan: chunk c of my build region has landed (SIG_CHUNK0 + c)
 };
 
@@ -58,6 +59,11 @@ __global__ void signal_peers_kernel(PeerPtrs peers, int world, int rank, int sig
     }
 }
 
+// my own region needs no transfer: raise all of its chunk flags in my own header
+static __global__ void signal_self_chunks_kernel(SharedHeader *hdr, int rank, int nchunks, const uint32_t *epoch) {
+    if ((int)threadIdx.x < nchunks) st_release_sys_u32(&hdr->sig[SIG_CHUNK0 + threadIdx.x][rank], *epoch);
+}
+
 // {matches, sums..., flags} of this rank into slot `rank` of every rank's header, then SIG_RESULT
 __global__ void push_result_kernel(PeerPtrs peers, int world, int rank, const unsigned long long *local,
                                    const uint32_t *extra_flag, const uint32_t *epoch) {
@@ -77,6 +83,94 @@ __global__ void reduce_result_kernel(const SharedHeader *hdr, int world, unsigne
         unsigned long long s = 0;
         for (int r = 0; r < world; ++r) s += reinterpret_cast<const volatile unsigned long long *>(hdr->result[r])[k];
         final8[k] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Pull variant of the broadcast (B200_BCAST=pull): instead of every rank pushing its region to seven peers, every
+// rank FETCHES the seven regions it needs — loads over NVLink, stores into local HBM.  Remote stores from an SM
+// kernel slow a concurrent local scatter by a third (profiles/r2_broadcast_variants.txt: posted writes queueing
+// behind the NVLink egress), remote loads do not share that path; and the kernel raises the per-chunk flags the
+// join waits on itself, locally, so no copy-engine operation is spent on flags and the join overlaps the transfer
+// chunk by chunk.  A small persistent grid on SMs the probe-side scatter leaves free; a slice of a peer's region is
+// fetched only after that peer has announced (SIG_READY) that its region is complete.
+// ---------------------------------------------------------------------------
+struct PullArgs {
+    const unsigned char *src_build[kMaxPeers];   // peer d's build buffer (region d of it is what d produced)
+    unsigned char       *dst_build;              // my build buffer
+    SharedHeader        *hdr;                    // my header: SIG_READY[d] written by peer d, SIG_CHUNK0+c[d] by this kernel
+    uint32_t             region_rows, chunk_rows, nchunks, slice_rows;
+    int                  rank, world;
+    uint32_t            *work;                   // slice counter, zero at launch
+    uint32_t            *done;                   // [kMaxChunks][kMaxPeers] slices completed, zero at launch
+    const uint32_t      *epoch;
+    uint32_t            *error;
+};
+// (1024 threads and nearly all of an SM's shared memory per CTA, so that a CTA owns its SM: the fetch kernel then
+// occupies exactly as many SMs as it has CTAs, and the scatter beside it finds the others free)
+constexpr int    kPullNT   = 1024;
+constexpr size_t kPullSmem = 200 * 1024;
+static __global__ void __launch_bounds__(kPullNT) pull_regions_kernel(const PullArgs a) {
+    extern __shared__ uint32_t pull_pad[];
+    __shared__ uint32_t s_item, s_ok;
+    if (a.world < 0) pull_pad[threadIdx.x] = 0;   // (keeps the dynamic allocation referenced)
+    const uint32_t tid   = threadIdx.x;
+    const uint32_t epoch = *a.epoch;
+    auto chunk_rows_of = [&](uint32_t c) -> uint32_t {
+        const uint64_t first = (uint64_t)c * a.chunk_rows;
+        return first < a.region_rows ? (uint32_t)min((uint64_t)a.chunk_rows, (uint64_t)a.region_rows - first) : 0u;
+    };
+    auto slices_of = [&](uint32_t c) -> uint32_t { return (chunk_rows_of(c) + a.slice_rows - 1) / a.slice_rows; };
+    const uint32_t npeer = (uint32_t)a.world - 1u;
+    uint32_t       per_peer = 0;
+    for (uint32_t c = 0; c < a.nchunks; ++c) per_peer += slices_of(c);
+    // items in (chunk, peer, slice) order: the first chunks of every region arrive first
+    const uint32_t total = per_peer * npeer;
+    constexpr int  U     = 4;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(a.work, 1u);
+        __syncthreads();
+        uint32_t item = s_item;
+        if (item >= total) break;
+        uint32_t c = 0;
+        while (item >= slices_of(c) * npeer) item -= slices_of(c++) * npeer;
+        const uint32_t j = item / slices_of(c), sl = item % slices_of(c);   // j-th peer after me
+        const int      d = (a.rank + 1 + (int)j) % a.world;
+        if (tid == 0) s_ok = spin_until_epoch(&a.hdr->sig[SIG_READY][d], epoch) ? 1u : 0u;
+        __syncthreads();
+        if (!s_ok) {
+            if (tid == 0) *a.error = 1u;
+            continue;
+        }
+        const size_t   first = (size_t)c * a.chunk_rows + (size_t)sl * a.slice_rows;
+        const uint32_t rows  = min(a.slice_rows, c * a.chunk_rows + chunk_rows_of(c) - (uint32_t)first);
+        const size_t   base  = ((size_t)d * a.region_rows + first) * 8;   // region d, both sides
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(a.src_build[d] + base);
+        ulonglong2       *dst = reinterpret_cast<ulonglong2 *>(a.dst_build + base);
+        const uint32_t pairs  = rows >> 1;   // region_rows, chunk_rows and slice_rows are even
+        for (uint32_t i0 = tid; i0 < pairs; i0 += kPullNT * U) {
+            ulonglong2 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t i = i0 + (uint32_t)u * kPullNT;
+                if (i < pairs) v[u] = __ldcg(src + i);   // (peer memory: L2 of the home GPU is the point of coherence)
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t i = i0 + (uint32_t)u * kPullNT;
+                if (i < pairs) dst[i] = v[u];
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t finished = atomicAdd(&a.done[c * kMaxPeers + d], 1u) + 1u;
+            if (finished == slices_of(c)) {
+                __threadfence();
+                st_release_sys_u32(&a.hdr->sig[SIG_CHUNK0 + c][d], epoch);
+            }
+        }
     }
 }
 

@@ -95,8 +95,11 @@ def main():
         pr, ps = orc.synth_column(nr, 1, 0, 3), orc.synth_column(ns, 1, 0, 13)
         want, wm = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
         d_kr, d_ks, d_pr, d_ps = shard(kr, nr), shard(ks, ns), shard(pr, nr), shard(ps, ns)
-        for graph in (0, 1):
+        for graph, bcast in ((0, "push"), (1, "push"), (0, "pull"), (1, "pull")):
+            if bcast == "pull" and plan_kind != b200.PLAN_BROADCAST:
+                continue
             os.environ["B200_MULTI_GRAPH"] = str(graph)
+            os.environ["B200_BCAST"] = bcast
             plan = sh.MultiJoin(b200, dist, rank, world, local, plan_kind, d_kr.numel(), d_ks.numel(),
                                 recv_rows_build=nr, recv_rows_probe=ns)
             for _ in range(3):

@@ -64,6 +64,18 @@ def test_broadcast_plan_emulated_ranks(gpu, orc, world, kr_bits, ns, chunks):
     _run(gpu, orc, gpu.PLAN_BROADCAST, world, kr, ks, pr, ps, chunks=chunks)
 
 
+@pytest.mark.parametrize("world,chunks", [(2, 0), (3, 2), (4, 8)])
+def test_broadcast_plan_pull_variant(gpu, orc, world, chunks, monkeypatch):
+    """B200_BCAST=pull: every rank fetches the peers' regions with a kernel (loads over NVLink) that raises the chunk
+    flags the join waits on, instead of pushing its own region with the copy engines."""
+    monkeypatch.setenv("B200_BCAST", "pull")
+    monkeypatch.setenv("B200_BCAST_SMS", "4")
+    kr = orc.synth_column(1 << 17, 0, 17, gpu.SEED_R)[: (1 << 17) - 5]
+    ks = orc.synth_column((1 << 22) + 3, 0, 20, gpu.SEED_S)
+    pr, ps = orc.synth_column(len(kr), 1, 0, 3), orc.synth_column(len(ks), 1, 0, 4)
+    _run(gpu, orc, gpu.PLAN_BROADCAST, world, kr, ks, pr, ps, chunks=chunks)
+
+
 def test_broadcast_plan_skewed_probe_keys_take_the_overflow_pass(gpu, orc):
     """Zipf probe keys overflow the histogram-free regions: finish() redoes the join with the exact overflow pass
     (world = 1: with several ranks on one GPU the second result exchange could not be driven phase by phase)."""
