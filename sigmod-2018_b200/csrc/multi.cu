@@ -213,10 +213,8 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
             a.region_rows = m.seg_rows;
             a.chunk_rows  = m.chunk_rows;
             a.nchunks     = (uint32_t)m.K;
-            a.slice_rows  = 32768;
             a.rank        = rank;
             a.world       = world;
-            a.work        = m.pull_work;
             a.done        = m.pull_work + 1;
             a.epoch       = m.d_epoch;
             a.error       = m.d_error;
@@ -229,7 +227,7 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
                                                    (int)kPullSmem));
                     smem_set = true;
                 }
-                pull_regions_kernel<<<m.pull_sms, kPullNT, kPullSmem, c.stream>>>(a);
+                pull_regions_kernel<<<m.pull_sms, 32, kPullSmem, c.stream>>>(a);
                 B200_LAUNCH_CHECK();
             }
             B200_CUDA(cudaEventRecord(m.ev_x, m.xstream));

@@ -87,90 +87,124 @@ __global__ void reduce_result_kernel(const SharedHeader *hdr, int world, unsigne
 }
 
 // ---------------------------------------------------------------------------
-// Pull variant of the broadcast (B200_BCAST=pull): instead of every rank pushing its region to seven peers, every
-// rank FETCHES the seven regions it needs — loads over NVLink, stores into local HBM.  Remote stores from an SM
-// kernel slow a concurrent local scatter by a third (profiles/r2_broadcast_variants.txt: posted writes queueing
-// behind the NVLink egress), remote loads do not share that path; and the kernel raises the per-chunk flags the
-// join waits on itself, locally, so no copy-engine operation is spent on flags and the join overlaps the transfer
-// chunk by chunk.  A small persistent grid on SMs the probe-side scatter leaves free; a slice of a peer's region is
-// fetched only after that peer has announced (SIG_READY) that its region is complete.
+// Pull variant of the broadcast (B200_BCAST=pull): instead of every rank pushing its region to seven peers with
+// the copy engines, every rank FETCHES the seven regions it needs with the TMA unit: one thread per CTA drives a ring
+// of 32 KB stages in shared memory — cp.async.bulk global(peer, over NVLink) -> shared, completion on an mbarrier,
+// then cp.async.bulk shared -> global(local HBM) — so that 160 KB per SM are in flight with no register or LSU
+// cost (a fetch kernel built on ordinary loads was latency-bound: 117 MB took 0.9 ms on 12 SMs,
+// profiles/r2_broadcast_variants.txt).  Remote LOADS do not disturb the concurrent probe scatter the way remote
+// stores do, and the kernel raises the per-chunk flags the join waits on itself, locally, so the join overlaps the
+// transfer chunk by chunk.  A small grid on SMs the probe-side scatter leaves free (a CTA takes nearly all of an
+// SM's shared memory, so it owns its SM); a piece of a peer's region is fetched only after that peer has announced
+// (SIG_READY) that the region is complete.
 // ---------------------------------------------------------------------------
 struct PullArgs {
     const unsigned char *src_build[kMaxPeers];   // peer d's build buffer (region d of it is what d produced)
     unsigned char       *dst_build;              // my build buffer
     SharedHeader        *hdr;                    // my header: SIG_READY[d] written by peer d, SIG_CHUNK0+c[d] by this kernel
-    uint32_t             region_rows, chunk_rows, nchunks, slice_rows;
+    uint32_t             region_rows, chunk_rows, nchunks;
     int                  rank, world;
-    uint32_t            *work;                   // slice counter, zero at launch
-    uint32_t            *done;                   // [kMaxChunks][kMaxPeers] slices completed, zero at launch
+    uint32_t            *done;                   // [kMaxChunks][kMaxPeers] pieces completed, zero at launch
     const uint32_t      *epoch;
     uint32_t            *error;
 };
-// (1024 threads and nearly all of an SM's shared memory per CTA, so that a CTA owns its SM: the fetch kernel then
-// occupies exactly as many SMs as it has CTAs, and the scatter beside it finds the others free)
-constexpr int    kPullNT   = 1024;
-constexpr size_t kPullSmem = 200 * 1024;
-static __global__ void __launch_bounds__(kPullNT) pull_regions_kernel(const PullArgs a) {
-    extern __shared__ uint32_t pull_pad[];
-    __shared__ uint32_t s_item, s_ok;
-    if (a.world < 0) pull_pad[threadIdx.x] = 0;   // (keeps the dynamic allocation referenced)
-    const uint32_t tid   = threadIdx.x;
-    const uint32_t epoch = *a.epoch;
-    auto chunk_rows_of = [&](uint32_t c) -> uint32_t {
-        const uint64_t first = (uint64_t)c * a.chunk_rows;
-        return first < a.region_rows ? (uint32_t)min((uint64_t)a.chunk_rows, (uint64_t)a.region_rows - first) : 0u;
-    };
-    auto slices_of = [&](uint32_t c) -> uint32_t { return (chunk_rows_of(c) + a.slice_rows - 1) / a.slice_rows; };
+constexpr uint32_t kPullStage  = 32 * 1024;   // bytes per ring stage = one piece
+constexpr int      kPullStages = 6;
+constexpr size_t   kPullSmem   = (size_t)kPullStage * kPullStages;
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+static __global__ void __launch_bounds__(32) pull_regions_kernel(const PullArgs a) {
+    extern __shared__ __align__(128) unsigned char pull_ring[];
+    __shared__ __align__(8) unsigned long long pull_full[kPullStages];
+    if (threadIdx.x != 0) return;   // one thread drives the whole pipeline: the TMA unit does the moving
+    const uint32_t epoch  = *a.epoch;
+    const uint32_t ring   = (uint32_t)__cvta_generic_to_shared(pull_ring);
+    const uint32_t mbar0  = (uint32_t)__cvta_generic_to_shared(pull_full);
+    for (int s = 0; s < kPullStages; ++s) mbar_init(mbar0 + 8u * s, 1u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    // pieces in (chunk, peer, position) order — the first chunks of every region arrive first — dealt round-robin to
+    // the CTAs; piece = (chunk c, j-th peer after me, k-th 32 KB of that chunk)
     const uint32_t npeer = (uint32_t)a.world - 1u;
-    uint32_t       per_peer = 0;
-    for (uint32_t c = 0; c < a.nchunks; ++c) per_peer += slices_of(c);
-    // items in (chunk, peer, slice) order: the first chunks of every region arrive first
-    const uint32_t total = per_peer * npeer;
-    constexpr int  U     = 4;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_item = atomicAdd(a.work, 1u);
-        __syncthreads();
-        uint32_t item = s_item;
-        if (item >= total) break;
+    auto chunk_bytes = [&](uint32_t c) -> uint32_t {
+        const uint64_t first = (uint64_t)c * a.chunk_rows;
+        return first < a.region_rows ? (uint32_t)(min((uint64_t)a.chunk_rows, (uint64_t)a.region_rows - first) * 8u) : 0u;
+    };
+    auto pieces_of = [&](uint32_t c) -> uint32_t { return (chunk_bytes(c) + kPullStage - 1) / kPullStage; };
+    uint32_t total = 0;
+    for (uint32_t c = 0; c < a.nchunks; ++c) total += pieces_of(c) * npeer;
+    struct Piece { uint32_t c, d, bytes; size_t off; };
+    auto piece_at = [&](uint32_t idx) -> Piece {
         uint32_t c = 0;
-        while (item >= slices_of(c) * npeer) item -= slices_of(c++) * npeer;
-        const uint32_t j = item / slices_of(c), sl = item % slices_of(c);   // j-th peer after me
-        const int      d = (a.rank + 1 + (int)j) % a.world;
-        if (tid == 0) s_ok = spin_until_epoch(&a.hdr->sig[SIG_READY][d], epoch) ? 1u : 0u;
-        __syncthreads();
-        if (!s_ok) {
-            if (tid == 0) *a.error = 1u;
-            continue;
+        while (idx >= pieces_of(c) * npeer) idx -= pieces_of(c++) * npeer;
+        const uint32_t j = idx / pieces_of(c), k = idx % pieces_of(c);
+        Piece          p;
+        p.c     = c;
+        p.d     = (uint32_t)((a.rank + 1 + (int)j) % a.world);
+        p.off   = ((size_t)p.d * a.region_rows + (size_t)c * a.chunk_rows) * 8 + (size_t)k * kPullStage;
+        p.bytes = min(kPullStage, chunk_bytes(c) - k * kPullStage);
+        return p;
+    };
+    uint32_t ready = 0;   // bit d: peer d has announced its region
+    auto issue_load = [&](uint32_t n /* my n-th piece */) {
+        const Piece p = piece_at(blockIdx.x + n * gridDim.x);
+        if (!((ready >> p.d) & 1u)) {
+            if (!spin_until_epoch(&a.hdr->sig[SIG_READY][p.d], epoch)) *a.error = 1u;
+            ready |= 1u << p.d;
         }
-        const size_t   first = (size_t)c * a.chunk_rows + (size_t)sl * a.slice_rows;
-        const uint32_t rows  = min(a.slice_rows, c * a.chunk_rows + chunk_rows_of(c) - (uint32_t)first);
-        const size_t   base  = ((size_t)d * a.region_rows + first) * 8;   // region d, both sides
-        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(a.src_build[d] + base);
-        ulonglong2       *dst = reinterpret_cast<ulonglong2 *>(a.dst_build + base);
-        const uint32_t pairs  = rows >> 1;   // region_rows, chunk_rows and slice_rows are even
-        for (uint32_t i0 = tid; i0 < pairs; i0 += kPullNT * U) {
-            ulonglong2 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t i = i0 + (uint32_t)u * kPullNT;
-                if (i < pairs) v[u] = __ldcg(src + i);   // (peer memory: L2 of the home GPU is the point of coherence)
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t i = i0 + (uint32_t)u * kPullNT;
-                if (i < pairs) dst[i] = v[u];
-            }
+        const uint32_t slot = n % kPullStages;
+        mbar_expect_tx(mbar0 + 8u * slot, p.bytes);
+        bulk_g2s(ring + slot * kPullStage, a.src_build[p.d] + p.off, p.bytes, mbar0 + 8u * slot);
+    };
+    auto account = [&](uint32_t n) {   // my n-th piece is in local memory
+        const Piece    p        = piece_at(blockIdx.x + n * gridDim.x);
+        const uint32_t finished = atomicAdd(&a.done[p.c * kMaxPeers + p.d], 1u) + 1u;
+        if (finished == pieces_of(p.c)) {
+            __threadfence();
+            st_release_sys_u32(&a.hdr->sig[SIG_CHUNK0 + p.c][p.d], epoch);
         }
+    };
+    const uint32_t mine = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    for (uint32_t n = 0; n < mine && n < (uint32_t)kPullStages; ++n) issue_load(n);   // piece p lives in stage p % kPullStages
+    for (uint32_t n = 0; n < mine; ++n) {
+        const uint32_t slot = n % kPullStages, parity = (n / kPullStages) & 1u;
+        const long long t0  = clock64();
+        while (!mbar_try_wait(mbar0 + 8u * slot, parity))
+            if (clock64() - t0 > 4000000000ll) { *a.error = 1u; return; }
+        const Piece p = piece_at(blockIdx.x + n * gridDim.x);
+        bulk_s2g(a.dst_build + p.off, ring + slot * kPullStage, p.bytes);
+        // every store but the one just issued is complete: piece n - 1 is in local memory and its stage is free
+        asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+        if (n >= 1) {
+            __threadfence();
+            account(n - 1);
+            if (n - 1 + kPullStages < mine) issue_load(n - 1 + kPullStages);   // into the stage piece n - 1 just left
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (mine) {
         __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t finished = atomicAdd(&a.done[c * kMaxPeers + d], 1u) + 1u;
-            if (finished == slices_of(c)) {
-                __threadfence();
-                st_release_sys_u32(&a.hdr->sig[SIG_CHUNK0 + c][d], epoch);
-            }
-        }
+        account(mine - 1);
     }
 }
 
