@@ -686,7 +686,9 @@ def run_config4(args):
     plan.close()
     if rank == 0:
         rows = [b + p for b, p in recv_all]
-        wire = 8 * (nr_loc + ns_loc) * (world - 1) / max(world, 1)        # bytes leaving this rank per step
+        # mean bytes leaving a rank per step: the rows that were exchanged (probe rows with a hot key are joined where
+        # they are and never travel), of which (world - 1) / world land on another GPU
+        wire = 8 * sum(rows) / world * (world - 1) / max(world, 1)
         canon = 40 * (nr + ns) + 16 * ns
         peak, peak_kind = measured_peaks()
         nvlink_peak = 770.0
@@ -702,6 +704,7 @@ def run_config4(args):
                                       "owners' receive buffers, ownership cuts balanced on the global histogram"},
             "checksums": sums, "matches": m, "checksum_ok": ok,
             "rows_received_per_rank": recv_all, "rows_received_max_over_mean": max(rows) / (sum(rows) / world),
+            "probe_rows_joined_in_place": ns - sum(p for _, p in recv_all),
             "hbm": {"canonical_bytes_per_step": canon, "achieved_gbs": canon / (ms * 1e-3) / 1e9 / world,
                     "frac_of_peak": canon / (ms * 1e-3) / 1e9 / world / peak, "peak_gbs": peak, "peak_source": peak_kind},
             "nvlink": {"out_bytes_per_rank": wire, "out_gbs_per_rank_over_step": wire / (ms * 1e-3) / 1e9,

@@ -20,8 +20,6 @@ PY
 }
 one 8 ce1g B200_MULTI_GRAPH=1
 one 8 pull12g B200_BCAST=pull B200_BCAST_SMS=12 B200_MULTI_GRAPH=1
-one 8 pull20g B200_BCAST=pull B200_BCAST_SMS=20 B200_MULTI_GRAPH=1
-one 8 pull12k4g B200_BCAST=pull B200_BCAST_SMS=12 B200_BCAST_CHUNKS=4 B200_MULTI_GRAPH=1
-one 8 pull12 B200_BCAST=pull B200_BCAST_SMS=12
-one 4 ce1g B200_MULTI_GRAPH=1
+one 8 pull16g B200_BCAST=pull B200_BCAST_SMS=16 B200_MULTI_GRAPH=1
+one 8 pull8g B200_BCAST=pull B200_BCAST_SMS=8 B200_MULTI_GRAPH=1
 one 4 pull12g B200_BCAST=pull B200_BCAST_SMS=12 B200_MULTI_GRAPH=1
