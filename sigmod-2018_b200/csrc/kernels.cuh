@@ -399,21 +399,36 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
         const PredSet &ps     = opt.pred;
         const bool     hot_on = ps.hot_keys != nullptr && __ldg(ps.hot_n) != 0u;
         if (vec) {
+            // One pass per predicate column: all U/2 128-bit loads of the column are issued back to back and only
+            // then compared, so a tile exposes ONE memory latency per column.  (Evaluating row by row — every
+            // column of rows j, j+1, then the comparison — exposed U/2 of them in sequence: 2.06 ms for config 3's
+            // 200 M-row fact relation with two predicate columns, 12 K tiles of 47 K cycles each.)
+            valid = U == 64 ? ~0ull : (1ull << U) - 1ull;
 #pragma unroll
-            for (int j = 0; j < U; j += 2) {
-                const uint32_t li = ((uint32_t)((j >> 1) * NT) + tid) * 2u;
-                uint64_t       v0[kMaxPredCols], v1[kMaxPredCols];
+            for (int cc = 0; cc < kMaxPredCols; ++cc) {
+                if (cc < ps.ncols) {
+                    ulonglong2 t[U / 2];
 #pragma unroll
-                for (int cc = 0; cc < kMaxPredCols; ++cc) {
-                    v0[cc] = v1[cc] = 0;
-                    if (cc < ps.ncols) {
-                        const ulonglong2 t = ld_stream_u64x2(ps.col[cc] + base + li);
-                        v0[cc]             = t.x;
-                        v1[cc]             = t.y;
+                    for (int j = 0; j < U; j += 2)
+                        t[j >> 1] = ld_stream_u64x2(ps.col[cc] + base + ((uint32_t)((j >> 1) * NT) + tid) * 2u);
+#pragma unroll
+                    for (int i = 0; i < kMaxPred; ++i) {
+                        if (i < ps.npred && ps.p[i].col == cc) {
+                            const int      cmp = ps.p[i].cmp;
+                            const uint64_t k   = ps.p[i].k;
+#pragma unroll
+                            for (int j = 0; j < U; j += 2) {
+                                if (!pred_holds(cmp, t[j >> 1].x, k)) valid &= ~(1ull << j);
+                                if (!pred_holds(cmp, t[j >> 1].y, k)) valid &= ~(1ull << (j + 1));
+                            }
+                        }
                     }
                 }
-                valid |= (uint64_t)(preds_hold(ps, v0) && !key_is_hot(ps, hot_on, (uint32_t)keys[j]) ? 1u : 0u) << j;
-                valid |= (uint64_t)(preds_hold(ps, v1) && !key_is_hot(ps, hot_on, (uint32_t)keys[j + 1]) ? 1u : 0u) << (j + 1);
+            }
+            if (hot_on) {
+#pragma unroll
+                for (int j = 0; j < U; ++j)
+                    if (((valid >> j) & 1ull) && key_is_hot(ps, true, (uint32_t)keys[j])) valid &= ~(1ull << j);
             }
         } else {
 #pragma unroll
