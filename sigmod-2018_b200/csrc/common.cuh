@@ -35,6 +35,18 @@ void set_last_error(const std::string &msg);
         if (!(cond)) ::b200::fatal(__FILE__, __LINE__, #cond, msg);                   \
     } while (0)
 
+// Checked build (make checked -> lib/libb200join_checked.so, -DB200_CHECKED): device-side bounds checks on the
+// hand-rolled shared-memory structures of the hot kernels (stage buffers, tag tables, warp queues) and on the
+// positions they write to.  compute-sanitizer is closed on the GPU pool this was developed on
+// (profiles/r2_sanitizer_unavailable.txt), so tests/test_checked_build_gpu.py runs a subset of the GPU tests over
+// this library instead; the shipped library compiles the checks out.
+#ifdef B200_CHECKED
+#include <cassert>
+#define B200_DCHECK(cond) assert(cond)
+#else
+#define B200_DCHECK(cond) ((void)0)
+#endif
+
 // Row ids and positions travel as 32-bit integers on the device; every length
 // that becomes a row id is checked against this bound at the API boundary.
 constexpr uint64_t kMaxRows = 0xFFFFFFFFull;

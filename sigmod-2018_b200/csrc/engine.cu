@@ -981,7 +981,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         auto scatter_build = [&](uint32_t *cursor) {
             TimedScope ts("scatter_b");
             if (pred_b) {
-                const OptArgs o{0, nullptr, nullptr, nullptr, B.preds};
+                const OptArgs o{0, nullptr, nullptr, nullptr, B.preds, B.src.n};
                 if (key64) launch_scatter_pred<uint64_t, false>(B.src, bits, cursor, tup_b->ptr, o);
                 else launch_scatter_pred<uint32_t, false>(B.src, bits, cursor, tup_b->ptr, o);
             } else if (pay.carry32 && !key64 && B.src.ids == nullptr && pay.ids[0] == nullptr && B.src.n >= (1u << 18) &&
@@ -1016,7 +1016,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             {
                 TimedScope ts(carry_p >= 0 ? "scatter_pc" : pred_p ? "filter_fused" : "scatter_p");   // pc: carried SUM column
                 const OptArgs oa{opt_cap, d_ovcnt, ov_tup->ptr, carry_p >= 0 ? proj[carry_p].col : nullptr,
-                                 pred_p ? P.preds : PredSet{}};
+                                 pred_p ? P.preds : PredSet{}, (uint64_t)opt_cap * nparts};
                 if (pred_p && key64) launch_scatter_pred<uint64_t, true>(P.src, bits, cur_p, tup_p->ptr, oa);
                 else if (pred_p) launch_scatter_pred<uint32_t, true>(P.src, bits, cur_p, tup_p->ptr, oa);
                 else if (carry_p >= 0 && key64) launch_scatter_carry_c<uint64_t, 1, true>(P.src, bits, cur_p, tup_p->ptr, oa);
@@ -1048,7 +1048,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             {
                 TimedScope ts(pred_p ? "filter_fused" : "scatter_p");
                 if (pred_p) {
-                    const OptArgs o{0, nullptr, nullptr, nullptr, P.preds};
+                    const OptArgs o{0, nullptr, nullptr, nullptr, P.preds, P.src.n};
                     if (key64) launch_scatter_pred<uint64_t, false>(P.src, bits, cur_p, tup_p->ptr, o);
                     else launch_scatter_pred<uint32_t, false>(P.src, bits, cur_p, tup_p->ptr, o);
                 } else if (key64)
@@ -1114,7 +1114,8 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
                                                                   cur_b, cur_p, items, cnt_p, 0u);
             B200_LAUNCH_CHECK();
             tup_p = dev_alloc((size_t)P.src.n * sizeof(Tup64));
-            const OptArgs oa{0, nullptr, nullptr, carry_p >= 0 ? proj[carry_p].col : nullptr, pred_p ? P.preds : PredSet{}};
+            const OptArgs oa{0, nullptr, nullptr, carry_p >= 0 ? proj[carry_p].col : nullptr, pred_p ? P.preds : PredSet{},
+                             P.src.n};
             if (pred_p) launch_scatter_pred<uint64_t, false>(P.src, bits, cur_p, tup_p->ptr, oa);
             else if (carry_p >= 0) launch_scatter_carry_c<uint64_t, 1, false>(P.src, bits, cur_p, tup_p->ptr, oa);
             else launch_scatter<uint64_t>(P.src, bits, cur_p, tup_p->ptr);
@@ -1171,7 +1172,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
                                                                   cur_b, cur_p, items, cnt_p, 0u);
             B200_LAUNCH_CHECK();
             tup_p = dev_alloc((size_t)P.src.n * tsz);
-            const OptArgs oa{0, nullptr, nullptr, nullptr, P.preds};
+            const OptArgs oa{0, nullptr, nullptr, nullptr, P.preds, P.src.n};
             if (pred_p && key64) launch_scatter_pred<uint64_t, false>(P.src, bits, cur_p, tup_p->ptr, oa);
             else if (pred_p) launch_scatter_pred<uint32_t, false>(P.src, bits, cur_p, tup_p->ptr, oa);
             else if (key64) launch_scatter<uint64_t>(P.src, bits, cur_p, tup_p->ptr);

@@ -311,6 +311,7 @@ struct OptArgs {
     void           *ov_out;
     const uint64_t *carry_col;   // CARRY instances only
     PredSet         pred;        // PRED instances only
+    uint64_t        out_rows = 0;   // capacity of `out` in tuples when the caller knows it (checked build only)
 };
 // CARRY: the row-id slot of a tuple carries (uint32)carry_col[row] instead of the row id (a SUM column whose
 // values fit 32 bits travels inside the tuple: the probe side of the multi-GPU exchange plan).  The column is
@@ -557,7 +558,9 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
                 t.rid = (uint32_t)base + li;
             }
             if constexpr (sizeof(KeyT) == 8) t.pad = 0;
-            stage[loc[(uint32_t)keys[j] & mask] + ((rank2[j >> 1] >> (16 * (j & 1))) & 0xFFFFu)] = t;
+            const uint32_t slot = loc[(uint32_t)keys[j] & mask] + ((rank2[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+            B200_DCHECK(slot < (uint32_t)(NT * U));
+            stage[slot] = t;
         }
     }
     // ---- (4) the reservations have arrived by now ----
@@ -586,8 +589,11 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     if constexpr (OPT) over = *s_over != 0u;
     if (!over) {
         auto put = [&](uint32_t i) {
-            const TupT t = stage[i];
-            out[gdelta[(uint32_t)t.key & mask] + i] = t;
+            const TupT     t   = stage[i];
+            const uint32_t pos = gdelta[(uint32_t)t.key & mask] + i;
+            if constexpr (OPT) B200_DCHECK(pos < ((((uint32_t)t.key & mask) + 1u) * opt.opt_cap));
+            B200_DCHECK(opt.out_rows == 0 || pos < opt.out_rows);
+            out[pos] = t;
         };
         if constexpr (FULL && !PRED) {
 #pragma unroll
@@ -601,8 +607,13 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
                 const TupT     t   = stage[i];
                 const uint32_t b   = (uint32_t)t.key & mask;
                 const uint32_t pos = gdelta[b] + i;
-                if (pos >= (b + 1u) * opt.opt_cap) static_cast<TupT *>(opt.ov_out)[ovdelta[b] + i] = t;
-                else out[pos] = t;
+                if (pos >= (b + 1u) * opt.opt_cap) {
+                    B200_DCHECK((uint64_t)ovdelta[b] + i < src.n);   // the overflow array holds src.n tuples
+                    static_cast<TupT *>(opt.ov_out)[ovdelta[b] + i] = t;
+                } else {
+                    B200_DCHECK(pos >= b * opt.opt_cap);
+                    out[pos] = t;
+                }
             }
         }
     }
@@ -1039,6 +1050,7 @@ hash_join_kernel(const JoinArgs a) {
     auto drain = [&](uint32_t have, uint32_t take) {
         if constexpr (MODE != MODE_COUNT) {
             const bool     mine = (uint32_t)lane < take;
+            B200_DCHECK(take <= have && have <= (uint32_t)kWarpQueue);
             const uint2    e    = wq[wid][mine ? have - take + lane : 0];
             uint32_t       brid = 0;
             if (mine) {
@@ -1539,6 +1551,7 @@ tag_join_kernel(const JoinArgs a) {
     // pop `take` (<= 32) entries, one per lane: a match entry is completed, a chain entry is walked
     // and the matches it finds are pushed back (or completed in place when the queue is full)
     auto drain = [&](uint32_t take) {
+        B200_DCHECK(take <= 32u && take <= queued && queued <= (uint32_t)QN);
         queued -= take;
         const bool  mine = lane < take;
         const uint32_t qa = my_q + (queued + (mine ? lane : 0u)) * QE;
@@ -1551,6 +1564,7 @@ tag_join_kernel(const JoinArgs a) {
         const uint32_t t = (e.x >> 16) & 0x7FFFu;
         // ---- match entries ----
         bool is_match = mine && (e.x & kQMatch) != 0u;
+        B200_DCHECK(!is_match || (e.x & kIdxMask) < s_item[2]);   // a position inside the build chunk
         [[maybe_unused]] uint32_t brid64 = 0;
         if constexpr (K64) {
             if (is_match) {   // verify the candidate: one 16-byte load gives the key and the row id / carried value
@@ -1599,6 +1613,7 @@ tag_join_kernel(const JoinArgs a) {
         uint32_t pos     = e.x & kIdxMask;
         while (__any_sync(kFullMask, walking)) {
             uint32_t w = kEmptyWord;
+            B200_DCHECK(!walking || pos < a.cap);
             if (walking) w = lds_u32(s_next + pos * 4u);
             const bool     hit = walking && (w >> kTagShift) == t;
             const uint32_t bal = __ballot_sync(kFullMask, hit);
@@ -1715,6 +1730,7 @@ tag_join_kernel(const JoinArgs a) {
                 if (i < b_count) {
                     uint32_t h, t;
                     slot_tag(bk[u], h, t);
+                    B200_DCHECK(h <= smask && i < a.cap && i <= kIdxMask && t <= 0x7FFFu);
                     uint32_t old = slots[h], assumed;
                     do {
                         assumed           = old;
@@ -1747,6 +1763,7 @@ tag_join_kernel(const JoinArgs a) {
                 if (act) {
                     // queued <= 31 here and a probe adds <= 32 entries: no overflow (QN = 64)
                     if (need) {
+                        B200_DCHECK(queued + (uint32_t)__popc(act & lt) < (uint32_t)QN);
                         const uint32_t qs = my_q + (queued + __popc(act & lt)) * QE;
                         sts_v2(qs, (is_m ? kQMatch : 0u) | (t[j] << 16) | (w[j] & 0xFFFFu), rid[j]);
                         if constexpr (K64) sts_v2(qs + 8u, (uint32_t)key[j], (uint32_t)((uint64_t)key[j] >> 32));

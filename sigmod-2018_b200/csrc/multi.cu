@@ -91,7 +91,8 @@ struct MultiPlan {
     // inputs of the step in flight (the overflow pass of finish() needs them)
     const uint64_t *in_bk = nullptr, *in_bp = nullptr, *in_pk = nullptr, *in_pp = nullptr;
     bool            pending = false;
-    // CUDA graph of the step (B200_MULTI_GRAPH=1): valid while the input pointers stay the same
+    // CUDA graph of the step (on by default with several GPUs, B200_MULTI_GRAPH=0/1): valid while the input pointers
+    // stay the same
     cudaGraphExec_t graph = nullptr;
     const uint64_t *g_in[4] = {nullptr, nullptr, nullptr, nullptr};
     int             use_graph = 0;
@@ -585,6 +586,7 @@ b200_multi *b200_multi_create(const b200_multi_config *cfg) {
     B200_CUDA(cudaEventCreateWithFlags(&m->ev_x, cudaEventDisableTiming));
     for (int k = 0; k < kMaxChunks; ++k) B200_CUDA(cudaEventCreateWithFlags(&m->ev_chunk[k], cudaEventDisableTiming));
     m->peer[m->rank] = m->shared;
+    m->use_graph = m->world > 1;   // measured at 8 GPUs: 0.612 -> 0.579 ms per config-2 step
     if (const char *g = getenv("B200_MULTI_GRAPH")) m->use_graph = atoi(g);
     B200_CUDA(cudaDeviceSynchronize());
     return reinterpret_cast<b200_multi *>(m);

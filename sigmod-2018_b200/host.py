@@ -122,7 +122,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path else LIB_PATH
+    # B200_LIB selects another build of the same library (the checked build, lib/libb200join_checked.so)
+    p = Path(path) if path else Path(os.environ.get("B200_LIB") or LIB_PATH)
     if not p.exists():
         raise ImportError(
             f"{p} is missing: build it with `make -C sigmod-2018_b200/csrc` "

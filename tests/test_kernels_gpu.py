@@ -602,3 +602,33 @@ def test_join_64bit_keys_that_share_their_low_32_bits(gpu, orc):
     assert m == len(o_r) and np.array_equal(sorted_pairs(r, s_), sorted_pairs(o_r, o_s))
     p = orc.synth_column(n, 1, 0, 9)
     assert gpu.join_sum(kr, ks, [p, p], [0, 1]) == orc.join_sum(kr, ks, [p, p], [0, 1], 4)
+
+
+# ---- repeatability: the same join many times over (what a race in the tile pipeline, the shared-memory CAS chains
+#      or the warp queues would disturb; compute-sanitizer's racecheck is not available on the GPU pool) ----
+@pytest.mark.parametrize("wide", [False, True])
+def test_join_sum_is_repeatable(gpu, orc, wide):
+    nr, ns = 1 << 18, (1 << 22) + 12345
+    kr = orc.synth_column(nr, 0, 18, gpu.SEED_R)
+    ks = orc.synth_column(ns, 3, 1 << 19, gpu.SEED_S)      # every build key is probed ~8 times, half the probes miss
+    if wide:
+        spread = lambda k: k | ((k * np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFF00000000000))
+        kr, ks = spread(kr), spread(ks)
+    pr, ps = orc.synth_column(nr, 1, 0, 7), orc.synth_column(ns, 1, 0, 8)
+    want, wm = orc.join_sum(kr, ks, [pr, ps], [0, 1], 4)
+    cols = [gpu.DeviceColumn(len(a)) for a in (kr, ks, pr, ps)]
+    try:
+        for c, a in zip(cols, (kr, ks, pr, ps)):
+            gpu.lib().b200_copy_to_device(c.ptr, a.ctypes.data, 8 * len(a))
+        max_key = int(max(kr.max(), ks.max()))
+        for register in (False, True):      # gathered SUM columns, then carried in the tuples
+            if register:
+                gpu.lib().b200_register_device_column(cols[2].ptr, cols[2].ptr, nr, int(pr.max()))
+                gpu.lib().b200_register_device_column(cols[3].ptr, cols[3].ptr, ns, int(ps.max()))
+            for rep in range(20):
+                got, m = gpu.join_sum_device(cols[0].ptr, nr, cols[1].ptr, ns, [cols[2].ptr, cols[3].ptr], [0, 1], max_key)
+                assert (got, m) == (want, wm), (register, rep)
+    finally:
+        gpu.lib().b200_unregister_all()
+        for c in cols:
+            c.free()
