@@ -501,7 +501,7 @@ CONFIG3_QUERY = "0 1 2 3|0.1=1.0&1.1=2.0&2.1=3.0&0.3>2499&0.3<7500&0.4=1|0.2 1.2
 def config3_shape(scale_bits: int):
     f = 200_000_000 >> scale_bits
     d1, d2, d3 = (1 << 24) >> scale_bits, (1 << 20) >> min(scale_bits, 8), (1 << 16) >> min(scale_bits, 4)
-    # (rows, [(kind, k, seed), ...]) — the same columns `scripts/run_config3.sh` hands to the reference driver
+    # (rows, [(kind, k, seed), ...]) — the columns the reference driver (oracle/_ref/ref_driver) is handed as well
     return [(f, [("iota", 0, 0), ("uni", d1, 11), ("pay", 0, 12), ("uni", 10000, 13), ("uni", 4, 14)]),
             (d1, [("iota", 0, 0), ("uni", d2, 21), ("pay", 0, 22)]),
             (d2, [("iota", 0, 0), ("uni", d3, 31), ("pay", 0, 32)]),

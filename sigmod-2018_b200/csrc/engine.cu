@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstring>
 #include <chrono>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <unordered_map>
@@ -443,10 +444,43 @@ void unregister_all_columns() {
 // ---------------------------------------------------------------------------
 static cudaStream_t launch_stream() { return ctx().stream; }
 
+// Dynamic shared memory above 48 KB is opt-in per kernel function.  The attribute is raised ONCE per (device, kernel)
+// to everything the SM offers beyond the kernel's static shared memory: worker threads launch the same instance with
+// different sizes concurrently, and re-setting the attribute to each launch's own size let one thread lower it under
+// another thread's launch ("invalid argument" at 4 workers on config 5 x100).
+static std::mutex                               g_smem_mu;
+static std::map<std::pair<int, const void *>, size_t> g_smem_max;
 template <typename KernelT>
 static void allow_smem(KernelT kernel, size_t bytes) {
-    if (bytes > 48 * 1024)
-        B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (bytes <= 48 * 1024) return;
+    const int    dev = ctx().device;
+    const void  *fn  = reinterpret_cast<const void *>(kernel);
+    size_t       max_dyn;
+    {
+        std::lock_guard<std::mutex> lk(g_smem_mu);
+        auto it = g_smem_max.find({dev, fn});
+        if (it == g_smem_max.end()) {
+            cudaFuncAttributes fa{};
+            int                optin = 0;
+            B200_CUDA(cudaFuncGetAttributes(&fa, kernel));
+            B200_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+            const size_t m = (size_t)optin > fa.sharedSizeBytes ? (size_t)optin - fa.sharedSizeBytes : 0;
+            B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m));
+            it = g_smem_max.emplace(std::make_pair(dev, fn), m).first;
+        }
+        max_dyn = it->second;
+    }
+    if (bytes > max_dyn) {
+        char msg[160];
+        snprintf(msg, sizeof(msg), "a kernel needs %zu bytes of shared memory, the SM offers %zu", bytes, max_dyn);
+        fatal(__FILE__, __LINE__, "shared memory", msg);
+    }
+}
+// shared memory one CTA may use (dynamic + static), with room for the kernels' few static words
+static size_t smem_budget() {
+    int optin = 0;
+    B200_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx().device));
+    return (size_t)optin - 2048;
 }
 
 constexpr int kPartNT = 512;
@@ -946,7 +980,12 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
                 pay.ids[0]   = proj[first].ids;
                 npay         = 1;   // selects the payload-aware scatter
             } else if (!key64) {   // (16-byte tuples leave no room to stage payload columns beside them)
-                for (int k = 0; k < nproj && npay < 2; ++k) {
+                // 8192-tuple tiles of radix_scatter_pay_kernel: 8 + 8 per staged column bytes each, beside three bin
+                // arrays (2^12 partitions leave room for one column, fewer partitions for two)
+                int max_pay = 2;
+                while (max_pay > 0 && 8192 * (sizeof(Tup32) + 8 * (size_t)max_pay) + 3 * (size_t)nparts * 4 > smem_budget())
+                    --max_pay;
+                for (int k = 0; k < nproj && npay < max_pay; ++k) {
                     if (proj[k].side != side_b) continue;
                     part_vals[k]  = dev_alloc((size_t)B.src.n * sizeof(uint64_t));
                     pay.col[npay] = proj[k].col;

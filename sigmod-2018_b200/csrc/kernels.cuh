@@ -608,7 +608,7 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
                 const uint32_t b   = (uint32_t)t.key & mask;
                 const uint32_t pos = gdelta[b] + i;
                 if (pos >= (b + 1u) * opt.opt_cap) {
-                    B200_DCHECK((uint64_t)ovdelta[b] + i < src.n);   // the overflow array holds src.n tuples
+                    B200_DCHECK((uint32_t)(ovdelta[b] + i) < src.n);   // the overflow array holds src.n tuples (32-bit wrap-around arithmetic)
                     static_cast<TupT *>(opt.ov_out)[ovdelta[b] + i] = t;
                 } else {
                     B200_DCHECK(pos >= b * opt.opt_cap);
@@ -1514,6 +1514,7 @@ tag_join_kernel(const JoinArgs a) {
 #pragma unroll
     for (int k = 0; k < NPA; ++k) my_sum[k] = pend[k] = 0;
     uint32_t b_start = 0;
+    [[maybe_unused]] uint32_t b_cnt = 0;   // build tuples of the current item (checked build)
     uint32_t queued  = 0;   // warp-uniform number of entries in this warp's queue
 
     // one match (build tuple at position pos of the chunk, probe row prid), handled in place
@@ -1564,7 +1565,7 @@ tag_join_kernel(const JoinArgs a) {
         const uint32_t t = (e.x >> 16) & 0x7FFFu;
         // ---- match entries ----
         bool is_match = mine && (e.x & kQMatch) != 0u;
-        B200_DCHECK(!is_match || (e.x & kIdxMask) < s_item[2]);   // a position inside the build chunk
+        B200_DCHECK(!is_match || (e.x & kIdxMask) < b_cnt);   // a position inside the build chunk
         [[maybe_unused]] uint32_t brid64 = 0;
         if constexpr (K64) {
             if (is_match) {   // verify the candidate: one 16-byte load gives the key and the row id / carried value
@@ -1679,6 +1680,7 @@ tag_join_kernel(const JoinArgs a) {
         const uint32_t b_count = s_item[2];
         const uint32_t p_start = s_item[3], p_count = s_item[4];
         const uint32_t item_w  = s_item[5];
+        b_cnt                  = b_count;
 
         // (a padding lane of the last round is recognised by its index, never by a row-id sentinel: the row-id slot
         // may carry an arbitrary 32-bit SUM value)

@@ -27,7 +27,7 @@ SUBSET = ("test_join_pairs_shapes and 100000 or test_join_sum_zipf_probe_side an
 def test_subset_passes_on_the_checked_build():
     assert CHECKED.exists(), f"{CHECKED} is missing: make -C sigmod-2018_b200/csrc checked (or __graft_entry__.build())"
     env = dict(os.environ, B200_LIB=str(CHECKED))
-    p = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider",
+    p = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-s", "-p", "no:cacheprovider",
                         "tests/test_kernels_gpu.py", "tests/test_multi_plan_gpu.py", "tests/test_filter_fusion_gpu.py",
                         "tests/test_operators_gpu.py", "-k", SUBSET],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)

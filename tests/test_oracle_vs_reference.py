@@ -67,7 +67,7 @@ def test_reference_loses_pairs_at_16_threads(orc, ref):
     buckets, structs.h:11) RadixHashJoin intermittently returns ~15/16 of the pairs (about one bucket's worth
     is missing); 2, 4 and 8 threads were exact in every run.  (Found at
     BASELINE config 3 full size, where the 16-thread reference disagrees with an independent numpy evaluation
-    that the 4/8-thread reference and the GPU library both match; scripts/run_config3.sh.)  bench.py therefore
+    that the 4/8-thread reference and the GPU library both match; bench.py --config 3.)  bench.py therefore
     times the reference with at most 8 threads."""
     g = rng(5)
     kr = g.integers(0, 1 << 16, 50000, dtype=np.uint64)
@@ -88,7 +88,7 @@ def test_reference_loses_tuples_of_tiny_relations(orc, ref):
     build) drops tuples when a relation has about as few tuples as there are threads, so RadixHashJoin returns
     too few pairs.  Found on BASELINE config 5 (small.work scaled x10): a filter leaves 6 rows, the next
     join loses 6 % of its result and the reference prints 20413494 8128195 where brute force, the oracle and
-    the GPU library give 21623406 8897701 (scripts/run_config5.sh).  The oracle follows the serial variant
+    the GPU library give 21623406 8897701 (bench.py --config 5 --factor 10 --check-reference).  The oracle follows the serial variant
     (preprocess.c:302-362), which is the specification; here it is checked against brute force."""
     g = rng(1)
     found = 0
