@@ -319,9 +319,28 @@ static void pool_stop(void) {
     for (int w = 0; w < g_pool.nworkers; ++w) pthread_join(g_pool.th[w], NULL);
 }
 
+/* B200_TIMING=2: every query's time and the library's kernel timers on stderr (one worker: the timers are per stream) */
+static void execute_query_timed(query_t *q, int i) {
+    static const char *names[] = {"filter", "hist_b", "hist_p", "scatter_b", "scatter_p", "scatter_pc", "filter_fused",
+                                  "join", "join_write", "overflow"};
+    b200_set_profiling(1);               /* forgets the timers of the previous query */
+    const double t0 = now_s();
+    execute_query(q);
+    char  buf[512];
+    char *p = buf;
+    for (unsigned k = 0; k < sizeof names / sizeof names[0]; ++k) {
+        const double ms = b200_last_kernel_ms(names[k]);
+        if (ms >= 0) p += sprintf(p, " %s=%.3f", names[k], ms);
+    }
+    fprintf(stderr, "b200_engine: query %d: %.3f ms |%s | %s\n", i, (now_s() - t0) * 1e3, buf, q->line);
+}
+
 static void run_batch(query_t *queries, int n) {
     if (g_pool.nworkers <= 1) {
-        for (int i = 0; i < n; ++i) execute_query(&queries[i]);
+        for (int i = 0; i < n; ++i) {
+            if (g_timing > 1) execute_query_timed(&queries[i], i);
+            else execute_query(&queries[i]);
+        }
     } else if (n > 0) {
         pthread_mutex_lock(&g_pool.mu);
         g_pool.queries  = queries;
@@ -358,7 +377,7 @@ int main(int argc, char **argv) {
         if (load_relation(buff, &g_map[g_nrel])) return 1;
         ++g_nrel;
     }
-    g_timing  = getenv("B200_TIMING") != NULL;
+    g_timing  = getenv("B200_TIMING") ? (atoi(getenv("B200_TIMING")) > 1 ? 2 : 1) : 0;
     double t0 = now_s();
     b200_init(-1);
     double t1 = now_s();
@@ -368,6 +387,7 @@ int main(int argc, char **argv) {
         if (shard_relations()) { fprintf(stderr, "b200_engine: cannot shard over %d GPUs: %s\n", g_gpus, b200_last_error()); return 1; }
         workers = 1;                            /* the multi-GPU plan runs one query at a time over all GPUs */
     }
+    if (g_timing > 1) b200_set_profiling(1);
     if (g_timing) fprintf(stderr, "b200_engine: CUDA start-up %.3f s, upload of %d relations %.3f s\n", t1 - t0, g_nrel, now_s() - t1);
 
     if (workers > 1) pool_start(workers);

@@ -185,6 +185,9 @@ int b200_set_tuning(int radix_bits, int force_key64) {
 
 int b200_set_profiling(int on) {
     set_profiling(on != 0);
+    // (re-)enabling forgets the calling thread's timers: what b200_last_kernel_ms reports afterwards was recorded since
+    if (on)
+        for (auto &kv : ctx().timers) kv.second.used = false;
     return 0;
 }
 

@@ -70,6 +70,7 @@ static void init_device(int device) {
     if (const char *v = getenv("B200_FORCE_KEY64")) t.force_key64 = atoi(v);
     if (const char *v = getenv("B200_CAP32")) t.cap32 = (uint32_t)atoi(v);
     if (const char *v = getenv("B200_CAP64")) t.cap64 = (uint32_t)atoi(v);
+    if (const char *v = getenv("B200_TAG64")) t.tag64 = atoi(v);
     if (const char *v = getenv("B200_SLICE")) t.slice = (uint32_t)atoi(v);
     if (const char *v = getenv("B200_DEBUG")) t.debug = atoi(v);
     if (const char *v = getenv("B200_SCATTER_CFG")) t.scatter_cfg = atoi(v);
@@ -795,8 +796,10 @@ static void launch_join_tag64(const JoinArgs &a, int mode) {
         launch_persistent_join_nt(tag_join_kernel<kJoin64NT, 1, kJoin64G, MODE_SUM, kMaxProj, false, true>, a, smem, kJoin64NT);
 }
 
-static void launch_join(const JoinArgs &a, bool key64, bool direct, int mode) {
-    if (key64 && !direct) {
+static void launch_join(const JoinArgs &a, bool key64, bool direct, int mode, bool chained64 = false) {
+    if (key64 && !direct && chained64) {
+        launch_join64<false>(a, mode, TableView<uint64_t>::bytes(a.cap, a.slots_log2));
+    } else if (key64 && !direct) {
         launch_join_tag64(a, mode);
     } else if (key64) {
         const size_t smem = TableView<uint64_t>::bytes(a.cap, a.slots_log2);
@@ -851,11 +854,11 @@ PartitionOut run_partition(const KeyVec &kv, int bits) {
 // Radix bits of a partitioned join: the fewest partitions whose build side — expected largest partition under a
 // uniform split, mean + 5 sigma; a larger one is split into build chunks — fits one shared-memory table.  Fewer
 // partitions mean longer runs per scatter tile.  The tag table (32-bit keys) needs radix_bits + slots_log2 >= 17.
-int auto_radix_bits(uint64_t n_build, bool key64) {
+int auto_radix_bits(uint64_t n_build, bool key64, bool chained64) {
     // (both key widths use the tag table, cap32 build tuples per table; only 32-bit keys need radix_bits +
-    // slots_log2 >= 17 so that slot and tag identify the key)
+    // slots_log2 >= 17 so that slot and tag identify the key.  chained64: the chained table of 64-bit keys, cap64)
     const Tuning  &t          = tuning();
-    const uint32_t cap        = t.cap32;
+    const uint32_t cap        = chained64 ? t.cap64 : t.cap32;
     const uint32_t slots_log2 = tag_slots_log2_for(cap);
     const int      min_bits   = key64 ? 1 : std::max(2, 17 - (int)slots_log2);
     if (t.radix_bits > 0) return std::max(min_bits, std::min(t.radix_bits, t.max_bits));
@@ -892,10 +895,12 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     // 32-bit keys (8-byte partition tuples, tag-table kernel) when every key fits
     const bool key64 = direct || t.force_key64 || B.max_val > 0xFFFFFFFFull || P.max_val > 0xFFFFFFFFull;
     // unpartitioned joins run the chained table (16-bit links, keys in shared memory), partitioned ones the tag table
-    const uint32_t cap = direct ? t.cap64 : t.cap32;
-    B200_REQUIRE(cap >= 32 && cap <= (direct ? 65534u : 32766u), "table capacity out of range");
-    const uint32_t slots_log2 = direct ? TableView<uint64_t>::slots_log2_for(cap) : tag_slots_log2_for(cap);
-    const int bits = direct ? 0 : auto_radix_bits(B.src.n, key64);
+    const bool chained64 = key64 && !direct && !t.tag64;   // the chained table for partitioned 64-bit-key joins
+    const bool chained   = direct || chained64;
+    const uint32_t cap = chained ? t.cap64 : t.cap32;
+    B200_REQUIRE(cap >= 32 && cap <= (chained ? 65534u : 32766u), "table capacity out of range");
+    const uint32_t slots_log2 = chained ? TableView<uint64_t>::slots_log2_for(cap) : tag_slots_log2_for(cap);
+    const int bits = direct ? 0 : auto_radix_bits(B.src.n, key64, chained64);
 
     JoinArgs a;
     memset(&a, 0, sizeof(a));
@@ -955,7 +960,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         const size_t tsz = key64 ? sizeof(Tup64) : sizeof(Tup32);
         // Histogram-free probe side (fused SUM, 32-bit keys): every partition owns a region a few percent
         // above the uniform expectation; what does not fit overflows and is partitioned exactly afterwards.
-        opt = t.opt_partition && P.src.n >= (1u << 20) && P.src.n <= (1u << 30);
+        opt = t.opt_partition && P.src.n >= (1u << 20) && P.src.n <= (1u << 30) && !chained64;
         if (opt) opt_cap = opt_region_cap(P.src.n, bits);
         tup_b = dev_alloc((size_t)B.src.n * tsz);
         tup_p = dev_alloc(opt ? (size_t)opt_cap * nparts * tsz : (size_t)P.src.n * tsz);
@@ -973,7 +978,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
                 }
             // one build-side projection whose column is known to hold 32-bit values: carry it in the row-id slot
             // (no other projection reads the build row id then)
-            if (n_build == 1 && t.carry32 && known_column_max(proj[first].col) <= 0xFFFFFFFFull) {
+            if (n_build == 1 && t.carry32 && !chained64 && known_column_max(proj[first].col) <= 0xFFFFFFFFull) {
                 carry_k      = first;
                 pay.carry32  = 1;
                 pay.col[0]   = proj[first].col;
@@ -1119,7 +1124,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         }
         {
             TimedScope ts("join");
-            launch_join(a, key64, direct, MODE_SUM);
+            launch_join(a, key64, direct, MODE_SUM, chained64);
         }
         auto read_back = [&]() {
             B200_CUDA(cudaMemcpyAsync(c.h_scratch, d_u64, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
@@ -1159,7 +1164,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             else if (carry_p >= 0) launch_scatter_carry_c<uint64_t, 1, false>(P.src, bits, cur_p, tup_p->ptr, oa);
             else launch_scatter<uint64_t>(P.src, bits, cur_p, tup_p->ptr);
             a.tup_p = tup_p->ptr;
-            launch_join(a, key64, direct, MODE_SUM);
+            launch_join(a, key64, direct, MODE_SUM, chained64);
             read_back();
             if (pred_p) valid_p = *reinterpret_cast<uint32_t *>(c.h_scratch + 18);
             res.valid_r = swapped ? valid_p : valid_b;
@@ -1178,7 +1183,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
             launch_scatter_tuples(ov_tup->as<uint64_t>(), n_over, bits, cur_p, ov_part->ptr);
             B200_CUDA(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), c.stream));
             a.tup_p = ov_part->ptr;
-            launch_join(a, key64, direct, MODE_SUM);
+            launch_join(a, key64, direct, MODE_SUM, chained64);
             read_back();
         }
         res.m = c.h_scratch[0];
@@ -1230,7 +1235,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
     a.item_count         = item_count->as<unsigned long long>();
     {
         TimedScope ts("join");
-        launch_join(a, key64, direct, MODE_COUNT);
+        launch_join(a, key64, direct, MODE_COUNT, chained64);
     }
     res.m = read_counter(a.total);
     if (direct && pred_p) {
@@ -1246,7 +1251,7 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         a.out_p = out_p->as<uint32_t>();
         B200_CUDA(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), c.stream));
         TimedScope ts("join_write");
-        launch_join(a, key64, direct, MODE_WRITE);
+        launch_join(a, key64, direct, MODE_WRITE, chained64);
     }
     res.r_ids = swapped ? out_p : out_b;
     res.s_ids = swapped ? out_b : out_p;

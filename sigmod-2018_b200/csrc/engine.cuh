@@ -56,6 +56,8 @@ struct Tuning {
     int      early_mat   = 1;        // carry build-side SUM projections through the scatter
     int      scatter_cfg = 1;        // see engine.cu PartCfg
     int      max_bits    = 12;
+    int      tag64       = 1;        // partitioned 64-bit-key joins: 1 = tag table with verified candidates (histogram-free
+                                     // probe side, carried SUM values), 0 = chained table with the keys in shared memory
     int      debug       = 0;
 };
 Tuning &tuning();
@@ -114,7 +116,7 @@ void       stage_scatter_build(const uint64_t *d_keys, uint64_t n, uint32_t rid_
                                uint64_t *const *pay_dst, int phase = 0);
 void       stage_scatter_probe(const uint64_t *d_keys, uint64_t n, int bits, uint32_t *d_cursor, void *d_tup_out);
 uint32_t   opt_region_cap(uint64_t n_probe, int bits);
-int        auto_radix_bits(uint64_t n_build, bool key64);
+int        auto_radix_bits(uint64_t n_build, bool key64, bool chained64 = false);
 void       stage_scatter_probe_opt(const uint64_t *d_keys, uint64_t n, int bits, uint32_t opt_cap, uint32_t *d_cursor,
                                    void *d_tup_out, void *d_ov, uint32_t *d_ovcnt,
                                    const uint64_t *carry_col = nullptr);
