@@ -395,13 +395,15 @@ int   b200_stage_exchange_segments(const void *d_src_tup, int npay,
  * one GPU: a process per GPU (peers' memory through CUDA IPC: b200_multi_export
  * / b200_multi_connect_ipc) or a host thread per GPU inside one process
  * (b200_multi_connect_ptr, b200_join_sum_multi).  Ranks synchronise through
- * epoch flags in each other's memory; a step enqueues device work only and may
- * be captured in a CUDA graph ($B200_MULTI_GRAPH=1).
+ * epoch flags in each other's memory; a step enqueues device work only and is
+ * captured in a CUDA graph when there are several ranks ($B200_MULTI_GRAPH=0/1).
  *   B200_PLAN_BROADCAST  small build side (config 2): every rank partitions its
- *       build shard once into its region of a rank-major build buffer, its copy
- *       engines push the region to every peer chunk by chunk, the probe shard
- *       is partitioned locally and never moves, the join overlaps the tail of
- *       the broadcast (it waits per partition for the chunks holding its runs).
+ *       build shard once into its region of a rank-major build buffer
+ *       (histogram in the region's head), its copy engines push the region to
+ *       every peer with one copy and one flag each, the probe shard is
+ *       partitioned locally meanwhile and never moves, the join waits per
+ *       partition for the regions holding its runs.  ($B200_BCAST=pull: every
+ *       rank fetches its peers' regions with a TMA kernel instead; slower.)
  *   B200_PLAN_EXCHANGE   radix-sharded all-to-all (config 4): both shards are
  *       partitioned locally (the probe shard in chunks), the exchange kernel
  *       stores every partition into its owner's receive buffer over NVLink (the

@@ -1517,65 +1517,21 @@ tag_join_kernel(const JoinArgs a) {
     [[maybe_unused]] uint32_t b_cnt = 0;   // build tuples of the current item (checked build)
     uint32_t queued  = 0;   // warp-uniform number of entries in this warp's queue
 
-    // one match (build tuple at position pos of the chunk, probe row prid), handled in place
-    auto handle_inline = [&](uint32_t pos, uint32_t prid, KeyT pkey) {
-        KeyT           bkey;
-        const uint32_t brid = (K64 || MODE != MODE_COUNT) ? build_rid(bphys(b_start + pos), bkey) : 0u;
-        if constexpr (K64) {
-            if (bkey != pkey) return;   // the tag matched, the key does not
-        }
-        ++my_matches;
-        if constexpr (MODE != MODE_COUNT) {
-            if constexpr (MODE == MODE_SUM) {
-#pragma unroll
-                for (int k = 0; k < NPA; ++k) {
-                    if (k < a.nproj) {
-                        if (a.proj[k].part_vals == B200_PROJ_IN_RID) {
-                            my_sum[k] += a.proj[k].side == 0 ? brid : prid;   // the slot carries the value
-                        } else if (a.proj[k].part_vals) {
-                            my_sum[k] += a.proj[k].part_vals[bphys(b_start + pos)];
-                        } else {
-                            const uint32_t r  = a.proj[k].side == 0 ? brid : prid;
-                            const uint32_t rr = a.proj[k].ids ? __ldg(a.proj[k].ids + r) : r;
-                            my_sum[k] += ld_gather_u64(a.proj[k].col + rr);
-                        }
-                    }
-                }
-            } else {
-                const uint32_t pos_out    = atomicAdd(&s_cursor, 1u);
-                a.out_b[s_base + pos_out] = brid;
-                a.out_p[s_base + pos_out] = prid;
-            }
-        }
-    };
-
-    // pop `take` (<= 32) entries, one per lane: a match entry is completed, a chain entry is walked
-    // and the matches it finds are pushed back (or completed in place when the queue is full)
-    auto drain = [&](uint32_t take) {
-        B200_DCHECK(take <= 32u && take <= queued && queued <= (uint32_t)QN);
-        queued -= take;
-        const bool  mine = lane < take;
-        const uint32_t qa = my_q + (queued + (mine ? lane : 0u)) * QE;
-        const uint2 e    = lds_v2(qa);
-        [[maybe_unused]] KeyT ekey = 0;
-        if constexpr (K64) {
-            const uint2 kk = lds_v2(qa + 8u);
-            ekey           = (uint64_t)kk.x | ((uint64_t)kk.y << 32);
-        }
-        const uint32_t t = (e.x >> 16) & 0x7FFFu;
-        // ---- match entries ----
-        bool is_match = mine && (e.x & kQMatch) != 0u;
-        B200_DCHECK(!is_match || (e.x & kIdxMask) < b_cnt);   // a position inside the build chunk
+    // complete up to 32 match entries, one per lane (is_match: this lane holds one): verification of a 64-bit
+    // candidate, then the SUM gathers / the pair / the count.  Payload loads are left in flight (pend[]) and consumed
+    // by the next call, so a run of calls keeps a warp's worth of gathers outstanding.
+    auto complete = [&](bool is_match, uint32_t ex, uint32_t ey, [[maybe_unused]] KeyT ekey) {
+        B200_DCHECK(!is_match || (ex & kIdxMask) < b_cnt);   // a position inside the build chunk
         [[maybe_unused]] uint32_t brid64 = 0;
         if constexpr (K64) {
             if (is_match) {   // verify the candidate: one 16-byte load gives the key and the row id / carried value
                 KeyT bkey;
-                brid64   = build_rid(bphys(b_start + (e.x & kIdxMask)), bkey);
+                brid64   = build_rid(bphys(b_start + (ex & kIdxMask)), bkey);
                 is_match = bkey == ekey;
             }
         }
         if constexpr (MODE == MODE_SUM) {
-            const uint32_t bpos = bphys(b_start + (e.x & kIdxMask));
+            const uint32_t bpos = bphys(b_start + (ex & kIdxMask));
             uint32_t       brid = 0;
             if constexpr (K64) brid = brid64;
             else if (is_match && a.need_brid) brid = SEG ? __ldcg(&tup_b[bpos].rid) : tup_b[bpos].rid;
@@ -1585,11 +1541,11 @@ tag_join_kernel(const JoinArgs a) {
                 pend[k] = 0;
                 if (k < a.nproj && is_match) {
                     if (a.proj[k].part_vals == B200_PROJ_IN_RID) {
-                        pend[k] = a.proj[k].side == 0 ? brid : e.y;   // the row-id slot carries the value
+                        pend[k] = a.proj[k].side == 0 ? brid : ey;   // the row-id slot carries the value
                     } else if (a.proj[k].part_vals) {
                         pend[k] = a.proj[k].part_vals[bpos];   // dense window of this partition, L2-resident
                     } else {
-                        const uint32_t r  = a.proj[k].side == 0 ? brid : e.y;
+                        const uint32_t r  = a.proj[k].side == 0 ? brid : ey;
                         const uint32_t rr = a.proj[k].ids ? __ldg(a.proj[k].ids + r) : r;
                         pend[k]           = ld_gather_u64(a.proj[k].col + rr);
                     }
@@ -1603,31 +1559,68 @@ tag_join_kernel(const JoinArgs a) {
             pos = __shfl_sync(kFullMask, pos, 0);
             if (is_match) {
                 const uint32_t o  = pos + __popc(bal & lt);
-                a.out_b[s_base + o] = K64 ? brid64 : tup_b[bphys(b_start + (e.x & kIdxMask))].rid;
-                a.out_p[s_base + o] = e.y;
+                a.out_b[s_base + o] = K64 ? brid64 : tup_b[bphys(b_start + (ex & kIdxMask))].rid;
+                a.out_p[s_base + o] = ey;
             }
         } else {
             my_matches += is_match ? 1u : 0u;
         }
+    };
+    // entry `slot` of this warp's queue
+    auto q_load = [&](uint32_t slot, uint2 &e, KeyT &ekey) {
+        const uint32_t qa = my_q + slot * QE;
+        e                 = lds_v2(qa);
+        ekey              = 0;
+        if constexpr (K64) {
+            const uint2 kk = lds_v2(qa + 8u);
+            ekey           = (uint64_t)kk.x | ((uint64_t)kk.y << 32);
+        }
+    };
+
+    // pop `take` (<= 32) entries, one per lane: a match entry is completed, a chain entry is walked and the matches
+    // it finds are pushed back as match entries.  When the queue cannot take another step's worth of them, the walk
+    // pauses and the newest entries — all of them matches this walk pushed — are completed, 32 at a time with every
+    // lane's loads in flight together.  (Completing a match right where the walk found it made every chain step wait
+    // for a dependent global load: config 5 x100 has keys with thousands of duplicates, and one of its queries took
+    // 0.97 s in this kernel instead of 0.03 s.)
+    auto drain = [&](uint32_t take) {
+        B200_DCHECK(take <= 32u && take <= queued && queued <= (uint32_t)QN);
+        queued -= take;
+        const bool mine = lane < take;
+        uint2      e;
+        KeyT       ekey;
+        q_load(queued + (mine ? lane : 0u), e, ekey);
+        const uint32_t t = (e.x >> 16) & 0x7FFFu;
+        complete(mine && (e.x & kQMatch) != 0u, e.x, e.y, ekey);
         // ---- chain entries ----
-        bool     walking = mine && (e.x & kNextBit) != 0u;
-        uint32_t pos     = e.x & kIdxMask;
+        const uint32_t base    = queued;   // entries below were queued by the probe loop and may be chain entries
+        bool           walking = mine && (e.x & kNextBit) != 0u;
+        uint32_t       pos     = e.x & kIdxMask;
         while (__any_sync(kFullMask, walking)) {
-            uint32_t w = kEmptyWord;
+            if (queued + 32u > (uint32_t)QN) {   // no room for a step's worth of hits: complete the newest matches
+                __syncwarp();
+                const uint32_t n = min(32u, queued - base);
+                B200_DCHECK(n >= 1u);
+                queued -= n;
+                uint2 e2;
+                KeyT  k2;
+                q_load(queued + (lane < n ? lane : 0u), e2, k2);
+                complete(lane < n, e2.x, e2.y, k2);
+                __syncwarp();
+                continue;
+            }
             B200_DCHECK(!walking || pos < a.cap);
+            uint32_t w = kEmptyWord;
             if (walking) w = lds_u32(s_next + pos * 4u);
             const bool     hit = walking && (w >> kTagShift) == t;
             const uint32_t bal = __ballot_sync(kFullMask, hit);
             if (hit) {
                 const uint32_t slot = queued + __popc(bal & lt);
-                if (slot < (uint32_t)QN) {
-                    sts_v2(my_q + slot * QE, kQMatch | (t << 16) | (w & kIdxMask), e.y);
-                    if constexpr (K64) sts_v2(my_q + slot * QE + 8u, (uint32_t)ekey, (uint32_t)((uint64_t)ekey >> 32));
-                } else {
-                    handle_inline(w & kIdxMask, e.y, ekey);
-                }
+                B200_DCHECK(slot < (uint32_t)QN);
+                sts_v2(my_q + slot * QE, kQMatch | (t << 16) | (w & kIdxMask), e.y);
+                if constexpr (K64) sts_v2(my_q + slot * QE + 8u, (uint32_t)ekey, (uint32_t)((uint64_t)ekey >> 32));
             }
-            queued  = min(queued + (uint32_t)__popc(bal), (uint32_t)QN);
+            queued += (uint32_t)__popc(bal);
             walking = walking && (w & kNextBit) != 0u;
             pos     = w & kIdxMask;
         }
