@@ -329,8 +329,9 @@ static void execute_query_timed(query_t *q, int i) {
     char  buf[512];
     char *p = buf;
     for (unsigned k = 0; k < sizeof names / sizeof names[0]; ++k) {
-        const double ms = b200_last_kernel_ms(names[k]);
-        if (ms >= 0) p += sprintf(p, " %s=%.3f", names[k], ms);
+        int          scopes = 0;
+        const double ms     = b200_sum_kernel_ms(names[k], &scopes);
+        if (ms >= 0) p += sprintf(p, " %s=%.3f(x%d)", names[k], ms, scopes);
     }
     fprintf(stderr, "b200_engine: query %d: %.3f ms |%s | %s\n", i, (now_s() - t0) * 1e3, buf, q->line);
 }

@@ -468,6 +468,8 @@ int   b200_join_sum_multi(int n_gpus, int plan_kind, const uint64_t *const *d_bu
  * SUM column), "join", "exchange" (b = build side, p = probe side).  Returns milliseconds, or a negative value if the
  * kernel did not run. */
 int    b200_set_profiling(int on);
+/* ... summed over every scope of that name since profiling was last enabled (out_scopes: how many) */
+double b200_sum_kernel_ms(const char *name, int *out_scopes);
 double b200_last_kernel_ms(const char *name);
 /* Number of kernels this library launched since the counter was reset. */
 uint64_t b200_kernel_launches(int reset);

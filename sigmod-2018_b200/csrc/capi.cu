@@ -187,8 +187,23 @@ int b200_set_profiling(int on) {
     set_profiling(on != 0);
     // (re-)enabling forgets the calling thread's timers: what b200_last_kernel_ms reports afterwards was recorded since
     if (on)
-        for (auto &kv : ctx().timers) kv.second.used = false;
+        for (auto &kv : ctx().timers) {
+            kv.second.used       = false;
+            kv.second.earlier_ms = 0;
+            kv.second.scopes     = 0;
+        }
     return 0;
+}
+
+// every scope of that name since profiling was (re-)enabled, not just the last one
+double b200_sum_kernel_ms(const char *name, int *out_scopes) {
+    Context &c  = ctx();
+    auto     it = c.timers.find(name);
+    if (out_scopes) *out_scopes = 0;
+    if (it == c.timers.end() || !it->second.used) return -1.0;
+    const double last = b200_last_kernel_ms(name);
+    if (out_scopes) *out_scopes = it->second.scopes;
+    return it->second.earlier_ms + (last > 0 ? last : 0.0);
 }
 
 double b200_last_kernel_ms(const char *name) {

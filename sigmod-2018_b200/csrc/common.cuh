@@ -54,6 +54,8 @@ constexpr uint64_t kMaxRows = 0xFFFFFFFFull;
 struct KernelTimer {
     cudaEvent_t start = nullptr, stop = nullptr;
     bool        used  = false;
+    double      earlier_ms = 0;   // scopes of this name that ended before the current one (since profiling was enabled)
+    int         scopes     = 0;
 };
 
 // One context per host thread: the reference fans a join out over pthreads

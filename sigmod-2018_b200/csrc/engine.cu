@@ -210,7 +210,13 @@ TimedScope::TimedScope(const char *name) {
         B200_CUDA(cudaEventCreate(&t->start));
         B200_CUDA(cudaEventCreate(&t->stop));
     }
+    if (t->used) {   // a scope of this name ran before: keep its time (profiling mode may synchronise)
+        float ms = 0.f;
+        if (cudaEventSynchronize(t->stop) == cudaSuccess && cudaEventElapsedTime(&ms, t->start, t->stop) == cudaSuccess)
+            t->earlier_ms += ms;
+    }
     t->used = true;
+    ++t->scopes;
     B200_CUDA(cudaEventRecord(t->start, c.stream));
 }
 TimedScope::~TimedScope() {
@@ -956,7 +962,10 @@ JoinResult run_join(const KeyVec &R, const KeyVec &S, JoinOut mode, int nproj, c
         a.n_items_direct = (uint32_t)(rc * sc);
         n_items          = rc * sc;
     } else {
-        a.slice = t.slice;
+        // probe tuples per work item: the configured slice, but never so large that a small join is a handful of
+        // items (config 3's last join: 25 M probe rows against 4 partitions were 96 items for 148 SMs) — about three
+        // items per SM, each still long enough to amortise building its table
+        a.slice = (uint32_t)std::min<uint64_t>(t.slice, std::max<uint64_t>(32768, (P.src.n / (3ull * sm_count()) + 1023) & ~1023ull));
         const size_t tsz = key64 ? sizeof(Tup64) : sizeof(Tup32);
         // Histogram-free probe side (fused SUM, 32-bit keys): every partition owns a region a few percent
         // above the uniform expectation; what does not fit overflows and is partitioned exactly afterwards.

@@ -241,6 +241,7 @@ def _declare(L: C.CDLL) -> None:
                                           P(C.c_void_p), u64p, C.c_int, u64p, u64p, P(C.c_double)]),
         "b200_set_profiling": (C.c_int, [C.c_int]),
         "b200_last_kernel_ms": (C.c_double, [C.c_char_p]),
+        "b200_sum_kernel_ms": (C.c_double, [C.c_char_p, C.POINTER(C.c_int)]),
         "b200_kernel_launches": (C.c_uint64, [C.c_int]),
     }
     for name, (res, args) in sig.items():
