@@ -92,8 +92,11 @@ bool     profiling_enabled();
 extern std::atomic<uint64_t> g_launches;
 
 // RAII timing scope: records events on the context stream when profiling is on.
+// ... and, with B200_NVTX=1, opens an NVTX range of the same name (header-only nvtx3: a timeline tool attached to the
+// process shows hist_b / scatter_pc / join / exchange ... per operator; no cost when no tool is attached).
 struct TimedScope {
     KernelTimer *t = nullptr;
+    bool         nvtx = false;
     explicit TimedScope(const char *name);
     ~TimedScope();
 };

@@ -4,6 +4,8 @@
 #include "engine.cuh"
 #include "kernels.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -202,7 +204,18 @@ Context &ctx() {
     return *h.c;
 }
 
+static bool nvtx_on() {
+    static const bool on = [] {
+        const char *v = getenv("B200_NVTX");
+        return v && atoi(v) != 0;
+    }();
+    return on;
+}
 TimedScope::TimedScope(const char *name) {
+    if (nvtx_on()) {
+        nvtxRangePushA(name);
+        nvtx = true;
+    }
     if (!g_profiling) return;
     Context &c = ctx();
     t          = &c.timers[name];
@@ -221,6 +234,7 @@ TimedScope::TimedScope(const char *name) {
 }
 TimedScope::~TimedScope() {
     if (t) cudaEventRecord(t->stop, ctx().stream);
+    if (nvtx) nvtxRangePop();
 }
 
 constexpr size_t kBigBuf       = 64ull << 20;    // blocks from this size up are recycled through the context
