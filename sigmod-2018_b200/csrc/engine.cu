@@ -545,7 +545,8 @@ static void launch_scatter_pred_carry(const KeySrc &src, int bits, uint32_t *cur
     constexpr int NT   = PartCfg<uint32_t, 1>::NT;
     constexpr int U    = PartCfg<uint32_t, 1>::U;
     constexpr int MINB = PartCfg<uint32_t, 1>::MINB;
-    const size_t  smem = (size_t)NT * U * sizeof(Tup32) + 3 * (size_t)(1u << bits) * sizeof(uint32_t);
+    const size_t  smem = (size_t)NT * U * sizeof(Tup32) + 3 * (size_t)(1u << bits) * sizeof(uint32_t) +
+                        (opt.pred.hot_keys ? kHotBitmapWords * sizeof(uint32_t) : 0);
     auto          k    = radix_scatter_kernel<NT, U, MINB, uint32_t, false, true, true>;
     allow_smem(k, smem);
     k<<<grid_for(src.n, NT * U, MINB), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor, static_cast<Tup32 *>(out),
@@ -561,7 +562,8 @@ static void launch_scatter_pred(const KeySrc &src, int bits, uint32_t *cursor, v
     constexpr int U    = PartCfg<KeyT, 1>::U;
     constexpr int MINB = PartCfg<KeyT, 1>::MINB;
     B200_REQUIRE(src.ids == nullptr && (opt.pred.npred > 0 || opt.pred.hot_keys), "fused predicates apply to base relations");
-    const size_t smem = (size_t)NT * U * sizeof(TupT) + (OPT ? 4 : 3) * (size_t)(1u << bits) * sizeof(uint32_t);
+    const size_t smem = (size_t)NT * U * sizeof(TupT) + (OPT ? 4 : 3) * (size_t)(1u << bits) * sizeof(uint32_t) +
+                        (opt.pred.hot_keys ? kHotBitmapWords * sizeof(uint32_t) : 0);
     auto         k    = radix_scatter_kernel<NT, U, MINB, KeyT, OPT, false, true>;
     allow_smem(k, smem);
     k<<<grid_for(src.n, NT * U, MINB), NT, smem, launch_stream()>>>(src, (uint32_t)bits, cursor, static_cast<TupT *>(out),

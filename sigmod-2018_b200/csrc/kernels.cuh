@@ -330,6 +330,16 @@ static_assert(kHotSlots == (1u << 13), "hot_slot produces 13 bits");
 __device__ __forceinline__ bool key_is_hot(const PredSet &ps, bool hot_on, uint32_t key) {
     return hot_on && key != kHotEmpty && __ldg(ps.hot_keys + hot_slot(key)) == key;
 }
+// Shared-memory pre-filter of the scatter: 2^16 bits, one set per hot key (bit = the top 16 bits of the hash whose top
+// 13 bits are the table slot).  A probe of the table is a random 4-byte global load per key — 32 sectors per warp
+// instruction through a load/store pipe that is the scatter's bottleneck; the bitmap answers "not hot" for all but a
+// few percent of the keys with one shared-memory load.
+constexpr uint32_t kHotBitmapWords = (1u << 16) / 32;
+__device__ __forceinline__ uint32_t hot_bit(uint32_t key) { return (key * 0x9E3779B1u) >> 16; }
+__device__ __forceinline__ bool key_maybe_hot(const uint32_t *hotbits, uint32_t key) {
+    const uint32_t h = hot_bit(key);
+    return ((hotbits[h >> 5] >> (h & 31u)) & 1u) != 0u;
+}
 
 // Raw tile loads of the scatter: 64-bit values exactly as the column holds them (two per 128-bit load on the vector
 // path).  They stay raw in registers across the copy-out of the previous tile and are narrowed to KeyT only at the
@@ -385,7 +395,7 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
                                              typename TupOf<KeyT>::type *stage, uint32_t *cnt, uint32_t *loc,
                                              uint32_t *gdelta, uint32_t *warp_sums, uint32_t *__restrict__ cursor,
                                              typename TupOf<KeyT>::type *__restrict__ out, const OptArgs &opt,
-                                             uint32_t *ovdelta, uint32_t *s_over) {
+                                             uint32_t *ovdelta, uint32_t *s_over, const uint32_t *hotbits = nullptr) {
     using TupT = typename TupOf<KeyT>::type;
     constexpr int  NW   = NT / 32;
     constexpr int  PER  = 2;   // bins per thread whose reservation stays in flight across the staging phase
@@ -429,13 +439,15 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
             if (hot_on) {
 #pragma unroll
                 for (int j = 0; j < U; ++j)
-                    if (((valid >> j) & 1ull) && key_is_hot(ps, true, (uint32_t)keys[j])) valid &= ~(1ull << j);
+                    if (((valid >> j) & 1ull) && key_maybe_hot(hotbits, (uint32_t)keys[j]) && key_is_hot(ps, true, (uint32_t)keys[j]))
+                        valid &= ~(1ull << j);
             }
         } else {
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 const uint32_t li = (uint32_t)(j * NT) + tid;
-                if (li < count && preds_hold_row(ps, base + li) && !key_is_hot(ps, hot_on, (uint32_t)keys[j]))
+                if (li < count && preds_hold_row(ps, base + li) &&
+                    !(hot_on && key_maybe_hot(hotbits, (uint32_t)keys[j]) && key_is_hot(ps, true, (uint32_t)keys[j])))
                     valid |= 1ull << j;
             }
         }
@@ -634,6 +646,7 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
     uint32_t *loc     = cnt + nbins;
     uint32_t *gdelta  = loc + nbins;
     uint32_t *ovdelta = gdelta + nbins;   // OPT only (the launch reserves 4 bin arrays then)
+    [[maybe_unused]] uint32_t *hotbits = gdelta + (OPT ? 2u : 1u) * nbins;   // PRED with a hot-key table: kHotBitmapWords more
     __shared__ uint32_t warp_sums[NT / 32 + 1];
     __shared__ uint32_t s_over;
 
@@ -648,6 +661,16 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
     const uint32_t per    = (nbins + NT - 1) / NT;
 
     for (uint32_t b = threadIdx.x; b < nbins; b += NT) cnt[b] = 0;
+    if constexpr (PRED) {
+        if (opt.pred.hot_keys != nullptr) {   // (the launch reserved the bitmap)
+            for (uint32_t w = threadIdx.x; w < kHotBitmapWords; w += NT) hotbits[w] = 0u;
+            __syncthreads();
+            for (uint32_t sl = threadIdx.x; sl < kHotSlots; sl += NT) {
+                const uint32_t k = __ldg(opt.pred.hot_keys + sl);
+                if (k != kHotEmpty) atomicOr(&hotbits[hot_bit(k) >> 5], 1u << (hot_bit(k) & 31u));
+            }
+        }
+    }
     uint64_t raw[U];
     uint64_t tile = blockIdx.x;
     if (tile < ntiles) {
@@ -674,11 +697,11 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
             if (vec)
                 scatter_tile<NT, U, KeyT, true, OPT, CARRY, true>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
                                                                   nbins, mask, per, stage, cnt, loc, gdelta, warp_sums,
-                                                                  cursor, out, opt, ovdelta, &s_over);
+                                                                  cursor, out, opt, ovdelta, &s_over, hotbits);
             else
                 scatter_tile<NT, U, KeyT, false, OPT, CARRY, true>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
                                                                    nbins, mask, per, stage, cnt, loc, gdelta, warp_sums,
-                                                                   cursor, out, opt, ovdelta, &s_over);
+                                                                   cursor, out, opt, ovdelta, &s_over, hotbits);
         } else if (vec) {
             scatter_tile<NT, U, KeyT, true, OPT, CARRY>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
                                                         nbins, mask, per, stage, cnt, loc, gdelta, warp_sums, cursor,
