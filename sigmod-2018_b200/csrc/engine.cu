@@ -44,6 +44,18 @@ std::atomic<uint64_t> g_launches{0};
 
 // keep freed blocks in the stream-ordered pool instead of returning them
 static void configure_device_pool(int device) {
+    {
+        // Keep the per-thread local-memory reservation at its high-water mark.  A few scatter instances spill some
+        // tens of bytes; by default the driver shrinks the reservation again after such a kernel, and the next launch
+        // of one resizes it under a device-wide synchronisation: config 5 showed 50-900 ms stalls in queries whose
+        // kernels sum to a few milliseconds, in some runs and not in others.  (Refused when another library already
+        // fixed the flags of an active context: then it stays as it is.)
+        unsigned flags = 0;
+        cudaSetDevice(device);
+        if (cudaGetDeviceFlags(&flags) != cudaSuccess) flags = 0;
+        if (cudaSetDeviceFlags(flags | cudaDeviceLmemResizeToMax) != cudaSuccess) cudaGetLastError();
+        cudaGetLastError();
+    }
     cudaMemPool_t pool;
     B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t threshold = UINT64_MAX;
