@@ -28,5 +28,8 @@ for env in variants:
     order = sorted(range(len(rows)), key=lambda i: -float(rows[i][1]))
     for i in order[:8]:
         print(f"   #{i:2d} {float(rows[i][1]):9.2f} ms  {queries[i] if i < len(queries) else ''}\n        {rows[i][2].strip()}")
+    for l in out.stderr.splitlines():
+        if "slow:" in l:
+            print("   " + l)
     if out.returncode:
         print(out.stderr[-1500:])

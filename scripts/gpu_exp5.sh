@@ -1,8 +1,12 @@
 #!/bin/bash
+# 1 x B200: multi-plan, checked-build and fused-filter tests, config 5 x100 per query with the host-side gap logger
+# (three runs), config 4 at the per-GPU load of the full config on one GPU
 set -u
-T=${1:-r2v}
+T=${1:-r2s}
 mkdir -p gpurun_out
-python scripts/exp_config5.py 100 "" "" B200_TAG64=0 "" > gpurun_out/${T}_exp_config5.log 2>&1; grep -A8 "^===" gpurun_out/${T}_exp_config5.log | cut -c1-260
-timeout 300 python bench.py --config 3 --steps 20 --no-cpu-baseline > gpurun_out/${T}_config3.json 2> gpurun_out/${T}_config3.err
+(timeout 600 python -m pytest tests/test_multi_plan_gpu.py tests/test_checked_build_gpu.py tests/test_filter_fusion_gpu.py -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest.log)
+tail -4 gpurun_out/${T}_pytest.log
+python scripts/exp_config5.py 100 B200_SLOWLOG=4 B200_SLOWLOG=4 B200_SLOWLOG=4 > gpurun_out/${T}_exp_config5.log 2>&1; grep -E "^===|slow:" gpurun_out/${T}_exp_config5.log | cut -c1-330 | head -60
+timeout 300 python bench.py --config 4 --gpus 1 --steps 10 > gpurun_out/${T}_config4_n1.json 2> gpurun_out/${T}_config4_n1.err
 python -c "
-import json; d=json.load(open('gpurun_out/${T}_config3.json')); print('config3', d['ms_per_step'], d['roofline']['per_kernel_ms'], d['checksum_ok'])"
+import json; d=json.load(open('gpurun_out/${T}_config4_n1.json')); print('config4 n1', d['ms_per_step'], d['roofline']['per_kernel_ms_rank0'], d['checksum_ok'])"

@@ -23,11 +23,18 @@ namespace b200 {
 [[noreturn]] void fatal(const char *file, int line, const char *what, const char *detail);
 void set_last_error(const std::string &msg);
 
+// B200_SLOWLOG=<ms>: every checked CUDA call and kernel launch is a checkpoint; when more than <ms> of host time
+// passed on the calling thread since its previous checkpoint, the two sites and the gap are printed to stderr — finds
+// the host-side stall (an allocation, a synchronisation, a launch that blocks) nsys would show, without nsys.
+extern int g_slowlog_ms;
+void       slow_checkpoint(const char *file, int line, const char *what);
+
 #define B200_CUDA(expr)                                                               \
     do {                                                                              \
         cudaError_t err__ = (expr);                                                   \
         if (err__ != cudaSuccess)                                                     \
             ::b200::fatal(__FILE__, __LINE__, #expr, cudaGetErrorString(err__));      \
+        if (::b200::g_slowlog_ms) ::b200::slow_checkpoint(__FILE__, __LINE__, #expr); \
     } while (0)
 
 #define B200_REQUIRE(cond, msg)                                                       \

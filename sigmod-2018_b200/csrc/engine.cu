@@ -106,6 +106,22 @@ void ensure_init() {
 }
 int  device_index() { return g_device; }
 int  sm_count() { return g_sm_count; }
+int g_slowlog_ms = [] {
+    const char *v = getenv("B200_SLOWLOG");
+    return v ? atoi(v) : 0;
+}();
+void slow_checkpoint(const char *file, int line, const char *what) {
+    static thread_local std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    static thread_local const char *last_what = "(start)";
+    static thread_local int         last_line = 0;
+    const auto   now = std::chrono::steady_clock::now();
+    const double ms  = std::chrono::duration<double, std::milli>(now - last).count();
+    if (ms > (double)g_slowlog_ms)
+        fprintf(stderr, "b200 slow: %.1f ms between line %d [%.60s] and %s:%d [%.60s]\n", ms, last_line, last_what, file, line, what);
+    last      = now;
+    last_what = what;
+    last_line = line;
+}
 bool profiling_enabled() { return g_profiling; }
 void set_profiling(bool on) { g_profiling = on; }
 
