@@ -379,17 +379,25 @@ int main(int argc, char **argv) {
         ++g_nrel;
     }
     g_timing  = getenv("B200_TIMING") ? (atoi(getenv("B200_TIMING")) > 1 ? 2 : 1) : 0;
-    double t0 = now_s();
+    double   t0 = now_s();
+    uint64_t reserved = 0;
     b200_init(-1);
     double t1 = now_s();
     b200_register_relations(g_map, g_nrel);     /* the untimed preparation phase: columns go to HBM once */
     b200_compute_column_stats(g_map, g_nrel);   /* relation_map.c:53-83's min / max / distinct, computed on the GPU */
+    {   /* still the preparation phase: room for the intermediates (a few times the relations) reserved in the pool */
+        uint64_t total = 0;
+        for (int r = 0; r < g_nrel; ++r) total += 8ull * g_map[r].num_tuples * g_map[r].num_columns;
+        const char *gb = getenv("B200_RESERVE_GB");
+        uint64_t want = gb ? (uint64_t)atoll(gb) << 30 : (4 * total > (4ull << 30) ? 4 * total : 4ull << 30);
+        reserved = b200_reserve_device_memory(want);
+    }
     if (g_gpus > 1) {
         if (shard_relations()) { fprintf(stderr, "b200_engine: cannot shard over %d GPUs: %s\n", g_gpus, b200_last_error()); return 1; }
         workers = 1;                            /* the multi-GPU plan runs one query at a time over all GPUs */
     }
     if (g_timing > 1) b200_set_profiling(1);
-    if (g_timing) fprintf(stderr, "b200_engine: CUDA start-up %.3f s, upload of %d relations %.3f s\n", t1 - t0, g_nrel, now_s() - t1);
+    if (g_timing) fprintf(stderr, "b200_engine: CUDA start-up %.3f s, upload of %d relations, statistics and %.1f GB reserved %.3f s\n", t1 - t0, g_nrel, (double)reserved / 1073741824.0, now_s() - t1);
 
     if (workers > 1) pool_start(workers);
     query_t *batch = NULL;

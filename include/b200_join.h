@@ -148,6 +148,10 @@ int  b200_unregister_relations(const relation_map *map, int count);
  * pointers (location 1 of b200_join_sum, b200_register_device_column). */
 void *b200_device_malloc(uint64_t bytes);
 void  b200_device_free(void *device_ptr);
+/* Preparation-phase hook (next to b200_register_relations, handler.c:52): reserve `bytes` of device memory in the
+ * library's pool now, so that no query pays the driver's physical allocations (5-100 ms each on a cold process).
+ * Returns the bytes reserved. */
+uint64_t b200_reserve_device_memory(uint64_t bytes);
 int   b200_copy_to_device(void *device_dst, const void *host_src, uint64_t bytes);
 int   b200_copy_to_host(void *host_dst, const void *device_src, uint64_t bytes);
 

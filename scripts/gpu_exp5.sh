@@ -10,3 +10,8 @@ python scripts/exp_config5.py 100 B200_SLOWLOG=4 B200_SLOWLOG=4 B200_SLOWLOG=4 >
 timeout 300 python bench.py --config 4 --gpus 1 --steps 10 > gpurun_out/${T}_config4_n1.json 2> gpurun_out/${T}_config4_n1.err
 python -c "
 import json; d=json.load(open('gpurun_out/${T}_config4_n1.json')); print('config4 n1', d['ms_per_step'], d['roofline']['per_kernel_ms_rank0'], d['checksum_ok'])"
+for f in 100 1000; do
+  timeout 500 python bench.py --config 5 --factor $f > gpurun_out/${T}_config5_x$f.json 2> gpurun_out/${T}_config5_x$f.err
+  python -c "
+import json; d=json.load(open('gpurun_out/${T}_config5_x$f.json')); print($f, d['ms_per_step'], {w: (r['batch_seconds'], r['startup'][-60:]) for w, r in d['runs_by_workers'].items()})"
+done

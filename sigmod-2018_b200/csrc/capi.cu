@@ -142,6 +142,30 @@ void *b200_device_malloc(uint64_t bytes) {
     return p;
 }
 
+// Warm the stream-ordered pool: one allocation of `bytes` that goes straight back to the pool (which never returns
+// memory to the driver, engine.cu configure_device_pool).  Physical allocations cost the driver 5-100 ms each on a
+// cold process (b200 slow-log, profiles/r2_config5_x100_per_query.txt); a host does this once in its preparation
+// phase so that no query pays for them.  Returns the bytes reserved (less when the device has less free memory).
+uint64_t b200_reserve_device_memory(uint64_t bytes) {
+    Context &c = ctx();
+    size_t   free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    const uint64_t room = free_b > (4ull << 30) ? free_b - (4ull << 30) : 0;   // leave the driver some air
+    if (bytes > room) bytes = room;
+    if (bytes == 0) return 0;
+    void *p = nullptr;
+    if (cudaMallocAsync(&p, bytes, c.stream) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    B200_CUDA(cudaFreeAsync(p, c.stream));
+    B200_CUDA(cudaStreamSynchronize(c.stream));
+    return bytes;
+}
+
 void b200_device_free(void *device_ptr) {
     if (device_ptr) cudaFree(device_ptr);
 }

@@ -539,16 +539,17 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     // the carried column of the tile (its lines were pulled into L2 one tile ahead): every load is issued here, ahead
     // of the barrier, so that ONE L2 latency is exposed per tile — ncu showed 17 % of the warp samples waiting on these
     // loads when each was issued right where its value was staged (profiles/r2_summary.txt)
-    [[maybe_unused]] uint64_t craw[(CARRY && FULL) ? U : 1];
-    if constexpr (CARRY && FULL) {
+    // (not in the PRED instances: with the validity mask and the predicate batches live as well the 64 registers of
+    // the batch spilled — 712 bytes of spill stores per thread and tile in the exchange plan's probe scatter — so a
+    // filtered scatter loads the carried value of each surviving row where it stages it)
+    constexpr bool kHoistCarry = CARRY && FULL && !PRED;
+    [[maybe_unused]] uint64_t craw[kHoistCarry ? U : 1];
+    if constexpr (kHoistCarry) {
 #pragma unroll
-        for (int j = 0; j < U; j += 2) {
-            // registers j, j+1 hold two consecutive rows: one 128-bit load for both (skipped when neither row is on)
-            if (!PRED || ((valid >> j) & 3ull) != 0ull) {
-                const ulonglong2 v = ld_stream_u64x2(opt.carry_col + base + ((uint32_t)((j >> 1) * NT) + tid) * 2u);
-                craw[j]            = v.x;
-                craw[j + 1]        = v.y;
-            }
+        for (int j = 0; j < U; j += 2) {   // registers j, j+1 hold two consecutive rows: one 128-bit load for both
+            const ulonglong2 v = ld_stream_u64x2(opt.carry_col + base + ((uint32_t)((j >> 1) * NT) + tid) * 2u);
+            craw[j]            = v.x;
+            craw[j + 1]        = v.y;
         }
     }
     __syncthreads();   // (C) local offsets visible
@@ -561,7 +562,7 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
             TupT t;
             t.key = keys[j];
             if constexpr (CARRY) {
-                if constexpr (FULL) {
+                if constexpr (kHoistCarry) {
                     t.rid = narrow_key<uint32_t>(craw[j]);
                 } else {
                     t.rid = (uint32_t)ld_stream_u64(opt.carry_col + base + li);

@@ -240,6 +240,7 @@ def _declare(L: C.CDLL) -> None:
         "b200_join_sum_multi": (C.c_int, [C.c_int, C.c_int, P(C.c_void_p), P(C.c_void_p), u64p, P(C.c_void_p),
                                           P(C.c_void_p), u64p, C.c_int, u64p, u64p, P(C.c_double)]),
         "b200_set_profiling": (C.c_int, [C.c_int]),
+        "b200_reserve_device_memory": (C.c_uint64, [C.c_uint64]),
         "b200_last_kernel_ms": (C.c_double, [C.c_char_p]),
         "b200_sum_kernel_ms": (C.c_double, [C.c_char_p, C.POINTER(C.c_int)]),
         "b200_kernel_launches": (C.c_uint64, [C.c_int]),
