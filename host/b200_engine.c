@@ -385,11 +385,11 @@ int main(int argc, char **argv) {
     double t1 = now_s();
     b200_register_relations(g_map, g_nrel);     /* the untimed preparation phase: columns go to HBM once */
     b200_compute_column_stats(g_map, g_nrel);   /* relation_map.c:53-83's min / max / distinct, computed on the GPU */
-    {   /* still the preparation phase: room for the intermediates (a few times the relations) reserved in the pool */
+    {   /* still the preparation phase: room for the intermediates (eight times the relations, at least 8 GB; $B200_RESERVE_GB) reserved in the pool */
         uint64_t total = 0;
         for (int r = 0; r < g_nrel; ++r) total += 8ull * g_map[r].num_tuples * g_map[r].num_columns;
         const char *gb = getenv("B200_RESERVE_GB");
-        uint64_t want = gb ? (uint64_t)atoll(gb) << 30 : (4 * total > (4ull << 30) ? 4 * total : 4ull << 30);
+        uint64_t want = gb ? (uint64_t)atoll(gb) << 30 : (8 * total > (8ull << 30) ? 8 * total : 8ull << 30);
         reserved = b200_reserve_device_memory(want);
     }
     if (g_gpus > 1) {
