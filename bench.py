@@ -677,7 +677,7 @@ def run_config4(args):
     for _ in range(3):
         step()
         torch.cuda.synchronize()
-        for name in ("hist", "scatter_b", "exchange", "join"):
+        for name in ("hot_sample", "hot_table", "hot_build", "hist", "layout", "scatter_b", "exchange", "join"):
             v = b200.last_kernel_ms(name)
             if v >= 0:
                 per_kernel.setdefault(name, []).append(round(v, 4))

@@ -345,6 +345,7 @@ static void enqueue_exchange(MultiPlan &m, int phases) {
             B200_CUDA(cudaMemsetAsync(my_cand, 0, 4, main));
             const uint64_t nsample = std::min<uint64_t>(np, 1u << 20);
             if (nsample) {
+                TimedScope ts("hot_sample");
                 hot_sample_kernel<<<grid_for(nsample, 256, 8), 256, 0, main>>>(m.in_pk, np, nsample, m.hs_keys, m.hs_cnt);
                 B200_LAUNCH_CHECK();
                 const uint32_t threshold = (uint32_t)std::max<uint64_t>(8, nsample >> 14);
@@ -356,12 +357,16 @@ static void enqueue_exchange(MultiPlan &m, int phases) {
     }
     if ((phases & 2) && m.hot) {
         wait_signal(m, main, SIG_HOT);
-        hot_table_kernel<<<1, 1024, 0, main>>>(m.cand(rank), world, m.hot_keys, m.hot_n);
-        B200_LAUNCH_CHECK();
+        {
+            TimedScope ts("hot_table");
+            hot_table_kernel<<<1, 1024, 0, main>>>(m.cand(rank), world, m.hot_keys, m.hot_n);
+            B200_LAUNCH_CHECK();
+        }
         // ---- how many of my build rows carry each hot key, and the sum of their SUM column ----
         unsigned long long *my_agg = m.agg(rank) + (size_t)rank * 2 * kHotSlots;
         B200_CUDA(cudaMemsetAsync(my_agg, 0, (size_t)kHotSlots * 16, main));
         if (nb) {
+            TimedScope ts("hot_build");
             hot_build_kernel<<<grid_for(nb, 256 * 4, 8), 256, 0, main>>>(m.in_bk, m.cfg.has_build_sum ? m.in_bp : nullptr, nb,
                                                                         m.hot_keys, m.hot_n, my_agg);
             B200_LAUNCH_CHECK();
@@ -403,6 +408,8 @@ static void enqueue_exchange(MultiPlan &m, int phases) {
         wait_signal(m, main, SIG_HIST2);
         // ---- ownership cuts on the global histogram, then where my segments go ----
         uint32_t *total_b = m.total, *total_p = m.total + P;
+        {
+        TimedScope ts_layout("layout");
         balanced_cuts_kernel<1024><<<1, 1024, 0, main>>>(m.hist_b(rank), (uint32_t)world, m.hist_p(rank),
                                                          (uint32_t)(world * K), P, (uint32_t)world, m.cut, total_b, total_p);
         B200_LAUNCH_CHECK();
@@ -414,6 +421,7 @@ static void enqueue_exchange(MultiPlan &m, int phases) {
                                                            (uint32_t)K, P, m.cut, (uint32_t)world, (uint32_t)rank, m.cap_p,
                                                            total_p, m.dst_start_p, m.own_total + P, m.need + 2, m.d_error);
         B200_LAUNCH_CHECK();
+        }
         auto exchange = [&](const void *staged, uint64_t n, const uint32_t *src_off, const uint32_t *dst_start, uint32_t cap,
                             bool build_side) {
             if (n == 0) return;

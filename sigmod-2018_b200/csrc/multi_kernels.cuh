@@ -284,26 +284,33 @@ hot_select_kernel(const uint32_t *__restrict__ t_keys, const uint32_t *__restric
 static __global__ void __launch_bounds__(1024)
 hot_table_kernel(const uint32_t *__restrict__ cand_all /* [world][1 + kHotMaxCand] */, int world,
                  uint32_t *__restrict__ hot_keys /* [kHotSlots] */, uint32_t *__restrict__ hot_n) {
-    __shared__ uint32_t s_tab[kHotSlots];
-    for (uint32_t i = threadIdx.x; i < kHotSlots; i += 1024) s_tab[i] = kHotEmpty;
+    // Every rank must end up with the same table: a slot belongs to the FIRST candidate, in (rank, position) order,
+    // that maps to it.  "First" is an atomicMin over that order, so all 1024 threads work on the lists (one thread
+    // walking up to world x 2048 candidates through dependent global loads took ~1 ms at 8 ranks).
+    __shared__ uint32_t s_ord[kHotSlots];
+    __shared__ uint32_t s_n;
+    for (uint32_t i = threadIdx.x; i < kHotSlots; i += 1024) s_ord[i] = 0xFFFFFFFFu;
+    if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {   // sequential on purpose: every rank must end up with the same table
-        uint32_t n = 0;
-        for (int r = 0; r < world; ++r) {
-            const uint32_t *c   = cand_all + (size_t)r * (1 + kHotMaxCand);
-            const uint32_t  cnt = min(c[0], kHotMaxCand);
-            for (uint32_t i = 0; i < cnt; ++i) {
-                const uint32_t key = c[1 + i], slot = hot_slot(key);
-                if (s_tab[slot] == kHotEmpty) {
-                    s_tab[slot] = key;
-                    ++n;
-                }
-            }
-        }
-        *hot_n = n;
+    for (int r = 0; r < world; ++r) {
+        const uint32_t *c   = cand_all + (size_t)r * (1 + kHotMaxCand);
+        const uint32_t  cnt = min(c[0], kHotMaxCand);
+        for (uint32_t i = threadIdx.x; i < cnt; i += 1024) atomicMin(&s_ord[hot_slot(c[1 + i])], (uint32_t)r * kHotMaxCand + i);
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < kHotSlots; i += 1024) hot_keys[i] = s_tab[i];
+    uint32_t mine = 0;
+    for (uint32_t slot = threadIdx.x; slot < kHotSlots; slot += 1024) {
+        const uint32_t ord = s_ord[slot];
+        uint32_t       key = kHotEmpty;
+        if (ord != 0xFFFFFFFFu) {
+            key = cand_all[(size_t)(ord / kHotMaxCand) * (1 + kHotMaxCand) + 1 + ord % kHotMaxCand];
+            ++mine;
+        }
+        hot_keys[slot] = key;
+    }
+    if (mine) atomicAdd(&s_n, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) *hot_n = s_n;
 }
 static __global__ void __launch_bounds__(256)
 hot_build_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals, uint64_t n,
