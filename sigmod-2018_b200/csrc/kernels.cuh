@@ -554,26 +554,41 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     }
     __syncthreads();   // (C) local offsets visible
     // ---- (3) tuples into shared memory in partition order ----
+    // (carried values that were not hoisted — filtered and ragged tiles — are loaded eight rows at a time, then staged:
+    // one exposed latency per eight rows instead of one per row)
+    constexpr int SB = 8;
+    static_assert(U % SB == 0, "staging batches");
 #pragma unroll
-    for (int j = 0; j < U; ++j) {
-        const uint32_t li = FULL ? ((uint32_t)((j >> 1) * NT) + tid) * 2u + (uint32_t)(j & 1)
-                                 : tile_local_index<NT, U>(j, vec);
-        if (row_on(j, li)) {
-            TupT t;
-            t.key = keys[j];
-            if constexpr (CARRY) {
-                if constexpr (kHoistCarry) {
-                    t.rid = narrow_key<uint32_t>(craw[j]);
-                } else {
-                    t.rid = (uint32_t)ld_stream_u64(opt.carry_col + base + li);
-                }
-            } else {
-                t.rid = (uint32_t)base + li;
+    for (int j0 = 0; j0 < U; j0 += SB) {
+        [[maybe_unused]] uint32_t cval[SB];
+        if constexpr (CARRY && !kHoistCarry) {
+#pragma unroll
+            for (int u = 0; u < SB; ++u) {
+                const int      j  = j0 + u;
+                const uint32_t li = FULL ? ((uint32_t)((j >> 1) * NT) + tid) * 2u + (uint32_t)(j & 1)
+                                         : tile_local_index<NT, U>(j, vec);
+                cval[u] = row_on(j, li) ? (uint32_t)ld_stream_u64(opt.carry_col + base + li) : 0u;
             }
-            if constexpr (sizeof(KeyT) == 8) t.pad = 0;
-            const uint32_t slot = loc[(uint32_t)keys[j] & mask] + ((rank2[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
-            B200_DCHECK(slot < (uint32_t)(NT * U));
-            stage[slot] = t;
+        }
+#pragma unroll
+        for (int u = 0; u < SB; ++u) {
+            const int      j  = j0 + u;
+            const uint32_t li = FULL ? ((uint32_t)((j >> 1) * NT) + tid) * 2u + (uint32_t)(j & 1)
+                                     : tile_local_index<NT, U>(j, vec);
+            if (row_on(j, li)) {
+                TupT t;
+                t.key = keys[j];
+                if constexpr (CARRY) {
+                    if constexpr (kHoistCarry) t.rid = narrow_key<uint32_t>(craw[j]);
+                    else t.rid = cval[u];
+                } else {
+                    t.rid = (uint32_t)base + li;
+                }
+                if constexpr (sizeof(KeyT) == 8) t.pad = 0;
+                const uint32_t slot = loc[(uint32_t)keys[j] & mask] + ((rank2[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+                B200_DCHECK(slot < (uint32_t)(NT * U));
+                stage[slot] = t;
+            }
         }
     }
     // ---- (4) the reservations have arrived by now ----
