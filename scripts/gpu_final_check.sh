@@ -28,3 +28,6 @@ B200_FUSE_FILTERS=0 timeout 200 python bench.py --config 3 --steps 20 --no-cpu-b
 timeout 400 python bench.py --config 5 --factor 100 --check-reference > gpurun_out/${T}_config5_x100.json 2> gpurun_out/${T}_config5_x100.err; show gpurun_out/${T}_config5_x100.json
 timeout 500 python bench.py --config 5 --factor 1000 > gpurun_out/${T}_config5.json 2> gpurun_out/${T}_config5.err; show gpurun_out/${T}_config5.json
 tail -3 gpurun_out/${T}_config5.err
+timeout 300 python bench.py --config 4 --gpus 1 --steps 10 > gpurun_out/${T}_config4_n1.json 2> gpurun_out/${T}_config4_n1.err
+python -c "
+import json; d=json.load(open('gpurun_out/${T}_config4_n1.json')); print('config4 n1', d['ms_per_step'], d['roofline']['per_kernel_ms_rank0'], d['checksum_ok'])"
