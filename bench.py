@@ -641,7 +641,7 @@ def run_config4(args):
         dist.all_reduce(want)
     want = [int(x) for x in want.cpu().numpy().view(np.uint64)]
     plan = sh.MultiJoin(b200, dist if world > 1 else None, rank, world, env.local, b200.PLAN_EXCHANGE, nr_loc, ns_loc,
-                        True, True, chunks=args.chunks)
+                        True, True, chunks=args.chunks, radix_bits=args.radix_bits)
     torch.cuda.synchronize()
 
     def step():
@@ -788,6 +788,7 @@ def main():
     ap.add_argument("--scale-bits", type=int, default=0, help="shrink the workload by 2^n (quick checks only)")
     ap.add_argument("--uniform", action="store_true", help="config 4 control: uniform probe keys")
     ap.add_argument("--chunks", type=int, default=0, help="config 4: probe chunks of the exchange (0 = default)")
+    ap.add_argument("--radix-bits", type=int, default=0, help="config 4: radix bits of the exchange plan (0 = automatic)")
     ap.add_argument("--factor", type=int, default=1000, help="config 5: scale factor of the small schema")
     ap.add_argument("--workers", type=lambda s: [int(x) for x in s.split(",")], default=[1, 4, 8])
     ap.add_argument("--workdir", default=None)

@@ -1594,6 +1594,59 @@ void stage_scatter_build_local(const uint64_t *d_keys, uint64_t n, uint32_t rid_
         launch_scatter_pay<uint32_t>(src, bits, cur_l, d_tup_out, pay, npay);
 }
 
+// Two-pass variant of stage_scatter_build_local for MANY partitions (the exchange plan at 2^11 .. 2^12): a 16 K-tuple
+// tile spread over 4096 partitions leaves runs of four tuples — one 32-byte sector each, and 4096 run reservations per
+// tile.  Pass 1 partitions the column(s) by the LOW half of the partition bits into d_tmp (packed tuples, the carried
+// value in the slot; rows with a hot key skipped), pass 2 partitions d_tmp by all the bits: its tiles hold tuples of
+// one coarse partition, i.e. of 2^(bits - cbits) fine ones, so the runs are long again.  8 more bytes per row read and
+// written, both passes at the rate of the well-behaved scatter.
+void stage_scatter_two_pass(const uint64_t *d_keys, uint64_t n, int bits, const uint32_t *d_hist_local, void *d_tup_out,
+                            const uint64_t *carry_col, void *d_tmp, const StageScratch *scr, uint32_t *d_off_out,
+                            const PredSet *skip) {
+    B200_REQUIRE(scr && carry_col && d_tmp && d_off_out, "two-pass scatter: scratch, carried column, buffer and offsets");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(d_keys) & 15) == 0 && (reinterpret_cast<uintptr_t>(carry_col) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(d_tmp) & 15) == 0, "two-pass scatter: 16-byte aligned inputs");
+    Context       &c      = ctx();
+    const uint32_t nparts = 1u << bits;
+    const int      cbits  = bits / 2;
+    const uint32_t nc     = 1u << cbits;
+    B200_REQUIRE(scr->bytes >= (5 * (size_t)(nparts + 1) + 6 * (size_t)(nc + 1)) * sizeof(uint32_t), "stage scratch too small");
+    uint32_t *base5 = static_cast<uint32_t *>(scr->ptr);
+    uint32_t *off_x = base5 + nparts + 1, *cur_l = off_x + nparts + 1, *cur_x = cur_l + nparts + 1, *items = cur_x + nparts + 1;
+    uint32_t *coarse = items + nparts + 1, *c_off = coarse + nc + 1, *c_offx = c_off + nc + 1, *c_cur = c_offx + nc + 1,
+             *c_curx = c_cur + nc + 1, *c_items = c_curx + nc + 1;
+    // fine plan: offsets the caller keeps, cursors of pass 2
+    partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(d_hist_local, d_hist_local, nparts, 1u, 1u, d_off_out, off_x, cur_l,
+                                                          cur_x, items, items, 0u);
+    B200_LAUNCH_CHECK();
+    if (n == 0) return;
+    coarse_hist_kernel<<<1, 1024, 0, c.stream>>>(d_hist_local, nparts, (uint32_t)cbits, coarse);
+    B200_LAUNCH_CHECK();
+    partition_plan_kernel<1024><<<1, 1024, 0, c.stream>>>(coarse, coarse, nc, 1u, 1u, c_off, c_offx, c_cur, c_curx, c_items,
+                                                          c_items, 0u);
+    B200_LAUNCH_CHECK();
+    TimedScope ts("scatter_b");
+    KeySrc     src{d_keys, nullptr, (uint32_t)n};
+    if (skip && skip->hot_keys) {
+        const OptArgs o{0, nullptr, nullptr, carry_col, *skip};
+        launch_scatter_pred_carry(src, cbits, c_cur, d_tmp, o);
+    } else {
+        launch_scatter_carry_tuned(src, cbits, c_cur, d_tmp, carry_col);
+    }
+    {
+        constexpr int NT   = PartCfg<uint32_t, 1>::NT;
+        constexpr int U    = PartCfg<uint32_t, 1>::U;
+        const size_t  smem = (size_t)NT * U * sizeof(Tup32) + 3 * (size_t)nparts * sizeof(uint32_t);
+        auto          k    = radix_scatter_kernel<NT, U, 1, uint32_t, false, false, false, true>;
+        allow_smem(k, smem);
+        KeySrc  tsrc{static_cast<const uint64_t *>(d_tmp), nullptr, (uint32_t)n};
+        OptArgs o{0, nullptr, nullptr, nullptr, PredSet{}};
+        o.n_dev = d_off_out + nparts;   // rows that survived pass 1 = the total of the fine histogram
+        k<<<grid_for(n, NT * U, 1), NT, smem, c.stream>>>(tsrc, (uint32_t)bits, cur_l, static_cast<Tup32 *>(d_tup_out), o);
+        B200_LAUNCH_CHECK();
+    }
+}
+
 void stage_scatter_probe(const uint64_t *d_keys, uint64_t n, int bits, uint32_t *d_cursor, void *d_tup_out) {
     if (n == 0) return;
     KeySrc src{d_keys, nullptr, (uint32_t)n};

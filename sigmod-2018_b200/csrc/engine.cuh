@@ -143,6 +143,10 @@ void       stage_scatter_build_local(const uint64_t *d_keys, uint64_t n, uint32_
                                      const uint64_t *const *pay_cols, uint64_t *const *pay_out,
                                      const StageScratch *scr = nullptr, uint32_t *d_off_out = nullptr,
                                      const PredSet *skip = nullptr);
+// the same result through two partition passes (coarse into d_tmp, then fine): for 2^11 partitions and more
+void       stage_scatter_two_pass(const uint64_t *d_keys, uint64_t n, int bits, const uint32_t *d_hist_local, void *d_tup_out,
+                                  const uint64_t *carry_col, void *d_tmp, const StageScratch *scr, uint32_t *d_off_out,
+                                  const PredSet *skip = nullptr);
 void       stage_build_cursors(const uint32_t *d_hist_all, int world, int rank, int bits, uint32_t *d_total,
                                uint32_t *d_my_start);
 void       stage_exchange_cursors(const uint32_t *d_hist_all, int world, int rank, int bits, uint32_t cap,

@@ -312,6 +312,7 @@ struct OptArgs {
     const uint64_t *carry_col;   // CARRY instances only
     PredSet         pred;        // PRED instances only
     uint64_t        out_rows = 0;   // capacity of `out` in tuples when the caller knows it (checked build only)
+    const uint32_t *n_dev    = nullptr;   // when set: the number of input rows, read on the device (src.n is its bound)
 };
 // CARRY: the row-id slot of a tuple carries (uint32)carry_col[row] instead of the row id (a SUM column whose
 // values fit 32 bits travels inside the tuple: the probe side of the multi-GPU exchange plan).  The column is
@@ -388,7 +389,9 @@ __device__ __forceinline__ KeyT narrow_key(uint64_t v) {
 // PRED (never FULL): rows that fail opt.pred are skipped — a filtered base relation feeds the join without a row-id
 // list, a host round trip or a compaction gather.  The predicate columns of a tile are pulled into L2
 // one tile ahead like a carried column and read with 128-bit loads at the top of the tile.
-template <int NT, int U, typename KeyT, bool FULL, bool OPT, bool CARRY = false, bool PRED = false>
+// TUPIN: the input is an array of packed 32-bit-key tuples {key32, slot32} (the first pass of a two-pass partition):
+// the key is the low half of the raw value, the slot travels on unchanged.
+template <int NT, int U, typename KeyT, bool FULL, bool OPT, bool CARRY = false, bool PRED = false, bool TUPIN = false>
 __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[U], uint64_t base, uint32_t count,
                                              bool vec, uint64_t nbase, uint32_t ncount, bool nvec, bool has_next,
                                              uint32_t nbins, uint32_t mask, uint32_t per,
@@ -403,8 +406,9 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     const uint32_t lane = tid & 31u, wid = tid >> 5;
     KeyT           keys[U];
 #pragma unroll
-    for (int j = 0; j < U; ++j) keys[j] = narrow_key<KeyT>(raw[j]);
+    for (int j = 0; j < U; ++j) keys[j] = TUPIN ? (KeyT)(uint32_t)raw[j] : narrow_key<KeyT>(raw[j]);
     static_assert(U <= 64, "one validity bit per key");
+    static_assert(!TUPIN || (sizeof(KeyT) == 4 && !CARRY && !PRED && !OPT), "packed tuples: plain 32-bit-key instance");
     [[maybe_unused]] uint64_t valid = 0;   // PRED: bit j = row of register j passes every predicate
     if constexpr (PRED) {
         const PredSet &ps     = opt.pred;
@@ -581,6 +585,8 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
                 if constexpr (CARRY) {
                     if constexpr (kHoistCarry) t.rid = narrow_key<uint32_t>(craw[j]);
                     else t.rid = cval[u];
+                } else if constexpr (TUPIN) {
+                    t.rid = (uint32_t)(raw[j] >> 32);
                 } else {
                     t.rid = (uint32_t)base + li;
                 }
@@ -648,7 +654,7 @@ __device__ __forceinline__ void scatter_tile(const KeySrc &src, uint64_t (&raw)[
     __syncthreads();   // (E) stage and bin arrays free for the next tile
 }
 
-template <int NT, int U, int MINB, typename KeyT, bool OPT, bool CARRY = false, bool PRED = false>
+template <int NT, int U, int MINB, typename KeyT, bool OPT, bool CARRY = false, bool PRED = false, bool TUPIN = false>
 __global__ void __launch_bounds__(NT, MINB)
 radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cursor,
                      typename TupOf<KeyT>::type *__restrict__ out, const OptArgs opt) {
@@ -667,7 +673,7 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
     __shared__ uint32_t s_over;
 
     // row ids are 32-bit: tile bases fit 32 bits as well
-    const uint64_t n      = src.n;
+    const uint64_t n      = opt.n_dev ? (uint64_t)*opt.n_dev : src.n;   // (a count only the device knows)
     const uint64_t ntiles = (n + TILE - 1) / TILE;
     bool           vec_ok = src.ids == nullptr && ((reinterpret_cast<uintptr_t>(src.col) & 15) == 0) &&
                   (!CARRY || (reinterpret_cast<uintptr_t>(opt.carry_col) & 15) == 0);
@@ -719,14 +725,26 @@ radix_scatter_kernel(KeySrc src, uint32_t radix_bits, uint32_t *__restrict__ cur
                                                                    nbins, mask, per, stage, cnt, loc, gdelta, warp_sums,
                                                                    cursor, out, opt, ovdelta, &s_over, hotbits);
         } else if (vec) {
-            scatter_tile<NT, U, KeyT, true, OPT, CARRY>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
+            scatter_tile<NT, U, KeyT, true, OPT, CARRY, false, TUPIN>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
                                                         nbins, mask, per, stage, cnt, loc, gdelta, warp_sums, cursor,
                                                         out, opt, ovdelta, &s_over);
         } else {
-            scatter_tile<NT, U, KeyT, false, OPT, CARRY>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
+            scatter_tile<NT, U, KeyT, false, OPT, CARRY, false, TUPIN>(src, raw, base, count, vec, nbase, ncount, nvec, has_next,
                                                          nbins, mask, per, stage, cnt, loc, gdelta, warp_sums, cursor,
                                                          out, opt, ovdelta, &s_over);
         }
+    }
+}
+
+// Two-pass partition: histogram over the low `cbits` of the partition index from the fine histogram
+// (coarse[c] = sum of fine[p] over p with p & (2^cbits - 1) == c).  One CTA.
+static __global__ void __launch_bounds__(1024)
+coarse_hist_kernel(const uint32_t *__restrict__ fine, uint32_t nparts, uint32_t cbits, uint32_t *__restrict__ coarse) {
+    const uint32_t nc = 1u << cbits;
+    for (uint32_t c = threadIdx.x; c < nc; c += 1024) {
+        uint32_t sum = 0;
+        for (uint32_t p = c; p < nparts; p += nc) sum += fine[p];
+        coarse[c] = sum;
     }
 }
 

@@ -75,7 +75,8 @@ struct MultiPlan {
     uint32_t      *d_epoch = nullptr, *d_error = nullptr, *cur_p = nullptr, *ovcnt = nullptr, *pull_work = nullptr;
     int            pull = 0, pull_sms = 12;   // broadcast plan: fetch the peers' regions with a kernel instead of pushing
     unsigned long long *d_result = nullptr, *d_final = nullptr;
-    void          *tup_p = nullptr, *ov_p = nullptr, *stage_b = nullptr, *stage_p = nullptr;
+    void          *tup_p = nullptr, *ov_p = nullptr, *stage_b = nullptr, *stage_p = nullptr, *stage_tmp = nullptr;
+    int            two_pass_bits = 11;   // probe chunks take two partition passes from this many radix bits up
     uint32_t      *src_off_b = nullptr, *src_off_p = nullptr, *dst_start_b = nullptr, *dst_start_p = nullptr;
     uint32_t      *own_total = nullptr, *total = nullptr, *cut = nullptr, *need = nullptr;
     // hot keys (exchange plan): sampling table, the agreed table, build-side aggregates, the hot rows' result
@@ -150,6 +151,7 @@ static void layout_local(MultiPlan &m, void *base, size_t *bytes) {
     } else {
         m.stage_b     = c.take<uint64_t>(std::max<size_t>(nb, 1));
         m.stage_p     = c.take<uint64_t>(std::max<size_t>(np, 1));
+        m.stage_tmp   = c.take<uint64_t>((np + (size_t)m.K - 1) / (size_t)m.K + 16);   // one chunk, between the two passes
         m.src_off_b   = c.take<uint32_t>(P + 1);
         m.src_off_p   = c.take<uint32_t>((size_t)m.K * (P + 1));
         m.dst_start_b = c.take<uint32_t>(P);
@@ -168,7 +170,10 @@ static void layout_local(MultiPlan &m, void *base, size_t *bytes) {
     *bytes = align_up(c.off, 256);
 }
 
-static uint32_t chunk_first(const MultiPlan &m, uint64_t n, int c) { return (uint32_t)(n * (uint64_t)c / (uint64_t)m.K); }
+// first row of chunk c of n rows (chunk K starts at n); even, so that 16-byte aligned shards give 16-byte aligned chunks
+static uint32_t chunk_first(const MultiPlan &m, uint64_t n, int c) {
+    return c >= m.K ? (uint32_t)n : (uint32_t)((n * (uint64_t)c / (uint64_t)m.K) & ~1ull);
+}
 
 // ---------------------------------------------------------------------------
 // steps
@@ -458,9 +463,16 @@ static void enqueue_exchange(MultiPlan &m, int phases) {
             const uint32_t a = chunk_first(m, np, k), b = chunk_first(m, np, k + 1);
             const uint64_t *pp[1] = {m.in_pp ? m.in_pp + a : nullptr};
             uint64_t *staged = static_cast<uint64_t *>(m.stage_p) + a;
-            stage_scatter_build_local(m.in_pk + a, b - a, a, m.bits, my_hp + (size_t)k * P, staged,
-                                      m.cfg.has_probe_sum ? 1 : 0, pp, nullptr, &m.scr_a, m.src_off_p + (size_t)k * (P + 1),
-                                      m.hot ? &skip : nullptr);
+            // (chunk starts are even, so a 16-byte aligned shard gives 16-byte aligned chunks)
+            const bool two_pass = m.bits >= m.two_pass_bits && m.cfg.has_probe_sum && b - a >= (1u << 20) && (a & 1u) == 0 &&
+                                  ((reinterpret_cast<uintptr_t>(m.in_pk) | reinterpret_cast<uintptr_t>(m.in_pp)) & 15) == 0;
+            if (two_pass)
+                stage_scatter_two_pass(m.in_pk + a, b - a, m.bits, my_hp + (size_t)k * P, staged, m.in_pp + a, m.stage_tmp,
+                                       &m.scr_a, m.src_off_p + (size_t)k * (P + 1), m.hot ? &skip : nullptr);
+            else
+                stage_scatter_build_local(m.in_pk + a, b - a, a, m.bits, my_hp + (size_t)k * P, staged,
+                                          m.cfg.has_probe_sum ? 1 : 0, pp, nullptr, &m.scr_a,
+                                          m.src_off_p + (size_t)k * (P + 1), m.hot ? &skip : nullptr);
             B200_CUDA(cudaEventRecord(m.ev_chunk[k], main));
             B200_CUDA(cudaStreamWaitEvent(m.xstream, m.ev_chunk[k], 0));
             exchange(staged, b - a, m.src_off_p + (size_t)k * (P + 1), m.dst_start_p + (size_t)k * P, m.cap_p, false);
@@ -594,6 +606,7 @@ b200_multi *b200_multi_create(const b200_multi_config *cfg) {
     B200_CUDA(cudaEventCreateWithFlags(&m->ev_x, cudaEventDisableTiming));
     for (int k = 0; k < kMaxChunks; ++k) B200_CUDA(cudaEventCreateWithFlags(&m->ev_chunk[k], cudaEventDisableTiming));
     m->peer[m->rank] = m->shared;
+    if (const char *e = getenv("B200_TWO_PASS_BITS")) m->two_pass_bits = atoi(e);
     m->use_graph = m->world > 1;   // measured at 8 GPUs: 0.612 -> 0.579 ms per config-2 step
     if (const char *g = getenv("B200_MULTI_GRAPH")) m->use_graph = atoi(g);
     B200_CUDA(cudaDeviceSynchronize());
