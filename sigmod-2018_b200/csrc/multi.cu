@@ -76,7 +76,8 @@ struct MultiPlan {
     int            pull = 0, pull_sms = 12;   // broadcast plan: fetch the peers' regions with a kernel instead of pushing
     unsigned long long *d_result = nullptr, *d_final = nullptr;
     void          *tup_p = nullptr, *ov_p = nullptr, *stage_b = nullptr, *stage_p = nullptr, *stage_tmp = nullptr;
-    int            two_pass_bits = 11;   // probe chunks take two partition passes from this many radix bits up
+    int            two_pass_bits = 99;   // B200_TWO_PASS_BITS: probe chunks take two partition passes from this many radix
+                                         // bits up (off by default: measured no faster than one pass)
     uint32_t      *src_off_b = nullptr, *src_off_p = nullptr, *dst_start_b = nullptr, *dst_start_p = nullptr;
     uint32_t      *own_total = nullptr, *total = nullptr, *cut = nullptr, *need = nullptr;
     // hot keys (exchange plan): sampling table, the agreed table, build-side aggregates, the hot rows' result
@@ -103,7 +104,7 @@ struct MultiPlan {
     uint32_t     *hist_p(int r) const { return reinterpret_cast<uint32_t *>(peer[r] + off_hist_p); }
     unsigned char *build(int r) const { return peer[r] + off_build; }
     unsigned char *recv_p(int r) const { return peer[r] + off_recv_p; }
-    uint32_t      *cand(int r) const { return reinterpret_cast<uint32_t *>(peer[r] + off_cand); }   // [world][1 + kHotMaxCand]
+    uint32_t      *cand(int r) const { return reinterpret_cast<uint32_t *>(peer[r] + off_cand); }   // [world][kHotCandWords]
     unsigned long long *agg(int r) const { return reinterpret_cast<unsigned long long *>(peer[r] + off_agg); }
     PeerPtrs peers() const {
         PeerPtrs p{};
@@ -125,7 +126,7 @@ static void layout_shared(MultiPlan &m) {
     } else {
         m.off_hist_p   = align_up(m.off_hist_b + (size_t)m.world * m.P * 4, 256);
         m.off_cand     = align_up(m.off_hist_p + (size_t)m.world * m.K * m.P * 4, 256);
-        m.off_agg      = align_up(m.off_cand + (size_t)m.world * (1 + kHotMaxCand) * 4, 256);
+        m.off_agg      = align_up(m.off_cand + (size_t)m.world * kHotCandWords * 4, 256);
         m.off_build    = align_up(m.off_agg + (size_t)m.world * kHotSlots * 16, 256);
         m.off_recv_p   = align_up(m.off_build + ((size_t)m.cap_b + 16) * 8, 256);
         m.shared_bytes = align_up(m.off_recv_p + ((size_t)m.cap_p + 16) * 8, 256);
@@ -332,7 +333,7 @@ static void enqueue_exchange(MultiPlan &m, int phases) {
     const uint64_t nb = m.cfg.n_build_local, np = m.cfg.n_probe_local;
     uint32_t *my_hb = m.hist_b(rank) + (size_t)rank * P;
     uint32_t *my_hp = m.hist_p(rank) + (size_t)rank * K * P;
-    const size_t cand_words = 1 + kHotMaxCand;
+    const size_t cand_words = kHotCandWords;
     if (phases & 1) {
         bump_epoch_kernel<<<1, 1, 0, main>>>(m.d_epoch);
         B200_LAUNCH_CHECK();

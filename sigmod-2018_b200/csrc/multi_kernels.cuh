@@ -244,15 +244,16 @@ static __global__ void __launch_bounds__(256) push_to_peers_kernel(const PushArg
 // streams by: matches += cnt[key], SUM(build) += sum[key], SUM(probe) += cnt[key] * value.  Such rows are neither
 // partitioned nor exchanged nor probed.
 //   hot_sample_kernel    counts a sample of the local probe keys in an open-addressing table
-//   hot_select_kernel    keys seen at least `threshold` times -> this rank's candidate list {n, keys...}
-//   hot_table_kernel     every rank, from the SAME gathered candidate lists in the same order: a direct-mapped
-//                        table of kHotSlots keys (a candidate whose slot is taken is simply not hot)
+//   hot_select_kernel    keys seen at least `threshold` times -> this rank's candidate list {n, keys..., sample counts...}
+//   hot_table_kernel     every rank, from the SAME gathered candidate lists: a direct-mapped table of kHotSlots keys
+//                        (of the candidates that share a slot the one with the largest sample count is hot)
 //   hot_build_kernel     local build rows with a hot key: agg[slot] += {1, value}
 //   hot_reduce_kernel    sum of all ranks' aggregates
 //   hot_hist_kernel      the probe-side histogram pass: hot rows are accumulated, the others counted
 // ---------------------------------------------------------------------------
 // (kHotSlots = 8192 direct-mapped slots, hot_slot(), kHotEmpty: kernels.cuh — the scatter skips hot rows too)
-constexpr uint32_t kHotMaxCand = 2048;       // candidates per rank
+constexpr uint32_t kHotMaxCand  = 2048;                  // candidates per rank
+constexpr uint32_t kHotCandWords = 1 + 2 * kHotMaxCand;  // a rank's list: count, keys[kHotMaxCand], sample counts[kHotMaxCand]
 constexpr uint32_t kHotSample  = 1u << 16;   // slots of the sampling table
 
 static __global__ void __launch_bounds__(256)
@@ -274,28 +275,37 @@ hot_sample_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint64_t nsampl
 }
 static __global__ void __launch_bounds__(256)
 hot_select_kernel(const uint32_t *__restrict__ t_keys, const uint32_t *__restrict__ t_cnt, uint32_t threshold,
-                  uint32_t *__restrict__ cand /* [1 + kHotMaxCand] */) {
+                  uint32_t *__restrict__ cand /* [kHotCandWords] */) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot < kHotSample && t_keys[slot] != kHotEmpty && t_cnt[slot] >= threshold) {
         const uint32_t at = atomicAdd(&cand[0], 1u);
-        if (at < kHotMaxCand) cand[1 + at] = t_keys[slot];
+        if (at < kHotMaxCand) {
+            cand[1 + at]               = t_keys[slot];
+            cand[1 + kHotMaxCand + at] = t_cnt[slot];
+        }
     }
 }
 static __global__ void __launch_bounds__(1024)
-hot_table_kernel(const uint32_t *__restrict__ cand_all /* [world][1 + kHotMaxCand] */, int world,
+hot_table_kernel(const uint32_t *__restrict__ cand_all /* [world][kHotCandWords] */, int world,
                  uint32_t *__restrict__ hot_keys /* [kHotSlots] */, uint32_t *__restrict__ hot_n) {
-    // Every rank must end up with the same table: a slot belongs to the FIRST candidate, in (rank, position) order,
-    // that maps to it.  "First" is an atomicMin over that order, so all 1024 threads work on the lists (one thread
-    // walking up to world x 2048 candidates through dependent global loads took ~1 ms at 8 ranks).
+    // Every rank must end up with the same table.  A slot belongs to the candidate with the LARGEST sample count that
+    // maps to it (the table is direct-mapped: losing the slot means being exchanged like any other key, which the
+    // hottest keys must not be), ties to the first in rank / position order: an atomicMin over
+    // [inverted count | rank, position], so all 1024 threads work on the lists (one thread walking up to
+    // world x 2048 candidates through dependent global loads took ~1 ms at 8 ranks).
+    static_assert(kMaxPeers * kHotMaxCand <= (1u << 14), "rank and position in 14 bits");
     __shared__ uint32_t s_ord[kHotSlots];
     __shared__ uint32_t s_n;
     for (uint32_t i = threadIdx.x; i < kHotSlots; i += 1024) s_ord[i] = 0xFFFFFFFFu;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     for (int r = 0; r < world; ++r) {
-        const uint32_t *c   = cand_all + (size_t)r * (1 + kHotMaxCand);
+        const uint32_t *c   = cand_all + (size_t)r * kHotCandWords;
         const uint32_t  cnt = min(c[0], kHotMaxCand);
-        for (uint32_t i = threadIdx.x; i < cnt; i += 1024) atomicMin(&s_ord[hot_slot(c[1 + i])], (uint32_t)r * kHotMaxCand + i);
+        for (uint32_t i = threadIdx.x; i < cnt; i += 1024) {
+            const uint32_t weight = min(c[1 + kHotMaxCand + i], 0x3FFFEu);
+            atomicMin(&s_ord[hot_slot(c[1 + i])], ((0x3FFFEu - weight) << 14) | ((uint32_t)r * kHotMaxCand + i));
+        }
     }
     __syncthreads();
     uint32_t mine = 0;
@@ -303,7 +313,8 @@ hot_table_kernel(const uint32_t *__restrict__ cand_all /* [world][1 + kHotMaxCan
         const uint32_t ord = s_ord[slot];
         uint32_t       key = kHotEmpty;
         if (ord != 0xFFFFFFFFu) {
-            key = cand_all[(size_t)(ord / kHotMaxCand) * (1 + kHotMaxCand) + 1 + ord % kHotMaxCand];
+            const uint32_t at = ord & 0x3FFFu;
+            key = cand_all[(size_t)(at / kHotMaxCand) * kHotCandWords + 1 + at % kHotMaxCand];
             ++mine;
         }
         hot_keys[slot] = key;

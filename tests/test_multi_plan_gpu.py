@@ -99,10 +99,12 @@ def test_broadcast_plan_projection_subsets(gpu, orc, has_b, has_p):
                                                               (3, 16, (1 << 20) + 77, False, 2, 0), (4, 15, 9, True, 0, 0),
                                                               (2, 17, 1 << 20, False, 8, 8), (8, 16, 1 << 21, True, 2, 0),
                                                               (2, 17, (1 << 22) + 70, True, 2, 12), (1, 16, (1 << 21) + 6, False, 2, 11)])
-def test_exchange_plan_emulated_ranks(gpu, orc, world, kr_bits, ns, zipf, chunks, bits, hot):
+def test_exchange_plan_emulated_ranks(gpu, orc, world, kr_bits, ns, zipf, chunks, bits, hot, monkeypatch):
     """hot: keys a large share of a sample of the probe rows carries are joined where they are, during the histogram
     pass (Zipf inputs have them, the uniform ones do not); off: everything is exchanged.  The last two cases have
     2^11 / 2^12 partitions and chunks of >= 2^20 rows: their probe chunks take the two-pass partition."""
+    if bits >= 11:
+        monkeypatch.setenv("B200_TWO_PASS_BITS", "11")      # (off by default)
     nr = (1 << kr_bits) - 9
     kr = orc.synth_column(1 << kr_bits, 0, kr_bits, gpu.SEED_R)[:nr]
     ks = orc.synth_column(ns, 2, kr_bits, 41) if zipf else orc.synth_column(ns, 0, kr_bits + 2, gpu.SEED_S)
