@@ -87,9 +87,10 @@ def parallelism_text(world: int) -> str:
     return (f"R and S position-sharded x{world}; " +
             ("both sides radix-partitioned locally, every partition stored into its owner's buffers over NVLink "
              "(exchange kernel, CUDA IPC), owners join" if exchange else
-             "each build shard partitioned once and pushed to every GPU by the copy engines (chunked, flags in peer "
-             "memory), probe shard partitioned locally, join overlaps the broadcast tail") +
-            "; no NCCL in the step, results summed from peer-written slots")
+             "each build shard partitioned once and pushed to every GPU by the copy engines (one region copy and one "
+             "flag in peer memory per peer), probe shard partitioned locally meanwhile, the join waits for the regions it "
+             "reads") +
+            "; no NCCL in the step, results summed from peer-written slots, the step replayed from a CUDA graph")
 
 
 # --------------------------------------------------------------------------

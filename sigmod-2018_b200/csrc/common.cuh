@@ -108,7 +108,11 @@ struct TimedScope {
     ~TimedScope();
 };
 
-inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern thread_local uint64_t t_launches;   // the calling thread's share of g_launches
+inline void count_launch() {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    ++t_launches;
+}
 
 #define B200_LAUNCH_CHECK()                                                           \
     do {                                                                              \

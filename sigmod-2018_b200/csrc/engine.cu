@@ -41,6 +41,7 @@ static int            g_device   = -1;
 static int            g_sm_count = 0;
 static bool           g_profiling = false;
 std::atomic<uint64_t> g_launches{0};
+thread_local uint64_t t_launches = 0;
 
 // keep freed blocks in the stream-ordered pool instead of returning them
 static void configure_device_pool(int device) {

@@ -98,6 +98,7 @@ struct MultiPlan {
     cudaGraphExec_t graph = nullptr;
     const uint64_t *g_in[4] = {nullptr, nullptr, nullptr, nullptr};
     int             use_graph = 0;
+    uint64_t        graph_kernels = 0;   // kernel launches one replay of the graph stands for (b200_kernel_launches)
 
     SharedHeader *hdr(int r) const { return reinterpret_cast<SharedHeader *>(peer[r]); }
     uint32_t     *hist_b(int r) const { return reinterpret_cast<uint32_t *>(peer[r] + off_hist_b); }
@@ -716,15 +717,20 @@ int b200_multi_enqueue(b200_multi *plan, const uint64_t *d_build_keys, const uin
             cudaGraph_t g = nullptr;
             {
                 StreamSwap sw(c, m->gstream);
+                const uint64_t before = t_launches;
                 B200_CUDA(cudaStreamBeginCapture(m->gstream, cudaStreamCaptureModeThreadLocal));
                 enqueue(*m, phases);
                 B200_CUDA(cudaStreamEndCapture(m->gstream, &g));
+                // the launch counter counts kernels that RUN: nothing ran during the capture, every replay runs them all
+                m->graph_kernels = t_launches - before;
+                g_launches.fetch_sub(m->graph_kernels);
             }
             B200_CUDA(cudaGraphInstantiate(&m->graph, g, 0));
             cudaGraphDestroy(g);
             memcpy(m->g_in, in, sizeof(in));
         }
         B200_CUDA(cudaGraphLaunch(m->graph, c.stream));
+        g_launches.fetch_add(m->graph_kernels);
     } else {
         enqueue(*m, phases);
     }
