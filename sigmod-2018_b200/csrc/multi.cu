@@ -99,6 +99,7 @@ struct MultiPlan {
     const uint64_t *g_in[4] = {nullptr, nullptr, nullptr, nullptr};
     int             use_graph = 0;
     uint64_t        graph_kernels = 0;   // kernel launches one replay of the graph stands for (b200_kernel_launches)
+    bool            pull_smem_set = false;
 
     SharedHeader *hdr(int r) const { return reinterpret_cast<SharedHeader *>(peer[r]); }
     uint32_t     *hist_b(int r) const { return reinterpret_cast<uint32_t *>(peer[r] + off_hist_b); }
@@ -229,11 +230,10 @@ static void enqueue_broadcast(MultiPlan &m, int phases) {
             if (world > 1) {
                 StreamSwap sw(c, m.xstream);
                 TimedScope ts("broadcast");
-                static bool smem_set = false;
-                if (!smem_set) {
+                if (!m.pull_smem_set) {   // per plan, i.e. per device: function attributes belong to the device's context
                     B200_CUDA(cudaFuncSetAttribute(pull_regions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)kPullSmem));
-                    smem_set = true;
+                    m.pull_smem_set = true;
                 }
                 pull_regions_kernel<<<m.pull_sms, 32, kPullSmem, c.stream>>>(a);
                 B200_LAUNCH_CHECK();
