@@ -589,11 +589,20 @@ b200_multi *b200_multi_create(const b200_multi_config *cfg) {
         if (const char *e = getenv("B200_HOT_KEYS")) m->hot = atoi(e) != 0;
     }
     layout_shared(*m);
-    B200_CUDA(cudaMalloc(&m->shared, m->shared_bytes));
-    B200_CUDA(cudaMemset(m->shared, 0, m->off_build));   // flags, result slots and histograms start at zero
     size_t local_bytes = 0;
     layout_local(*m, nullptr, &local_bytes);
-    B200_CUDA(cudaMalloc(&m->local, local_bytes));
+    // (out of memory is the caller's to handle, not a reason to end the process)
+    if (cudaMalloc(&m->shared, m->shared_bytes) != cudaSuccess || cudaMalloc(&m->local, local_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        if (m->shared) cudaFree(m->shared);
+        char msg[160];
+        snprintf(msg, sizeof(msg), "b200_multi_create: cannot allocate %zu + %zu bytes of device memory", m->shared_bytes,
+                 local_bytes);
+        delete m;
+        set_last_error(msg);
+        return nullptr;
+    }
+    B200_CUDA(cudaMemset(m->shared, 0, m->off_build));   // flags, result slots and histograms start at zero
     layout_local(*m, m->local, &local_bytes);
     B200_CUDA(cudaMemset(m->local, 0, 4096));
     B200_CUDA(cudaMallocHost(&m->h_final, 64));
