@@ -31,6 +31,17 @@ def test_library_exports_every_declared_symbol(b200):
     assert L.b200_is_cuda() == 1
 
 
+def test_checked_build_exports_the_same_symbols(b200):
+    """lib/libb200join_checked.so (the same sources with device-side bounds checks, -DB200_CHECKED) is a drop-in for
+    the shipped library: B200_LIB selects it (tests/test_checked_build_gpu.py runs GPU tests over it)."""
+    from pathlib import Path
+    checked = Path(b200.LIB_PATH).with_name("libb200join_checked.so")
+    assert checked.exists(), f"{checked} is missing: make -C sigmod-2018_b200/csrc checked (or __graft_entry__.build())"
+    L = b200.load_library(checked)
+    for name in b200.declared_symbols():
+        assert hasattr(L, name), name
+
+
 def test_no_cpu_fallback_when_library_missing(b200, tmp_path):
     with pytest.raises(ImportError):
         b200.load_library(tmp_path / "libb200join.so")
