@@ -6,21 +6,30 @@
 //                                      row-id list) view, never an AoS copy
 //   K3  preprocess.c:189-192        -> radix_hist_kernel
 //   K4  preprocess.c:83-102         -> partition_plan_kernel
-//   K5  preprocess.c:262-296,350-359-> radix_scatter_kernel (+ its histogram-free
-//                                      OPT and payload-carrying CARRY instances),
-//                                      radix_scatter_pay_kernel
-//   K6  rhjoin.c:227-248,270-271    -> tag_join_kernel (32-bit keys) /
-//   K7  rhjoin.c:154-216               hash_join_kernel (64-bit keys, small
-//                                      unpartitioned builds): build, probe
+//   K5  preprocess.c:262-296,350-359-> radix_scatter_kernel (+ its instances: OPT
+//                                      histogram-free, CARRY a SUM value in the
+//                                      row-id slot, PRED filter predicates / hot
+//                                      keys evaluated in the load stage, TUPIN
+//                                      packed-tuple input), radix_scatter_pay_kernel
+//   K6  rhjoin.c:227-248,270-271    -> tag_join_kernel (both key widths; K64
+//   K7  rhjoin.c:154-216               verifies candidates, SEG reads a build side
+//                                      made of one run per source GPU) /
+//                                      hash_join_kernel (small unpartitioned
+//                                      builds): build, probe
 //   K8  inter_res.c:79-98,119-137;
 //       filter.c:60-76; inter_res.c:304-313 -> gather_columns_kernel
 //   K9  inter_res.c:332-333         -> checksum_kernel / the MODE_SUM instances
 //                                      of the join kernels
 //   K11 inter_res.c:376-385         -> inter_equal_kernel
-//   multi-GPU (absent in the reference): build_cursors_kernel,
-//                                      segment_broadcast_kernel,
-//                                      exchange_cursors_kernel,
-//                                      segment_exchange_kernel
+//   loader statistics relation_map.c:53-83 -> column_minmax_kernel,
+//                                      column_mark_kernel, bitmap_count_kernel
+//   multi-GPU (absent in the reference): segment_offsets_kernel, coarse_hist_kernel
+//                                      here; flags, pushes, hot keys, ownership
+//                                      cuts, exchange and fetch kernels in
+//                                      multi_kernels.cuh.  build_cursors_kernel,
+//                                      exchange_cursors_kernel and
+//                                      segment_exchange_kernel serve the staged
+//                                      entry points (b200_stage_*) of round 1
 //
 // Integer/byte work only: no tensor cores.  Row ids and positions are 32-bit
 // on the device; keys are 32-bit when the column maxima allow it (8-byte
